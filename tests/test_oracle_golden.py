@@ -158,7 +158,7 @@ def test_multimodal_matches_reference(golden):
         if k.startswith('grad.') and not k.startswith('grad.patch_classifier'):
             ref = gold[k]
             got = sd[k[5:]].grad.numpy()
-            assert np.allclose(got, ref, rtol=5e-3, atol=1e-3 * max(np.abs(ref).max(), 1e-6)), k
+            assert np.allclose(got, ref, rtol=5e-3, atol=max(1e-3 * np.abs(ref).max(), 1e-7)), k  # pre-BN bias grads are exactly 0 in theory
             n += 1
         if k.startswith('after.') and 'num_batches' not in k:
             assert np.allclose(stats[k[6:]].numpy(), gold[k], rtol=1e-4, atol=1e-5), k
