@@ -155,7 +155,7 @@ def test_multimodal_matches_reference(golden):
     assert nfg == int(gold['nfg'])
     n = 0
     for k in gold.files:
-        if k.startswith('grad.') and not k.startswith('grad.patch_classifier'):
+        if k.startswith('grad.'):   # patch_classifier.* aliases image_classifier.* (same tensors)
             ref = gold[k]
             got = sd[k[5:]].grad.numpy()
             assert np.allclose(got, ref, rtol=5e-3, atol=max(1e-3 * np.abs(ref).max(), 1e-7)), k  # pre-BN bias grads are exactly 0 in theory
