@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI shared library (include/gridnext_b200.h).
+
+PyTorch only provides device memory and the CUDA stream; every kernel on the hot path is a plain
+``extern "C"`` entry point taking raw device pointers, sizes and a ``cudaStream_t``.  There is NO
+fallback: if the library is missing or a call fails, the caller gets an exception.
+"""
+import ctypes
+import os
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libgridnext_b200.so')
+
+_lib = None
+
+vp, ci, cl, cf, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_double
+
+# name -> argtypes (all functions return int except where noted); mirrors include/gridnext_b200.h
+_SIGS = {
+    'gn_version': [],
+    'gn_device_sm_count': [],
+    'gn_hexconv_n_taps': [ci],
+    'gn_hexconv_pack': [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp],
+    'gn_hexconv_unpack_grad': [vp, vp, vp, vp, vp, ci, ci, ci, vp],
+    'gn_hexconv_fwd': [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
+    'gn_hexconv_wgrad': [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
+    'gn_bn_finalize': [vp, vp, vp, vp, vp, cf, cf, cd, vp, vp, vp, ci, ci, vp],
+    'gn_bn_eval_affine': [vp, vp, vp, vp, cf, vp, vp, vp, ci, vp],
+    'gn_bn_stats': [vp, vp, ci, ci, cl, vp],
+    'gn_bn_act_fwd': [vp, vp, vp, vp, ci, ci, cl, ci, vp],
+    'gn_bn_act_bwd': [vp, vp, vp, vp, vp, vp, cd, ci, vp, vp, vp, ci, ci, cl, ci, vp],
+    'gn_masked_ce': [vp, vp, vp, vp, vp, vp, cf, ci, ci, cl, vp],
+    'gn_spot_table': [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp],
+    'gn_patch_gather': [vp, cl, ci, ci, vp, ci, ci, vp, vp, vp, ci, vp],
+}
+
+
+def declared_symbols():
+    return sorted(_SIGS) + ['gn_last_error']
+
+
+def load():
+    """Load the library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "gridnext_b200: CUDA library %s is missing. Build it with `python -m gridnext_b200.build` "
+            "(there is no CPU fallback)." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.gn_last_error.restype = ctypes.c_char_p
+    lib.gn_last_error.argtypes = []
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def register(sigs):
+    """Used by sibling modules to add entry points (keeps one table for the symbol test)."""
+    _SIGS.update(sigs)
+    if _lib is not None:
+        for name, args in sigs.items():
+            fn = getattr(_lib, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = args
+
+
+def check(rc, what=''):
+    if rc == 0:
+        return
+    msg = load().gn_last_error().decode(errors='replace')
+    if rc < 0:
+        raise ValueError('gridnext_b200 %s: %s (code %d)' % (what, msg, rc))
+    raise RuntimeError('gridnext_b200 %s: CUDA error %d: %s' % (what, rc, msg))
+
+
+def call(name, *args):
+    lib = load()
+    check(getattr(lib, name)(*args), name)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gridnext_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)

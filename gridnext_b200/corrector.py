@@ -1,0 +1,162 @@
+"""Fused execution of the hexagonal g corrector (forward + backward) in the Visium layout.
+
+Runs the ``nn.Sequential`` built by ``GridNetHex._init_corrector``
+(/root/reference/gridnext/gridnet_models.py:128-148: hex hex [BN] ReLU hex hex [BN] ReLU hex) as ONE
+autograd node: BatchNorm statistics come out of the preceding hexconv's epilogue, BatchNorm-apply +
+ReLU is the next hexconv's prologue (the activated tensor is never materialised), and the rot90/flip
+re-indexing of gridnet_models.py:177-185 is gone because the kernels take the row parity directly.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ptr, stream, call
+from . import hexagdly as hx
+
+
+def parse_corrector(seq):
+    """-> list of stages [(hex_module, bn_module | None, relu_before: bool)] or None if not fusable.
+
+    Stage j = optional (BatchNorm2d, ReLU | ReLU) applied to the running tensor, then a hex conv."""
+    if not isinstance(seq, nn.Sequential):
+        return None
+    stages, bn, relu = [], None, False
+    for m in seq:
+        if isinstance(m, hx.Conv2d):
+            if bn is not None and not relu:
+                return None           # BN without ReLU before a conv: not a pattern we fuse
+            stages.append((m, bn, relu))
+            bn, relu = None, False
+        elif isinstance(m, nn.BatchNorm2d):
+            if bn is not None or relu or not stages or not m.track_running_stats or not m.affine:
+                return None
+            bn = m
+        elif isinstance(m, nn.ReLU):
+            if relu or not stages:
+                return None
+            relu = True
+        else:
+            return None
+    if bn is not None or relu or not stages:
+        return None
+    return stages
+
+
+class _CorrectorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, meta, *params):
+        """meta: list per stage of dict(ksize, cin, cout, nk, has_bias, bn: None | dict(training, momentum, eps), relu)
+        params: flattened per stage: kernels..., [bias], [bn.weight, bn.bias]; BN running buffers travel in meta."""
+        _lib.require_cuda(x)
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        dev = x.device
+        saved = []          # per stage: input tensor, scale, shift, mean_invstd
+        it = iter(params)
+        cur = x
+        cur_stats = None    # fp64 [2*C] stats of `cur` if a BN follows
+        per_stage_params = []
+        for j, st in enumerate(meta):
+            ks = [next(it).contiguous() for _ in range(st['nk'])]
+            bias = next(it) if st['has_bias'] else None
+            gamma = beta = None
+            scale = shift = mi = None
+            if st['bn'] is not None:
+                gamma, beta = next(it), next(it)
+                C = st['cin']
+                scale = torch.empty(C, device=dev); shift = torch.empty(C, device=dev); mi = torch.empty(2 * C, device=dev)
+                bn = st['bn']
+                if bn['training']:
+                    call('gn_bn_finalize', ptr(cur_stats), ptr(gamma), ptr(beta), ptr(bn['running_mean']), ptr(bn['running_var']),
+                         bn['momentum'], bn['eps'], float(B * H * W), ptr(scale), ptr(shift), ptr(mi), C, 1, stream())
+                else:
+                    call('gn_bn_eval_affine', ptr(gamma), ptr(beta), ptr(bn['running_mean']), ptr(bn['running_var']), bn['eps'],
+                         ptr(scale), ptr(shift), ptr(mi), C, stream())
+            elif st['relu']:
+                C = st['cin']
+                scale = torch.ones(C, device=dev); shift = torch.zeros(C, device=dev)
+            wp = hx.pack_weights(ks, st['ksize'], st['cin'], st['cout'], 0)
+            nxt = meta[j + 1] if j + 1 < len(meta) else None
+            want_stats = nxt is not None and nxt['bn'] is not None and nxt['bn']['training']
+            stats = torch.zeros(2 * st['cout'], device=dev, dtype=torch.float64) if want_stats else None
+            out = hx.hexconv_fwd(cur, wp, bias, st['cout'], st['ksize'], scale, shift, stats)
+            saved.append((cur, scale, shift, mi))
+            per_stage_params.append((ks, bias, gamma, beta))
+            cur, cur_stats = out, stats
+        ctx.meta = meta
+        ctx.saved = saved
+        ctx.stage_params = per_stage_params
+        ctx.dims = (B, H, W)
+        return cur
+
+    @staticmethod
+    def backward(ctx, dout):
+        meta, saved, sp = ctx.meta, ctx.saved, ctx.stage_params
+        B, H, W = ctx.dims
+        grad = dout.contiguous().float()
+        dev = grad.device
+        grads = [None] * len(meta)
+        for j in range(len(meta) - 1, -1, -1):
+            st = meta[j]
+            inp, scale, shift, mi = saved[j]
+            ks, bias, gamma, beta = sp[j]
+            dwp, db = hx.hexconv_wgrad(inp, grad, st['ksize'], scale, shift, want_bias=bias is not None)
+            gks = hx.unpack_grad(dwp, [k.shape for k in ks], st['ksize'], st['cin'], st['cout'])
+            dgamma = dbeta = None
+            need_dx = j > 0 or ctx.needs_input_grad[0]
+            if need_dx:
+                wpt = hx.pack_weights(ks, st['ksize'], st['cin'], st['cout'], 1)
+                dA = hx.hexconv_fwd(grad, wpt, None, st['cin'], st['ksize'])
+                if scale is not None:
+                    C = st['cin']
+                    dH = torch.empty_like(dA)
+                    sums = torch.empty(2 * C, device=dev, dtype=torch.float64)
+                    if st['bn'] is not None:
+                        dgamma = torch.empty(C, device=dev); dbeta = torch.empty(C, device=dev)
+                        training = 1 if st['bn']['training'] else 0
+                    else:
+                        mi = torch.zeros(2 * C, device=dev); mi[C:] = 1.0
+                        training = 0
+                    call('gn_bn_act_bwd', ptr(dA), ptr(inp), ptr(scale), ptr(shift), ptr(mi), ptr(sums), float(B * H * W), training,
+                         ptr(dH), ptr(dgamma), ptr(dbeta), B, C, H * W, 1, stream())
+                    grad = dH
+                else:
+                    grad = dA
+            elif st['bn'] is not None:
+                raise RuntimeError('corrector: first stage cannot have a BatchNorm prologue')
+            grads[j] = (gks, db, dgamma, dbeta)
+        flat = []
+        for j, st in enumerate(meta):
+            gks, db, dgamma, dbeta = grads[j]
+            flat.extend(gks)
+            if st['has_bias']:
+                flat.append(db)
+            if st['bn'] is not None:
+                flat.extend([dgamma, dbeta])
+        dx = grad if ctx.needs_input_grad[0] else None
+        ctx.saved = None
+        return (dx, None) + tuple(flat)
+
+
+def run_corrector(stages, x, training):
+    """x: (B, f_dim, H, W) Visium layout -> (B, n_out, H, W)."""
+    meta, params = [], []
+    for (hexm, bn, relu) in stages:
+        k = hexm.hexbase_size
+        m = dict(ksize=k, cin=hexm.in_channels, cout=hexm.out_channels, nk=k + 1, has_bias=hexm.bias_tensor is not None, bn=None, relu=relu)
+        params.extend(getattr(hexm, 'kernel%d' % i) for i in range(k + 1))
+        if hexm.bias_tensor is not None:
+            params.append(hexm.bias_tensor)
+        if bn is not None:
+            bn_train = bool(training and bn.training)
+            if bn_train and bn.momentum is None:
+                raise NotImplementedError('BatchNorm2d(momentum=None) (cumulative average) is not supported')
+            m['bn'] = dict(training=bn_train, momentum=float(bn.momentum if bn.momentum is not None else 0.1), eps=float(bn.eps),
+                           running_mean=bn.running_mean, running_var=bn.running_var)
+            params.extend([bn.weight, bn.bias])
+            if bn_train and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        meta.append(m)
+    if x.shape[1] != meta[0]['cin']:
+        raise ValueError('corrector: expected %d input channels, got %d' % (meta[0]['cin'], x.shape[1]))
+    return _CorrectorFn.apply(x, meta, *params)

@@ -1,0 +1,180 @@
+// Spot-patch gather: crop a P x P window around every Visium spot of a full-resolution RGB image,
+// optionally apply ToTensor (/255) + Normalize(mean, std), and write the (78, 64, 3, P, P) grid tensor.
+//
+// Replaces the python loop of /root/reference/gridnext/imgprocess.py:185-238 (grid_from_wsi_visium):
+//   * pseudo_hex_to_oddr (imgprocess.py:26-32): x = col//2 (even row) | (col-1)//2 (odd row), y = row
+//   * centre = int(np.rint(pxl))  -> rint() in fp64 here (round-half-even)        (imgprocess.py:213-214)
+//   * np.pad(mode='edge') by w//2  -> coordinates are clamped to the image instead (imgprocess.py:198)
+//   * patch rows [cy - w//2, cy + w//2), cols [cx - w//2, cx + w//2)                (imgprocess.py:220)
+//   * out-of-tissue cells stay exactly 0                                           (imgprocess.py:206)
+// Pure-crop case only (2*(w//2) == P): a same-size PIL resize is the identity.
+//
+// One CTA stages RPC patch rows (3*P contiguous bytes each, arbitrary byte alignment) into shared
+// memory with 16-byte loads, then every thread turns 4 pixels x 3 channels into three vector
+// stores, one per NCHW channel plane.  HBM-bound: 3*P*P bytes in, 3*P*P*sizeof(out) bytes out per spot.
+#include "gn_common.cuh"
+
+// cells[n] = {cx, cy, valid} for grid cell n = y_ind * w_st + x_ind
+__global__ void spot_table_kernel(const unsigned char* __restrict__ in_tissue, const int* __restrict__ array_row,
+                                  const int* __restrict__ array_col, const double* __restrict__ pxl_row,
+                                  const double* __restrict__ pxl_col, int n_spots, int h_st, int w_st, int* __restrict__ cells,
+                                  int* __restrict__ n_dropped) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_spots) return;
+    if (in_tissue[i] != 1) return;
+    const int row = array_row[i], col = array_col[i];
+    // python: int(col/2) for even rows, int((col-1)/2) for odd rows (true division, truncation toward zero)
+    const int num = (row % 2 == 0) ? col : col - 1;
+    const int x_ind = num / 2;     // C division truncates toward zero like int(float)
+    const int y_ind = row;
+    if (y_ind < 0 || y_ind >= h_st || x_ind < 0 || x_ind >= w_st) {
+        atomicAdd(n_dropped, 1);   // reference prints a warning and skips (imgprocess.py:232-234)
+        return;
+    }
+    int* c = cells + 3 * (y_ind * w_st + x_ind);
+    c[0] = (int)rint(pxl_col[i]);
+    c[1] = (int)rint(pxl_row[i]);
+    c[2] = 1;
+}
+
+template <typename OutT> struct Pack4;
+template <> struct Pack4<float> {
+    static __device__ __forceinline__ void store(float* p, float a, float b, float c, float d) {
+        *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+    }
+};
+template <> struct Pack4<__nv_bfloat16> {
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, float a, float b, float c, float d) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+        uint2 u;
+        u.x = *reinterpret_cast<unsigned*>(&lo);
+        u.y = *reinterpret_cast<unsigned*>(&hi);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) patch_gather_kernel(const unsigned char* __restrict__ img, long pitch, long img_bytes, int H, int W,
+                                                           const int* __restrict__ cells, int P, int rpc, int row_buf,
+                                                           const float* __restrict__ mean, const float* __restrict__ stdv,
+                                                           OutT* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    float* lut = reinterpret_cast<float*>(sm);                 // [3][256]
+    unsigned char* rows = sm + 3 * 256 * sizeof(float);        // [rpc][row_buf]
+    __shared__ int s_off[64];                                  // byte offset of the staged segment inside its row buffer
+
+    const int cell = blockIdx.x;
+    const int r0 = blockIdx.y * rpc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cx = cells[3 * cell + 0], cy = cells[3 * cell + 1], valid = cells[3 * cell + 2];
+    const int hw = P / 2;
+    OutT* ocell = out + (long)cell * 3 * P * P;
+    const int nrows = min(rpc, P - r0);
+    const int groups = P / 4;
+
+    if (!valid) {   // out-of-tissue cell: exact zeros
+        for (int e = tid; e < 3 * nrows * groups; e += 256) {
+            int c = e / (nrows * groups), r = (e / groups) % nrows, g = e % groups;
+            Pack4<OutT>::store(ocell + ((long)c * P + r0 + r) * P + 4 * g, 0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
+    // value table: raw u8 -> float, or ((v / 255) - mean) / std in IEEE fp32 like ToTensor + Normalize
+    for (int e = tid; e < 3 * 256; e += 256) {
+        const int c = e >> 8, v = e & 255;
+        float f = (float)v;
+        if (mean != nullptr) f = __fdiv_rn(__fsub_rn(__fdiv_rn(f, 255.0f), mean[c]), stdv[c]);
+        lut[e] = f;
+    }
+    const int x_lo = cx - hw;
+    const int xs = max(x_lo, 0), xe = min(x_lo + P, W);       // staged source columns [xs, xe)
+    for (int r = warp; r < nrows; r += 8) {
+        const int gy = min(max(cy - hw + r0 + r, 0), H - 1);
+        unsigned char* dst = rows + (long)r * row_buf;
+        if (xe > xs) {
+            const long a_begin = (long)gy * pitch + 3L * xs;
+            const long a_end = (long)gy * pitch + 3L * xe;
+            const long a0 = a_begin & ~15L;
+            if (lane == 0) s_off[r] = (int)(a_begin - a0);
+            const int nchunks = (int)((a_end - a0 + 15) >> 4);
+            for (int ch = lane; ch < nchunks; ch += 32) {
+                const long a = a0 + 16L * ch;
+                uint4 v;
+                if (a + 16 <= img_bytes) {
+                    v = __ldg(reinterpret_cast<const uint4*>(img + a));
+                } else {   // last bytes of the allocation: guarded byte loads
+                    unsigned char tmp[16];
+                    for (int q = 0; q < 16; ++q) tmp[q] = (a + q < img_bytes) ? img[a + q] : 0;
+                    v = *reinterpret_cast<uint4*>(tmp);
+                }
+                *reinterpret_cast<uint4*>(dst + 16 * ch) = v;
+            }
+        } else if (lane == 0) {
+            s_off[r] = 0;
+        }
+    }
+    __syncthreads();
+    // all pixels of a row outside the image horizontally (xe <= xs) cannot happen for centres inside the image,
+    // but clamp anyway: source column = clamp(x_lo + px, 0, W-1); if nothing was staged read the edge pixel directly.
+    for (int e = tid; e < nrows * groups; e += 256) {
+        const int r = e / groups, g = e % groups;
+        const unsigned char* src = rows + (long)r * row_buf + s_off[r];
+        float v[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int sxg = min(max(x_lo + 4 * g + j, 0), W - 1);
+            if (xe > xs) {
+                const unsigned char* p = src + 3 * (sxg - xs);
+                v[0][j] = lut[p[0]]; v[1][j] = lut[256 + p[1]]; v[2][j] = lut[512 + p[2]];
+            } else {
+                const int gy = min(max(cy - hw + r0 + r, 0), H - 1);
+                const unsigned char* p = img + (long)gy * pitch + 3L * sxg;
+                v[0][j] = lut[p[0]]; v[1][j] = lut[256 + p[1]]; v[2][j] = lut[512 + p[2]];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            Pack4<OutT>::store(ocell + ((long)c * P + r0 + r) * P + 4 * g, v[c][0], v[c][1], v[c][2], v[c][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+GN_API int gn_spot_table(const unsigned char* in_tissue, const int* array_row, const int* array_col, const double* pxl_row,
+                         const double* pxl_col, int n_spots, int h_st, int w_st, int* cells /* [h_st*w_st][3] */,
+                         int* n_dropped /* [1] */, cudaStream_t stream) {
+    GN_REQUIRE(in_tissue && array_row && array_col && pxl_row && pxl_col && cells && n_dropped && n_spots >= 0 && h_st > 0 && w_st > 0,
+               GN_EINVAL, "spot_table: bad arguments");
+    GN_CUDA(cudaMemsetAsync(cells, 0, (size_t)h_st * w_st * 3 * sizeof(int), stream));
+    GN_CUDA(cudaMemsetAsync(n_dropped, 0, sizeof(int), stream));
+    if (n_spots > 0) {
+        spot_table_kernel<<<gn_ceil_div(n_spots, 256), 256, 0, stream>>>(in_tissue, array_row, array_col, pxl_row, pxl_col, n_spots, h_st,
+                                                                          w_st, cells, n_dropped);
+        GN_LAUNCH_CHECK();
+    }
+    return GN_OK;
+}
+
+GN_API int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, const int* cells, int n_cells, int P, const float* mean,
+                           const float* stdv, void* out, int out_bf16, cudaStream_t stream) {
+    GN_REQUIRE(img && cells && out && H > 0 && W > 0 && n_cells > 0, GN_EINVAL, "patch_gather: bad arguments");
+    GN_REQUIRE(pitch >= 3L * W, GN_EINVAL, "patch_gather: pitch %ld < 3*W", pitch);
+    GN_REQUIRE(P >= 4 && P % 4 == 0 && P <= 1024, GN_EUNSUPPORTED, "patch_gather: patch size %d must be a multiple of 4 in [4, 1024]", P);
+    GN_REQUIRE((mean == nullptr) == (stdv == nullptr), GN_EINVAL, "patch_gather: mean/std must come together");
+    GN_REQUIRE(((uintptr_t)img & 15) == 0 && ((uintptr_t)out & 15) == 0, GN_EALIGN, "patch_gather: img/out must be 16-byte aligned");
+    const int row_buf = ((3 * P + 15 + 15) / 16 + 1) * 16;
+    int rpc = (40 * 1024) / row_buf;
+    if (rpc > 64) rpc = 64;
+    if (rpc > P) rpc = P;
+    if (rpc >= 8) rpc &= ~7;
+    GN_REQUIRE(rpc >= 1, GN_EUNSUPPORTED, "patch_gather: patch too wide");
+    const size_t smem = 3 * 256 * sizeof(float) + (size_t)rpc * row_buf;
+    const long img_bytes = (long)(H - 1) * pitch + 3L * W;
+    dim3 grid(n_cells, gn_ceil_div(P, rpc));
+    if (out_bf16)
+        patch_gather_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(img, pitch, img_bytes, H, W, cells, P, rpc, row_buf, mean, stdv,
+                                                                        (__nv_bfloat16*)out);
+    else
+        patch_gather_kernel<float><<<grid, 256, smem, stream>>>(img, pitch, img_bytes, H, W, cells, P, rpc, row_buf, mean, stdv, (float*)out);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}

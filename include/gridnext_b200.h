@@ -1,0 +1,78 @@
+/* gridnext_b200 -- C-ABI of the B200 (sm_100a) GridNet hot path.
+ *
+ * The reference (adaly/gridnext) is pure Python/PyTorch and has no FFI; the functions below are the
+ * entry points a maintainer binds (ctypes stub in INTEGRATION.md) to replace the ATen/cuDNN call
+ * sequences named beside each one.  Conventions:
+ *   - plain C, raw DEVICE pointers, sizes, and the cudaStream_t to enqueue on (void* here so the
+ *     header needs no CUDA include); no torch types;
+ *   - the CALLER owns every buffer, workspaces included; the library never allocates or frees
+ *     device memory and keeps no pointer after returning;
+ *   - all work is stream-ordered and asynchronous; functions are re-entrant;
+ *   - return value: 0 ok, <0 argument/shape/alignment error, >0 a cudaError_t.
+ *     gn_last_error() returns a thread-local description of the last failure.
+ *   - tensors are contiguous; activations of the g network are fp32 NCHW in the Visium odd-r
+ *     layout (B, C, H=78, W=64), labels int64 (B, H, W).
+ */
+#ifndef GRIDNEXT_B200_H
+#define GRIDNEXT_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gn_stream_t; /* cudaStream_t */
+
+int gn_version(void);
+const char* gn_last_error(void);
+int gn_device_sm_count(void);
+
+/* ---- hexagonal convolution: replaces hexagdly.Conv2d.forward/backward (stride 1) as built by
+ * gridnext/gridnet_models.py:128-148 plus the rot90/flip pair of gridnet_models.py:177-185.
+ * kernel_i has shape (Cout, Cin, 2k+1-i, 1 if i==0 else 2); ksize k in 1..3. */
+int gn_hexconv_n_taps(int ksize);
+/* mode 0: wp[T][cin][cout] for the forward; mode 1: reflected+transposed weights so that the SAME
+ * forward kernel computes dX from dY (call gn_hexconv_fwd with cin:=Cout, cout:=Cin, bias NULL). */
+int gn_hexconv_pack(const float* k0, const float* k1, const float* k2, const float* k3, int ksize, int cin, int cout,
+                    int mode, float* wp, gn_stream_t stream);
+int gn_hexconv_unpack_grad(const float* dwp, float* dk0, float* dk1, float* dk2, float* dk3, int ksize, int cin, int cout,
+                           gn_stream_t stream);
+/* y = hexconv(x') + bias, x' = in_scale ? relu(x*in_scale[c]+in_shift[c]) : x  (BatchNorm2d-apply +
+ * ReLU of gridnet_models.py:134-136 fused as prologue).  stats (nullable, fp64 [2*cout], caller
+ * zeroes) accumulates per-channel sum and sum of squares of y for the next BatchNorm2d. */
+int gn_hexconv_fwd(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift,
+                   float* y, double* stats, int B, int cin, int cout, int H, int W, int ksize, gn_stream_t stream);
+/* dwp[T][cin][cout] += sum dY * x' ; dbias[cout] += sum dY  (caller zeroes both). */
+int gn_hexconv_wgrad(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp,
+                     float* dbias, int B, int cin, int cout, int H, int W, int ksize, gn_stream_t stream);
+
+/* ---- BatchNorm2d (+ReLU): replaces nn.BatchNorm2d(32)/nn.ReLU of gridnet_models.py:134-136,142-144 */
+int gn_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   float momentum, float eps, double count, float* scale, float* shift, float* mean_invstd, int C,
+                   int update_running, gn_stream_t stream);
+int gn_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                      float* scale, float* shift, float* mean_invstd, int C, gn_stream_t stream);
+int gn_bn_stats(const float* x, double* stats, int B, int C, long HW, gn_stream_t stream);
+int gn_bn_act_fwd(const float* x, const float* scale, const float* shift, float* y, int B, int C, long HW, int relu,
+                  gn_stream_t stream);
+/* dH from dA through [ReLU](BN(h)); sums is a [2*C] fp64 workspace; dgamma/dbeta nullable. */
+int gn_bn_act_bwd(const float* dA, const float* h, const float* scale, const float* shift, const float* mean_invstd,
+                  double* sums, double count, int training, float* dH, float* dgamma, float* dbeta, int B, int C, long HW,
+                  int relu, gn_stream_t stream);
+
+/* ---- foreground-masked cross-entropy: replaces gridnext/training.py:152-160 (+ its backward).
+ * acc fp64[4]: {sum of spot losses, n_foreground, n_correct, -}; loss_out[0] = mean * loss_scale;
+ * dlogits (nullable) = d(loss_out)/d(logits).  n_fg_override (nullable, device fp64[1]) replaces the
+ * local foreground count as the normaliser (global count under data parallelism). */
+int gn_masked_ce(const float* logits, const long long* labels, float* dlogits, double* acc, float* loss_out,
+                 const double* n_fg_override, float loss_scale, int B, int C, long HW, gn_stream_t stream);
+
+/* ---- spot-patch gather: replaces gridnext/imgprocess.py:185-238 (grid_from_wsi_visium) */
+int gn_spot_table(const unsigned char* in_tissue, const int* array_row, const int* array_col, const double* pxl_row,
+                  const double* pxl_col, int n_spots, int h_st, int w_st, int* cells, int* n_dropped, gn_stream_t stream);
+int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, const int* cells, int n_cells, int P,
+                    const float* mean, const float* stdv, void* out, int out_bf16, gn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

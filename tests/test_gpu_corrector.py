@@ -1,0 +1,168 @@
+"""GPU parity: hexagonal convolution, fused corrector, masked CE and the count GridNet step against the
+CPU oracle and the reference-generated golden vectors.  Everything goes through the C-ABI library."""
+import json, os
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, shapes as S
+from oracle import gridnet_ref as R
+from oracle.hexconv_ref import hexconv_visium, hexconv_hexagdly, kernel_shapes
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+MAN = json.load(open(os.path.join(GOLDEN, 'manifest.json')))
+TOL = 1e-5   # north_star: hex-conv outputs and gradients within 1e-5 fp32
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+def rand_hex(cin, cout, k, B, H, W, seed):
+    g = torch.Generator(); g.manual_seed(seed)
+    ks = [torch.randn(s, generator=g) * (1.0 / (cin * 7) ** 0.5) for s in kernel_shapes(cin, cout, k)]
+    b = torch.randn(cout, generator=g) * 0.1
+    x = torch.randn(B, cin, H, W, generator=g)
+    dy = torch.randn(B, cout, H, W, generator=g)
+    return ks, b, x, dy
+
+
+@pytest.mark.parametrize('k', [1, 2, 3])
+@pytest.mark.parametrize('cfg', [(7, 32, 2, 78, 64), (32, 32, 1, 78, 64), (32, 7, 3, 78, 64), (3, 5, 2, 7, 9),
+                                 (4, 4, 1, 4, 4), (14, 32, 1, 9, 70), (64, 64, 1, 13, 64), (16, 40, 2, 8, 130)])
+def test_hexconv_fwd_bwd_matches_oracle(k, cfg):
+    from gridnext_b200.hexagdly import hexconv_visium as gpu_hexconv
+    cin, cout, B, H, W = cfg
+    ks, b, x, dy = rand_hex(cin, cout, k, B, H, W, seed=k * 1000 + cin + H)
+    ks_r = [t.clone().double().requires_grad_(True) for t in ks]
+    b_r = b.clone().double().requires_grad_(True)
+    x_r = x.clone().double().requires_grad_(True)
+    y_r = hexconv_visium(x_r, ks_r, b_r)
+    y_r.backward(dy.double())
+    ks_g = [t.clone().to(dev()).requires_grad_(True) for t in ks]
+    b_g = b.clone().to(dev()).requires_grad_(True)
+    x_g = x.clone().to(dev()).requires_grad_(True)
+    y_g = gpu_hexconv(x_g, ks_g, b_g)
+    y_g.backward(dy.to(dev()))
+    assert rel_err(y_g, y_r) < TOL
+    assert rel_err(x_g.grad, x_r.grad) < TOL
+    assert rel_err(b_g.grad, b_r.grad) < TOL
+    for a, r in zip(ks_g, ks_r):
+        assert rel_err(a.grad, r.grad) < TOL
+
+
+def test_hexagdly_module_layout_matches_upstream_composition():
+    import gridnext_b200.hexagdly as hx
+    torch.manual_seed(3)
+    m = hx.Conv2d(5, 6, kernel_size=2).to(dev())
+    assert sorted(k for k, _ in m.named_parameters()) == ['bias_tensor', 'kernel0', 'kernel1', 'kernel2']
+    assert repr(m) == 'Conv2d(5, 6, kernel_size=2, stride=1)'
+    x = torch.randn(2, 5, 64, 78)      # HexagDLy layout (rows, cols): parity on the last index
+    y = m(x.to(dev()))
+    ref = hexconv_hexagdly(x.double(), [getattr(m, 'kernel%d' % i).detach().cpu().double() for i in range(3)],
+                           m.bias_tensor.detach().cpu().double())
+    assert tuple(y.shape) == (2, 6, 64, 78)
+    assert rel_err(y, ref) < TOL
+
+
+def _load_into(module, sd):
+    missing = module.load_state_dict({k: v.detach().clone() for k, v in sd.items()}, strict=True)
+    return module
+
+
+@pytest.mark.parametrize('use_bn,training', [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize('shape', [(2, 7, 78, 64), (3, 14, 9, 7)])
+def test_fused_corrector_matches_oracle(use_bn, training, shape):
+    import torch.nn as nn
+    from gridnext_b200.gridnet_models import GridNetHexOddr
+    B, f_dim, H, W = shape
+    n_cls = 5
+    net = GridNetHexOddr(nn.Identity(), (f_dim,), (H, W), n_cls, use_bn=use_bn, f_dim=f_dim)
+    sd = synth.synth_state_dict(S.gridnet_shapes({}, f_dim, n_cls, use_bn), 77)
+    _load_into(net, sd)
+    net.to(dev())
+    net.train(training)
+    g = torch.Generator(); g.manual_seed(B * 31 + H)
+    x = torch.randn(B, f_dim, H, W, generator=g)
+    dy = torch.randn(B, n_cls, H, W, generator=g)
+    # oracle (fp64)
+    sd_r = {k: (v.double().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v) for k, v in R.sub(sd, 'corrector.').items()}
+    x_r = x.double().requires_grad_(True)
+    stats = {}
+    y_r = R.corrector_forward(sd_r, x_r, use_bn=use_bn, training=training, stats_out=stats)
+    y_r.backward(dy.double())
+    # product
+    x_g = x.to(dev()).requires_grad_(True)
+    y_g = net._correct_visium(x_g)
+    y_g.backward(dy.to(dev()))
+    assert rel_err(y_g, y_r) < TOL
+    assert rel_err(x_g.grad, x_r.grad) < 2 * TOL
+    for name, p in net.corrector.named_parameters():
+        ref = sd_r[name].grad
+        # gradients that are exactly zero in theory (bias before a train-mode BN) compare absolutely
+        scale = max(float(ref.abs().max()), 1e-3)
+        assert float((p.grad.double().cpu() - ref).abs().max()) / scale < 2 * TOL, name
+    if use_bn and training:
+        for k, v in stats.items():
+            assert rel_err(dict(net.corrector.named_buffers())[k], v) < TOL, k
+        assert int(net.corrector[2].num_batches_tracked) == 1
+
+
+def test_masked_ce_matches_oracle():
+    from gridnext_b200.losses import masked_cross_entropy
+    g = torch.Generator(); g.manual_seed(5)
+    logits = torch.randn(3, 7, 78, 64, generator=g) * 3
+    labels = synth.synth_labels(3, 7, seed=2)
+    lr = logits.double().requires_grad_(True)
+    loss_r, ncorr, nfg = R.masked_ce(lr, labels, accum_iters=2)
+    loss_r.backward()
+    lg = logits.to(dev()).requires_grad_(True)
+    loss_g, acc = masked_cross_entropy(lg, labels.to(dev()), accum_iters=2)
+    loss_g.backward()
+    acc = acc.tolist()
+    assert abs(float(loss_g) - float(loss_r)) < 1e-6
+    assert (int(acc[2]), int(acc[1])) == (ncorr, nfg)
+    assert rel_err(lg.grad, lr.grad) < TOL
+    # all-background batch: CrossEntropyLoss over an empty selection is NaN in the reference too
+    loss_e, acc_e = masked_cross_entropy(logits.to(dev()), torch.zeros_like(labels).to(dev()))
+    assert torch.isnan(loss_e) and acc_e.tolist()[1] == 0
+
+
+def test_count_gridnet_step_matches_reference_golden():
+    """One train_gridwise iteration of the count model against vectors from the REAL reference."""
+    import torch.nn as nn
+    from gridnext_b200.gridnet_models import GridNetHexOddr
+    from gridnext_b200.training import gridwise_step
+    m = MAN['g1_count_gridnet']
+    gold = np.load(os.path.join(GOLDEN, 'g1_count_gridnet.npz'))
+    G, n_cls, B = m['G'], m['n_cls'], m['B']
+    f = nn.Sequential(nn.Linear(G, 500), nn.Linear(500, 100), nn.BatchNorm1d(100), nn.ReLU(),
+                      nn.Linear(100, 100), nn.Linear(100, 50), nn.BatchNorm1d(50), nn.ReLU(), nn.Linear(50, n_cls))
+    net = GridNetHexOddr(f, (G,), (78, 64), n_cls, use_bn=True)
+    sd = synth.synth_state_dict(S.gridnet_shapes(S.mlp_shapes(G, n_cls), n_cls, n_cls), m['seed_w'])
+    _load_into(net, sd)
+    net.to(dev())
+    x = synth.synth_counts(B, G, seed=m['seed_x']).to(dev())
+    y = synth.synth_labels(B, n_cls, seed=m['seed_y']).to(dev())
+    net.train(); net.patch_classifier.eval()
+    out = net(x)
+    loss, acc, _ = gridwise_step(net, x, y, nn.CrossEntropyLoss(), 1, True)
+    assert rel_err(out, torch.from_numpy(gold['out'])) < 1e-3
+    assert abs(float(loss) - float(gold['loss'])) < 1e-4
+    assert int(acc.tolist()[1]) == int(gold['nfg'])
+    assert abs(int(acc.tolist()[2]) - int(gold['ncorr'])) <= 2     # near-tied logits may flip under TF32
+    n = 0
+    for k in gold.files:
+        if k.startswith('grad.'):
+            p = dict(net.named_parameters())[k[5:]]
+            ref = torch.from_numpy(gold[k])
+            scale = max(float(ref.abs().max()), 1e-4)
+            assert float((p.grad.cpu() - ref).abs().max()) / scale < 5e-3, k
+            n += 1
+    assert n >= 30

@@ -1,0 +1,191 @@
+"""Drive tools/umma_probe.cu: one GPU run answers which tcgen05 smem-descriptor encodings are right.
+Writes gpurun_out/umma_probe.json.   python tools/umma_probe.py"""
+import ctypes, json, os, sys
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+lib = ctypes.CDLL(os.path.join(HERE, 'libumma_probe.so'))
+lib.probe_run.restype = ctypes.c_int
+lib.probe_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_uint,
+                          ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                          ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+
+SW_NONE, SW128, SW64, SW32 = 0, 2, 4, 6
+
+
+def desc(lbo, sbo, layout, base_offset=0):
+    return (((lbo >> 4) & 0x3FFF) << 16) | (((sbo >> 4) & 0x3FFF) << 32) | (1 << 46) | ((base_offset & 7) << 49) | (layout << 61)
+
+
+def idesc(M, N, tf32=False, a_mn=0, b_mn=0):
+    fmt = 2 if tf32 else 1
+    return (1 << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
+
+
+def to_bytes(vals, tf32):
+    """logical values (float) -> per-element bytes"""
+    if tf32:
+        return np.asarray(vals, dtype=np.float32).view(np.uint8).reshape(-1, 4)
+    t = torch.tensor(np.asarray(vals, dtype=np.float32)).to(torch.bfloat16).view(torch.int16).numpy()
+    return t.view(np.uint8).reshape(-1, 2)
+
+
+def image(X, offset_fn, e, tf32, size):
+    """X[r, k] logical matrix -> smem byte image using offset_fn(r, k) -> byte offset"""
+    img = np.full(size, 0, dtype=np.uint8)
+    # NaN-fill the image so that unwritten bytes poison the result
+    nanpat = np.array([0x00, 0x00, 0xc0, 0x7f], dtype=np.uint8)
+    img[:] = np.tile(nanpat, size // 4)
+    R, K = X.shape
+    b = to_bytes(X.reshape(-1), tf32)
+    i = 0
+    for r in range(R):
+        for k in range(K):
+            o = offset_fn(r, k)
+            img[o:o + e] = b[i]
+            i += 1
+    return img
+
+
+def kmajor_sw(e, sw_bytes=128, row0=0):
+    """K-major swizzled tile, one k-block of sw_bytes per row; rows are ABSOLUTE rows (row0 + r)."""
+    mask = sw_bytes // 16 - 1
+
+    def f(r, k):
+        R = row0 + r
+        byte = k * e
+        chunk = (byte // 16) ^ ((R % 8) & mask) if sw_bytes == 128 else (byte // 16) ^ (((R % 8) >> (1 if sw_bytes == 64 else 2)) & mask)
+        return R * sw_bytes + chunk * 16 + byte % 16
+    return f
+
+
+def mnmajor_sw128(e, lbo, per_row):
+    """MN-major SW128: rows are k, 128 B of MN elements each."""
+    def f(mn, k):
+        byte = (mn % per_row) * e
+        return (mn // per_row) * lbo + k * 128 + (((byte // 16) ^ (k % 8)) * 16) + byte % 16
+    return f
+
+
+def planes_kmajor(e, plane, row0=0):
+    per = 16 // e
+
+    def f(r, k):
+        return (k // per) * plane + (row0 + r) * 16 + (k % per) * e
+    return f
+
+
+def planes_mnmajor(e, plane, k0=0):
+    per = 16 // e
+
+    def f(mn, k):
+        return (mn // per) * plane + (k0 + k) * 16 + (mn % per) * e
+    return f
+
+
+def run_case(name, A, B, a_fn, b_fn, a_desc, b_desc, idsc, ksteps, a_step, b_step, tf32, a_off=0, b_off=0, a_size=96 * 1024, b_size=96 * 1024, expect_rows=None, A_expect=None, B_expect=None):
+    e = 4 if tf32 else 2
+    a_img = torch.from_numpy(image(A, a_fn, e, tf32, a_size)).cuda()
+    b_img = torch.from_numpy(image(B, b_fn, e, tf32, b_size)).cuda()
+    N = B.shape[0]
+    D = torch.full((128, N), float('nan'), device='cuda')
+    rc = lib.probe_run(a_img.data_ptr(), a_size, b_img.data_ptr(), b_size, a_off, b_off, a_desc, b_desc, idsc, ksteps, a_step, b_step,
+                       1 if tf32 else 0, N, D.data_ptr(), None)
+    torch.cuda.synchronize()
+    Aeff = A if expect_rows is None else A[expect_rows]
+    if A_expect is not None:
+        Aeff = A_expect
+    Beff = B if B_expect is None else B_expect
+    N = Beff.shape[0]
+    ref = Aeff.astype(np.float64) @ Beff.astype(np.float64).T
+    got = D.cpu().numpy().astype(np.float64)
+    ok = bool(rc == 0 and np.array_equal(np.nan_to_num(got, nan=1e30), ref))
+    err = float(np.nanmax(np.abs(got - ref))) if np.isfinite(got).any() else float('nan')
+    res = dict(case=name, ok=ok, rc=rc, max_err=err, nan=int(np.isnan(got).sum()))
+    print(json.dumps(res), flush=True)
+    return res
+
+
+def main():
+    rng = np.random.default_rng(0)
+    out = []
+
+    def ints(r, k):
+        return rng.integers(-4, 5, (r, k)).astype(np.float32)
+
+    # 1. baseline: bf16 K-major SW128, K = 64 (4 steps of 32 B), N in {32, 64, 128, 256}
+    for N in (32, 64, 128, 256):
+        A, B = ints(128, 64), ints(N, 64)
+        out.append(run_case('kmaj_sw128_bf16_N%d' % N, A, B, kmajor_sw(2), kmajor_sw(2), desc(0, 1024, SW128), desc(0, 1024, SW128),
+                            idesc(128, N), 4, 32, 32, False))
+    # 1b. LBO value irrelevance for swizzled K-major (LBO = 1 as some code sets)
+    A, B = ints(128, 64), ints(64, 64)
+    out.append(run_case('kmaj_sw128_bf16_lbo16', A, B, kmajor_sw(2), kmajor_sw(2), desc(16, 1024, SW128), desc(16, 1024, SW128), idesc(128, 64), 4, 32, 32, False))
+
+    # 2. row-shifted start inside a taller SW128 K-major tile: hypothesis A base_offset = 0, B base_offset = s % 8
+    for s in (1, 3, 8, 9):
+        Abig, B = ints(128 + 16, 64), ints(32, 64)
+        rows = np.arange(s, s + 128)
+        for hyp, bo in (('abs', 0), ('bo', s % 8)):
+            out.append(run_case('kmaj_sw128_shift%d_%s' % (s, hyp), Abig, B, kmajor_sw(2), kmajor_sw(2), desc(0, 1024, SW128, bo), desc(0, 1024, SW128),
+                                idesc(128, 32), 4, 32, 32, False, a_off=s * 128, expect_rows=rows))
+
+    # 3. bf16 MN-major SW128:  A (M=128 -> two 64-wide groups, LBO = 64 k-rows * 128 B), B K-major
+    A, B = ints(128, 64), ints(64, 64)
+    out.append(run_case('A_mnmaj_sw128_bf16', A, B, mnmajor_sw128(2, 8192, 64), kmajor_sw(2), desc(8192, 1024, SW128), desc(0, 1024, SW128),
+                        idesc(128, 64, a_mn=1), 4, 2048, 32, False))
+    out.append(run_case('A_mnmaj_sw128_bf16_swapLS', A, B, mnmajor_sw128(2, 8192, 64), kmajor_sw(2), desc(1024, 8192, SW128), desc(0, 1024, SW128),
+                        idesc(128, 64, a_mn=1), 4, 2048, 32, False))
+    for N in (32, 64, 128):
+        A, B = ints(128, 64), ints(N, 64)
+        out.append(run_case('B_mnmaj_sw128_bf16_N%d' % N, A, B, kmajor_sw(2), mnmajor_sw128(2, 8192, 64), desc(0, 1024, SW128), desc(8192, 1024, SW128),
+                            idesc(128, N, b_mn=1), 4, 32, 2048, False))
+    A, B = ints(128, 64), ints(32, 64)
+    out.append(run_case('AB_mnmaj_sw128_bf16_N32', A, B, mnmajor_sw128(2, 8192, 64), mnmajor_sw128(2, 8192, 64), desc(8192, 1024, SW128),
+                        desc(8192, 1024, SW128), idesc(128, 32, a_mn=1, b_mn=1), 4, 2048, 2048, False))
+
+    # 4. no-swizzle "planes" K-major: [k/8][row][8 elems]; row shift = +16 B.  4a: LBO=plane, SBO=128;  4b: swapped
+    PL = 160 * 16
+    for s in (0, 5):
+        Abig, B = ints(128 + 16, 64), ints(32, 64)
+        rows = np.arange(s, s + 128)
+        for hyp, (l, sb) in (('lboPlane', (PL, 128)), ('sboPlane', (128, PL))):
+            out.append(run_case('planes_kmaj_shift%d_%s' % (s, hyp), Abig, B, planes_kmajor(2, PL), planes_kmajor(2, 40 * 16),
+                                desc(l, sb, SW_NONE), desc(40 * 16 if hyp == 'lboPlane' else 128, 128 if hyp == 'lboPlane' else 40 * 16, SW_NONE),
+                                idesc(128, 32), 4, 2 * PL, 2 * 40 * 16, False, a_off=s * 16, expect_rows=rows))
+
+    # 5. no-swizzle "planes" MN-major: [mn/8][k][8 elems]; k shift = +16 B.  5a: SBO=plane, LBO=128;  5b: swapped
+    KT = 64 + 16
+    PLm = KT * 16
+    for s in (0, 5):
+        # logical A here is [M=128, K=KT]; MMA consumes k in [s, s+64)
+        Afull, B = ints(128, KT), ints(32, 64)
+        Aeff = Afull[:, s:s + 64]
+        for hyp, (l, sb) in (('sboPlane', (128, PLm)), ('lboPlane', (PLm, 128))):
+            r = run_case('planes_mnmaj_A_shift%d_%s' % (s, hyp), Afull, B, planes_mnmajor(2, PLm), kmajor_sw(2),
+                         desc(l, sb, SW_NONE), desc(0, 1024, SW128), idesc(128, 32, a_mn=1), 4, 256, 32, False, a_off=s * 16, A_expect=Aeff)
+            # expected uses the shifted window: recompute verdict
+            out.append(r)
+        # B operand MN-major planes, N = 32
+        A2, Bfull = ints(128, 64), ints(32, KT)
+        for hyp, (l, sb) in (('sboPlane', (128, PLm)), ('lboPlane', (PLm, 128))):
+            out.append(run_case('planes_mnmaj_B_shift%d_%s' % (s, hyp), A2, Bfull, kmajor_sw(2), planes_mnmajor(2, PLm),
+                                desc(0, 1024, SW128), desc(l, sb, SW_NONE), idesc(128, 32, b_mn=1), 4, 32, 256, False, b_off=s * 16, B_expect=Bfull[:, s:s + 64]))
+
+    # 6. tf32: K-major SW128 (32 elems / row, UMMA_K = 8 -> 32 B step) and MN-major SW128 A (32 elems / row)
+    A, B = ints(128, 32), ints(64, 32)
+    out.append(run_case('kmaj_sw128_tf32', A, B, kmajor_sw(4), kmajor_sw(4), desc(0, 1024, SW128), desc(0, 1024, SW128), idesc(128, 64, tf32=True), 4, 32, 32, True))
+    out.append(run_case('A_mnmaj_sw128_tf32', A, B, mnmajor_sw128(4, 4096, 32), kmajor_sw(4), desc(4096, 1024, SW128), desc(0, 1024, SW128),
+                        idesc(128, 64, tf32=True, a_mn=1), 4, 1024, 32, True))
+    # 7. bf16 K-major SW64 (K block = 32 elems, 64 B rows, SBO = 512)
+    A, B = ints(128, 32), ints(32, 32)
+    out.append(run_case('kmaj_sw64_bf16', A, B, kmajor_sw(2, 64), kmajor_sw(2, 64), desc(0, 512, SW64), desc(0, 512, SW64), idesc(128, 32), 2, 32, 32, False))
+
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump(out, open('gpurun_out/umma_probe.json', 'w'), indent=1)
+    print('PASS %d / %d' % (sum(r['ok'] for r in out), len(out)))
+
+
+if __name__ == '__main__':
+    main()
