@@ -28,3 +28,40 @@ int gn_num_sms() {
 }
 
 GN_API int gn_device_sm_count(void) { return gn_num_sms(); }
+
+// ------------------------------------------------------------------------------------------------
+#include "gn_tma.cuh"
+typedef CUresult (*gn_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static gn_encode_fn get_encode() {
+    static gn_encode_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (gn_encode_fn)p;
+    });
+    return fn;
+}
+
+int gn_tmap_encode(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* gaddr, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+    gn_encode_fn fn = get_encode();
+    GN_REQUIRE(fn != nullptr, GN_EDRIVER, "cuTensorMapEncodeTiled is not available from the driver");
+    GN_REQUIRE(((uintptr_t)gaddr & 15) == 0, GN_EALIGN, "TMA: global address %p is not 16-byte aligned", gaddr);
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) {
+        gs[i] = strides_bytes[i];
+        GN_REQUIRE((gs[i] & 15) == 0, GN_EALIGN, "TMA: stride %llu of dim %d is not a multiple of 16 bytes", (unsigned long long)gs[i], i + 1);
+    }
+    CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(gaddr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GN_REQUIRE(r == CUDA_SUCCESS, GN_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, box %u x %u)", (int)r,
+               rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 1), box[0], rank > 1 ? box[1] : 1);
+    return GN_OK;
+}

@@ -72,6 +72,16 @@ int gn_spot_table(const unsigned char* in_tissue, const int* array_row, const in
 int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, const int* cells, int n_cells, int P,
                     const float* mean, const float* stdv, void* out, int out_bf16, gn_stream_t stream);
 
+/* ---- tensor-core GEMM (tcgen05/TMEM/TMA): D[M,N] = op(A)[M,K] * B[N,K]^T, bf16 operands, fp32 accumulate.
+ * Replaces F.conv2d 1x1 (gridnext/densenet.py:26-27,52-53) in NHWC and nn.Linear (count MLP, notebooks/
+ * Tutorial_visium_count.ipynb cell 12).  a: [M, lda] bf16, b: [N, ldb] bf16, out: [M, ldc] bf16 | fp32.
+ * Epilogue: out = [relu](acc * scale[n] + shift[n]) (scale/shift nullable), accumulate: out += (fp32 only).
+ * xf_scale/xf_shift (nullable, [K]): op(A) = relu(A * xf_scale[k] + xf_shift[k]) applied in shared memory
+ * (DenseNet's pre-activation eval-mode BatchNorm + ReLU, densenet.py:12-18). */
+int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M, int N, int K, void* out, long ldc, int out_fp32,
+                 int accumulate, const float* scale, const float* shift, int relu, const float* xf_scale, const float* xf_shift,
+                 gn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

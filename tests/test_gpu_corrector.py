@@ -106,8 +106,11 @@ def test_fused_corrector_matches_oracle(use_bn, training, shape):
     for name, p in net.corrector.named_parameters():
         ref = sd_r[name].grad
         # gradients that are exactly zero in theory (bias before a train-mode BN) compare absolutely
-        scale = max(float(ref.abs().max()), 1e-3)
-        assert float((p.grad.double().cpu() - ref).abs().max()) / scale < 2 * TOL, name
+        err = float((p.grad.double().cpu() - ref).abs().max())
+        if float(ref.abs().max()) < 1e-9:
+            assert err < 2e-4, name      # fp32 cancellation noise of a sum over B*H*W cells whose exact value is 0
+        else:
+            assert err / float(ref.abs().max()) < 2 * TOL, name
     if use_bn and training:
         for k, v in stats.items():
             assert rel_err(dict(net.corrector.named_buffers())[k], v) < TOL, k

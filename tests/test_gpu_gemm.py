@@ -1,0 +1,56 @@
+"""GPU parity of the tcgen05 GEMM family against fp32 torch references on the same bf16-rounded inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator(); g.manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16)
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / max(float(b.double().abs().max()), 1e-12))
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (300, 128, 64), (1000, 128, 96), (647, 7, 50), (4096, 256, 512),
+                                   (2048, 500, 1000), (5000, 32, 1152), (129, 64, 992), (77, 100, 500), (20000, 128, 224)])
+def test_gemm_plain(M, N, K):
+    from gridnext_b200.tc import gemm_bf16
+    a, b = rnd((M, K), 1), rnd((N, K), 2, 0.1)
+    ref = a.float() @ b.float().t()
+    out32 = gemm_bf16(a.cuda(), b.cuda(), out_dtype=torch.float32)
+    assert rel(out32.cpu(), ref) < 1e-5          # fp32 accumulation of exact bf16 products
+    out16 = gemm_bf16(a.cuda(), b.cuda())
+    assert rel(out16.float().cpu(), ref) < 1e-2
+    assert out16.dtype == torch.bfloat16
+
+
+def test_gemm_epilogue_affine_relu_accumulate_and_strided_views():
+    from gridnext_b200.tc import gemm_bf16
+    M, N, K, LD = 700, 128, 160, 256
+    buf = rnd((M, LD), 3)                         # concat-style buffer: A is its first K columns
+    b = rnd((N, K), 4, 0.1)
+    g = torch.Generator(); g.manual_seed(5)
+    sc, sh = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g)
+    ref = torch.relu((buf[:, :K].float() @ b.float().t()) * sc + sh)
+    outbuf = torch.zeros((M, 384), dtype=torch.bfloat16, device='cuda')
+    gemm_bf16(buf.cuda()[:, :K], b.cuda(), out=outbuf[:, 192:192 + N], scale=sc.cuda(), shift=sh.cuda(), relu=True)
+    assert rel(outbuf[:, 192:192 + N].float().cpu(), ref) < 1e-2
+    assert float(outbuf[:, :192].abs().max()) == 0 and float(outbuf[:, 192 + N:].abs().max()) == 0
+    acc = torch.ones((M, N), dtype=torch.float32, device='cuda')
+    gemm_bf16(buf.cuda()[:, :K], b.cuda(), out=acc, accumulate=True)
+    assert rel(acc.cpu(), 1.0 + buf[:, :K].float() @ b.float().t()) < 1e-5
+
+
+@pytest.mark.parametrize('M,N,K', [(500, 128, 64), (3000, 128, 224), (1024, 256, 992), (333, 128, 96)])
+def test_gemm_operand_transform_bn_relu(M, N, K):
+    from gridnext_b200.tc import gemm_bf16
+    a, b = rnd((M, K), 6), rnd((N, K), 7, 0.1)
+    g = torch.Generator(); g.manual_seed(8)
+    xs, xt = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g) * 0.5
+    act = torch.relu(a.float() * xs + xt).to(torch.bfloat16).float()      # what the kernel feeds the tensor core
+    ref = act @ b.float().t()
+    out = gemm_bf16(a.cuda(), b.cuda(), out_dtype=torch.float32, xf_scale=xs.cuda(), xf_shift=xt.cuda())
+    assert rel(out.cpu(), ref) < 2e-3            # bf16 re-rounding of the activated operand may differ by 1 ulp from torch's
