@@ -32,6 +32,9 @@ _SIGS = {
     'gn_masked_ce': [vp, vp, vp, vp, vp, vp, cf, ci, ci, cl, vp],
     'gn_spot_table': [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp],
     'gn_patch_gather': [vp, cl, ci, ci, vp, ci, ci, vp, vp, vp, ci, vp],
+    'gn_gemm_tn_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, vp, vp, vp],
+    'gn_conv3x3_pack': [vp, ci, ci, ci, vp, ci, vp],
+    'gn_conv3x3_bf16': [vp, cl, ci, ci, ci, ci, vp, ci, ci, vp, cl, vp, cl, ci, vp, vp, vp, vp, vp, ci, vp],
     'gn_gemm_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, ci, ci, vp, vp, ci, vp, vp, vp],
 }
 

@@ -32,3 +32,49 @@ def gemm_bf16(a, b, out=None, out_dtype=torch.bfloat16, accumulate=False, scale=
     call('gn_gemm_bf16', ptr(a), lda, ptr(b), ldb, M, N, K, ptr(out), ldc, 1 if out.dtype == torch.float32 else 0,
          1 if accumulate else 0, ptr(scale), ptr(shift), 1 if relu else 0, ptr(xf_scale), ptr(xf_shift), stream())
     return out
+
+
+def gemm_tn_bf16(a, b, out, xf_scale=None, xf_shift=None):
+    """out[Mo, No] (fp32) += a[Kp, Mo].T @ op(b)[Kp, No]  (weight gradients; reduction over rows)."""
+    _lib.require_cuda(a, b, out)
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or out.dtype != torch.float32:
+        raise ValueError('gemm_tn_bf16: a, b must be bfloat16 and out float32')
+    Kp, Mo, lda = _rows_pitch(a)
+    Kb, No, ldb = _rows_pitch(b)
+    if Kp != Kb:
+        raise ValueError('gemm_tn_bf16: reduction length mismatch %d vs %d' % (Kp, Kb))
+    Mo2, No2, ldo = _rows_pitch(out)
+    if (Mo2, No2) != (Mo, No):
+        raise ValueError('gemm_tn_bf16: out shape %s != (%d, %d)' % (tuple(out.shape), Mo, No))
+    call('gn_gemm_tn_bf16', ptr(a), lda, ptr(b), ldb, Mo, No, Kp, ptr(out), ldo, ptr(xf_scale), ptr(xf_shift), stream())
+    return out
+
+
+def conv3x3_pack(w, mode, ldw=None):
+    """fp32 (CO, CI, 3, 3) -> bf16 [9*CO, ldw] (mode 0) | flipped+transposed [9*CI, ldw] (mode 1, data gradient)."""
+    _lib.require_cuda(w)
+    CO, CI = int(w.shape[0]), int(w.shape[1])
+    cols = CI if mode == 0 else CO
+    ldw = ldw or ((cols + 7) // 8) * 8
+    wp = torch.empty((9 * (CO if mode == 0 else CI), ldw), device=w.device, dtype=torch.bfloat16)
+    call('gn_conv3x3_pack', ptr(w.contiguous().float()), CO, CI, mode, ptr(wp), ldw, stream())
+    return wp
+
+
+def conv3x3_bf16(x2d, Nimg, H, W, CI, wp, CO, out2d, bn=None):
+    """x2d: [Nimg*H*W, >=CI] bf16 NHWC rows (pitch = stride(0)); out2d: [Nimg*H*W, CO] view (may be a column slice).
+    bn: dict(ref, ref_is_raw, sc, sh, p0, p1, colsum) for the fused BN+ReLU-backward epilogue."""
+    _lib.require_cuda(x2d, wp, out2d)
+    M, _, ldx = _rows_pitch(x2d)
+    Mo, COo, ldo = _rows_pitch(out2d)
+    if M != Nimg * H * W or Mo != M or COo != CO:
+        raise ValueError('conv3x3_bf16: shape mismatch')
+    if bn is None:
+        args = (None, 0, 0, None, None, None, None, None, 0)
+    else:
+        _, _, ldref = _rows_pitch(bn['ref'])
+        cs = bn.get('colsum')
+        args = (ptr(bn['ref']), ldref, 1 if bn['ref_is_raw'] else 0, ptr(bn['sc']), ptr(bn.get('sh')), ptr(bn['p0']), ptr(bn['p1']),
+                ptr(cs), cs.shape[1] if cs is not None else 0)
+    call('gn_conv3x3_bf16', ptr(x2d), ldx, Nimg, H, W, CI, ptr(wp), wp.stride(0), CO, ptr(out2d), ldo, *args, stream())
+    return out2d

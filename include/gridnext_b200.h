@@ -82,6 +82,24 @@ int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M, int N,
                  int accumulate, const float* scale, const float* shift, int relu, const float* xf_scale, const float* xf_shift,
                  gn_stream_t stream);
 
+/* Weight-gradient GEMM: out[Mo, No] (fp32, pitch ldo) += a[Kp, Mo]^T * op(b)[Kp, No]; rows of a and b are the
+ * reduction index (pixels / spots).  op(b) = relu(b * xf_scale[n] + xf_shift[n]) when given.  Split over the
+ * reduction dimension with vector atomics: the caller zeroes (or pre-loads) out.  Replaces the weight gradient
+ * of F.conv2d 1x1 / nn.Linear that autograd computes for densenet.py:26-27,52-53 and the count MLP. */
+int gn_gemm_tn_bf16(const void* a, long lda, const void* b, long ldb, int Mo, int No, int Kp, float* out, long ldo,
+                    const float* xf_scale, const float* xf_shift, gn_stream_t stream);
+
+/* ---- 3x3 / pad 1 convolution, NHWC bf16, tcgen05 implicit GEMM: replaces F.conv2d of densenet.py:30-31 (conv2 of
+ * each dense layer) and its data gradient.  gn_conv3x3_pack: fp32 (CO, CI, 3, 3) weights -> bf16 [9*CO, ldw]
+ * (mode 0, forward) or flipped/transposed [9*CI, ldw] (mode 1, data gradient; then call gn_conv3x3_bf16 with the
+ * roles of CI and CO swapped).  Optional BN+ReLU-backward epilogue (bn_ref != NULL):
+ *   g = acc * [a > 0], out = g * bn_sc[n], colsum[n] += sum g, colsum[bn_ldsum + n] += sum g * (ref - p0[n]) * p1[n]
+ *   with a = ref * sc + sh (bn_ref_is_raw) or a = ref. */
+int gn_conv3x3_pack(const float* w, int CO, int CI, int mode, void* wp, int ldw, gn_stream_t stream);
+int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int CI, const void* wp, int ldw, int CO, void* out, long ldo,
+                    const void* bn_ref, long bn_ldref, int bn_ref_is_raw, const float* bn_sc, const float* bn_sh,
+                    const float* bn_p0, const float* bn_p1, float* bn_colsum, int bn_ldsum, gn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,8 +14,8 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / max(float(b.double().abs().max()), 1e-12))
 
 
-@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (300, 128, 64), (1000, 128, 96), (647, 7, 50), (4096, 256, 512),
-                                   (2048, 500, 1000), (5000, 32, 1152), (129, 64, 992), (77, 100, 500), (20000, 128, 224)])
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (300, 128, 64), (1000, 128, 96), (647, 7, 56), (4096, 256, 512),
+                                   (2048, 500, 1000), (5000, 32, 1152), (129, 64, 992), (77, 100, 504), (20000, 128, 224)])
 def test_gemm_plain(M, N, K):
     from gridnext_b200.tc import gemm_bf16
     a, b = rnd((M, K), 1), rnd((N, K), 2, 0.1)
@@ -54,3 +54,20 @@ def test_gemm_operand_transform_bn_relu(M, N, K):
     ref = act @ b.float().t()
     out = gemm_bf16(a.cuda(), b.cuda(), out_dtype=torch.float32, xf_scale=xs.cuda(), xf_shift=xt.cuda())
     assert rel(out.cpu(), ref) < 2e-3            # bf16 re-rounding of the activated operand may differ by 1 ulp from torch's
+
+
+@pytest.mark.parametrize('Kp,Mo,No,xf', [(64, 128, 256, False), (1000, 128, 64, False), (20000, 128, 224, True), (5000, 128, 992, True),
+                                         (9984, 500, 5000, False), (3000, 256, 512, True), (777, 7, 56, False), (4096, 32, 1152, False)])
+def test_gemm_tn_weight_gradient(Kp, Mo, No, xf):
+    from gridnext_b200.tc import gemm_tn_bf16
+    lda, ldb = Mo + 8, No + 24                    # operands are column slices of wider buffers
+    a, b = rnd((Kp, lda), 11, 0.5), rnd((Kp, ldb), 12)
+    g = torch.Generator(); g.manual_seed(13)
+    xs, xt = torch.rand(No, generator=g) + 0.5, torch.randn(No, generator=g) * 0.5
+    bb = b[:, :No].float()
+    if xf:
+        bb = torch.relu(bb * xs + xt).to(torch.bfloat16).float()
+    ref = (a[:, :Mo].double().t() @ bb.double()).float() + 1.0
+    out = torch.ones((Mo, No), dtype=torch.float32, device='cuda')
+    gemm_tn_bf16(a.cuda()[:, :Mo], b.cuda()[:, :No], out, xs.cuda() if xf else None, xt.cuda() if xf else None)
+    assert rel(out.cpu(), ref) < (3e-3 if xf else 2e-5)
