@@ -35,7 +35,9 @@ _SIGS = {
     'gn_gemm_tn_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, vp, vp, vp],
     'gn_conv3x3_pack': [vp, ci, ci, ci, vp, ci, vp],
     'gn_conv3x3_bf16': [vp, cl, ci, ci, ci, ci, vp, ci, ci, vp, cl, vp, cl, ci, vp, vp, vp, vp, vp, ci, vp],
-    'gn_gemm_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, ci, ci, vp, vp, ci, vp, vp, vp],
+    'gn_gemm_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, ci, ci, vp, vp, ci, vp, vp, vp, cl, ci, vp, vp, vp, vp, vp, ci, ci, vp],
+    'gn_conv3x3_wgrad_bf16': [vp, cl, vp, cl, ci, ci, ci, ci, ci, vp, vp],
+    'gn_conv3x3_unpack_grad': [vp, ci, ci, vp, vp],
 }
 
 

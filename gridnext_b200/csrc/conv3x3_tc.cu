@@ -311,3 +311,206 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
+
+// ================================================================================================
+// Weight gradient of the 3x3 convolution:  dW[t][c][co] += sum_P  X[P + off_t, c] * dY[P, co]
+//
+// Same padded-position index space.  The reduction index is the position P, so both operands are "MN-major":
+// A = the activation halo buffer (rows = positions, 64 channels per 128-byte row, two channel groups -> UMMA M = 128),
+// started at the row of tap t; B = the dY tile in padded layout (its border positions are TMA zero-fill, so halo
+// products vanish).  Nine accumulators (one per tap) of 128 x NP fp32 live in TMEM for the whole persistent CTA and are
+// added to global memory with vector atomics once at the end.
+struct Conv3WgParams {
+    int Nimg, H, W, CI, CO, NP;     // NP = CO rounded up to 16 (UMMA N)
+    int a_rows, b_rows;             // buffer rows (positions) per stage for X halo and dY
+    int n_tiles;
+    float* dwp;                     // [9][CI][CO] fp32
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const Conv3WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_done;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W2 = p.W + 2, H2 = p.H + 2, HALO = p.W + 3;
+    const int a_group_bytes = p.a_rows * 128;
+    const int a_bytes = 2 * a_group_bytes;
+    const int b_bytes = p.b_rows * 128;
+    const int stage_bytes = a_bytes + b_bytes;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmDY);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        mbar_init(&bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const bool has_work = (int)blockIdx.x < p.n_tiles;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(&bar_empty[stage], phase ^ 1);
+                uint8_t* sa = sm + (size_t)stage * stage_bytes;
+                const long P0 = (long)tile * 128;
+                const long lo = P0 - HALO;
+                const long R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
+                const long R1 = (P0 + 127 + HALO) / W2;
+                const int nr = (int)(R1 - R0 + 1);
+                const long Q0 = P0 / W2, Q1 = (P0 + 127) / W2;
+                const int nq = (int)(Q1 - Q0 + 1);
+                mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)((2 * nr + nq) * W2 * 128));
+                for (int r = 0; r < nr; ++r) {
+                    const long R = R0 + r;
+                    int n, yp;
+                    if (R >= 0) { n = (int)(R / H2); yp = (int)(R % H2); } else { n = -1; yp = 0; }
+                    for (int g = 0; g < 2; ++g)
+                        tma_load_4d(&tmX, &bar_full[stage], sa + (size_t)g * a_group_bytes + (size_t)r * W2 * 128, g * 64, -1, yp - 1, n);
+                }
+                for (int r = 0; r < nq; ++r) {
+                    const long R = Q0 + r;
+                    tma_load_4d(&tmDY, &bar_full[stage], sa + a_bytes + (size_t)r * W2 * 128, 0, -1, (int)(R % H2) - 1, (int)(R / H2));
+                }
+                stage ^= 1;
+                if (stage == 0) phase ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = idesc_bf16(128, p.NP, 1, 1);
+            const uint64_t tmplA = smem_desc_template((uint32_t)a_group_bytes, 1024, LAYOUT_SW128);
+            const uint64_t tmplB = smem_desc_template(0, 1024, LAYOUT_SW128);
+            int stage = 0;
+            uint32_t phase = 0;
+            bool first_tile = true;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(&bar_full[stage], phase);
+                tc_fence_after();
+                const long P0 = (long)tile * 128;
+                const long lo = P0 - HALO;
+                const long R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
+                const int a_row0 = (int)(P0 - R0 * W2);
+                const int b_row0 = (int)(P0 - (P0 / W2) * W2);
+                const uint32_t a_base = smem_u32(sm + (size_t)stage * stage_bytes);
+                const uint32_t b_base = a_base + a_bytes + b_row0 * 128;
+                for (int t = 0; t < 9; ++t) {
+                    const uint32_t a_addr = a_base + (a_row0 + (t / 3 - 1) * W2 + (t % 3 - 1)) * 128;
+                    const uint32_t d = tmem_base + (uint32_t)(t * p.NP);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)    // 128 positions = 8 x 16 reduction rows
+                        umma_bf16(d, smem_desc(tmplA, a_addr + k * 2048), smem_desc(tmplB, b_base + k * 2048), idesc,
+                                  (uint32_t)(!first_tile || k != 0));
+                }
+                umma_commit(&bar_empty[stage]);
+                first_tile = false;
+                stage ^= 1;
+                if (stage == 0) phase ^= 1;
+            }
+            umma_commit(&bar_done);
+        }
+    } else if (has_work) {
+        const int g = warp & 3;
+        mbar_wait(&bar_done, 0);
+        tc_fence_after();
+        const int c = g * 32 + lane;                 // activation channel (accumulator row)
+        for (int t = 0; t < 9; ++t) {
+            for (int c0 = 0; c0 < p.NP; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(t * p.NP + c0), r);
+                tmem_ld_wait();
+                if (c < p.CI) {
+                    float* o = p.dwp + ((long)t * p.CI + c) * p.CO + c0;
+                    const int ncols = min(32, p.CO - c0);   // columns beyond NP-c0 hold the next tap and are never used
+                    if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            atomicAdd(reinterpret_cast<float4*>(o + 4 * q),
+                                      make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                                  __uint_as_float(r[4 * q + 3])));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < ncols) atomicAdd(o + j, __uint_as_float(r[j]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// dw[co][c][ky][kx] = dwp[t][c][co]
+__global__ void conv3_unpack_grad_kernel(const float* __restrict__ dwp, int CO, int CI, float* __restrict__ dw) {
+    const long total = 9L * CO * CI;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int t = (int)(e % 9);
+        const int c = (int)((e / 9) % CI);
+        const int co = (int)(e / (9L * CI));
+        dw[e] = dwp[((long)t * CI + c) * CO + co];
+    }
+}
+
+// x: activations [Nimg*H*W, >=CI] (pitch ldx), dy: output gradient [Nimg*H*W, >=CO] (pitch ldy), dwp: [9][CI][CO] fp32 (+=)
+GN_API int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long ldy, int Nimg, int H, int W, int CI, int CO, float* dwp,
+                                 cudaStream_t stream) {
+    GN_REQUIRE(x && dy && dwp && Nimg > 0 && H > 0 && W > 0 && CI > 0 && CO > 0, GN_EINVAL, "conv3x3_wgrad: bad arguments");
+    GN_REQUIRE(CI <= 128 && CI % 8 == 0, GN_EUNSUPPORTED, "conv3x3_wgrad: activation channels %d must be a multiple of 8, <= 128", CI);
+    GN_REQUIRE(CO <= 48 && CO % 8 == 0, GN_EUNSUPPORTED, "conv3x3_wgrad: gradient channels %d must be a multiple of 8, <= 48", CO);
+    GN_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= CI && ldy >= CO, GN_EALIGN, "conv3x3_wgrad: bad pitches");
+    GN_REQUIRE(W + 2 <= 256, GN_EUNSUPPORTED, "conv3x3_wgrad: width %d too large", W);
+    Conv3WgParams p;
+    p.Nimg = Nimg; p.H = H; p.W = W; p.CI = CI; p.CO = CO; p.NP = ((CO + 15) / 16) * 16;
+    const int W2 = W + 2, HALO = W + 3;
+    p.a_rows = ((127 + 2 * HALO) / W2 + 2) * W2;
+    p.b_rows = (127 / W2 + 2) * W2;
+    p.n_tiles = (int)(((long)(H + 2) * W2 * Nimg + 127) / 128);
+    p.dwp = dwp;
+    const size_t smem = 2 * (size_t)(2 * p.a_rows + p.b_rows) * 128 + 1024;
+    GN_REQUIRE(smem <= 227 * 1024 - 256, GN_EUNSUPPORTED, "conv3x3_wgrad: tile does not fit shared memory (%zu B)", smem);
+    CUtensorMap tmX, tmDY;
+    {
+        uint64_t dims[4] = {(uint64_t)CI, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+        uint64_t strides[3] = {(uint64_t)ldx * 2, (uint64_t)W * ldx * 2, (uint64_t)H * W * ldx * 2};
+        uint32_t box[4] = {64, (uint32_t)W2, 1, 1};
+        int rc = gn_tmap_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)CO, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+        uint64_t strides[3] = {(uint64_t)ldy * 2, (uint64_t)W * ldy * 2, (uint64_t)H * W * ldy * 2};
+        uint32_t box[4] = {64, (uint32_t)W2, 1, 1};
+        int rc = gn_tmap_encode(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    static int max_set = 0;
+    if ((int)smem > max_set) {
+        GN_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set = (int)smem;
+    }
+    const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
+    conv3x3_wgrad_kernel<<<grid, 192, smem, stream>>>(tmX, tmDY, p);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+GN_API int gn_conv3x3_unpack_grad(const float* dwp, int CO, int CI, float* dw, cudaStream_t stream) {
+    GN_REQUIRE(dwp && dw && CO > 0 && CI > 0, GN_EINVAL, "conv3x3_unpack_grad: bad arguments");
+    conv3_unpack_grad_kernel<<<gn_ceil_div(9L * CO * CI, 256), 256, 0, stream>>>(dwp, CO, CI, dw);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}

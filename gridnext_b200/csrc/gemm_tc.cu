@@ -18,6 +18,7 @@
 #include "gn_common.cuh"
 #include "gn_ptx.cuh"
 #include "gn_tma.cuh"
+#include "gn_epilogue.cuh"
 
 using namespace gnptx;
 
@@ -38,6 +39,8 @@ struct GemmParams {
     int relu;
     const float* xf_scale;     // per K index (XFORM kernels)
     const float* xf_shift;
+    int epi_mode;              // 0: affine/ReLU store, 1: BN+ReLU backward (BnBwdEpi), bf16 output
+    BnBwdEpi bn;
 };
 
 template <int BN> struct GemmCfg {
@@ -203,18 +206,77 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int g = warp & 3;   // TMEM lane group this warp may access
         int acc = 0;
         uint32_t acc_phase = 0;
+        constexpr int NCH = BN / 32;
+        float cs_g[NCH], cs_x[NCH];   // BN-backward column partial sums (column = nb*BN + ch*32 + lane)
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) { cs_g[i] = 0.f; cs_x[i] = 0.f; }
+        int cur_nb = -1;
+        auto flush_colsums = [&]() {
+            if (p.epi_mode == 1 && p.bn.colsum != nullptr && cur_nb >= 0) {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const int col = cur_nb * BN + ch * 32 + lane;
+                    if (col < p.N) {
+                        atomicAdd(p.bn.colsum + col, cs_g[ch]);
+                        atomicAdd(p.bn.colsum + p.bn.ldsum + col, cs_x[ch]);
+                    }
+                    cs_g[ch] = 0.f; cs_x[ch] = 0.f;
+                }
+            }
+        };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int nb = tile / p.num_m_blocks, mb = tile % p.num_m_blocks;
+            if (nb != cur_nb) { flush_colsums(); cur_nb = nb; }
             mbar_wait(&bar_tfull[acc], acc_phase);
             tc_fence_after();
             const int row = mb * GEMM_BM + g * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * BN);
+            if (p.epi_mode == 0) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c0, r);
-                tmem_ld_wait();
-                epi_store_row(p, row, nb * BN + c0, r);
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+                    epi_store_row(p, row, nb * BN + c0, r);
+                }
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + ch * 32, r);
+                    tmem_ld_wait();
+                    const int col = nb * BN + ch * 32;
+                    const int ncols = min(32, p.N - col);
+                    float v[32], gx[32];
+                    if (row < p.M && ncols > 0) {
+                        float ref[32];
+                        gn_load_bf16_32(p.bn.ref + (long)row * p.bn.ldref + col, ref, ncols);
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long)row * p.ldc + col;
+                        float old[32];
+                        if (p.bn.rmw) gn_load_bf16_32(o, old, ncols);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < ncols) {
+                                const float sc = __ldg(p.bn.sc + col + j);
+                                const float a = p.bn.ref_is_raw ? fmaf(ref[j], sc, __ldg(p.bn.sh + col + j)) : ref[j];
+                                const float gg = a > 0.f ? __uint_as_float(r[j]) : 0.f;
+                                gx[j] = gg * (ref[j] - __ldg(p.bn.p0 + col + j)) * __ldg(p.bn.p1 + col + j);
+                                v[j] = gg;
+                                ref[j] = p.bn.rmw ? fmaf(gg, sc, old[j]) : gg * sc;
+                            } else {
+                                gx[j] = 0.f; v[j] = 0.f; ref[j] = 0.f;
+                            }
+                        }
+                        gn_store_bf16_32(o, ref, ncols);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { v[j] = 0.f; gx[j] = 0.f; }
+                    }
+                    if (p.bn.colsum != nullptr) {
+                        cs_g[ch] += gn_warp_colsum32(v, lane);
+                        cs_x[ch] += gn_warp_colsum32(gx, lane);
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -222,6 +284,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        flush_colsums();
     } else if (XFORM) {
         // ===================== operand transform: A <- relu(A * scale[k] + shift[k]) in place =====================
         const int w = warp - 6;
@@ -284,7 +347,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 // a: [M, K] bf16 with row pitch lda; b: [N, K] bf16 with row pitch ldb; out: [M, ldc] bf16 or fp32
 GN_API int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M, int N, int K, void* out, long ldc, int out_fp32,
                         int accumulate, const float* scale, const float* shift, int relu, const float* xf_scale, const float* xf_shift,
-                        cudaStream_t stream) {
+                        const void* bn_ref, long bn_ldref, int bn_ref_is_raw, const float* bn_sc, const float* bn_sh, const float* bn_p0,
+                        const float* bn_p1, float* bn_colsum, int bn_ldsum, int bn_rmw, cudaStream_t stream) {
     GN_REQUIRE(a && b && out && M > 0 && N > 0 && K > 0, GN_EINVAL, "gemm_bf16: bad arguments");
     GN_REQUIRE(lda >= K && ldb >= K && ldc >= N, GN_EINVAL, "gemm_bf16: pitch smaller than extent");
     GN_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, GN_EALIGN, "gemm_bf16: lda/ldb must be multiples of 8 elements (16 bytes)");
@@ -300,6 +364,14 @@ GN_API int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M,
     p.num_k_blocks = gn_ceil_div(K, GEMM_BK);
     p.out = out; p.ldc = ldc; p.out_fp32 = out_fp32; p.accumulate = accumulate;
     p.scale = scale; p.shift = shift; p.relu = relu; p.xf_scale = xf_scale; p.xf_shift = xf_shift;
+    p.epi_mode = bn_ref != nullptr ? 1 : 0;
+    memset(&p.bn, 0, sizeof(p.bn));
+    if (p.epi_mode == 1) {
+        GN_REQUIRE(!out_fp32 && !accumulate && !scale && !shift && !relu, GN_EINVAL, "gemm_bf16: BN-backward epilogue needs a plain bf16 output");
+        GN_REQUIRE(bn_sc && bn_p0 && bn_p1 && (!bn_ref_is_raw || bn_sh), GN_EINVAL, "gemm_bf16: incomplete BN-backward epilogue arguments");
+        p.bn.ref = (const __nv_bfloat16*)bn_ref; p.bn.ldref = bn_ldref; p.bn.ref_is_raw = bn_ref_is_raw;
+        p.bn.sc = bn_sc; p.bn.sh = bn_sh; p.bn.p0 = bn_p0; p.bn.p1 = bn_p1; p.bn.colsum = bn_colsum; p.bn.ldsum = bn_ldsum; p.bn.rmw = bn_rmw;
+    }
     CUtensorMap tmA, tmB;
     int rc = gn_tmap_bf16_2d(&tmA, a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BK, GEMM_BM);
     if (rc) return rc;

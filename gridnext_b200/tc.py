@@ -10,8 +10,17 @@ def _rows_pitch(t):
     return t.shape[0], t.shape[1], t.stride(0)
 
 
+def _bn_args(bn):
+    if bn is None:
+        return (None, 0, 0, None, None, None, None, None, 0)
+    _, _, ldref = _rows_pitch(bn['ref'])
+    cs = bn.get('colsum')
+    return (ptr(bn['ref']), ldref, 1 if bn['ref_is_raw'] else 0, ptr(bn['sc']), ptr(bn.get('sh')), ptr(bn['p0']), ptr(bn['p1']),
+            ptr(cs), cs.shape[1] if cs is not None else 0)
+
+
 def gemm_bf16(a, b, out=None, out_dtype=torch.bfloat16, accumulate=False, scale=None, shift=None, relu=False,
-              xf_scale=None, xf_shift=None):
+              xf_scale=None, xf_shift=None, bn=None):
     """out[M, N] = [relu]((op(a) @ b.T) * scale + shift);  a [M, K], b [N, K] bf16 (row pitch may exceed K).
 
     ``out`` may be a column slice of a wider row-major buffer (e.g. a DenseNet concat buffer)."""
@@ -30,7 +39,8 @@ def gemm_bf16(a, b, out=None, out_dtype=torch.bfloat16, accumulate=False, scale=
     if out.dtype not in (torch.bfloat16, torch.float32):
         raise ValueError('gemm_bf16: out must be bfloat16 or float32')
     call('gn_gemm_bf16', ptr(a), lda, ptr(b), ldb, M, N, K, ptr(out), ldc, 1 if out.dtype == torch.float32 else 0,
-         1 if accumulate else 0, ptr(scale), ptr(shift), 1 if relu else 0, ptr(xf_scale), ptr(xf_shift), stream())
+         1 if accumulate else 0, ptr(scale), ptr(shift), 1 if relu else 0, ptr(xf_scale), ptr(xf_shift),
+         *_bn_args(bn), 1 if (bn is not None and bn.get('rmw')) else 0, stream())
     return out
 
 
@@ -69,12 +79,20 @@ def conv3x3_bf16(x2d, Nimg, H, W, CI, wp, CO, out2d, bn=None):
     Mo, COo, ldo = _rows_pitch(out2d)
     if M != Nimg * H * W or Mo != M or COo != CO:
         raise ValueError('conv3x3_bf16: shape mismatch')
-    if bn is None:
-        args = (None, 0, 0, None, None, None, None, None, 0)
-    else:
-        _, _, ldref = _rows_pitch(bn['ref'])
-        cs = bn.get('colsum')
-        args = (ptr(bn['ref']), ldref, 1 if bn['ref_is_raw'] else 0, ptr(bn['sc']), ptr(bn.get('sh')), ptr(bn['p0']), ptr(bn['p1']),
-                ptr(cs), cs.shape[1] if cs is not None else 0)
+    args = _bn_args(bn)
     call('gn_conv3x3_bf16', ptr(x2d), ldx, Nimg, H, W, CI, ptr(wp), wp.stride(0), CO, ptr(out2d), ldo, *args, stream())
     return out2d
+
+
+def conv3x3_wgrad_bf16(x2d, dy2d, Nimg, H, W, CI, CO):
+    """-> fp32 (CO, CI, 3, 3) weight gradient of the 3x3 convolution from activations x2d [M, >=CI] and dy2d [M, >=CO]."""
+    _lib.require_cuda(x2d, dy2d)
+    M, _, ldx = _rows_pitch(x2d)
+    M2, _, ldy = _rows_pitch(dy2d)
+    if M != Nimg * H * W or M2 != M:
+        raise ValueError('conv3x3_wgrad_bf16: shape mismatch')
+    dwp = torch.zeros((9, CI, CO), device=x2d.device, dtype=torch.float32)
+    call('gn_conv3x3_wgrad_bf16', ptr(x2d), ldx, ptr(dy2d), ldy, Nimg, H, W, CI, CO, ptr(dwp), stream())
+    dw = torch.empty((CO, CI, 3, 3), device=x2d.device, dtype=torch.float32)
+    call('gn_conv3x3_unpack_grad', ptr(dwp), CO, CI, ptr(dw), stream())
+    return dw

@@ -80,7 +80,9 @@ int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, const in
  * (DenseNet's pre-activation eval-mode BatchNorm + ReLU, densenet.py:12-18). */
 int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M, int N, int K, void* out, long ldc, int out_fp32,
                  int accumulate, const float* scale, const float* shift, int relu, const float* xf_scale, const float* xf_shift,
-                 gn_stream_t stream);
+                 const void* bn_ref, long bn_ldref, int bn_ref_is_raw, const float* bn_sc, const float* bn_sh, const float* bn_p0,
+                 const float* bn_p1, float* bn_colsum, int bn_ldsum, int bn_rmw, gn_stream_t stream);
+/* bn_ref != NULL selects the BN+ReLU-backward epilogue of gn_conv3x3_bf16 (bf16 out; bn_rmw: out += g * bn_sc). */
 
 /* Weight-gradient GEMM: out[Mo, No] (fp32, pitch ldo) += a[Kp, Mo]^T * op(b)[Kp, No]; rows of a and b are the
  * reduction index (pixels / spots).  op(b) = relu(b * xf_scale[n] + xf_shift[n]) when given.  Split over the
@@ -99,6 +101,12 @@ int gn_conv3x3_pack(const float* w, int CO, int CI, int mode, void* wp, int ldw,
 int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int CI, const void* wp, int ldw, int CO, void* out, long ldo,
                     const void* bn_ref, long bn_ldref, int bn_ref_is_raw, const float* bn_sc, const float* bn_sh,
                     const float* bn_p0, const float* bn_p1, float* bn_colsum, int bn_ldsum, gn_stream_t stream);
+
+/* Weight gradient of the 3x3 convolution: dwp[9][CI][CO] (fp32) += sum over pixels x[p + tap] * dy[p];
+ * gn_conv3x3_unpack_grad reorders to the (CO, CI, 3, 3) parameter layout. */
+int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long ldy, int Nimg, int H, int W, int CI, int CO, float* dwp,
+                          gn_stream_t stream);
+int gn_conv3x3_unpack_grad(const float* dwp, int CO, int CI, float* dw, gn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -63,3 +63,19 @@ def test_conv3x3_data_gradient_with_bn_relu_backward(Nimg, H, W, Cin, Cout):
     assert rel(dz.float().cpu(), ref_dz) < 1.5e-2
     assert rel(colsum[0].cpu(), ref_sum_g) < 1e-2
     assert rel(colsum[1].cpu(), ref_sum_gx) < 1e-2
+
+
+@pytest.mark.parametrize('Nimg,H,W', SHAPES)
+@pytest.mark.parametrize('CI,CO', [(128, 32), (16, 8), (64, 48)])
+def test_conv3x3_weight_gradient(Nimg, H, W, CI, CO):
+    from gridnext_b200.tc import conv3x3_wgrad_bf16
+    M = Nimg * H * W
+    x = torch.relu(rnd((Nimg, H, W, CI), 7)).to(torch.bfloat16)
+    dy = rnd((Nimg, H, W, CO), 8).to(torch.bfloat16)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+    w = torch.zeros((CO, CI, 3, 3), requires_grad=True)
+    F.conv2d(xr, w, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    xbuf = torch.zeros((M, CI + 8), dtype=torch.bfloat16, device='cuda'); xbuf[:, :CI] = x.reshape(M, CI).cuda()
+    dbuf = torch.zeros((M, CO + 200), dtype=torch.bfloat16, device='cuda'); dbuf[:, 96:96 + CO] = dy.reshape(M, CO).cuda()
+    dw = conv3x3_wgrad_bf16(xbuf[:, :CI], dbuf[:, 96:96 + CO], Nimg, H, W, CI, CO)
+    assert rel(dw.cpu(), w.grad) < 1e-4

@@ -60,7 +60,7 @@ def test_gemm_operand_transform_bn_relu(M, N, K):
                                          (9984, 500, 5000, False), (3000, 256, 512, True), (777, 7, 56, False), (4096, 32, 1152, False)])
 def test_gemm_tn_weight_gradient(Kp, Mo, No, xf):
     from gridnext_b200.tc import gemm_tn_bf16
-    lda, ldb = Mo + 8, No + 24                    # operands are column slices of wider buffers
+    lda, ldb = (Mo + 7) // 8 * 8 + 8, (No + 7) // 8 * 8 + 24                    # operands are column slices of wider buffers
     a, b = rnd((Kp, lda), 11, 0.5), rnd((Kp, ldb), 12)
     g = torch.Generator(); g.manual_seed(13)
     xs, xt = torch.rand(No, generator=g) + 0.5, torch.randn(No, generator=g) * 0.5
@@ -71,3 +71,30 @@ def test_gemm_tn_weight_gradient(Kp, Mo, No, xf):
     out = torch.ones((Mo, No), dtype=torch.float32, device='cuda')
     gemm_tn_bf16(a.cuda()[:, :Mo], b.cuda()[:, :No], out, xs.cuda() if xf else None, xt.cuda() if xf else None)
     assert rel(out.cpu(), ref) < (3e-3 if xf else 2e-5)
+
+
+@pytest.mark.parametrize('M,N,K', [(1000, 224, 128), (4100, 992, 128), (300, 64, 128), (2048, 512, 256)])
+def test_gemm_bn_relu_backward_epilogue(M, N, K):
+    """Data gradient of a pre-activation 1x1 conv: dC[:, :N] += (dZ @ W) * [bn(C) > 0] * s, plus BN gradient column sums."""
+    from gridnext_b200.tc import gemm_bf16
+    dz, wt = rnd((M, K), 21, 0.5), rnd((N, K), 22, 0.1)          # wt[n, k] = W[k, n]
+    craw = rnd((M, N + 32), 23)                                   # raw concat buffer (wider than N)
+    g = torch.Generator(); g.manual_seed(24)
+    mean, invstd = torch.randn(N, generator=g) * 0.2, torch.rand(N, generator=g) + 0.5
+    gamma, beta = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.3
+    sc = gamma * invstd
+    sh = beta - mean * sc
+    dc0 = rnd((M, N + 32), 25)
+    acc = dz.float() @ wt.float().t()
+    a = craw[:, :N].float() * sc + sh
+    gg = acc * (a > 0)
+    ref_dc = dc0[:, :N].float() + gg * sc
+    ref_g = gg.sum(0)
+    ref_gx = (gg * (craw[:, :N].float() - mean) * invstd).sum(0)
+    dc = dc0.clone().cuda()
+    colsum = torch.zeros((2, N), dtype=torch.float32, device='cuda')
+    gemm_bf16(dz.cuda(), wt.cuda(), out=dc[:, :N],
+              bn=dict(ref=craw.cuda()[:, :N], ref_is_raw=True, sc=sc.cuda(), sh=sh.cuda(), p0=mean.cuda(), p1=invstd.cuda(), colsum=colsum, rmw=True))
+    assert rel(dc[:, :N].float().cpu(), ref_dc) < 1.5e-2
+    assert torch.equal(dc[:, N:].cpu(), dc0[:, N:])
+    assert rel(colsum[0].cpu(), ref_g) < 2e-3 and rel(colsum[1].cpu(), ref_gx) < 2e-3
