@@ -33,6 +33,15 @@ _SIGS = {
     'gn_spot_table': [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp],
     'gn_patch_gather': [vp, cl, ci, ci, vp, ci, ci, vp, vp, vp, ci, vp],
     'gn_gemm_tn_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, vp, vp, vp],
+    'gn_im2col7x7s2': [vp, ci, ci, ci, vp, ci, vp],
+    'gn_maxpool3s2_fwd': [vp, cl, ci, ci, ci, ci, vp, cl, vp, vp],
+    'gn_maxpool3s2_bnrelu_bwd': [vp, cl, vp, vp, cl, ci, ci, ci, ci, vp, vp, vp, vp, cl, vp, ci, vp],
+    'gn_bnrelu_avgpool2_fwd': [vp, cl, ci, ci, ci, ci, vp, vp, vp, cl, vp],
+    'gn_pool_bnrelu_bwd': [vp, cl, ci, vp, cl, ci, ci, ci, ci, vp, vp, vp, vp, vp, cl, vp, ci, vp],
+    'gn_bnrelu_gap_fwd': [vp, cl, ci, ci, ci, vp, vp, vp, cl, vp],
+    'gn_linear_small_fwd': [vp, cl, vp, vp, ci, ci, ci, vp, vp],
+    'gn_linear_small_bwd': [vp, vp, cl, vp, ci, ci, ci, vp, cl, vp, vp, vp],
+    'gn_bn_eval_consts': [vp, vp, vp, vp, cf, ci, vp, vp, vp, vp, vp],
     'gn_conv3x3_pack': [vp, ci, ci, ci, vp, ci, vp],
     'gn_conv3x3_bf16': [vp, cl, ci, ci, ci, ci, vp, ci, ci, vp, cl, vp, cl, ci, vp, vp, vp, vp, vp, ci, vp],
     'gn_gemm_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, ci, ci, vp, vp, ci, vp, vp, vp, cl, ci, vp, vp, vp, vp, vp, ci, ci, vp],

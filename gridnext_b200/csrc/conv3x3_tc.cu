@@ -21,6 +21,7 @@ using namespace gnptx;
 
 struct Conv3Params {
     int Nimg, H, W, CI, CO;
+    int NP;               // CO rounded up to 16 (UMMA N)
     int kblocks;          // ceil(CI / 64)
     int w_row_bytes;      // bytes per weight row per k-block: 128 (SW128) or 64 (SW64)
     int buf_rows;         // rows (positions) per activation stage buffer
@@ -42,7 +43,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int W2 = p.W + 2, H2 = p.H + 2, PP = W2 * H2, HALO = p.W + 3;
-    const int w_tile_bytes = p.CO * p.w_row_bytes;                       // one (tap, k-block) weight tile
+    const int w_tile_bytes = p.NP * p.w_row_bytes;                       // one (tap, k-block) weight tile (rows beyond CO: next tap / zero fill, never stored)
     const int w_bytes = ((9 * p.kblocks * w_tile_bytes + 1023) / 1024) * 1024;
     const int kb_buf_bytes = p.buf_rows * 128;                           // one k-block of one stage
     const int stage_bytes = p.kblocks * kb_buf_bytes;
@@ -97,7 +98,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = idesc_bf16(128, p.CO, 0, 0);
+            const uint32_t idesc = idesc_bf16(128, p.NP, 0, 0);
             const uint64_t tmplA = smem_desc_template(0, 1024, LAYOUT_SW128);
             const uint64_t tmplW = p.w_row_bytes == 128 ? smem_desc_template(0, 1024, LAYOUT_SW128) : smem_desc_template(0, 512, LAYOUT_SW64);
             mbar_wait(&bar_w, 0);
@@ -257,12 +258,11 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     GN_REQUIRE(x && wp && out && Nimg > 0 && H > 0 && W > 0 && CI > 0 && CO > 0, GN_EINVAL, "conv3x3: bad arguments");
     GN_REQUIRE(CO % 8 == 0 && CO <= 256, GN_EUNSUPPORTED, "conv3x3: output channels %d must be a multiple of 8, <= 256", CO);
     GN_REQUIRE(CI % 8 == 0 && CI <= 256, GN_EUNSUPPORTED, "conv3x3: input channels %d must be a multiple of 8, <= 256", CI);
-    GN_REQUIRE(CO % 16 == 0, GN_EUNSUPPORTED, "conv3x3: output channels %d must be a multiple of 16 (UMMA M=128)", CO);
     GN_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= CI && ldw >= CI && ldo >= CO, GN_EALIGN, "conv3x3: bad pitches");
     GN_REQUIRE(W + 2 <= 256, GN_EUNSUPPORTED, "conv3x3: width %d too large", W);
     Conv3Params p;
     memset(&p, 0, sizeof(p));
-    p.Nimg = Nimg; p.H = H; p.W = W; p.CI = CI; p.CO = CO;
+    p.Nimg = Nimg; p.H = H; p.W = W; p.CI = CI; p.CO = CO; p.NP = ((CO + 15) / 16) * 16;
     p.kblocks = gn_ceil_div(CI, 64);
     p.w_row_bytes = (CI <= 32) ? 64 : 128;
     const int W2 = W + 2, HALO = W + 3;
@@ -277,7 +277,7 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
         p.bn.ref = (const __nv_bfloat16*)bn_ref; p.bn.ldref = bn_ldref; p.bn.ref_is_raw = bn_ref_is_raw;
         p.bn.sc = bn_sc; p.bn.sh = bn_sh; p.bn.p0 = bn_p0; p.bn.p1 = bn_p1; p.bn.colsum = bn_colsum; p.bn.ldsum = bn_ldsum; p.bn.rmw = 0;
     }
-    const int w_bytes = ((9 * p.kblocks * CO * p.w_row_bytes + 1023) / 1024) * 1024;
+    const int w_bytes = ((9 * p.kblocks * p.NP * p.w_row_bytes + 1023) / 1024) * 1024;
     const int stage_bytes = p.kblocks * p.buf_rows * 128;
     const int budget = 227 * 1024 - 1024 - 256;
     GN_REQUIRE(w_bytes + stage_bytes <= budget, GN_EUNSUPPORTED, "conv3x3: tile does not fit shared memory (weights %d B + stage %d B)", w_bytes,
@@ -296,7 +296,7 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     {
         uint64_t dims[2] = {(uint64_t)CI, (uint64_t)9 * CO};
         uint64_t strides[1] = {(uint64_t)ldw * 2};
-        uint32_t box[2] = {(uint32_t)(p.w_row_bytes / 2), (uint32_t)CO};
+        uint32_t box[2] = {(uint32_t)(p.w_row_bytes / 2), (uint32_t)p.NP};
         int rc = gn_tmap_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wp, dims, strides, box,
                                 p.w_row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
@@ -324,6 +324,7 @@ struct Conv3WgParams {
     int Nimg, H, W, CI, CO, NP;     // NP = CO rounded up to 16 (UMMA N)
     int a_rows, b_rows;             // buffer rows (positions) per stage for X halo and dY
     int n_tiles;
+    int stages;
     float* dwp;                     // [9][CI][CO] fp32
 };
 
@@ -384,8 +385,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     const long R = Q0 + r;
                     tma_load_4d(&tmDY, &bar_full[stage], sa + a_bytes + (size_t)r * W2 * 128, 0, -1, (int)(R % H2) - 1, (int)(R / H2));
                 }
-                stage ^= 1;
-                if (stage == 0) phase ^= 1;
+                if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -416,8 +416,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 }
                 umma_commit(&bar_empty[stage]);
                 first_tile = false;
-                stage ^= 1;
-                if (stage == 0) phase ^= 1;
+                if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
             }
             umma_commit(&bar_done);
         }
@@ -480,7 +479,9 @@ GN_API int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long l
     p.b_rows = (127 / W2 + 2) * W2;
     p.n_tiles = (int)(((long)(H + 2) * W2 * Nimg + 127) / 128);
     p.dwp = dwp;
-    const size_t smem = 2 * (size_t)(2 * p.a_rows + p.b_rows) * 128 + 1024;
+    const size_t stage_b = (size_t)(2 * p.a_rows + p.b_rows) * 128;
+    p.stages = (2 * stage_b + 1024 <= 227 * 1024 - 256) ? 2 : 1;
+    const size_t smem = p.stages * stage_b + 1024;
     GN_REQUIRE(smem <= 227 * 1024 - 256, GN_EUNSUPPORTED, "conv3x3_wgrad: tile does not fit shared memory (%zu B)", smem);
     CUtensorMap tmX, tmDY;
     {

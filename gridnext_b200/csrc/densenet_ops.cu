@@ -1,0 +1,464 @@
+// Memory-bound pieces of the DenseNet-BC f network in NHWC bf16 (everything that is not a GEMM / 3x3 conv):
+// stem im2col + max-pool, transition BN-ReLU-avgpool, head BN-ReLU-global-average-pool + classifier, and their
+// backward passes with the BatchNorm parameter-gradient column sums fused in.
+//
+// Reference: /root/reference/gridnext/densenet.py  conv0/norm0/relu0/pool0 (:103-112), _Transition (:47-54),
+// norm_final + F.relu + adaptive_avg_pool2d + classifier (:134,152-158).  BatchNorm is eval-mode (training.py:126):
+// y = x * scale[c] + shift[c], scale = gamma / sqrt(var + eps), shift = beta - mean * scale.
+// Each thread handles 8 consecutive channels (one 16-byte vector) of one pixel.
+#include "gn_common.cuh"
+#include "gn_epilogue.cuh"
+#include <algorithm>
+
+struct V8 { float v[8]; };
+
+__device__ __forceinline__ V8 ld_bf16x8(const __nv_bfloat16* p) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+    V8 r;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+        r.v[2 * e] = f.x; r.v[2 * e + 1] = f.y;
+    }
+    return r;
+}
+__device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const V8& a) {
+    uint4 t;
+    t.x = gn_pack_bf16x2(a.v[0], a.v[1]); t.y = gn_pack_bf16x2(a.v[2], a.v[3]);
+    t.z = gn_pack_bf16x2(a.v[4], a.v[5]); t.w = gn_pack_bf16x2(a.v[6], a.v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+}
+__device__ __forceinline__ V8 ld_f32x8(const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    V8 r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+
+// per-thread column partial sums -> shared -> global (colsum[0][c] += g, colsum[1][c] += gx)
+struct ColAcc {
+    float g[8], x[8];
+    int cg;   // channel group the registers belong to (-1: none yet)
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { g[j] = 0.f; x[j] = 0.f; }
+        cg = -1;
+    }
+    __device__ __forceinline__ void flush(float* s_sum, int C) {
+        if (cg >= 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&s_sum[cg * 8 + j], g[j]);
+                atomicAdd(&s_sum[C + cg * 8 + j], x[j]);
+                g[j] = 0.f; x[j] = 0.f;
+            }
+        }
+    }
+    __device__ __forceinline__ void select(int new_cg, float* s_sum, int C) {
+        if (new_cg != cg) { flush(s_sum, C); cg = new_cg; }
+    }
+};
+
+__device__ __forceinline__ void colsum_block_begin(float* s_sum, int C) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_sum[i] = 0.f;
+    __syncthreads();
+}
+__device__ __forceinline__ void colsum_block_end(float* s_sum, int C, float* colsum, int ldsum) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        const float a = s_sum[i], b = s_sum[C + i];
+        if (a != 0.f) atomicAdd(colsum + i, a);
+        if (b != 0.f) atomicAdd(colsum + ldsum + i, b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stem
+// A0[m, c*49 + ky*7 + kx] = x[n, c, 2*oy - 3 + ky, 2*ox - 3 + kx]  (0 outside), columns >= 147 zero
+template <typename InT>
+__global__ void __launch_bounds__(256) im2col7x7s2_kernel(const InT* __restrict__ x, int N, int P, int Ho, __nv_bfloat16* __restrict__ a0, int ldk) {
+    const long total = (long)N * Ho * Ho * ldk;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(e % ldk);
+        const long m = e / ldk;
+        float v = 0.f;
+        if (k < 147) {
+            const int ox = (int)(m % Ho), oy = (int)((m / Ho) % Ho), n = (int)(m / ((long)Ho * Ho));
+            const int c = k / 49, ky = (k % 49) / 7, kx = k % 7;
+            const int iy = 2 * oy - 3 + ky, ix = 2 * ox - 3 + kx;
+            if (iy >= 0 && iy < P && ix >= 0 && ix < P) v = (float)x[(((long)n * 3 + c) * P + iy) * P + ix];
+        }
+        a0[e] = __float2bfloat16_rn(v);
+    }
+}
+
+// 3x3 / stride 2 / pad 1 max pool, NHWC; idx = ky*3+kx of the first maximum (PyTorch tie rule)
+__global__ void __launch_bounds__(256) maxpool3s2_fwd_kernel(const __nv_bfloat16* __restrict__ in, long ldi, int N, int Hi, int Wi, int C,
+                                                              __nv_bfloat16* __restrict__ out, long ldo, unsigned char* __restrict__ idx) {
+    const int Ho = Hi / 2, Wo = Wi / 2, G = C / 8;
+    const long total = (long)N * Ho * Wo * G;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(e % G);
+        const long op = e / G;
+        const int ox = (int)(op % Wo), oy = (int)((op / Wo) % Ho), n = (int)(op / ((long)Wo * Ho));
+        V8 best; unsigned char bi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best.v[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy - 1 + ky;
+            if (iy < 0 || iy >= Hi) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                if (ix < 0 || ix >= Wi) continue;
+                const V8 v = ld_bf16x8(in + (((long)n * Hi + iy) * Wi + ix) * ldi + cg * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (v.v[j] > best.v[j]) { best.v[j] = v.v[j]; bi[j] = (unsigned char)(ky * 3 + kx); }
+            }
+        }
+        st_bf16x8(out + op * ldo + cg * 8, best);
+        uint2 pk;
+        pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+        pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+        *reinterpret_cast<uint2*>(idx + op * C + cg * 8) = pk;
+    }
+}
+
+// dZ0[pixel, c] = (sum of dPool over the windows whose arg-max is this pixel) * [act0 > 0] * s0[c]; BN0 column sums.
+// act0 is the ACTIVATED stem output: xhat = (act0 - beta) / gamma where act0 > 0.
+__global__ void __launch_bounds__(256) maxpool3s2_bnrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, long ldp,
+                                                                    const unsigned char* __restrict__ idx,
+                                                                    const __nv_bfloat16* __restrict__ act, long lda, int N, int Hi, int Wi,
+                                                                    int C, const float* __restrict__ sc, const float* __restrict__ p0,
+                                                                    const float* __restrict__ p1, __nv_bfloat16* __restrict__ dz, long ldz,
+                                                                    float* __restrict__ colsum, int ldsum) {
+    extern __shared__ float s_sum[];
+    colsum_block_begin(s_sum, C);
+    const int Ho = Hi / 2, Wo = Wi / 2, G = C / 8;
+    const long total = (long)N * Hi * Wi * G;
+    ColAcc ca; ca.init();
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(e % G);
+        const long ip = e / G;
+        const int ix = (int)(ip % Wi), iy = (int)((ip / Wi) % Hi), n = (int)(ip / ((long)Wi * Hi));
+        ca.select(cg, s_sum, C);
+        V8 g;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+        for (int oy = iy >> 1; oy <= ((iy + 1) >> 1); ++oy) {
+            if (oy >= Ho) continue;
+            const int ky = iy - (2 * oy - 1);
+            for (int ox = ix >> 1; ox <= ((ix + 1) >> 1); ++ox) {
+                if (ox >= Wo) continue;
+                const int k = ky * 3 + (ix - (2 * ox - 1));
+                const long op = ((long)n * Ho + oy) * Wo + ox;
+                const uint2 pk = *reinterpret_cast<const uint2*>(idx + op * C + cg * 8);
+                const V8 d = ld_bf16x8(dpool + op * ldp + cg * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const unsigned b = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xff;
+                    if ((int)b == k) g.v[j] += d.v[j];
+                }
+            }
+        }
+        const V8 a = ld_bf16x8(act + ip * lda + cg * 8);
+        V8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cg * 8 + j;
+            const float gg = a.v[j] > 0.f ? g.v[j] : 0.f;
+            ca.g[j] += gg;
+            ca.x[j] += gg * (a.v[j] - __ldg(p0 + c)) * __ldg(p1 + c);
+            o.v[j] = gg * __ldg(sc + c);
+        }
+        st_bf16x8(dz + ip * ldz + cg * 8, o);
+    }
+    ca.flush(s_sum, C);
+    colsum_block_end(s_sum, C, colsum, ldsum);
+}
+
+// ------------------------------------------------------------------------------------------------ transition
+// out[n, y, x, c] = 1/4 sum_{2x2} relu(in * sc + sh)
+__global__ void __launch_bounds__(256) bnrelu_avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ in, long ldi, int N, int H, int W, int C,
+                                                                   const float* __restrict__ sc, const float* __restrict__ sh,
+                                                                   __nv_bfloat16* __restrict__ out, long ldo) {
+    const int Ho = H / 2, Wo = W / 2, G = C / 8;
+    const long total = (long)N * Ho * Wo * G;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(e % G);
+        const long op = e / G;
+        const int ox = (int)(op % Wo), oy = (int)((op / Wo) % Ho), n = (int)(op / ((long)Wo * Ho));
+        const V8 s = ld_f32x8(sc + cg * 8), t = ld_f32x8(sh + cg * 8);
+        V8 acc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const V8 v = ld_bf16x8(in + (((long)n * H + 2 * oy + dy) * W + 2 * ox + dx) * ldi + cg * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc.v[j] += fmaxf(fmaf(v.v[j], s.v[j], t.v[j]), 0.f);
+            }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] *= 0.25f;
+        st_bf16x8(out + op * ldo + cg * 8, acc);
+    }
+}
+
+// dC[pixel, c] = dP[pooled pixel, c] / 4 * [raw*sc+sh > 0] * sc   (WRITE: first contribution to the block's gradient buffer)
+// pool_div = 4 with (H, W) -> (H/2, W/2) for the transitions; for the head pass Hp = Wp = 1 semantics via `gap` = 1:
+//   gap: dP is fp32 [N, C] (gradient of the pooled features), divisor H*W.
+template <bool GAP>
+__global__ void __launch_bounds__(256) pool_bnrelu_bwd_kernel(const void* __restrict__ dpool, long ldp, const __nv_bfloat16* __restrict__ raw,
+                                                               long ldr, int N, int H, int W, int C, const float* __restrict__ sc,
+                                                               const float* __restrict__ sh, const float* __restrict__ p0,
+                                                               const float* __restrict__ p1, __nv_bfloat16* __restrict__ dC, long ldc,
+                                                               float* __restrict__ colsum, int ldsum) {
+    extern __shared__ float s_sum[];
+    colsum_block_begin(s_sum, C);
+    const int G = C / 8;
+    const long total = (long)N * H * W * G;
+    const float inv = GAP ? 1.f / (float)(H * W) : 0.25f;
+    ColAcc ca; ca.init();
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(e % G);
+        const long ip = e / G;
+        const int ix = (int)(ip % W), iy = (int)((ip / W) % H), n = (int)(ip / ((long)W * H));
+        ca.select(cg, s_sum, C);
+        V8 d;
+        if (GAP) d = ld_f32x8(reinterpret_cast<const float*>(dpool) + (long)n * ldp + cg * 8);
+        else d = ld_bf16x8(reinterpret_cast<const __nv_bfloat16*>(dpool) + (((long)n * (H / 2) + (iy >> 1)) * (W / 2) + (ix >> 1)) * ldp + cg * 8);
+        const V8 r = ld_bf16x8(raw + ip * ldr + cg * 8);
+        V8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cg * 8 + j;
+            const float s = __ldg(sc + c);
+            const float a = fmaf(r.v[j], s, __ldg(sh + c));
+            const float gg = a > 0.f ? d.v[j] * inv : 0.f;
+            ca.g[j] += gg;
+            ca.x[j] += gg * (r.v[j] - __ldg(p0 + c)) * __ldg(p1 + c);
+            o.v[j] = gg * s;
+        }
+        st_bf16x8(dC + ip * ldc + cg * 8, o);
+    }
+    ca.flush(s_sum, C);
+    colsum_block_end(s_sum, C, colsum, ldsum);
+}
+
+// ------------------------------------------------------------------------------------------------ head
+// feat[n, c] = mean_{hw} relu(in * sc + sh)     (fp32)
+__global__ void __launch_bounds__(256) bnrelu_gap_fwd_kernel(const __nv_bfloat16* __restrict__ in, long ldi, int N, int HW, int C,
+                                                              const float* __restrict__ sc, const float* __restrict__ sh,
+                                                              float* __restrict__ feat, long ldf) {
+    const int G = C / 8;
+    const long total = (long)N * G;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(e % G);
+        const long n = e / G;
+        const V8 s = ld_f32x8(sc + cg * 8), t = ld_f32x8(sh + cg * 8);
+        V8 acc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+        for (int p = 0; p < HW; ++p) {
+            const V8 v = ld_bf16x8(in + (n * HW + p) * ldi + cg * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc.v[j] += fmaxf(fmaf(v.v[j], s.v[j], t.v[j]), 0.f);
+        }
+        const float inv = 1.f / (float)HW;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) feat[n * ldf + cg * 8 + j] = acc.v[j] * inv;
+    }
+}
+
+// logits[n, j] = sum_c feat[n, c] * w[j, c] + b[j]        one warp per spot, J <= 64
+__global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __restrict__ feat, long ldf, const float* __restrict__ w,
+                                                               const float* __restrict__ b, int N, int C, int J, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    for (long n = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5); n < N; n += (long)gridDim.x * (blockDim.x >> 5)) {
+        for (int j = 0; j < J; ++j) {
+            float acc = 0.f;
+            for (int c = lane; c < C; c += 32) acc = fmaf(feat[n * ldf + c], __ldg(w + (long)j * C + c), acc);
+            acc = gn_warp_sum(acc);
+            if (lane == 0) out[n * J + j] = acc + (b ? b[j] : 0.f);
+        }
+    }
+}
+// dfeat[n, c] = sum_j dlog[n, j] * w[j, c]
+__global__ void __launch_bounds__(256) linear_small_bwd_data_kernel(const float* __restrict__ dlog, const float* __restrict__ w, int N, int C,
+                                                                    int J, float* __restrict__ dfeat, long ldf) {
+    const long total = (long)N * C;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C);
+        const long n = e / C;
+        float acc = 0.f;
+        for (int j = 0; j < J; ++j) acc = fmaf(__ldg(dlog + n * J + j), __ldg(w + (long)j * C + c), acc);
+        dfeat[n * ldf + c] = acc;
+    }
+}
+// dw[j, c] += sum_n dlog[n, j] * feat[n, c];  db[j] += sum_n dlog[n, j]     (grid.y splits the spots)
+__global__ void __launch_bounds__(256) linear_small_bwd_weight_kernel(const float* __restrict__ dlog, const float* __restrict__ feat, long ldf,
+                                                                      int N, int C, int J, float* __restrict__ dw, float* __restrict__ db) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const long per = (N + gridDim.y - 1) / gridDim.y;
+    const long n0 = blockIdx.y * per, n1 = min((long)N, n0 + per);
+    for (int j0 = 0; j0 < J; j0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        if (c < C) {
+            for (long n = n0; n < n1; ++n) {
+                const float f = feat[n * ldf + c];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (j0 + q < J) acc[q] = fmaf(__ldg(dlog + n * J + j0 + q), f, acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (j0 + q < J) atomicAdd(dw + (long)(j0 + q) * C + c, acc[q]);
+        }
+    }
+    if (db != nullptr && blockIdx.x == 0 && threadIdx.x < J) {
+        float s = 0.f;
+        for (long n = n0; n < n1; ++n) s += dlog[n * J + threadIdx.x];
+        atomicAdd(db + threadIdx.x, s);
+    }
+}
+
+// eval-mode BatchNorm constants for a whole list of layers at once: scale, shift, invstd   (C total entries)
+__global__ void bn_eval_consts_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                                      const float* __restrict__ var, float eps, int C, float* __restrict__ scale, float* __restrict__ shift,
+                                      float* __restrict__ invstd, float* __restrict__ inv_gamma) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float is = 1.f / sqrtf(var[c] + eps);
+    const float s = gamma[c] * is;
+    scale[c] = s;
+    shift[c] = beta[c] - mean[c] * s;
+    invstd[c] = is;
+    inv_gamma[c] = 1.f / gamma[c];
+}
+
+// ------------------------------------------------------------------------------------------------ C-ABI
+static inline unsigned grid_for(long items, int mult) {
+    long b = (items + 255) / 256;
+    const long cap = (long)gn_num_sms() * mult;
+    if (b > cap) b = cap;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+// grid whose total thread count is a multiple of G (keeps a thread's channel group fixed in grid-stride loops)
+static inline unsigned grid_for_groups(long items, int mult, int G) {
+    unsigned g = grid_for(items, mult);
+    if ((256 % G) == 0) return g;
+    // make 256 * g a multiple of G
+    long step = G / std::__gcd((long)256, (long)G);
+    g = (unsigned)(((g + step - 1) / step) * step);
+    return g;
+}
+
+GN_API int gn_im2col7x7s2(const void* x, int x_is_bf16, int N, int P, void* a0, int ldk, cudaStream_t stream) {
+    GN_REQUIRE(x && a0 && N > 0 && P >= 8 && P % 2 == 0, GN_EINVAL, "im2col7x7s2: bad arguments (P must be even)");
+    GN_REQUIRE(ldk >= 147 && ldk % 8 == 0, GN_EALIGN, "im2col7x7s2: ldk must be >= 147 and a multiple of 8");
+    const int Ho = P / 2;
+    const long total = (long)N * Ho * Ho * ldk;
+    if (x_is_bf16)
+        im2col7x7s2_kernel<__nv_bfloat16><<<grid_for(total, 16), 256, 0, stream>>>((const __nv_bfloat16*)x, N, P, Ho, (__nv_bfloat16*)a0, ldk);
+    else
+        im2col7x7s2_kernel<float><<<grid_for(total, 16), 256, 0, stream>>>((const float*)x, N, P, Ho, (__nv_bfloat16*)a0, ldk);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+GN_API int gn_maxpool3s2_fwd(const void* in, long ldi, int N, int Hi, int Wi, int C, void* out, long ldo, unsigned char* idx,
+                             cudaStream_t stream) {
+    GN_REQUIRE(in && out && idx && N > 0 && Hi % 2 == 0 && Wi % 2 == 0 && C % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0, GN_EINVAL,
+               "maxpool3s2_fwd: bad arguments");
+    const long total = (long)N * (Hi / 2) * (Wi / 2) * (C / 8);
+    maxpool3s2_fwd_kernel<<<grid_for(total, 16), 256, 0, stream>>>((const __nv_bfloat16*)in, ldi, N, Hi, Wi, C, (__nv_bfloat16*)out, ldo, idx);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+GN_API int gn_maxpool3s2_bnrelu_bwd(const void* dpool, long ldp, const unsigned char* idx, const void* act, long lda, int N, int Hi, int Wi,
+                                    int C, const float* sc, const float* p0, const float* p1, void* dz, long ldz, float* colsum, int ldsum,
+                                    cudaStream_t stream) {
+    GN_REQUIRE(dpool && idx && act && sc && p0 && p1 && dz && colsum && N > 0 && C % 8 == 0 && C <= 2048, GN_EINVAL,
+               "maxpool3s2_bnrelu_bwd: bad arguments");
+    const long total = (long)N * Hi * Wi * (C / 8);
+    maxpool3s2_bnrelu_bwd_kernel<<<grid_for_groups(total, 8, C / 8), 256, 2 * C * sizeof(float), stream>>>(
+        (const __nv_bfloat16*)dpool, ldp, idx, (const __nv_bfloat16*)act, lda, N, Hi, Wi, C, sc, p0, p1, (__nv_bfloat16*)dz, ldz, colsum, ldsum);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+GN_API int gn_bnrelu_avgpool2_fwd(const void* in, long ldi, int N, int H, int W, int C, const float* sc, const float* sh, void* out, long ldo,
+                                  cudaStream_t stream) {
+    GN_REQUIRE(in && out && sc && sh && N > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0, GN_EINVAL,
+               "bnrelu_avgpool2_fwd: bad arguments");
+    const long total = (long)N * (H / 2) * (W / 2) * (C / 8);
+    bnrelu_avgpool2_fwd_kernel<<<grid_for(total, 16), 256, 0, stream>>>((const __nv_bfloat16*)in, ldi, N, H, W, C, sc, sh, (__nv_bfloat16*)out, ldo);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+// gap = 0: dpool bf16 [N*(H/2)*(W/2), ldp] (transition);  gap = 1: dpool fp32 [N, ldp] (head)
+GN_API int gn_pool_bnrelu_bwd(const void* dpool, long ldp, int gap, const void* raw, long ldr, int N, int H, int W, int C, const float* sc,
+                              const float* sh, const float* p0, const float* p1, void* dC, long ldc, float* colsum, int ldsum,
+                              cudaStream_t stream) {
+    GN_REQUIRE(dpool && raw && sc && sh && p0 && p1 && dC && colsum && N > 0 && C % 8 == 0 && C <= 4096, GN_EINVAL, "pool_bnrelu_bwd: bad arguments");
+    GN_REQUIRE(gap || (H % 2 == 0 && W % 2 == 0), GN_EINVAL, "pool_bnrelu_bwd: odd spatial size");
+    const long total = (long)N * H * W * (C / 8);
+    const unsigned grid = grid_for_groups(total, 8, C / 8);
+    const size_t smem = 2 * C * sizeof(float);
+    if (gap)
+        pool_bnrelu_bwd_kernel<true><<<grid, 256, smem, stream>>>(dpool, ldp, (const __nv_bfloat16*)raw, ldr, N, H, W, C, sc, sh, p0, p1,
+                                                                 (__nv_bfloat16*)dC, ldc, colsum, ldsum);
+    else
+        pool_bnrelu_bwd_kernel<false><<<grid, 256, smem, stream>>>(dpool, ldp, (const __nv_bfloat16*)raw, ldr, N, H, W, C, sc, sh, p0, p1,
+                                                                  (__nv_bfloat16*)dC, ldc, colsum, ldsum);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+GN_API int gn_bnrelu_gap_fwd(const void* in, long ldi, int N, int HW, int C, const float* sc, const float* sh, float* feat, long ldf,
+                             cudaStream_t stream) {
+    GN_REQUIRE(in && sc && sh && feat && N > 0 && HW > 0 && C % 8 == 0 && ldi % 8 == 0, GN_EINVAL, "bnrelu_gap_fwd: bad arguments");
+    bnrelu_gap_fwd_kernel<<<grid_for((long)N * (C / 8), 16), 256, 0, stream>>>((const __nv_bfloat16*)in, ldi, N, HW, C, sc, sh, feat, ldf);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+GN_API int gn_linear_small_fwd(const float* feat, long ldf, const float* w, const float* b, int N, int C, int J, float* out, cudaStream_t stream) {
+    GN_REQUIRE(feat && w && out && N > 0 && C > 0 && J > 0, GN_EINVAL, "linear_small_fwd: bad arguments");
+    linear_small_fwd_kernel<<<grid_for((long)N * 32, 16), 256, 0, stream>>>(feat, ldf, w, b, N, C, J, out);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+GN_API int gn_linear_small_bwd(const float* dlog, const float* feat, long ldf, const float* w, int N, int C, int J, float* dfeat, long lddf,
+                               float* dw, float* db, cudaStream_t stream) {
+    GN_REQUIRE(dlog && feat && w && N > 0 && C > 0 && J > 0 && J <= 256, GN_EINVAL, "linear_small_bwd: bad arguments");
+    if (dfeat) {
+        linear_small_bwd_data_kernel<<<grid_for((long)N * C, 16), 256, 0, stream>>>(dlog, w, N, C, J, dfeat, lddf);
+        GN_LAUNCH_CHECK();
+    }
+    if (dw) {
+        int ys = (2 * gn_num_sms()) / gn_ceil_div(C, 256);
+        if (ys < 1) ys = 1;
+        if (ys > N) ys = N;
+        dim3 grid(gn_ceil_div(C, 256), ys);
+        linear_small_bwd_weight_kernel<<<grid, 256, 0, stream>>>(dlog, feat, ldf, N, C, J, dw, db);
+        GN_LAUNCH_CHECK();
+    }
+    return GN_OK;
+}
+
+GN_API int gn_bn_eval_consts(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int C, float* scale,
+                             float* shift, float* invstd, float* inv_gamma, cudaStream_t stream) {
+    GN_REQUIRE(gamma && beta && mean && var && scale && shift && invstd && inv_gamma && C > 0, GN_EINVAL, "bn_eval_consts: bad arguments");
+    bn_eval_consts_kernel<<<gn_ceil_div(C, 256), 256, 0, stream>>>(gamma, beta, mean, var, eps, C, scale, shift, invstd, inv_gamma);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}

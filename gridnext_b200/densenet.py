@@ -1,0 +1,439 @@
+"""DenseNet-BC spot classifier (f) with the reference's constructor, module tree and state-dict keys,
+executed on hand-written sm_100a kernels.
+
+Mirrors /root/reference/gridnext/densenet.py: ``DenseNet(growth_rate, block_config, compression,
+num_init_features, bn_size, drop_rate, num_classes, small_inputs, efficient, classify)`` (:93-95), parameters
+``features.conv0 / norm0 / denseblock{i}.denselayer{j}.{norm1,conv1,norm2,conv2} / transition{i}.{norm,conv} /
+norm_final`` and ``classifier`` (:102-138), He-normal conv init (:141-150), ``forward`` (:152-159).
+
+Underneath (B200-first, not a translation of the module graph):
+  * activations live in NHWC bf16; every dense block owns ONE pre-allocated concat buffer and each layer's conv2
+    writes its growth channels in place (no ``torch.cat``, densenet.py:14,75);
+  * conv1 (1x1) = tcgen05 GEMM whose A operand gets norm1+ReLU applied in shared memory between TMA and MMA and whose
+    epilogue applies norm2+ReLU, so neither activated tensor round-trips HBM un-fused;
+  * conv2 (3x3) = padded-position implicit GEMM with the nine taps as descriptor offsets into one TMA-loaded tile;
+  * backward = the mirrored kernels with BatchNorm/ReLU backward and BN parameter gradients fused into the
+    data-gradient epilogues; weight gradients are split-K tcgen05 GEMMs.
+BatchNorm is evaluated with running statistics: f is always in eval mode on the grid-wise hot path
+(/root/reference/gridnext/training.py:126).  Train-mode BN of f (train_spotwise) is not implemented here.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ptr, stream, call
+from . import tc
+
+BN_EPS = 1e-5
+MAX_SPOTS_RESIDENT = 8192     # spots whose activations are kept for the backward; beyond that f is re-run chunk by chunk
+
+
+class _DenseLayer(nn.Module):
+    def __init__(self, num_input_features, growth_rate, bn_size, drop_rate, efficient=False):
+        super().__init__()
+        self.add_module('norm1', nn.BatchNorm2d(num_input_features))
+        self.add_module('relu1', nn.ReLU(inplace=True))
+        self.add_module('conv1', nn.Conv2d(num_input_features, bn_size * growth_rate, kernel_size=1, stride=1, bias=False))
+        self.add_module('norm2', nn.BatchNorm2d(bn_size * growth_rate))
+        self.add_module('relu2', nn.ReLU(inplace=True))
+        self.add_module('conv2', nn.Conv2d(bn_size * growth_rate, growth_rate, kernel_size=3, stride=1, padding=1, bias=False))
+        self.drop_rate = drop_rate
+        self.efficient = efficient
+
+
+class _Transition(nn.Sequential):
+    def __init__(self, num_input_features, num_output_features):
+        super().__init__()
+        self.add_module('norm', nn.BatchNorm2d(num_input_features))
+        self.add_module('relu', nn.ReLU(inplace=True))
+        self.add_module('conv', nn.Conv2d(num_input_features, num_output_features, kernel_size=1, stride=1, bias=False))
+        self.add_module('pool', nn.AvgPool2d(kernel_size=2, stride=2))
+
+
+class _DenseBlock(nn.Module):
+    def __init__(self, num_layers, num_input_features, bn_size, growth_rate, drop_rate, efficient=False):
+        super().__init__()
+        for i in range(num_layers):
+            self.add_module('denselayer%d' % (i + 1),
+                            _DenseLayer(num_input_features + i * growth_rate, growth_rate, bn_size, drop_rate, efficient))
+
+
+def _bn_list(net):
+    """BatchNorm modules in execution order."""
+    out = [net.features.norm0]
+    for name, m in net.features.named_children():
+        if name.startswith('denseblock'):
+            for layer in m.children():
+                out += [layer.norm1, layer.norm2]
+        elif name.startswith('transition'):
+            out.append(m.norm)
+    out.append(net.features.norm_final)
+    return out
+
+
+class _Consts:
+    """Per-call derived constants: eval-BN scale/shift/invstd/1/gamma for every BN, bf16 weight copies."""
+
+    def __init__(self, net):
+        bns = _bn_list(net)
+        dev = net.classifier.weight.device
+        sizes = [b.num_features for b in bns]
+        tot = sum(sizes)
+        g = torch.cat([b.weight.detach() for b in bns]).float().contiguous()
+        be = torch.cat([b.bias.detach() for b in bns]).float().contiguous()
+        mu = torch.cat([b.running_mean for b in bns]).float().contiguous()
+        var = torch.cat([b.running_var for b in bns]).float().contiguous()
+        buf = torch.empty((4, tot), device=dev, dtype=torch.float32)
+        call('gn_bn_eval_consts', ptr(g), ptr(be), ptr(mu), ptr(var), float(bns[0].eps), tot, ptr(buf[0]), ptr(buf[1]), ptr(buf[2]), ptr(buf[3]), stream())
+        self.bn = {}
+        off = 0
+        for b, n in zip(bns, sizes):
+            self.bn[id(b)] = dict(sc=buf[0, off:off + n], sh=buf[1, off:off + n], invstd=buf[2, off:off + n], inv_gamma=buf[3, off:off + n],
+                                  mean=mu[off:off + n], beta=be[off:off + n], off=off, n=n)
+            off += n
+        self.bn_total = tot
+        self.bns = bns
+
+    def of(self, bn):
+        return self.bn[id(bn)]
+
+
+def _w2d_bf16(conv):
+    w = conv.weight.detach()
+    return w.reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+
+
+class _Geometry:
+    def __init__(self, net, P):
+        if P % 4 != 0:
+            raise ValueError('DenseNet (B200): patch size %d must be a multiple of 4' % P)
+        self.P = P
+        self.H0 = P // 2            # conv0 output
+        self.H1 = self.H0 // 2      # pool0 output = block 1 resolution
+        self.blocks = []            # (block module, transition | None, H, c_in, c_total, layers)
+        H = self.H1
+        names = [n for n, _ in net.features.named_children()]
+        c = net.features.conv0.out_channels
+        nb = sum(1 for n in names if n.startswith('denseblock'))
+        for i in range(1, nb + 1):
+            blk = getattr(net.features, 'denseblock%d' % i)
+            layers = list(blk.children())
+            g = layers[0].conv2.out_channels
+            ct = c + len(layers) * g
+            tr = getattr(net.features, 'transition%d' % i) if i != nb else None
+            self.blocks.append(dict(block=blk, trans=tr, H=H, c_in=c, c_tot=ct, layers=layers, growth=g, bott=layers[0].conv1.out_channels))
+            if tr is not None:
+                if H % 2 != 0:
+                    raise ValueError('DenseNet (B200): odd feature-map size %d before a transition (patch size %d)' % (H, P))
+                c = tr.conv.out_channels
+                H //= 2
+            else:
+                c = ct
+        self.c_final = c
+
+
+def _check_supported(net):
+    if net.small_inputs:
+        raise NotImplementedError('DenseNet (B200): small_inputs=True (3x3 stem) is not on the GridNet hot path')
+    f = net.features
+    if f.conv0.out_channels % 8:
+        raise NotImplementedError('DenseNet (B200): num_init_features must be a multiple of 8')
+    for name, m in f.named_children():
+        if name.startswith('denseblock'):
+            for l in m.children():
+                g, b = l.conv2.out_channels, l.conv1.out_channels
+                if g % 8 or g > 48 or b % 16 or b > 128:
+                    raise NotImplementedError('DenseNet (B200): growth_rate must be a multiple of 8 (<= 48) and bn_size*growth_rate a multiple of 16 (<= 128)')
+                if l.drop_rate > 0 and l.training:
+                    raise NotImplementedError('DenseNet (B200): dropout in training mode is not implemented')
+        if name.startswith('transition') and m.conv.out_channels % 8:
+            raise NotImplementedError('DenseNet (B200): transition widths must be multiples of 8')
+    if any(b.training for b in _bn_list(net)):
+        raise NotImplementedError('DenseNet (B200): BatchNorm must be in eval mode (train_gridwise puts f in eval, training.py:126); '
+                                  'train-mode f is not implemented')
+
+
+def _forward_chunk(net, geo, cst, x, save):
+    """x: (n, 3, P, P) fp32|bf16 CUDA.  Returns (out, saved | None)."""
+    n, P, dev = x.shape[0], geo.P, x.device
+    f = net.features
+    bf = torch.bfloat16
+    # ---- stem: conv0 (7x7/2) as im2col + GEMM with norm0+ReLU epilogue, then 3x3/2 max-pool into block 1's buffer
+    M0 = n * geo.H0 * geo.H0
+    a0 = torch.empty((M0, 160), device=dev, dtype=bf)
+    call('gn_im2col7x7s2', ptr(x), 1 if x.dtype == bf else 0, n, P, ptr(a0), 160, stream())
+    w0 = torch.zeros((f.conv0.out_channels, 160), device=dev, dtype=bf)
+    w0[:, :147] = f.conv0.weight.detach().reshape(f.conv0.out_channels, 147).to(bf)
+    b0 = cst.of(f.norm0)
+    c0 = f.conv0.out_channels
+    act0 = tc.gemm_bf16(a0, w0, scale=b0['sc'], shift=b0['sh'], relu=True)
+    saved = dict(a0=a0, act0=act0, blocks=[]) if save else None
+    blk0 = geo.blocks[0]
+    M = n * blk0['H'] * blk0['H']
+    C = torch.empty((M, blk0['c_tot']), device=dev, dtype=bf)
+    idx0 = torch.empty((M, c0), device=dev, dtype=torch.uint8)
+    call('gn_maxpool3s2_fwd', ptr(act0), c0, n, geo.H0, geo.H0, c0, ptr(C), blk0['c_tot'], ptr(idx0), stream())
+    if save:
+        saved['idx0'] = idx0
+    # ---- dense blocks
+    for bi, blk in enumerate(geo.blocks):
+        H, g, bott = blk['H'], blk['growth'], blk['bott']
+        M = n * H * H
+        a2s = []
+        a2 = None
+        cin = blk['c_in']
+        for layer in blk['layers']:
+            k1, k2 = cst.of(layer.norm1), cst.of(layer.norm2)
+            if save or a2 is None:
+                a2 = torch.empty((M, bott), device=dev, dtype=bf)
+            tc.gemm_bf16(C[:, :cin], _w2d_bf16(layer.conv1), out=a2, scale=k2['sc'], shift=k2['sh'], relu=True,
+                         xf_scale=k1['sc'], xf_shift=k1['sh'])
+            wp = tc.conv3x3_pack(layer.conv2.weight.detach(), 0)
+            tc.conv3x3_bf16(a2, n, H, H, bott, wp, g, C[:, cin:cin + g])
+            if save:
+                a2s.append(a2)
+            cin += g
+        rec = dict(C=C, a2=a2s)
+        if blk['trans'] is not None:
+            tr = blk['trans']
+            kt = cst.of(tr.norm)
+            ct = blk['c_tot']
+            pooled = torch.empty((M // 4, ct), device=dev, dtype=bf)
+            call('gn_bnrelu_avgpool2_fwd', ptr(C), ct, n, H, H, ct, ptr(kt['sc']), ptr(kt['sh']), ptr(pooled), ct, stream())
+            nxt = geo.blocks[bi + 1]
+            Cn = torch.empty((M // 4, nxt['c_tot']), device=dev, dtype=bf)
+            tc.gemm_bf16(pooled, _w2d_bf16(tr.conv), out=Cn[:, :nxt['c_in']])
+            rec['pooled'] = pooled
+            if save:
+                saved['blocks'].append(rec)
+            C = Cn
+        elif save:
+            saved['blocks'].append(rec)
+    # ---- head
+    kf = cst.of(f.norm_final)
+    last = geo.blocks[-1]
+    feat = torch.empty((n, geo.c_final), device=dev, dtype=torch.float32)
+    call('gn_bnrelu_gap_fwd', ptr(C), last['c_tot'], n, last['H'] * last['H'], geo.c_final, ptr(kf['sc']), ptr(kf['sh']), ptr(feat), geo.c_final, stream())
+    if net.classify:
+        J = net.classifier.out_features
+        out = torch.empty((n, J), device=dev, dtype=torch.float32)
+        call('gn_linear_small_fwd', ptr(feat), geo.c_final, ptr(net.classifier.weight.detach().float().contiguous()),
+             ptr(net.classifier.bias.detach().float().contiguous()), n, geo.c_final, J, ptr(out), stream())
+    else:
+        out = feat
+    if save:
+        saved['feat'] = feat
+        saved['n'] = n
+    return out, saved
+
+
+class _Grads:
+    """fp32 gradient accumulators keyed like the module's parameters."""
+
+    def __init__(self, net, cst):
+        dev = net.classifier.weight.device
+        self.bn_colsum = torch.zeros((2, cst.bn_total), device=dev, dtype=torch.float32)   # row 0: d beta, row 1: d gamma
+        self.w = {}
+
+    def acc(self, param, g):
+        k = id(param)
+        if k in self.w:
+            self.w[k] += g
+        else:
+            self.w[k] = g
+
+    def buf(self, param, shape):
+        k = id(param)
+        if k not in self.w:
+            self.w[k] = torch.zeros(shape, device=param.device, dtype=torch.float32)
+        return self.w[k]
+
+
+def _backward_chunk(net, geo, cst, saved, dout, grads):
+    n, dev, bf = saved['n'], dout.device, torch.bfloat16
+    f = net.features
+    last = geo.blocks[-1]
+    cs = grads.bn_colsum
+    tot = cst.bn_total
+
+    def colsum_of(k):
+        return cs[:, k['off']:k['off'] + k['n']]
+
+    # ---- head
+    Cf = geo.c_final
+    if net.classify:
+        J = net.classifier.out_features
+        dfeat = torch.empty((n, Cf), device=dev, dtype=torch.float32)
+        dw = grads.buf(net.classifier.weight, (J, Cf))
+        db = grads.buf(net.classifier.bias, (J,))
+        call('gn_linear_small_bwd', ptr(dout), ptr(saved['feat']), Cf, ptr(net.classifier.weight.detach().float().contiguous()), n, Cf, J,
+             ptr(dfeat), Cf, ptr(dw), ptr(db), stream())
+    else:
+        dfeat = dout
+    kf = cst.of(f.norm_final)
+    C = saved['blocks'][-1]['C']
+    M = n * last['H'] * last['H']
+    dC = torch.empty((M, last['c_tot']), device=dev, dtype=bf)
+    call('gn_pool_bnrelu_bwd', ptr(dfeat), Cf, 1, ptr(C), last['c_tot'], n, last['H'], last['H'], Cf, ptr(kf['sc']), ptr(kf['sh']),
+         ptr(kf['mean']), ptr(kf['invstd']), ptr(dC), last['c_tot'], ptr(colsum_of(kf)), tot, stream())
+    # ---- blocks, last to first
+    for bi in range(len(geo.blocks) - 1, -1, -1):
+        blk, rec = geo.blocks[bi], saved['blocks'][bi]
+        H, g, bott = blk['H'], blk['growth'], blk['bott']
+        C = rec['C']
+        M = n * H * H
+        dz = torch.empty((M, bott), device=dev, dtype=bf)
+        cin = blk['c_tot']
+        for li in range(len(blk['layers']) - 1, -1, -1):
+            layer = blk['layers'][li]
+            cin -= g
+            k1, k2 = cst.of(layer.norm1), cst.of(layer.norm2)
+            a2 = rec['a2'][li]
+            dY = dC[:, cin:cin + g]
+            grads.acc(layer.conv2.weight, tc.conv3x3_wgrad_bf16(a2, dY, n, H, H, bott, g))
+            wpt = tc.conv3x3_pack(layer.conv2.weight.detach(), 1)
+            tc.conv3x3_bf16(dY, n, H, H, g, wpt, bott, dz,
+                            bn=dict(ref=a2, ref_is_raw=False, sc=k2['sc'], sh=None, p0=k2['beta'], p1=k2['inv_gamma'], colsum=colsum_of(k2)))
+            dw1 = grads.buf(layer.conv1.weight, (bott, cin))
+            tc.gemm_tn_bf16(dz, C[:, :cin], dw1, k1['sc'], k1['sh'])
+            w1t = layer.conv1.weight.detach().reshape(bott, cin).t().contiguous().to(bf)      # [cin, bott]
+            tc.gemm_bf16(dz, w1t, out=dC[:, :cin],
+                         bn=dict(ref=C[:, :cin], ref_is_raw=True, sc=k1['sc'], sh=k1['sh'], p0=k1['mean'], p1=k1['invstd'],
+                                 colsum=colsum_of(k1), rmw=True))
+        if bi > 0:
+            prev, prec = geo.blocks[bi - 1], saved['blocks'][bi - 1]
+            tr = prev['trans']
+            kt = cst.of(tr.norm)
+            ctp, c_in = prev['c_tot'], blk['c_in']
+            d_out = dC[:, :c_in]
+            dwt = grads.buf(tr.conv.weight, (c_in, ctp))
+            tc.gemm_tn_bf16(d_out, prec['pooled'], dwt)
+            wtt = tr.conv.weight.detach().reshape(c_in, ctp).t().contiguous().to(bf)          # [ctp, c_in]
+            dP = tc.gemm_bf16(d_out, wtt)
+            Hp = prev['H']
+            dCp = torch.empty((n * Hp * Hp, ctp), device=dev, dtype=bf)
+            call('gn_pool_bnrelu_bwd', ptr(dP), ctp, 0, ptr(prec['C']), ctp, n, Hp, Hp, ctp, ptr(kt['sc']), ptr(kt['sh']), ptr(kt['mean']),
+                 ptr(kt['invstd']), ptr(dCp), ctp, ptr(colsum_of(kt)), tot, stream())
+            dC = dCp
+        else:
+            c0 = f.conv0.out_channels
+            k0 = cst.of(f.norm0)
+            M0 = n * geo.H0 * geo.H0
+            dz0 = torch.empty((M0, c0), device=dev, dtype=bf)
+            call('gn_maxpool3s2_bnrelu_bwd', ptr(dC), blk['c_tot'], ptr(saved['idx0']), ptr(saved['act0']), c0, n, geo.H0, geo.H0, c0,
+                 ptr(k0['sc']), ptr(k0['beta']), ptr(k0['inv_gamma']), ptr(dz0), c0, ptr(colsum_of(k0)), tot, stream())
+            dw0 = grads.buf(f.conv0.weight, (c0, 160))
+            tc.gemm_tn_bf16(dz0, saved['a0'], dw0)
+
+
+class _DenseNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, net, *params):
+        _lib.require_cuda(x)
+        _check_supported(net)
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3]:
+            raise ValueError('DenseNet (B200): expected (N, 3, P, P) patches, got %s' % (tuple(x.shape),))
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        geo = _Geometry(net, int(x.shape[2]))
+        cst = _Consts(net)
+        N = x.shape[0]
+        need_grad = any(ctx.needs_input_grad[2:])
+        ctx.net, ctx.geo, ctx.cst = net, geo, cst
+        ctx.plist = list(net.parameters())
+        assert len(ctx.plist) == len(params)
+        if N <= MAX_SPOTS_RESIDENT:
+            out, saved = _forward_chunk(net, geo, cst, x, need_grad)
+            ctx.saved, ctx.x = saved, None
+        else:
+            outs = [_forward_chunk(net, geo, cst, x[i:i + MAX_SPOTS_RESIDENT], False)[0] for i in range(0, N, MAX_SPOTS_RESIDENT)]
+            out = torch.cat(outs, 0)
+            ctx.saved, ctx.x = None, (x if need_grad else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        net, geo, cst = ctx.net, ctx.geo, ctx.cst
+        dout = dout.contiguous().float()
+        grads = _Grads(net, cst)
+        if ctx.saved is not None:
+            _backward_chunk(net, geo, cst, ctx.saved, dout, grads)
+            ctx.saved = None
+        else:
+            x = ctx.x
+            for i in range(0, x.shape[0], MAX_SPOTS_RESIDENT):
+                _, saved = _forward_chunk(net, geo, cst, x[i:i + MAX_SPOTS_RESIDENT], True)
+                _backward_chunk(net, geo, cst, saved, dout[i:i + MAX_SPOTS_RESIDENT].contiguous(), grads)
+                del saved
+            ctx.x = None
+        # map accumulated gradients onto the parameter list
+        out = []
+        bn_of_param = {}
+        for b in cst.bns:
+            k = cst.of(b)
+            bn_of_param[id(b.weight)] = grads.bn_colsum[1, k['off']:k['off'] + k['n']]
+            bn_of_param[id(b.bias)] = grads.bn_colsum[0, k['off']:k['off'] + k['n']]
+        for p in ctx.plist:
+            if id(p) in bn_of_param:
+                out.append(bn_of_param[id(p)].clone())
+            elif id(p) in grads.w:
+                gpar = grads.w[id(p)]
+                if p is net.features.conv0.weight:
+                    gpar = gpar[:, :147]
+                out.append(gpar.reshape(p.shape).contiguous())
+            else:
+                out.append(None)
+        return (None, None) + tuple(out)
+
+
+class DenseNet(nn.Module):
+    r"""Densenet-BC (`"Densely Connected Convolutional Networks" <https://arxiv.org/pdf/1608.06993.pdf>`).
+
+    Args: growth_rate, block_config, compression, num_init_features, bn_size, drop_rate, num_classes,
+    small_inputs (True: 3x3 stem for 32x32 images; False: 7x7/2 stem + max-pool), efficient (accepted for API
+    compatibility; activations are managed by the kernels), classify (return logits vs. pooled features).
+    """
+
+    def __init__(self, growth_rate=12, block_config=(16, 16, 16), compression=0.5,
+                 num_init_features=24, bn_size=4, drop_rate=0,
+                 num_classes=10, small_inputs=True, efficient=False, classify=True):
+        super(DenseNet, self).__init__()
+        assert 0 < compression <= 1, 'compression of densenet should be between 0 and 1'
+        self.small_inputs = small_inputs
+        if small_inputs:
+            self.features = nn.Sequential(OrderedDict([
+                ('conv0', nn.Conv2d(3, num_init_features, kernel_size=3, stride=1, padding=1, bias=False))]))
+        else:
+            self.features = nn.Sequential(OrderedDict([
+                ('conv0', nn.Conv2d(3, num_init_features, kernel_size=7, stride=2, padding=3, bias=False))]))
+            self.features.add_module('norm0', nn.BatchNorm2d(num_init_features))
+            self.features.add_module('relu0', nn.ReLU(inplace=True))
+            self.features.add_module('pool0', nn.MaxPool2d(kernel_size=3, stride=2, padding=1, ceil_mode=False))
+        num_features = num_init_features
+        for i, num_layers in enumerate(block_config):
+            self.features.add_module('denseblock%d' % (i + 1),
+                                     _DenseBlock(num_layers, num_features, bn_size, growth_rate, drop_rate, efficient))
+            num_features = num_features + num_layers * growth_rate
+            if i != len(block_config) - 1:
+                self.features.add_module('transition%d' % (i + 1), _Transition(num_features, int(num_features * compression)))
+                num_features = int(num_features * compression)
+        self.features.add_module('norm_final', nn.BatchNorm2d(num_features))
+        self.classify = classify
+        self.classifier = nn.Linear(num_features, num_classes)
+        for name, param in self.named_parameters():
+            if 'conv' in name and 'weight' in name:
+                n = param.size(0) * param.size(2) * param.size(3)
+                param.data.normal_().mul_(math.sqrt(2. / n))
+            elif 'norm' in name and 'weight' in name:
+                param.data.fill_(1)
+            elif 'norm' in name and 'bias' in name:
+                param.data.fill_(0)
+            elif 'classifier' in name and 'bias' in name:
+                param.data.fill_(0)
+
+    def forward(self, x):
+        return _DenseNetFn.apply(x, self, *self.parameters())

@@ -108,6 +108,29 @@ int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long ldy, int
                           gn_stream_t stream);
 int gn_conv3x3_unpack_grad(const float* dwp, int CO, int CI, float* dw, gn_stream_t stream);
 
+/* ---- memory-bound DenseNet pieces (NHWC bf16, eval-mode BatchNorm folded to scale/shift); each replaces the ATen
+ * ops of the cited densenet.py lines.  colsum is fp32 [2][ldsum]: row 0 += sum g (d beta), row 1 += sum g*xhat (d gamma). */
+/* conv0 operand: A0[m, c*49+ky*7+kx] for the 7x7 / stride 2 / pad 3 stem (densenet.py:107) from NCHW fp32|bf16 patches */
+int gn_im2col7x7s2(const void* x, int x_is_bf16, int N, int P, void* a0, int ldk, gn_stream_t stream);
+/* pool0: MaxPool2d(3, 2, 1) (densenet.py:111-112); idx keeps the arg-max tap for the backward */
+int gn_maxpool3s2_fwd(const void* in, long ldi, int N, int Hi, int Wi, int C, void* out, long ldo, unsigned char* idx, gn_stream_t stream);
+int gn_maxpool3s2_bnrelu_bwd(const void* dpool, long ldp, const unsigned char* idx, const void* act, long lda, int N, int Hi, int Wi, int C,
+                             const float* sc, const float* p0, const float* p1, void* dz, long ldz, float* colsum, int ldsum,
+                             gn_stream_t stream);
+/* _Transition (densenet.py:47-54): avg-pool commutes with the 1x1 conv, so BN+ReLU+AvgPool2d(2) runs first */
+int gn_bnrelu_avgpool2_fwd(const void* in, long ldi, int N, int H, int W, int C, const float* sc, const float* sh, void* out, long ldo,
+                           gn_stream_t stream);
+int gn_pool_bnrelu_bwd(const void* dpool, long ldp, int gap, const void* raw, long ldr, int N, int H, int W, int C, const float* sc,
+                       const float* sh, const float* p0, const float* p1, void* dC, long ldc, float* colsum, int ldsum, gn_stream_t stream);
+/* head (densenet.py:134,153-158): norm_final + relu + adaptive_avg_pool2d(1) -> fp32 features; Linear classifier */
+int gn_bnrelu_gap_fwd(const void* in, long ldi, int N, int HW, int C, const float* sc, const float* sh, float* feat, long ldf,
+                      gn_stream_t stream);
+int gn_linear_small_fwd(const float* feat, long ldf, const float* w, const float* b, int N, int C, int J, float* out, gn_stream_t stream);
+int gn_linear_small_bwd(const float* dlog, const float* feat, long ldf, const float* w, int N, int C, int J, float* dfeat, long lddf,
+                        float* dw, float* db, gn_stream_t stream);
+int gn_bn_eval_consts(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int C, float* scale,
+                      float* shift, float* invstd, float* inv_gamma, gn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

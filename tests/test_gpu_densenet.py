@@ -1,0 +1,80 @@
+"""GPU parity of the DenseNet f network (forward logits and parameter gradients) against the CPU oracle and the
+reference-generated golden vectors.  bf16 tensor-core path: north_star tolerance 2e-2 on logits."""
+import json, os
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, shapes as S
+from oracle import gridnet_ref as R
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+MAN = json.load(open(os.path.join(GOLDEN, 'manifest.json')))
+
+
+def build(tag_or_cfg, seed):
+    from gridnext_b200.densenet import DenseNet
+    kw = tag_or_cfg
+    net = DenseNet(num_classes=7, small_inputs=False, efficient=False, drop_rate=0, **kw)
+    sd = synth.synth_state_dict(S.densenet_shapes(kw['growth_rate'], tuple(kw['block_config']), kw['num_init_features'], kw['bn_size']), seed)
+    net.load_state_dict(sd)            # strict: key set identical to the reference's
+    return net.cuda().eval(), sd
+
+
+def relmax(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+@pytest.mark.parametrize('tag', ['d2_densenet_tiny_p32', 'd1_densenet121_p64'])
+def test_densenet_matches_reference_golden(tag):
+    m = MAN[tag]
+    gold = np.load(os.path.join(GOLDEN, tag + '.npz'))
+    kw = dict(growth_rate=m['growth_rate'], block_config=tuple(m['block_config']), num_init_features=m['num_init_features'], bn_size=m['bn_size'])
+    net, sd = build(kw, m['seed_w'])
+    g = torch.Generator(); g.manual_seed(m['seed_x'])
+    x = torch.randn(m['N'], 3, m['P'], m['P'], generator=g)
+    logits = net(x.cuda())
+    assert relmax(logits, gold['logits']) < 2e-2
+    g = torch.Generator(); g.manual_seed(m['seed_dy'])
+    dy = torch.randn(logits.shape, generator=g)
+    (logits * dy.cuda()).sum().backward()
+    params = dict(net.named_parameters())
+    norms = dict(zip(gold['grad_norm_keys'].tolist(), gold['grad_norm_vals'].tolist()))
+    bad = []
+    for k, v in norms.items():
+        got = float(params[k].grad.norm())
+        if abs(got - v) > 5e-2 * max(v, 1e-3):
+            bad.append((k, got, v))
+    assert not bad, bad[:10]
+    for k in gold.files:
+        if k.startswith('grad.'):
+            ref = gold[k]
+            assert relmax(params[k[5:]].grad, ref) < 6e-2, k
+
+
+def test_densenet121_p128_matches_oracle_and_argmax():
+    """Full benchmark shape (3x128x128) on a handful of spots: logits vs the fp32 oracle, bf16 tolerance + argmax agreement."""
+    kw = dict(growth_rate=32, block_config=(6, 12, 24, 16), num_init_features=64, bn_size=4)
+    net, sd = build(kw, 77)
+    g = torch.Generator(); g.manual_seed(5)
+    x = torch.rand(6, 3, 128, 128, generator=g)
+    x = (x - 0.45) / 0.225
+    with torch.no_grad():
+        ref = R.densenet_forward(sd, x)
+        out = net(x.cuda()).cpu()
+    assert relmax(out, ref) < 2e-2
+    top2 = ref.topk(2, 1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 2e-2 * ref.abs().max()
+    assert torch.equal(out.argmax(1)[clear], ref.argmax(1)[clear])
+
+
+def test_densenet_rejects_unsupported_modes():
+    from gridnext_b200.densenet import DenseNet
+    net = DenseNet(num_classes=7, small_inputs=False, growth_rate=8, block_config=(2, 2), num_init_features=16, bn_size=2).cuda()
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 32, 32, device='cuda'))
+    with pytest.raises(RuntimeError):
+        net.eval()(torch.zeros(1, 3, 32, 32))
