@@ -16,7 +16,7 @@ def _bn_args(bn):
     _, _, ldref = _rows_pitch(bn['ref'])
     cs = bn.get('colsum')
     return (ptr(bn['ref']), ldref, 1 if bn['ref_is_raw'] else 0, ptr(bn['sc']), ptr(bn.get('sh')), ptr(bn['p0']), ptr(bn['p1']),
-            ptr(cs), cs.shape[1] if cs is not None else 0)
+            ptr(cs), cs.stride(0) if cs is not None else 0)
 
 
 def gemm_bf16(a, b, out=None, out_dtype=torch.bfloat16, accumulate=False, scale=None, shift=None, relu=False,
