@@ -32,6 +32,7 @@ _SIGS = {
     'gn_masked_ce': [vp, vp, vp, vp, vp, vp, cf, ci, ci, cl, vp],
     'gn_spot_table': [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp],
     'gn_patch_gather': [vp, cl, ci, ci, vp, ci, ci, vp, vp, vp, ci, vp],
+    'gn_normalize_u8': [vp, vp, cl, ci, vp, vp, vp, ci, vp],
     'gn_gemm_tn_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, vp, vp, vp],
     'gn_im2col7x7s2': [vp, ci, ci, ci, vp, ci, vp],
     'gn_maxpool3s2_fwd': [vp, cl, ci, ci, ci, ci, vp, cl, vp, vp],
@@ -93,8 +94,23 @@ def check(rc, what=''):
     raise RuntimeError('gridnext_b200 %s: CUDA error %d: %s' % (what, rc, msg))
 
 
+# kernels launched per C-ABI call (for the benchmark's gpu_launches count); default 1
+KERNELS_PER_CALL = {'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0,
+                    'gn_device_sm_count': 0, 'gn_hexconv_n_taps': 0}
+LAUNCHES = [0]
+PROFILE = None      # when a dict: name -> [n_calls, [cuda event pairs]]
+
+
 def call(name, *args):
     lib = load()
+    LAUNCHES[0] += KERNELS_PER_CALL.get(name, 1)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib, name)(*args), name)
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1, args))
+        return
     check(getattr(lib, name)(*args), name)
 
 

@@ -178,3 +178,53 @@ GN_API int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, c
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// ToTensor (/255) + Normalize(mean, std) of an already-cropped uint8 patch grid (cells, 3, P, P) -> bf16 | fp32,
+// the device half of PatchGridDataset.__getitem__ (/root/reference/gridnext/image_datasets.py:205-232 applies the
+// torchvision transform per present patch; absent cells stay exactly 0).  valid: nullable u8[cells].
+template <typename OutT>
+__global__ void __launch_bounds__(256) normalize_u8_kernel(const unsigned char* __restrict__ in, const unsigned char* __restrict__ valid,
+                                                           long n_cells, long plane, const float* __restrict__ mean,
+                                                           const float* __restrict__ stdv, OutT* __restrict__ out) {
+    __shared__ float lut[3 * 256];
+    for (int e = threadIdx.x; e < 3 * 256; e += 256) {
+        const int c = e >> 8, v = e & 255;
+        float f = (float)v;
+        if (mean != nullptr) f = __fdiv_rn(__fsub_rn(__fdiv_rn(f, 255.0f), mean[c]), stdv[c]);
+        lut[e] = f;
+    }
+    __syncthreads();
+    const long groups = n_cells * 3 * plane / 16;
+    for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < groups; g += (long)gridDim.x * blockDim.x) {
+        const long e0 = g * 16;
+        const long cell = e0 / (3 * plane);
+        const int c = (int)((e0 / plane) % 3);
+        const bool ok = valid == nullptr || valid[cell] != 0;
+        const uint4 raw = ok ? __ldg(reinterpret_cast<const uint4*>(in + e0)) : make_uint4(0, 0, 0, 0);
+        const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float f[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[j] = ok ? lut[c * 256 + ((w[q] >> (8 * j)) & 0xff)] : 0.f;
+            Pack4<OutT>::store(out + e0 + 4 * q, f[0], f[1], f[2], f[3]);
+        }
+    }
+}
+
+GN_API int gn_normalize_u8(const unsigned char* in, const unsigned char* valid, long n_cells, int P, const float* mean, const float* stdv,
+                           void* out, int out_bf16, cudaStream_t stream) {
+    GN_REQUIRE(in && out && n_cells > 0 && P > 0 && (P * P) % 16 == 0, GN_EINVAL, "normalize_u8: bad arguments (P*P must be a multiple of 16)");
+    GN_REQUIRE((mean == nullptr) == (stdv == nullptr), GN_EINVAL, "normalize_u8: mean/std must come together");
+    GN_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, GN_EALIGN, "normalize_u8: in/out must be 16-byte aligned");
+    const long plane = (long)P * P;
+    long blocks = (n_cells * 3 * plane / 16 + 255) / 256;
+    if (blocks > 16L * gn_num_sms()) blocks = 16L * gn_num_sms();
+    if (out_bf16)
+        normalize_u8_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, stream>>>(in, valid, n_cells, plane, mean, stdv, (__nv_bfloat16*)out);
+    else
+        normalize_u8_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>(in, valid, n_cells, plane, mean, stdv, (float*)out);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}

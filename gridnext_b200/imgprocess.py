@@ -77,6 +77,20 @@ def gather_patches(img, cells, patch_size, mean=None, std=None, out_dtype=torch.
     return out
 
 
+def normalize_patches(patches_u8, mean=None, std=None, out_dtype=torch.float32, valid=None):
+    """uint8 (..., 3, P, P) CUDA patch grid -> ToTensor + Normalize on the device (absent cells stay 0)."""
+    _lib.require_cuda(patches_u8)
+    if patches_u8.dtype != torch.uint8 or not patches_u8.is_contiguous() or patches_u8.shape[-3] != 3:
+        raise ValueError('normalize_patches: expected a contiguous uint8 (..., 3, P, P) tensor')
+    P = int(patches_u8.shape[-1])
+    n_cells = patches_u8.numel() // (3 * P * P)
+    out = torch.empty(patches_u8.shape, device=patches_u8.device, dtype=out_dtype)
+    m = torch.tensor(mean, device=out.device, dtype=torch.float32) if mean is not None else None
+    s = torch.tensor(std, device=out.device, dtype=torch.float32) if std is not None else None
+    call('gn_normalize_u8', ptr(patches_u8), ptr(valid), n_cells, P, ptr(m), ptr(s), ptr(out), 1 if out_dtype == torch.bfloat16 else 0, stream())
+    return out
+
+
 def read_positions(spaceranger_dir):
     """tissue_positions(.csv|_list.csv) -> dict of numpy columns (Spaceranger >= 2 has a header row)."""
     import pandas as pd

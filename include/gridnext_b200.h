@@ -69,6 +69,9 @@ int gn_masked_ce(const float* logits, const long long* labels, float* dlogits, d
 /* ---- spot-patch gather: replaces gridnext/imgprocess.py:185-238 (grid_from_wsi_visium) */
 int gn_spot_table(const unsigned char* in_tissue, const int* array_row, const int* array_col, const double* pxl_row,
                   const double* pxl_col, int n_spots, int h_st, int w_st, int* cells, int* n_dropped, gn_stream_t stream);
+/* ToTensor + Normalize of a pre-cropped uint8 patch grid (cells, 3, P, P); valid (nullable) marks present cells */
+int gn_normalize_u8(const unsigned char* in, const unsigned char* valid, long n_cells, int P, const float* mean, const float* stdv,
+                    void* out, int out_bf16, gn_stream_t stream);
 int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, const int* cells, int n_cells, int P,
                     const float* mean, const float* stdv, void* out, int out_bf16, gn_stream_t stream);
 
