@@ -285,7 +285,11 @@ def main():
                         share_of_step=table[dom]['share'], peak_source=pk['src'])
         roof['whole_step_tensor_frac'] = (F_FLOP_FWD_BWD * SPOTS / (ms / args.steps * 1e-3)) / 1e12 / pk['bf16']
         if args.profile_out:
-            json.dump(dict(step_ms=ms / args.steps, instrumented_total_ms=total, kernels=table), open(args.profile_out, 'w'), indent=1, sort_keys=True)
+            def ints(g):
+                return [a if isinstance(a, int) else (None if a is None else 'p') for a in g]
+            calls = {k: [dict(ms=a.elapsed_time(b), args=ints(g)) for a, b, g in v] for k, v in prof.items()
+                     if k in ('gn_gemm_bf16', 'gn_gemm_tn_bf16', 'gn_conv3x3_bf16', 'gn_conv3x3_wgrad_bf16')}
+            json.dump(dict(step_ms=ms / args.steps, instrumented_total_ms=total, kernels=table, calls=calls), open(args.profile_out, 'w'), indent=1, sort_keys=True)
 
     if rank == 0:
         cpu = None

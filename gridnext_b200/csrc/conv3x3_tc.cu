@@ -2,16 +2,17 @@
 //
 // DenseNet's conv2 of every dense layer (/root/reference/gridnext/densenet.py:30-31, 128 -> 32 channels) and its
 // data gradient (32 -> 128 with flipped taps).  Index space: every image is addressed with a one-pixel zero border,
-// PP = (H+2)(W+2) positions per image, global position P = n*PP + y'*(W+2) + x'.  A tile is 128 CONSECUTIVE
-// positions; the input position of tap (ky, kx) is P + (ky-1)(W+2) + (kx-1): the SAME constant row shift for every
-// row of the tile.  So the activations of a tile (plus W+3 positions of halo on both sides) are loaded ONCE by TMA as
-// whole padded image rows (box = 64 channels x (W+2) x 1 x 1, out-of-bounds coordinates zero-filled = the padding),
-// and the nine taps are nine UMMA descriptor start addresses into that one SWIZZLE_128B buffer (the 128B swizzle is
-// a function of the absolute shared-memory address, so any 128-byte row offset is legal -- checked on hardware with
-// tools/umma_probe).  Weights for all nine taps stay resident in shared memory for the life of the persistent CTA.
-// Outputs at border positions are computed and dropped (efficiency HW / PP).
+// (H+2) padded rows of (W+2) positions per image.  A tile is R = floor(128 / (W+2)) CONSECUTIVE PADDED ROWS (they may
+// span images); accumulator row i is position i of the tile and the input position of tap (ky, kx) is
+// i + (ky-1)(W+2) + (kx-1): the SAME constant row shift for every row of the tile.  So the activations of a tile
+// (R + 2 padded rows) are loaded ONCE by TMA as whole padded image rows (box = 64 channels x (W+2) x 1 x 1,
+// out-of-bounds coordinates zero-filled = the padding), and the nine taps are nine UMMA descriptor start addresses
+// into that one SWIZZLE_128B buffer (the 128B swizzle is a function of the absolute shared-memory address, so any
+// 128-byte row offset is legal -- checked on hardware with tools/umma_probe).  Weights for all nine taps stay
+// resident in shared memory for the life of the persistent CTA.  The epilogue is staged through shared memory:
+// the BN reference tile arrives by TMA (one box per padded row), results are written in place and leave as TMA row
+// stores whose border positions (x' = 0, W+1) fall outside the tensor map and are dropped by the hardware.
 //
-//   warp 0: TMA producer   warp 1: MMA issuer (9 taps x kblocks x k16 MMAs of 128 x CO x 16)   warps 2-5: epilogue
 #include "gn_common.cuh"
 #include "gn_ptx.cuh"
 #include "gn_tma.cuh"
@@ -24,45 +25,90 @@ struct Conv3Params {
     int NP;               // CO rounded up to 16 (UMMA N)
     int kblocks;          // ceil(CI / 64)
     int w_row_bytes;      // bytes per weight row per k-block: 128 (SW128) or 64 (SW64)
-    int buf_rows;         // rows (positions) per activation stage buffer
+    int R;                // padded image rows per tile (R * (W+2) <= 128 positions)
+    int a_rows;           // 128-byte rows per k-block of one activation stage (slack included), multiple of 8
     int stages;
     int n_tiles;
-    __nv_bfloat16* out;   // [Nimg*H*W, ldo]
-    long ldo;
-    int epi_mode;         // 0 plain store, 1 BnBwdEpi
+    int nsub;             // 64-channel output sub-tiles per tile
+    int e_stages;         // epilogue sub-tile ring depth
+    int epi_mode;         // 0 plain store, 1 BnBwdEpi (reference tile fetched by TMA)
     BnBwdEpi bn;
 };
 
-__global__ void __launch_bounds__(192, 1)
-conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Conv3Params p) {
+#define C3_SUB_BYTES 16384
+#define C3_MAX_ESTAGES 4
+#define C3_EPI_WARPS 8
+#define C3_MAX_CO 256
+
+__device__ __forceinline__ uint32_t c3_pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 c3_unpack_bf16x2(uint32_t w) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w)); }
+
+// padded row index -> (image, padded y); rows outside [0, Nimg*H2) map to an out-of-bounds image index
+__device__ __forceinline__ void c3_row_coords(long Rg, long total_rows, int H2, int Nimg, int& n, int& yp) {
+    if (Rg < 0) { n = -1; yp = 0; }
+    else if (Rg >= total_rows) { n = Nimg; yp = 0; }
+    else { n = (int)(Rg / H2); yp = (int)(Rg % H2); }
+}
+
+// Tile = R consecutive PADDED image rows (R * (W+2) <= 128 positions, accumulator row i = position i of the tile).
+//   warp 0: TMA producer (R+2 padded rows per k-block)      warp 1: MMA issuer (9 taps x kblocks x k16)
+//   warp 2: epilogue feeder (TMA loads of the BN reference tile, one box per padded row)
+//   warp 3: TMEM allocator + epilogue drain (TMA row stores; border positions fall outside the tensor map and are dropped)
+//   warps 4-11: epilogue (tcgen05.ld -> math -> swizzled st.shared in place)
+__global__ void __launch_bounds__(384, 1)
+conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmRef, const Conv3Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_w, bar_full[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_efull[C3_MAX_ESTAGES], bar_eready[C3_MAX_ESTAGES], bar_eempty[C3_MAX_ESTAGES];
     __shared__ uint32_t tmem_slot;
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const int W2 = p.W + 2, H2 = p.H + 2, PP = W2 * H2, HALO = p.W + 3;
+    const int W2 = p.W + 2, H2 = p.H + 2, R = p.R;
+    const long total_rows = (long)p.Nimg * H2;
     const int w_tile_bytes = p.NP * p.w_row_bytes;                       // one (tap, k-block) weight tile (rows beyond CO: next tap / zero fill, never stored)
     const int w_bytes = ((9 * p.kblocks * w_tile_bytes + 1023) / 1024) * 1024;
-    const int kb_buf_bytes = p.buf_rows * 128;                           // one k-block of one stage
+    const int kb_buf_bytes = p.a_rows * 128;                             // one k-block of one stage
     const int stage_bytes = p.kblocks * kb_buf_bytes;
     uint8_t* s_w = sm;
     uint8_t* s_a = sm + w_bytes;
+    uint8_t* s_slots = s_a + (size_t)p.stages * stage_bytes;
+    float* s_epi = reinterpret_cast<float*>(s_slots + (size_t)p.e_stages * C3_SUB_BYTES);      // [4][C3_MAX_CO]
 
+    if (p.epi_mode == 1) {
+        for (int i = threadIdx.x; i < C3_MAX_CO; i += blockDim.x) {
+            const bool in = i < p.CO;
+            s_epi[i] = in ? p.bn.sc[i] : 0.f;
+            s_epi[C3_MAX_CO + i] = (in && p.bn.sh) ? p.bn.sh[i] : 0.f;
+            s_epi[2 * C3_MAX_CO + i] = in ? p.bn.p0[i] : 0.f;
+            s_epi[3 * C3_MAX_CO + i] = in ? p.bn.p1[i] : 0.f;
+        }
+    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmOut);
+        if (p.epi_mode == 1) tma_prefetch_desc(&tmRef);
         mbar_init(&bar_w, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
             mbar_init(&bar_tfull[s], 1);
-            mbar_init(&bar_tempty[s], 4);
+            mbar_init(&bar_tempty[s], C3_EPI_WARPS);
+        }
+        for (int s = 0; s < C3_MAX_ESTAGES; ++s) {
+            mbar_init(&bar_efull[s], 1);
+            mbar_init(&bar_eready[s], C3_EPI_WARPS);
+            mbar_init(&bar_eempty[s], 1);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<512>(&tmem_slot);
+    if (warp == 3) tmem_alloc<512>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -79,18 +125,13 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 mbar_wait(&bar_empty[stage], phase ^ 1);
-                const long P0 = (long)tile * 128;
-                const long lo = P0 - HALO;
-                const long R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);     // floor division
-                const long R1 = (P0 + 127 + HALO) / W2;
-                const int nr = (int)(R1 - R0 + 1);
-                mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(nr * W2 * 128 * p.kblocks));
-                for (int r = 0; r < nr; ++r) {
-                    const long R = R0 + r;
+                const long Rg0 = (long)tile * R;
+                mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)((R + 2) * W2 * 128 * p.kblocks));
+                for (int lr = 0; lr < R + 2; ++lr) {
                     int n, yp;
-                    if (R >= 0) { n = (int)(R / H2); yp = (int)(R % H2); } else { n = -1; yp = 0; }
+                    c3_row_coords(Rg0 - 1 + lr, total_rows, H2, p.Nimg, n, yp);
                     for (int kb = 0; kb < p.kblocks; ++kb)
-                        tma_load_4d(&tmX, &bar_full[stage], s_a + (size_t)stage * stage_bytes + (size_t)kb * kb_buf_bytes + (size_t)r * W2 * 128,
+                        tma_load_4d(&tmX, &bar_full[stage], s_a + (size_t)stage * stage_bytes + (size_t)kb * kb_buf_bytes + 1024 + (size_t)lr * W2 * 128,
                                     kb * 64, -1, yp - 1, n);
                 }
                 if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
@@ -106,20 +147,16 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            const uint32_t w_base = smem_u32(s_w);
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
                 mbar_wait(&bar_full[stage], phase);
                 tc_fence_after();
-                const long P0 = (long)tile * 128;
-                const long lo = P0 - HALO;
-                const long R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
-                const int base_row = (int)(P0 - R0 * W2);                 // buffer row of position P0
                 const uint32_t d = tmem_base + (uint32_t)(acc * 256);
-                const uint32_t a_stage = smem_u32(s_a + (size_t)stage * stage_bytes);
-                const uint32_t w_base = smem_u32(s_w);
+                const uint32_t a_stage = smem_u32(s_a + (size_t)stage * stage_bytes) + 1024;   // buffer row 0 = local padded row -1, x' = 0
                 uint32_t first = 1;
                 for (int t = 0; t < 9; ++t) {
-                    const int row = base_row + (t / 3 - 1) * W2 + (t % 3 - 1);
+                    const int row = (t / 3) * W2 + (t % 3) - 1;          // buffer row feeding accumulator row 0 for this tap
                     for (int kb = 0; kb < p.kblocks; ++kb) {
                         const int kc = min(64, p.CI - kb * 64);
                         const int k16n = (kc + 15) >> 4;
@@ -138,64 +175,134 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 if (acc == 0) acc_phase ^= 1;
             }
         }
+    } else if (warp == 2) {
+        // ---- epilogue feeder
+        if (elect_one()) {
+            int es = 0;
+            uint32_t eph = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const long Rg0 = (long)tile * R;
+                for (int j = 0; j < p.nsub; ++j) {
+                    mbar_wait(&bar_eempty[es], eph ^ 1);
+                    if (p.epi_mode == 1) {
+                        uint8_t* slot = s_slots + (size_t)es * C3_SUB_BYTES;
+                        mbar_arrive_expect_tx(&bar_efull[es], (uint32_t)(R * W2 * 128));
+                        for (int r = 0; r < R; ++r) {
+                            int n, yp;
+                            c3_row_coords(Rg0 + r, total_rows, H2, p.Nimg, n, yp);
+                            tma_load_4d(&tmRef, &bar_efull[es], slot + (size_t)r * W2 * 128, j * 64, -1, yp - 1, n);
+                        }
+                    } else {
+                        mbar_arrive(&bar_efull[es]);
+                    }
+                    if (++es == p.e_stages) { es = 0; eph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ---- epilogue drain
+        if (elect_one()) {
+            int es = 0, prev_es = -1;
+            uint32_t eph = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const long Rg0 = (long)tile * R;
+                for (int j = 0; j < p.nsub; ++j) {
+                    mbar_wait(&bar_eready[es], eph);
+                    const uint8_t* slot = s_slots + (size_t)es * C3_SUB_BYTES;
+                    for (int r = 0; r < R; ++r) {
+                        int n, yp;
+                        c3_row_coords(Rg0 + r, total_rows, H2, p.Nimg, n, yp);
+                        if (n >= 0 && n < p.Nimg && yp >= 1 && yp <= p.H)
+                            tma_store_4d(&tmOut, slot + (size_t)r * W2 * 128, j * 64, -1, yp - 1, n);
+                    }
+                    tma_store_commit();
+                    if (prev_es >= 0) {
+                        tma_store_wait_read<1>();
+                        mbar_arrive(&bar_eempty[prev_es]);
+                    }
+                    prev_es = es;
+                    if (++es == p.e_stages) { es = 0; eph ^= 1; }
+                }
+            }
+            tma_store_wait_all<0>();
+        }
+        __syncwarp();
     } else {
+        // ---- epilogue: thread = (accumulator row, 32-channel half of each 64-channel sub-tile)
         const int g = warp & 3;
+        const int h = (warp - 4) >> 2;
+        const int trow = g * 32 + lane;
+        const uint32_t sw = (uint32_t)(trow & 7);
+        const int r_loc = trow / W2, xp = trow % W2;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const int nchunks = (p.CO + 31) / 32;
-        float cs_g[8], cs_x[8];       // per-lane column partial sums, columns chunk*32 + lane
+        int es = 0;
+        uint32_t eph = 0;
+        float cs_g[4], cs_x[4];       // per-lane column partial sums, channel j*64 + h*32 + lane
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { cs_g[i] = 0.f; cs_x[i] = 0.f; }
+        for (int i = 0; i < 4; ++i) { cs_g[i] = 0.f; cs_x[i] = 0.f; }
+        const bool want_sums = p.epi_mode == 1 && p.bn.colsum != nullptr;
+        const bool is_raw = p.bn.ref_is_raw != 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&bar_tfull[acc], acc_phase);
             tc_fence_after();
-            const long P = (long)tile * 128 + g * 32 + lane;
-            const int n = (int)(P / PP);
-            const int q = (int)(P % PP);
-            const int yp = q / W2, xp = q % W2;
-            const bool valid = n < p.Nimg && yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
-            const long m = ((long)n * p.H + (yp - 1)) * p.W + (xp - 1);
+            int n, yp;
+            c3_row_coords((long)tile * R + r_loc, total_rows, H2, p.Nimg, n, yp);
+            const bool valid = r_loc < R && n >= 0 && n < p.Nimg && yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * 256);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                if (ch >= nchunks) break;
-                uint32_t r[32];
-                tmem_ld32(taddr + ch * 32, r);
-                tmem_ld_wait();
-                const int col = ch * 32;
-                const int ncols = min(32, p.CO - col);
-                float v[32];
+            for (int j = 0; j < 4; ++j) {
+                if (j < p.nsub) {
+                    mbar_wait(&bar_efull[es], eph);
+                    uint8_t* rowp = s_slots + (size_t)es * C3_SUB_BYTES + trow * 128;
+                    const int c0 = j * 64 + h * 32;
+                    __syncwarp();
+                    if (c0 < p.NP) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + c0, r);
+                        tmem_ld_wait();
+                        const float* cst = s_epi + c0;
+                        float v[32], gx[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.epi_mode == 0) {
-                    if (valid) gn_store_bf16_32(p.out + m * p.ldo + col, v, ncols);
-                } else {
-                    float gx[32];
-                    if (valid) {
-                        float ref[32];
-                        gn_load_bf16_32(p.bn.ref + m * p.bn.ldref + col, ref, ncols);
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t off = (((uint32_t)(h * 4 + q)) ^ sw) << 4;
+                            uint32_t res[4];
+                            if (p.epi_mode == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < ncols) {
-                                const float sc = __ldg(p.bn.sc + col + j);
-                                const float a = p.bn.ref_is_raw ? fmaf(ref[j], sc, __ldg(p.bn.sh + col + j)) : ref[j];
-                                const float gg = a > 0.f ? v[j] : 0.f;
-                                gx[j] = gg * (ref[j] - __ldg(p.bn.p0 + col + j)) * __ldg(p.bn.p1 + col + j);
-                                v[j] = gg;
-                                ref[j] = gg * sc;
+                                for (int e2 = 0; e2 < 4; ++e2)
+                                    res[e2] = c3_pack_bf16x2(__uint_as_float(r[8 * q + 2 * e2]), __uint_as_float(r[8 * q + 2 * e2 + 1]));
                             } else {
-                                gx[j] = 0.f; v[j] = 0.f; ref[j] = 0.f;
-                            }
-                        }
-                        gn_store_bf16_32(p.out + m * p.ldo + col, ref, ncols);
-                    } else {
+                                const uint4 rv = *reinterpret_cast<const uint4*>(rowp + off);
+                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { v[j] = 0.f; gx[j] = 0.f; }
+                                for (int e2 = 0; e2 < 4; ++e2) {
+                                    const float2 rf = c3_unpack_bf16x2(rw[e2]);
+                                    float o2[2];
+#pragma unroll
+                                    for (int u = 0; u < 2; ++u) {
+                                        const int e = 8 * q + 2 * e2 + u;
+                                        const float ref = u ? rf.y : rf.x;
+                                        const float sc = cst[e];
+                                        const float a = is_raw ? fmaf(ref, sc, cst[C3_MAX_CO + e]) : ref;
+                                        const float gg = (valid && a > 0.f) ? __uint_as_float(r[e]) : 0.f;
+                                        gx[e] = gg * (ref - cst[2 * C3_MAX_CO + e]) * cst[3 * C3_MAX_CO + e];
+                                        v[e] = gg;
+                                        o2[u] = gg * sc;
+                                    }
+                                    res[e2] = c3_pack_bf16x2(o2[0], o2[1]);
+                                }
+                            }
+                            *reinterpret_cast<uint4*>(rowp + off) = make_uint4(res[0], res[1], res[2], res[3]);
+                        }
+                        if (want_sums) {
+                            cs_g[j] += gn_warp_colsum32(v, lane);
+                            cs_x[j] += gn_warp_colsum32(gx, lane);
+                        }
                     }
-                    if (p.bn.colsum != nullptr) {
-                        cs_g[ch] += gn_warp_colsum32(v, lane);
-                        cs_x[ch] += gn_warp_colsum32(gx, lane);
-                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_eready[es]);
+                    if (++es == p.e_stages) { es = 0; eph ^= 1; }
                 }
             }
             tc_fence_before();
@@ -204,20 +311,20 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (p.epi_mode == 1 && p.bn.colsum != nullptr) {
+        if (want_sums) {
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                const int col = ch * 32 + lane;
-                if (ch < nchunks && col < p.CO) {
-                    atomicAdd(p.bn.colsum + col, cs_g[ch]);
-                    atomicAdd(p.bn.colsum + p.bn.ldsum + col, cs_x[ch]);
+            for (int j = 0; j < 4; ++j) {
+                const int col = j * 64 + h * 32 + lane;
+                if (j < p.nsub && col < p.CO) {
+                    atomicAdd(p.bn.colsum + col, cs_g[j]);
+                    atomicAdd(p.bn.colsum + p.bn.ldsum + col, cs_x[j]);
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<512>(tmem_base);
+    if (warp == 3) tmem_dealloc<512>(tmem_base);
 }
 
 // weight repack:  mode 0 (forward)   wp[(t*CO + co), c] = w[co, c, ky, kx]          rows: 9*CO, cols: CI (pitch ldw)
@@ -259,33 +366,39 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     GN_REQUIRE(CO % 8 == 0 && CO <= 256, GN_EUNSUPPORTED, "conv3x3: output channels %d must be a multiple of 8, <= 256", CO);
     GN_REQUIRE(CI % 8 == 0 && CI <= 256, GN_EUNSUPPORTED, "conv3x3: input channels %d must be a multiple of 8, <= 256", CI);
     GN_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= CI && ldw >= CI && ldo >= CO, GN_EALIGN, "conv3x3: bad pitches");
-    GN_REQUIRE(W + 2 <= 256, GN_EUNSUPPORTED, "conv3x3: width %d too large", W);
     Conv3Params p;
     memset(&p, 0, sizeof(p));
     p.Nimg = Nimg; p.H = H; p.W = W; p.CI = CI; p.CO = CO; p.NP = ((CO + 15) / 16) * 16;
     p.kblocks = gn_ceil_div(CI, 64);
     p.w_row_bytes = (CI <= 32) ? 64 : 128;
-    const int W2 = W + 2, HALO = W + 3;
-    const int nr_max = (127 + 2 * HALO) / W2 + 2;
-    p.buf_rows = nr_max * W2;
-    const long PPt = (long)(H + 2) * W2 * Nimg;
-    p.n_tiles = (int)((PPt + 127) / 128);
-    p.out = (__nv_bfloat16*)out; p.ldo = ldo;
+    const int W2 = W + 2;
+    GN_REQUIRE(W2 <= 128, GN_EUNSUPPORTED, "conv3x3: width %d too large (W + 2 must fit one 128-position tile)", W);
+    p.R = 128 / W2;
+    p.a_rows = ((2 * W2 + 137 + 7) / 8) * 8;
+    const long total_rows = (long)(H + 2) * Nimg;
+    p.n_tiles = (int)((total_rows + p.R - 1) / p.R);
+    p.nsub = (CO + 63) / 64;
     p.epi_mode = bn_ref != nullptr ? 1 : 0;
+    GN_REQUIRE(((uintptr_t)out & 15) == 0 && ldo % 8 == 0, GN_EALIGN, "conv3x3: output view must be 16-byte aligned with a pitch that is a multiple of 8");
     if (p.epi_mode == 1) {
         GN_REQUIRE(bn_sc && bn_p0 && bn_p1 && (!bn_ref_is_raw || bn_sh), GN_EINVAL, "conv3x3: incomplete BN-backward epilogue arguments");
+        GN_REQUIRE(((uintptr_t)bn_ref & 15) == 0 && bn_ldref % 8 == 0 && bn_ldref >= CO, GN_EALIGN, "conv3x3: reference view must be 16-byte aligned with a pitch that is a multiple of 8");
         p.bn.ref = (const __nv_bfloat16*)bn_ref; p.bn.ldref = bn_ldref; p.bn.ref_is_raw = bn_ref_is_raw;
         p.bn.sc = bn_sc; p.bn.sh = bn_sh; p.bn.p0 = bn_p0; p.bn.p1 = bn_p1; p.bn.colsum = bn_colsum; p.bn.ldsum = bn_ldsum; p.bn.rmw = 0;
     }
     const int w_bytes = ((9 * p.kblocks * p.NP * p.w_row_bytes + 1023) / 1024) * 1024;
-    const int stage_bytes = p.kblocks * p.buf_rows * 128;
-    const int budget = 227 * 1024 - 1024 - 256;
-    GN_REQUIRE(w_bytes + stage_bytes <= budget, GN_EUNSUPPORTED, "conv3x3: tile does not fit shared memory (weights %d B + stage %d B)", w_bytes,
-               stage_bytes);
-    p.stages = (w_bytes + 2 * stage_bytes <= budget) ? 2 : 1;
-    const size_t smem = (size_t)w_bytes + (size_t)p.stages * stage_bytes + 1024;
+    const int stage_bytes = p.kblocks * p.a_rows * 128;
+    const int epi_fixed = 4 * C3_MAX_CO * 4;
+    const int budget = 227 * 1024 - 1024 - 512;
+    GN_REQUIRE(w_bytes + stage_bytes + 2 * C3_SUB_BYTES + epi_fixed <= budget, GN_EUNSUPPORTED,
+               "conv3x3: tile does not fit shared memory (weights %d B + stage %d B)", w_bytes, stage_bytes);
+    p.stages = (w_bytes + 2 * stage_bytes + 2 * C3_SUB_BYTES + epi_fixed <= budget) ? 2 : 1;
+    p.e_stages = (budget - w_bytes - p.stages * stage_bytes - epi_fixed) / C3_SUB_BYTES;
+    if (p.e_stages > C3_MAX_ESTAGES) p.e_stages = C3_MAX_ESTAGES;
+    const size_t smem = (size_t)w_bytes + (size_t)p.stages * stage_bytes + (size_t)p.e_stages * C3_SUB_BYTES + epi_fixed + 1024;
 
-    CUtensorMap tmX, tmW;
+    CUtensorMap tmX, tmW, tmOut, tmRef;
+    memset(&tmRef, 0, sizeof(tmRef));
     {
         uint64_t dims[4] = {(uint64_t)CI, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t strides[3] = {(uint64_t)ldx * 2, (uint64_t)W * ldx * 2, (uint64_t)H * W * ldx * 2};
@@ -301,13 +414,27 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
                                 p.w_row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
     }
+    {
+        uint64_t dims[4] = {(uint64_t)CO, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+        uint64_t strides[3] = {(uint64_t)ldo * 2, (uint64_t)W * ldo * 2, (uint64_t)H * W * ldo * 2};
+        uint32_t box[4] = {64, (uint32_t)W2, 1, 1};
+        int rc = gn_tmap_encode(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    if (p.epi_mode == 1) {
+        uint64_t dims[4] = {(uint64_t)CO, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+        uint64_t strides[3] = {(uint64_t)bn_ldref * 2, (uint64_t)W * bn_ldref * 2, (uint64_t)H * W * bn_ldref * 2};
+        uint32_t box[4] = {64, (uint32_t)W2, 1, 1};
+        int rc = gn_tmap_encode(&tmRef, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, bn_ref, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
     static int max_set = 0;
     if ((int)smem > max_set) {
         GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         max_set = (int)smem;
     }
     const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
-    conv3x3_kernel<<<grid, 192, smem, stream>>>(tmX, tmW, p);
+    conv3x3_kernel<<<grid, 384, smem, stream>>>(tmX, tmW, tmOut, tmRef, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -6,15 +6,24 @@
 // conv1 of each dense layer, the transitions), their data gradients, and the Linear layers of the count MLP
 // (notebooks/Tutorial_visium_count.ipynb cell 12).
 //
+// These GEMMs are HBM-bound (K = 64..1024 against N = 128, or K = 128 against N = 64..992 with a read-modify-write
+// output), so the kernel is built to STREAM: every global access on the data path is a TMA bulk copy.
+//
 // Persistent, warp-specialised, one CTA per SM:
-//   warp 0      TMA producer     (cp.async.bulk.tensor 2-D boxes of 128 x 64 / BN x 64 bf16, SWIZZLE_128B)
-//   warp 1      MMA issuer       (one elected thread, tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16)
-//   warps 2-5   epilogue         (tcgen05.ld 32x32b -> affine / ReLU -> bf16|fp32 global stores), double-buffered
-//                                 TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 6-9   operand transform (XFORM only): DenseNet's pre-activation BatchNorm+ReLU
-//                                 (densenet.py:12-18: conv(relu(norm(cat)))) is applied IN PLACE to the A tile in
-//                                 shared memory between TMA arrival and the MMA, so the activated tensor is never
-//                                 written to HBM.  BN is eval-mode (training.py:126): x * scale[k] + shift[k].
+//   warp 0       TMA producer      (A/B k-blocks: boxes of 128 x 64 / BN x 64 bf16, SWIZZLE_128B, `stages` deep ring)
+//   warp 1       MMA issuer        (one elected thread, tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16)
+//   warp 2       epilogue feeder   (TMA loads of the tiles the epilogue reads: the BN reference tile and, for
+//                                   read-modify-write, the old output tile; `e_stages` deep ring of 128 x 64 sub-tiles)
+//   warp 3       TMEM allocator + epilogue drain (one TMA store per finished sub-tile, frees the slot once read)
+//   warps 4-11   epilogue          (tcgen05.ld 32x32b -> math -> swizzled st.shared, in place over the staged tile);
+//                                   two warps per TMEM lane group, double-buffered TMEM accumulators so the epilogue
+//                                   of tile i overlaps the MMAs of tile i+1
+//   warps 12-15  operand transform (XFORM only): DenseNet's pre-activation BatchNorm+ReLU
+//                                   (densenet.py:12-18: conv(relu(norm(cat)))) is applied IN PLACE to the A tile in
+//                                   shared memory between TMA arrival and the MMA, so the activated tensor is never
+//                                   written to HBM.  BN is eval-mode (training.py:126): x * scale[k] + shift[k].
+// EPI_DIRECT keeps a register -> global epilogue for what TMA cannot express (fp32 output / accumulate, unaligned
+// views, N > 1024).
 #include "gn_common.cuh"
 #include "gn_ptx.cuh"
 #include "gn_tma.cuh"
@@ -26,6 +35,14 @@ using namespace gnptx;
 #define GEMM_BK 64
 #define GEMM_A_BYTES (GEMM_BM * GEMM_BK * 2)
 #define GEMM_MAX_XF_K 1024
+#define GEMM_EPI_MAX_N 1024
+#define GEMM_SUB_BYTES 16384      // one epilogue sub-tile: 128 rows x 64 bf16 (128-byte rows, SWIZZLE_128B)
+#define GEMM_MAX_STAGES 8
+#define GEMM_MAX_ESTAGES 6
+#define GEMM_EPI_WARPS 8
+#define GEMM_EPI_THREADS (GEMM_EPI_WARPS * 32)
+
+enum { EPI_STORE = 0, EPI_BNBWD = 1, EPI_DIRECT = 2 };
 
 struct GemmParams {
     int M, N, K;
@@ -41,22 +58,25 @@ struct GemmParams {
     const float* xf_shift;
     int epi_mode;              // 0: affine/ReLU store, 1: BN+ReLU backward (BnBwdEpi), bf16 output
     BnBwdEpi bn;
+    int stages;                // main-loop ring depth
+    int e_stages;              // epilogue sub-tile ring depth (TMA epilogues)
+    int slot_bytes;            // GEMM_SUB_BYTES, or 2x for read-modify-write (reference tile + old/new output tile)
 };
 
 template <int BN> struct GemmCfg {
-    static constexpr int STAGES = (BN <= 128) ? 6 : 4;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr size_t smem_bytes(bool xform) { return (size_t)STAGES * STAGE_BYTES + 1024 + (xform ? 2 * GEMM_MAX_XF_K * 4 : 0); }
+    static constexpr int NSUB = BN >= 64 ? BN / 64 : 1;      // 64-column epilogue sub-tiles per tile
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w)); }
 
-// store 32 consecutive columns of one row (mode-0 epilogue)
+// store 32 consecutive columns of one row (EPI_DIRECT, mode 0)
 __device__ __forceinline__ void epi_store_row(const GemmParams& p, int row, int col, const uint32_t (&r)[32]) {
     if (row >= p.M || col >= p.N) return;
     float v[32];
@@ -95,35 +115,27 @@ __device__ __forceinline__ void epi_store_row(const GemmParams& p, int row, int 
         }
     } else {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long)row * p.ldc + col;
-        const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-        if (vec) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint4 t;
-                t.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
-                t.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-                t.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-                t.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-                *reinterpret_cast<uint4*>(o + 8 * q) = t;
-            }
-        } else {
-            for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(v[j]);
-        }
+        gn_store_bf16_32(o, v, ncols);
     }
 }
 
-template <int BN, bool XFORM>
-__global__ void __launch_bounds__(XFORM ? 320 : 192, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+template <int BN, bool XFORM, int EPI>
+__global__ void __launch_bounds__(XFORM ? 512 : 384, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ CUtensorMap tmRef, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int NSUB = Cfg::NSUB;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[STAGES], bar_xf[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_full[GEMM_MAX_STAGES], bar_xf[GEMM_MAX_STAGES], bar_empty[GEMM_MAX_STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_efull[GEMM_MAX_ESTAGES], bar_eready[GEMM_MAX_ESTAGES], bar_eempty[GEMM_MAX_ESTAGES];
     __shared__ uint32_t tmem_slot;
 
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    float* s_xf = reinterpret_cast<float*>(sm + (size_t)STAGES * Cfg::STAGE_BYTES);   // [2][GEMM_MAX_XF_K]
+    const int STAGES = p.stages;
+    uint8_t* s_slots = sm + (size_t)STAGES * Cfg::STAGE_BYTES;                                   // e_stages x slot_bytes
+    float* s_epi = reinterpret_cast<float*>(s_slots + (EPI == EPI_DIRECT ? 0 : (size_t)p.e_stages * p.slot_bytes));   // [4][GEMM_EPI_MAX_N]
+    float* s_xf = s_epi + (EPI == EPI_DIRECT ? 0 : 4 * GEMM_EPI_MAX_N);                           // [2][GEMM_MAX_XF_K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (XFORM) {
@@ -133,21 +145,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             s_xf[GEMM_MAX_XF_K + i] = i < p.K ? p.xf_shift[i] : 0.f;
         }
     }
+    if (EPI != EPI_DIRECT) {
+        // per-column epilogue constants, zero beyond N (those accumulator columns are zero as well)
+        const int npad = min(GEMM_EPI_MAX_N, ((p.N + 63) / 64) * 64);
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+            const bool in = i < p.N;
+            if (EPI == EPI_STORE) {
+                s_epi[i] = in ? (p.scale ? p.scale[i] : 1.f) : 0.f;
+                s_epi[GEMM_EPI_MAX_N + i] = in ? (p.shift ? p.shift[i] : 0.f) : 0.f;
+            } else {
+                s_epi[i] = in ? p.bn.sc[i] : 0.f;
+                s_epi[GEMM_EPI_MAX_N + i] = (in && p.bn.sh) ? p.bn.sh[i] : 0.f;
+                s_epi[2 * GEMM_EPI_MAX_N + i] = in ? p.bn.p0[i] : 0.f;
+                s_epi[3 * GEMM_EPI_MAX_N + i] = in ? p.bn.p1[i] : 0.f;
+            }
+        }
+    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) {
+        if (EPI != EPI_DIRECT) tma_prefetch_desc(&tmOut);
+        if (EPI == EPI_BNBWD) tma_prefetch_desc(&tmRef);
+        for (int s = 0; s < GEMM_MAX_STAGES; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_xf[s], 4);
             mbar_init(&bar_empty[s], 1);
         }
+        for (int s = 0; s < GEMM_MAX_ESTAGES; ++s) {
+            mbar_init(&bar_efull[s], 1);
+            mbar_init(&bar_eready[s], GEMM_EPI_WARPS);
+            mbar_init(&bar_eempty[s], 1);
+        }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_tfull[a], 1);
-            mbar_init(&bar_tempty[a], 4);
+            mbar_init(&bar_tempty[a], GEMM_EPI_WARPS);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
+    if (warp == 3) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -201,80 +236,205 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (acc == 0) acc_phase ^= 1;
             }
         }
-    } else if (warp < 6) {
+    } else if (warp == 2) {
+        // ===================== epilogue feeder =====================
+        if (EPI != EPI_DIRECT && elect_one()) {
+            int es = 0;
+            uint32_t eph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int nb = tile / p.num_m_blocks, mb = tile % p.num_m_blocks;
+                const int nsub = (min(BN, p.N - nb * BN) + 63) >> 6;
+                for (int j = 0; j < nsub; ++j) {
+                    mbar_wait(&bar_eempty[es], eph ^ 1);
+                    if (EPI == EPI_BNBWD) {
+                        uint8_t* slot = s_slots + (size_t)es * p.slot_bytes;
+                        mbar_arrive_expect_tx(&bar_efull[es], (uint32_t)p.slot_bytes);
+                        tma_load_2d(&tmRef, &bar_efull[es], slot, nb * BN + j * 64, mb * GEMM_BM);
+                        if (p.bn.rmw) tma_load_2d(&tmOut, &bar_efull[es], slot + GEMM_SUB_BYTES, nb * BN + j * 64, mb * GEMM_BM);
+                    } else {
+                        mbar_arrive(&bar_efull[es]);
+                    }
+                    if (++es == p.e_stages) { es = 0; eph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== epilogue drain: one TMA store per finished sub-tile =====================
+        if (EPI != EPI_DIRECT && elect_one()) {
+            int es = 0, prev_es = -1;
+            uint32_t eph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int nb = tile / p.num_m_blocks, mb = tile % p.num_m_blocks;
+                const int nsub = (min(BN, p.N - nb * BN) + 63) >> 6;
+                for (int j = 0; j < nsub; ++j) {
+                    mbar_wait(&bar_eready[es], eph);
+                    tma_store_2d(&tmOut, s_slots + (size_t)es * p.slot_bytes + (p.slot_bytes - GEMM_SUB_BYTES), nb * BN + j * 64, mb * GEMM_BM);
+                    tma_store_commit();
+                    if (prev_es >= 0) {
+                        tma_store_wait_read<1>();          // the previous sub-tile's store has drained its slot
+                        mbar_arrive(&bar_eempty[prev_es]);
+                    }
+                    prev_es = es;
+                    if (++es == p.e_stages) { es = 0; eph ^= 1; }
+                }
+            }
+            tma_store_wait_all<0>();
+        }
+        __syncwarp();
+    } else if (warp >= 4 && warp < 4 + GEMM_EPI_WARPS) {
         // ===================== epilogue =====================
-        const int g = warp & 3;   // TMEM lane group this warp may access
+        const int g = warp & 3;            // TMEM lane group this warp may access
+        const int h = (warp - 4) >> 2;     // which 32-column half of every 64-column sub-tile
         int acc = 0;
         uint32_t acc_phase = 0;
-        constexpr int NCH = BN / 32;
-        float cs_g[NCH], cs_x[NCH];   // BN-backward column partial sums (column = nb*BN + ch*32 + lane)
+        float cs_g[NSUB], cs_x[NSUB];      // BN-backward column partial sums (column = nb*BN + j*64 + h*32 + lane)
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) { cs_g[i] = 0.f; cs_x[i] = 0.f; }
+        for (int i = 0; i < NSUB; ++i) { cs_g[i] = 0.f; cs_x[i] = 0.f; }
         int cur_nb = -1;
+        const bool want_sums = (EPI == EPI_BNBWD || (EPI == EPI_DIRECT && p.epi_mode == 1)) && p.bn.colsum != nullptr;
         auto flush_colsums = [&]() {
-            if (p.epi_mode == 1 && p.bn.colsum != nullptr && cur_nb >= 0) {
+            if (want_sums && cur_nb >= 0) {
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                    const int col = cur_nb * BN + ch * 32 + lane;
+                for (int j = 0; j < NSUB; ++j) {
+                    const int col = cur_nb * BN + j * 64 + h * 32 + lane;
                     if (col < p.N) {
-                        atomicAdd(p.bn.colsum + col, cs_g[ch]);
-                        atomicAdd(p.bn.colsum + p.bn.ldsum + col, cs_x[ch]);
+                        atomicAdd(p.bn.colsum + col, cs_g[j]);
+                        atomicAdd(p.bn.colsum + p.bn.ldsum + col, cs_x[j]);
                     }
-                    cs_g[ch] = 0.f; cs_x[ch] = 0.f;
+                    cs_g[j] = 0.f; cs_x[j] = 0.f;
                 }
             }
         };
+        int es = 0;
+        uint32_t eph = 0;
+        const bool active = (BN >= 64) || h == 0;       // BN = 32: the upper half-warps have no accumulator columns
+        const int trow = g * 32 + lane;                 // row of the tile owned by this thread
+        const uint32_t sw = (uint32_t)(trow & 7);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int nb = tile / p.num_m_blocks, mb = tile % p.num_m_blocks;
             if (nb != cur_nb) { flush_colsums(); cur_nb = nb; }
             mbar_wait(&bar_tfull[acc], acc_phase);
             tc_fence_after();
-            const int row = mb * GEMM_BM + g * 32 + lane;
+            const int row = mb * GEMM_BM + trow;
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * BN);
-            if (p.epi_mode == 0) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c0, r);
-                    tmem_ld_wait();
-                    epi_store_row(p, row, nb * BN + c0, r);
-                }
-            } else {
+            if (EPI == EPI_DIRECT) {
 #pragma unroll
-                for (int ch = 0; ch < NCH; ++ch) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + ch * 32, r);
-                    tmem_ld_wait();
-                    const int col = nb * BN + ch * 32;
-                    const int ncols = min(32, p.N - col);
-                    float v[32], gx[32];
-                    if (row < p.M && ncols > 0) {
-                        float ref[32];
-                        gn_load_bf16_32(p.bn.ref + (long)row * p.bn.ldref + col, ref, ncols);
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long)row * p.ldc + col;
-                        float old[32];
-                        if (p.bn.rmw) gn_load_bf16_32(o, old, ncols);
+                for (int j = 0; j < NSUB; ++j) {
+                    const int c0 = j * 64 + h * 32;
+                    if (c0 < BN) {
+                        uint32_t r[32];
+                        __syncwarp();
+                        tmem_ld32(taddr + c0, r);
+                        tmem_ld_wait();
+                        const int col = nb * BN + c0;
+                        if (p.epi_mode == 0) {
+                            epi_store_row(p, row, col, r);
+                        } else {
+                            const int ncols = min(32, p.N - col);
+                            float v[32], gx[32];
+                            if (row < p.M && ncols > 0) {
+                                float ref[32];
+                                gn_load_bf16_32(p.bn.ref + (long)row * p.bn.ldref + col, ref, ncols);
+                                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long)row * p.ldc + col;
+                                float old[32];
+                                if (p.bn.rmw) gn_load_bf16_32(o, old, ncols);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < ncols) {
-                                const float sc = __ldg(p.bn.sc + col + j);
-                                const float a = p.bn.ref_is_raw ? fmaf(ref[j], sc, __ldg(p.bn.sh + col + j)) : ref[j];
-                                const float gg = a > 0.f ? __uint_as_float(r[j]) : 0.f;
-                                gx[j] = gg * (ref[j] - __ldg(p.bn.p0 + col + j)) * __ldg(p.bn.p1 + col + j);
-                                v[j] = gg;
-                                ref[j] = p.bn.rmw ? fmaf(gg, sc, old[j]) : gg * sc;
+                                for (int e = 0; e < 32; ++e) {
+                                    if (e < ncols) {
+                                        const float sc = __ldg(p.bn.sc + col + e);
+                                        const float a = p.bn.ref_is_raw ? fmaf(ref[e], sc, __ldg(p.bn.sh + col + e)) : ref[e];
+                                        const float gg = a > 0.f ? __uint_as_float(r[e]) : 0.f;
+                                        gx[e] = gg * (ref[e] - __ldg(p.bn.p0 + col + e)) * __ldg(p.bn.p1 + col + e);
+                                        v[e] = gg;
+                                        ref[e] = p.bn.rmw ? fmaf(gg, sc, old[e]) : gg * sc;
+                                    } else {
+                                        gx[e] = 0.f; v[e] = 0.f; ref[e] = 0.f;
+                                    }
+                                }
+                                gn_store_bf16_32(o, ref, ncols);
                             } else {
-                                gx[j] = 0.f; v[j] = 0.f; ref[j] = 0.f;
+#pragma unroll
+                                for (int e = 0; e < 32; ++e) { v[e] = 0.f; gx[e] = 0.f; }
+                            }
+                            if (want_sums) {
+                                cs_g[j] += gn_warp_colsum32(v, lane);
+                                cs_x[j] += gn_warp_colsum32(gx, lane);
                             }
                         }
-                        gn_store_bf16_32(o, ref, ncols);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) { v[j] = 0.f; gx[j] = 0.f; }
                     }
-                    if (p.bn.colsum != nullptr) {
-                        cs_g[ch] += gn_warp_colsum32(v, lane);
-                        cs_x[ch] += gn_warp_colsum32(gx, lane);
+                }
+            } else {
+                const int nsub = (min(BN, p.N - nb * BN) + 63) >> 6;
+#pragma unroll
+                for (int j = 0; j < NSUB; ++j) {
+                    if (j < nsub) {
+                        mbar_wait(&bar_efull[es], eph);
+                        uint8_t* slot = s_slots + (size_t)es * p.slot_bytes;
+                        uint8_t* ref_row = slot + trow * 128;
+                        uint8_t* out_row = ref_row + (p.slot_bytes - GEMM_SUB_BYTES);     // same tile unless read-modify-write
+                        __syncwarp();
+                        if (active) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + j * 64 + h * 32, r);
+                        tmem_ld_wait();
+                        const float* cst = s_epi + nb * BN + j * 64 + h * 32;
+                        if (EPI == EPI_STORE) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float o[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float x = fmaf(__uint_as_float(r[8 * q + e]), cst[8 * q + e], cst[GEMM_EPI_MAX_N + 8 * q + e]);
+                                    o[e] = p.relu ? fmaxf(x, 0.f) : x;
+                                }
+                                uint4 t;
+                                t.x = pack_bf16x2(o[0], o[1]); t.y = pack_bf16x2(o[2], o[3]);
+                                t.z = pack_bf16x2(o[4], o[5]); t.w = pack_bf16x2(o[6], o[7]);
+                                *reinterpret_cast<uint4*>(out_row + ((((uint32_t)(h * 4 + q)) ^ sw) << 4)) = t;
+                            }
+                        } else {
+                            float v[32], gx[32];
+                            const bool rmw = p.bn.rmw != 0, is_raw = p.bn.ref_is_raw != 0;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t off = (((uint32_t)(h * 4 + q)) ^ sw) << 4;
+                                const uint4 rv = *reinterpret_cast<const uint4*>(ref_row + off);
+                                uint4 ov = make_uint4(0u, 0u, 0u, 0u);
+                                if (rmw) ov = *reinterpret_cast<const uint4*>(out_row + off);
+                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+                                const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+                                uint32_t res[4];
+#pragma unroll
+                                for (int e2 = 0; e2 < 4; ++e2) {
+                                    const float2 rf = unpack_bf16x2(rw[e2]);
+                                    const float2 of = unpack_bf16x2(ow[e2]);
+                                    float o2[2];
+#pragma unroll
+                                    for (int u = 0; u < 2; ++u) {
+                                        const int e = 8 * q + 2 * e2 + u;
+                                        const float ref = u ? rf.y : rf.x;
+                                        const float old = u ? of.y : of.x;
+                                        const float sc = cst[e];
+                                        const float a = is_raw ? fmaf(ref, sc, cst[GEMM_EPI_MAX_N + e]) : ref;
+                                        const float gg = a > 0.f ? __uint_as_float(r[e]) : 0.f;
+                                        gx[e] = gg * (ref - cst[2 * GEMM_EPI_MAX_N + e]) * cst[3 * GEMM_EPI_MAX_N + e];
+                                        v[e] = gg;
+                                        o2[u] = rmw ? fmaf(gg, sc, old) : gg * sc;
+                                    }
+                                    res[e2] = pack_bf16x2(o2[0], o2[1]);
+                                }
+                                *reinterpret_cast<uint4*>(out_row + off) = make_uint4(res[0], res[1], res[2], res[3]);
+                            }
+                            if (want_sums) {
+                                cs_g[j] += gn_warp_colsum32(v, lane);
+                                cs_x[j] += gn_warp_colsum32(gx, lane);
+                            }
+                        }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_eready[es]);
+                        if (++es == p.e_stages) { es = 0; eph ^= 1; }
                     }
                 }
             }
@@ -285,9 +445,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (acc == 0) acc_phase ^= 1;
         }
         flush_colsums();
-    } else if (XFORM) {
+    } else if (XFORM && warp >= 12) {
         // ===================== operand transform: A <- relu(A * scale[k] + shift[k]) in place =====================
-        const int w = warp - 6;
+        const int w = warp - 12;
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -306,13 +466,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const float4 t0 = *reinterpret_cast<const float4*>(s_xf + GEMM_MAX_XF_K + k0);
                     const float4 t1 = *reinterpret_cast<const float4*>(s_xf + GEMM_MAX_XF_K + k0 + 4);
                     float2 f;
-                    f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v.x));
+                    f = unpack_bf16x2(v.x);
                     v.x = pack_bf16x2(fmaxf(fmaf(f.x, s0.x, t0.x), 0.f), fmaxf(fmaf(f.y, s0.y, t0.y), 0.f));
-                    f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v.y));
+                    f = unpack_bf16x2(v.y);
                     v.y = pack_bf16x2(fmaxf(fmaf(f.x, s0.z, t0.z), 0.f), fmaxf(fmaf(f.y, s0.w, t0.w), 0.f));
-                    f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v.z));
+                    f = unpack_bf16x2(v.z);
                     v.z = pack_bf16x2(fmaxf(fmaf(f.x, s1.x, t1.x), 0.f), fmaxf(fmaf(f.y, s1.y, t1.y), 0.f));
-                    f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v.w));
+                    f = unpack_bf16x2(v.w);
                     v.w = pack_bf16x2(fmaxf(fmaf(f.x, s1.z, t1.z), 0.f), fmaxf(fmaf(f.y, s1.w, t1.w), 0.f));
                     *ptr = v;
                 }
@@ -325,24 +485,53 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (warp == 3) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int BN, bool XFORM>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+template <int BN, bool XFORM, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRef, GemmParams& p,
+                       cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
-    static bool attr_set = false;
-    const size_t smem = Cfg::smem_bytes(XFORM);
-    if (!attr_set) {
-        GN_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    const int budget = 227 * 1024 - 1024 - 512;        // dynamic shared memory minus alignment slack and static barriers
+    int fixed = XFORM ? 2 * GEMM_MAX_XF_K * 4 : 0;
+    if (EPI != EPI_DIRECT) {
+        p.slot_bytes = (EPI == EPI_BNBWD && p.bn.rmw) ? 2 * GEMM_SUB_BYTES : GEMM_SUB_BYTES;
+        p.e_stages = p.slot_bytes == GEMM_SUB_BYTES ? 4 : 3;
+        fixed += 4 * GEMM_EPI_MAX_N * 4 + p.e_stages * p.slot_bytes;
+    } else {
+        p.slot_bytes = 0;
+        p.e_stages = 1;
+    }
+    int stages = (budget - fixed) / Cfg::STAGE_BYTES;
+    if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
+    if (stages > 2 * p.num_k_blocks && stages > 2) stages = 2 * p.num_k_blocks > 2 ? 2 * p.num_k_blocks : 2;
+    GN_REQUIRE(stages >= 2, GN_EUNSUPPORTED, "gemm_bf16: shared memory budget exhausted (BN %d)", BN);
+    p.stages = stages;
+    const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + fixed + 1024;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        GN_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, XFORM, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
     }
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     const int grid = tiles < gn_num_sms() ? tiles : gn_num_sms();
-    gemm_bf16_kernel<BN, XFORM><<<grid, XFORM ? 320 : 192, smem, stream>>>(tmA, tmB, p);
+    gemm_bf16_kernel<BN, XFORM, EPI><<<grid, XFORM ? 512 : 384, smem, stream>>>(tmA, tmB, tmOut, tmRef, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
+
+template <int BN>
+static int dispatch_gemm(bool xform, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRef,
+                         GemmParams& p, cudaStream_t stream) {
+    if (epi == EPI_BNBWD) return launch_gemm<BN, false, EPI_BNBWD>(tmA, tmB, tmOut, tmRef, p, stream);
+    if (epi == EPI_STORE)
+        return xform ? launch_gemm<BN, true, EPI_STORE>(tmA, tmB, tmOut, tmRef, p, stream)
+                     : launch_gemm<BN, false, EPI_STORE>(tmA, tmB, tmOut, tmRef, p, stream);
+    return xform ? launch_gemm<BN, true, EPI_DIRECT>(tmA, tmB, tmOut, tmRef, p, stream)
+                 : launch_gemm<BN, false, EPI_DIRECT>(tmA, tmB, tmOut, tmRef, p, stream);
+}
+
+static inline bool tma_ok(const void* ptr, long ld_elems) { return ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) && (ld_elems % 8 == 0); }
 
 // a: [M, K] bf16 with row pitch lda; b: [N, K] bf16 with row pitch ldb; out: [M, ldc] bf16 or fp32
 GN_API int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M, int N, int K, void* out, long ldc, int out_fp32,
@@ -358,6 +547,7 @@ GN_API int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M,
     GN_REQUIRE(!xform || K <= GEMM_MAX_XF_K, GN_EUNSUPPORTED, "gemm_bf16: operand transform supports K <= %d", GEMM_MAX_XF_K);
     const int BN = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
     GemmParams p;
+    memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K;
     p.num_m_blocks = gn_ceil_div(M, GEMM_BM);
     p.num_n_blocks = gn_ceil_div(N, BN);
@@ -365,27 +555,37 @@ GN_API int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M,
     p.out = out; p.ldc = ldc; p.out_fp32 = out_fp32; p.accumulate = accumulate;
     p.scale = scale; p.shift = shift; p.relu = relu; p.xf_scale = xf_scale; p.xf_shift = xf_shift;
     p.epi_mode = bn_ref != nullptr ? 1 : 0;
-    memset(&p.bn, 0, sizeof(p.bn));
     if (p.epi_mode == 1) {
         GN_REQUIRE(!out_fp32 && !accumulate && !scale && !shift && !relu, GN_EINVAL, "gemm_bf16: BN-backward epilogue needs a plain bf16 output");
+        GN_REQUIRE(!xform, GN_EUNSUPPORTED, "gemm_bf16: BN-backward epilogue cannot be combined with the operand transform");
         GN_REQUIRE(bn_sc && bn_p0 && bn_p1 && (!bn_ref_is_raw || bn_sh), GN_EINVAL, "gemm_bf16: incomplete BN-backward epilogue arguments");
         p.bn.ref = (const __nv_bfloat16*)bn_ref; p.bn.ldref = bn_ldref; p.bn.ref_is_raw = bn_ref_is_raw;
         p.bn.sc = bn_sc; p.bn.sh = bn_sh; p.bn.p0 = bn_p0; p.bn.p1 = bn_p1; p.bn.colsum = bn_colsum; p.bn.ldsum = bn_ldsum; p.bn.rmw = bn_rmw;
     }
-    CUtensorMap tmA, tmB;
+    // TMA-staged epilogue whenever the output (and reference) views can be described by a tensor map
+    int epi = EPI_DIRECT;
+    if (!out_fp32 && N <= GEMM_EPI_MAX_N && tma_ok(out, ldc) && (p.epi_mode == 0 || tma_ok(bn_ref, bn_ldref)))
+        epi = p.epi_mode == 1 ? EPI_BNBWD : EPI_STORE;
+    CUtensorMap tmA, tmB, tmOut, tmRef;
+    memset(&tmOut, 0, sizeof(tmOut));
+    memset(&tmRef, 0, sizeof(tmRef));
     int rc = gn_tmap_bf16_2d(&tmA, a, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BK, GEMM_BM);
     if (rc) return rc;
     rc = gn_tmap_bf16_2d(&tmB, b, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, GEMM_BK, (uint32_t)BN);
     if (rc) return rc;
-#define GN_DISPATCH(BNv)                                                                  \
-    case BNv:                                                                             \
-        return xform ? launch_gemm<BNv, true>(tmA, tmB, p, stream) : launch_gemm<BNv, false>(tmA, tmB, p, stream);
-    switch (BN) {
-        GN_DISPATCH(32)
-        GN_DISPATCH(64)
-        GN_DISPATCH(128)
-        GN_DISPATCH(256)
+    if (epi != EPI_DIRECT) {
+        rc = gn_tmap_bf16_2d(&tmOut, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 64, GEMM_BM);
+        if (rc) return rc;
+        if (epi == EPI_BNBWD) {
+            rc = gn_tmap_bf16_2d(&tmRef, bn_ref, (uint64_t)M, (uint64_t)N, (uint64_t)bn_ldref, 64, GEMM_BM);
+            if (rc) return rc;
+        }
     }
-#undef GN_DISPATCH
+    switch (BN) {
+        case 32: return dispatch_gemm<32>(xform, epi, tmA, tmB, tmOut, tmRef, p, stream);
+        case 64: return dispatch_gemm<64>(xform, epi, tmA, tmB, tmOut, tmRef, p, stream);
+        case 128: return dispatch_gemm<128>(xform, epi, tmA, tmB, tmOut, tmRef, p, stream);
+        case 256: return dispatch_gemm<256>(xform, epi, tmA, tmB, tmOut, tmRef, p, stream);
+    }
     return GN_EINVAL;
 }
