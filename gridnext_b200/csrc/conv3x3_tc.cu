@@ -11,7 +11,8 @@
 // 128-byte row offset is legal -- checked on hardware with tools/umma_probe).  Weights for all nine taps stay
 // resident in shared memory for the life of the persistent CTA.  The epilogue is staged through shared memory:
 // the BN reference tile arrives by TMA (one box per padded row), results are written in place and leave as TMA row
-// stores whose border positions (x' = 0, W+1) fall outside the tensor map and are dropped by the hardware.
+// stores of the W interior positions of every padded row (TMA stores fault on a negative start coordinate --
+// measured with tools/tma_store_probe -- so the x' = 0 border is skipped by the source address instead).
 //
 #include "gn_common.cuh"
 #include "gn_ptx.cuh"
@@ -213,7 +214,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                         int n, yp;
                         c3_row_coords(Rg0 + r, total_rows, H2, p.Nimg, n, yp);
                         if (n >= 0 && n < p.Nimg && yp >= 1 && yp <= p.H)
-                            tma_store_4d(&tmOut, slot + (size_t)r * W2 * 128, j * 64, -1, yp - 1, n);
+                            tma_store_4d(&tmOut, slot + ((size_t)r * W2 + 1) * 128, j * 64, 0, yp - 1, n);   // skip the x' = 0 border position
                     }
                     tma_store_commit();
                     if (prev_es >= 0) {
@@ -417,7 +418,7 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     {
         uint64_t dims[4] = {(uint64_t)CO, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t strides[3] = {(uint64_t)ldo * 2, (uint64_t)W * ldo * 2, (uint64_t)H * W * ldo * 2};
-        uint32_t box[4] = {64, (uint32_t)W2, 1, 1};
+        uint32_t box[4] = {64, (uint32_t)W, 1, 1};        // stores may not start at a negative coordinate (tools/tma_store_probe)
         int rc = gn_tmap_encode(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
