@@ -47,11 +47,48 @@ __device__ __forceinline__ uint32_t c3_pack_bf16x2(float a, float b) {
 }
 __device__ __forceinline__ float2 c3_unpack_bf16x2(uint32_t w) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w)); }
 
-// padded row index -> (image, padded y); rows outside [0, Nimg*H2) map to an out-of-bounds image index
-__device__ __forceinline__ void c3_row_coords(long Rg, long total_rows, int H2, int Nimg, int& n, int& yp) {
-    if (Rg < 0) { n = -1; yp = 0; }
+// padded row index -> (image, padded y); rows outside [0, Nimg*H2) map to an out-of-bounds image index.
+// 32-bit arithmetic only: a 64-bit division per TMA row made the single producer thread the bottleneck.
+__device__ __forceinline__ void c3_row_coords(int Rg, int total_rows, int H2, int Nimg, int& n, int& yp) {
+    if (Rg < 0) { n = -1; yp = H2 + Rg; }          // only Rg = -1 occurs: continue into image 0 at yp = 0 after one step
     else if (Rg >= total_rows) { n = Nimg; yp = 0; }
-    else { n = (int)(Rg / H2); yp = (int)(Rg % H2); }
+    else { n = Rg / H2; yp = Rg - n * H2; }
+}
+__device__ __forceinline__ void c3_row_next(int H2, int& n, int& yp) {
+    if (++yp == H2) { yp = 0; ++n; }
+}
+
+// All MMAs of one tile, straight-line when the k-block structure is known at compile time (KB_T k-blocks of K16_T
+// 16-channel steps; KB_T = 0: run-time loops).  The single issuing thread must not spend more than ~45 cycles per
+// MMA on index arithmetic or it, not the tensor pipe, sets the pace (measured with tools/umma_rate).
+template <int KB_T, int K16_T>
+__device__ __forceinline__ void c3_issue_tile(uint32_t d, uint64_t descA, uint64_t descW, uint32_t idesc, int W2, int kb_buf16, int w_tile16,
+                                              int kblocks, int CI) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int row = (t / 3) * W2 + (t % 3) - 1;          // buffer row feeding accumulator row 0 for this tap
+        const uint64_t da = descA + (uint64_t)(int64_t)(row * 8);
+        if (KB_T > 0) {
+            const uint64_t dw = descW + (uint64_t)(t * KB_T * w_tile16);
+#pragma unroll
+            for (int kb = 0; kb < KB_T; ++kb)
+#pragma unroll
+                for (int k = 0; k < K16_T; ++k) {
+                    umma_bf16(d, da + (uint64_t)(kb * kb_buf16 + k * 2), dw + (uint64_t)(kb * w_tile16 + k * 2), idesc, acc);
+                    acc = 1;
+                }
+        } else {
+            const uint64_t dw = descW + (uint64_t)(t * kblocks * w_tile16);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int k16n = (min(64, CI - kb * 64) + 15) >> 4;
+                for (int k = 0; k < k16n; ++k) {
+                    umma_bf16(d, da + (uint64_t)(kb * kb_buf16 + k * 2), dw + (uint64_t)(kb * w_tile16 + k * 2), idesc, acc);
+                    acc = 1;
+                }
+            }
+        }
+    }
 }
 
 // Tile = R consecutive PADDED image rows (R * (W+2) <= 128 positions, accumulator row i = position i of the tile).
@@ -71,7 +108,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int W2 = p.W + 2, H2 = p.H + 2, R = p.R;
-    const long total_rows = (long)p.Nimg * H2;
+    const int total_rows = p.Nimg * H2;
     const int w_tile_bytes = p.NP * p.w_row_bytes;                       // one (tap, k-block) weight tile (rows beyond CO: next tap / zero fill, never stored)
     const int w_bytes = ((9 * p.kblocks * w_tile_bytes + 1023) / 1024) * 1024;
     const int kb_buf_bytes = p.a_rows * 128;                             // one k-block of one stage
@@ -126,14 +163,17 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 mbar_wait(&bar_empty[stage], phase ^ 1);
-                const long Rg0 = (long)tile * R;
+                const int Rg0 = tile * R;
+                int n, yp;
+                c3_row_coords(Rg0 - 1, total_rows, H2, p.Nimg, n, yp);
                 mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)((R + 2) * W2 * 128 * p.kblocks));
+                uint8_t* dst = s_a + (size_t)stage * stage_bytes + 1024;
                 for (int lr = 0; lr < R + 2; ++lr) {
-                    int n, yp;
-                    c3_row_coords(Rg0 - 1 + lr, total_rows, H2, p.Nimg, n, yp);
+                    const int nn = n < p.Nimg ? n : p.Nimg;     // past the last image: any out-of-bounds index (zero fill)
                     for (int kb = 0; kb < p.kblocks; ++kb)
-                        tma_load_4d(&tmX, &bar_full[stage], s_a + (size_t)stage * stage_bytes + (size_t)kb * kb_buf_bytes + 1024 + (size_t)lr * W2 * 128,
-                                    kb * 64, -1, yp - 1, n);
+                        tma_load_4d(&tmX, &bar_full[stage], dst + (size_t)kb * kb_buf_bytes, kb * 64, -1, yp - 1, nn);
+                    dst += W2 * 128;
+                    c3_row_next(H2, n, yp);
                 }
                 if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
             }
@@ -154,21 +194,12 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 mbar_wait(&bar_full[stage], phase);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(acc * 256);
-                const uint32_t a_stage = smem_u32(s_a + (size_t)stage * stage_bytes) + 1024;   // buffer row 0 = local padded row -1, x' = 0
-                uint32_t first = 1;
-                for (int t = 0; t < 9; ++t) {
-                    const int row = (t / 3) * W2 + (t % 3) - 1;          // buffer row feeding accumulator row 0 for this tap
-                    for (int kb = 0; kb < p.kblocks; ++kb) {
-                        const int kc = min(64, p.CI - kb * 64);
-                        const int k16n = (kc + 15) >> 4;
-                        const uint32_t a_addr = a_stage + kb * kb_buf_bytes + row * 128;
-                        const uint32_t w_addr = w_base + (t * p.kblocks + kb) * w_tile_bytes;
-                        for (int k = 0; k < k16n; ++k) {
-                            umma_bf16(d, smem_desc(tmplA, a_addr + k * 32), smem_desc(tmplW, w_addr + k * 32), idesc, first ^ 1u);
-                            first = 0;
-                        }
-                    }
-                }
+                const uint64_t descA = smem_desc(tmplA, smem_u32(s_a + (size_t)stage * stage_bytes) + 1024);   // buffer row 0 = local padded row -1, x' = 0
+                const uint64_t descW = smem_desc(tmplW, w_base);
+                const int kb_buf16 = kb_buf_bytes >> 4, w_tile16 = w_tile_bytes >> 4;
+                if (p.CI == 128) c3_issue_tile<2, 4>(d, descA, descW, idesc, W2, kb_buf16, w_tile16, p.kblocks, p.CI);
+                else if (p.CI == 32) c3_issue_tile<1, 2>(d, descA, descW, idesc, W2, kb_buf16, w_tile16, p.kblocks, p.CI);
+                else c3_issue_tile<0, 0>(d, descA, descW, idesc, W2, kb_buf16, w_tile16, p.kblocks, p.CI);
                 umma_commit(&bar_empty[stage]);
                 umma_commit(&bar_tfull[acc]);
                 if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
@@ -182,16 +213,17 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             int es = 0;
             uint32_t eph = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const long Rg0 = (long)tile * R;
+                const int Rg0 = tile * R;
                 for (int j = 0; j < p.nsub; ++j) {
                     mbar_wait(&bar_eempty[es], eph ^ 1);
                     if (p.epi_mode == 1) {
                         uint8_t* slot = s_slots + (size_t)es * C3_SUB_BYTES;
                         mbar_arrive_expect_tx(&bar_efull[es], (uint32_t)(R * W2 * 128));
+                        int n, yp;
+                        c3_row_coords(Rg0, total_rows, H2, p.Nimg, n, yp);
                         for (int r = 0; r < R; ++r) {
-                            int n, yp;
-                            c3_row_coords(Rg0 + r, total_rows, H2, p.Nimg, n, yp);
-                            tma_load_4d(&tmRef, &bar_efull[es], slot + (size_t)r * W2 * 128, j * 64, -1, yp - 1, n);
+                            tma_load_4d(&tmRef, &bar_efull[es], slot + (size_t)r * W2 * 128, j * 64, -1, yp - 1, n < p.Nimg ? n : p.Nimg);
+                            c3_row_next(H2, n, yp);
                         }
                     } else {
                         mbar_arrive(&bar_efull[es]);
@@ -206,15 +238,17 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             int es = 0, prev_es = -1;
             uint32_t eph = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const long Rg0 = (long)tile * R;
+                const int Rg0 = tile * R;
+                int n0, yp0;
+                c3_row_coords(Rg0, total_rows, H2, p.Nimg, n0, yp0);
                 for (int j = 0; j < p.nsub; ++j) {
                     mbar_wait(&bar_eready[es], eph);
                     const uint8_t* slot = s_slots + (size_t)es * C3_SUB_BYTES;
+                    int n = n0, yp = yp0;
                     for (int r = 0; r < R; ++r) {
-                        int n, yp;
-                        c3_row_coords(Rg0 + r, total_rows, H2, p.Nimg, n, yp);
-                        if (n >= 0 && n < p.Nimg && yp >= 1 && yp <= p.H)
+                        if (n < p.Nimg && yp >= 1 && yp <= p.H)
                             tma_store_4d(&tmOut, slot + ((size_t)r * W2 + 1) * 128, j * 64, 0, yp - 1, n);   // skip the x' = 0 border position
+                        c3_row_next(H2, n, yp);
                     }
                     tma_store_commit();
                     if (prev_es >= 0) {
@@ -248,7 +282,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             mbar_wait(&bar_tfull[acc], acc_phase);
             tc_fence_after();
             int n, yp;
-            c3_row_coords((long)tile * R + r_loc, total_rows, H2, p.Nimg, n, yp);
+            c3_row_coords(tile * R + r_loc, total_rows, H2, p.Nimg, n, yp);
             const bool valid = r_loc < R && n >= 0 && n < p.Nimg && yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * 256);
 #pragma unroll
@@ -286,7 +320,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                                         const float sc = cst[e];
                                         const float a = is_raw ? fmaf(ref, sc, cst[C3_MAX_CO + e]) : ref;
                                         const float gg = (valid && a > 0.f) ? __uint_as_float(r[e]) : 0.f;
-                                        gx[e] = gg * (ref - cst[2 * C3_MAX_CO + e]) * cst[3 * C3_MAX_CO + e];
+                                        gx[e] = gg * ref;          // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
                                         v[e] = gg;
                                         o2[u] = gg * sc;
                                     }
@@ -318,7 +352,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 const int col = j * 64 + h * 32 + lane;
                 if (j < p.nsub && col < p.CO) {
                     atomicAdd(p.bn.colsum + col, cs_g[j]);
-                    atomicAdd(p.bn.colsum + p.bn.ldsum + col, cs_x[j]);
+                    atomicAdd(p.bn.colsum + p.bn.ldsum + col, __ldg(p.bn.p1 + col) * (cs_x[j] - __ldg(p.bn.p0 + col) * cs_g[j]));
                 }
             }
         }
@@ -494,24 +528,24 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 mbar_wait(&bar_empty[stage], phase ^ 1);
                 uint8_t* sa = sm + (size_t)stage * stage_bytes;
-                const long P0 = (long)tile * 128;
-                const long lo = P0 - HALO;
-                const long R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
-                const long R1 = (P0 + 127 + HALO) / W2;
+                const int P0 = tile * 128;
+                const int lo = P0 - HALO;
+                const int R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
+                const int R1 = (P0 + 127 + HALO) / W2;
                 const int nr = (int)(R1 - R0 + 1);
-                const long Q0 = P0 / W2, Q1 = (P0 + 127) / W2;
+                const int Q0 = P0 / W2, Q1 = (P0 + 127) / W2;
                 const int nq = (int)(Q1 - Q0 + 1);
                 mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)((2 * nr + nq) * W2 * 128));
                 for (int r = 0; r < nr; ++r) {
-                    const long R = R0 + r;
+                    const int R = R0 + r;
                     int n, yp;
-                    if (R >= 0) { n = (int)(R / H2); yp = (int)(R % H2); } else { n = -1; yp = 0; }
+                    if (R >= 0) { n = R / H2; yp = R - n * H2; } else { n = -1; yp = 0; }
                     for (int g = 0; g < 2; ++g)
                         tma_load_4d(&tmX, &bar_full[stage], sa + (size_t)g * a_group_bytes + (size_t)r * W2 * 128, g * 64, -1, yp - 1, n);
                 }
                 for (int r = 0; r < nq; ++r) {
-                    const long R = Q0 + r;
-                    tma_load_4d(&tmDY, &bar_full[stage], sa + a_bytes + (size_t)r * W2 * 128, 0, -1, (int)(R % H2) - 1, (int)(R / H2));
+                    const int R = Q0 + r;
+                    tma_load_4d(&tmDY, &bar_full[stage], sa + a_bytes + (size_t)r * W2 * 128, 0, -1, R % H2 - 1, R / H2);
                 }
                 if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
             }
@@ -527,9 +561,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 mbar_wait(&bar_full[stage], phase);
                 tc_fence_after();
-                const long P0 = (long)tile * 128;
-                const long lo = P0 - HALO;
-                const long R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
+                const int P0 = tile * 128;
+                const int lo = P0 - HALO;
+                const int R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
                 const int a_row0 = (int)(P0 - R0 * W2);
                 const int b_row0 = (int)(P0 - (P0 / W2) * W2);
                 const uint32_t a_base = smem_u32(sm + (size_t)stage * stage_bytes);

@@ -299,7 +299,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int col = cur_nb * BN + j * 64 + h * 32 + lane;
                     if (col < p.N) {
                         atomicAdd(p.bn.colsum + col, cs_g[j]);
-                        atomicAdd(p.bn.colsum + p.bn.ldsum + col, cs_x[j]);
+                        const float sx = EPI == EPI_BNBWD ? __ldg(p.bn.p1 + col) * (cs_x[j] - __ldg(p.bn.p0 + col) * cs_g[j]) : cs_x[j];
+                        atomicAdd(p.bn.colsum + p.bn.ldsum + col, sx);
                     }
                     cs_g[j] = 0.f; cs_x[j] = 0.f;
                 }
@@ -417,7 +418,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                         const float sc = cst[e];
                                         const float a = is_raw ? fmaf(ref, sc, cst[GEMM_EPI_MAX_N + e]) : ref;
                                         const float gg = a > 0.f ? __uint_as_float(r[e]) : 0.f;
-                                        gx[e] = gg * (ref - cst[2 * GEMM_EPI_MAX_N + e]) * cst[3 * GEMM_EPI_MAX_N + e];
+                                        gx[e] = gg * ref;          // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
                                         v[e] = gg;
                                         o2[u] = rmw ? fmaf(gg, sc, old) : gg * sc;
                                     }
@@ -452,29 +453,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&bar_full[stage], phase);
-                uint8_t* sa = sm + (size_t)stage * Cfg::STAGE_BYTES;
+                // row & 7 of the rows this lane touches is ((i & 1) * 4 + (lane >> 3)): two sets of 8 constants per k-block
+                const int pc = lane & 7;                            // physical 16-byte chunk in the 128-byte row
+                float cs[2][8], ct[2][8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = w * 32 + i * 4 + (lane >> 3);
-                    const int pc = lane & 7;                        // physical 16-byte chunk in the 128-byte row
-                    const int k0 = kb * GEMM_BK + ((pc ^ (row & 7)) << 3);   // logical K index of its first element
-                    uint4* ptr = reinterpret_cast<uint4*>(sa + row * 128 + pc * 16);
-                    uint4 v = *ptr;
+                for (int par = 0; par < 2; ++par) {
+                    const int k0 = kb * GEMM_BK + ((pc ^ (par * 4 + (lane >> 3))) << 3);   // logical K index of the chunk's first element
                     const float4 s0 = *reinterpret_cast<const float4*>(s_xf + k0);
                     const float4 s1 = *reinterpret_cast<const float4*>(s_xf + k0 + 4);
                     const float4 t0 = *reinterpret_cast<const float4*>(s_xf + GEMM_MAX_XF_K + k0);
                     const float4 t1 = *reinterpret_cast<const float4*>(s_xf + GEMM_MAX_XF_K + k0 + 4);
+                    cs[par][0] = s0.x; cs[par][1] = s0.y; cs[par][2] = s0.z; cs[par][3] = s0.w;
+                    cs[par][4] = s1.x; cs[par][5] = s1.y; cs[par][6] = s1.z; cs[par][7] = s1.w;
+                    ct[par][0] = t0.x; ct[par][1] = t0.y; ct[par][2] = t0.z; ct[par][3] = t0.w;
+                    ct[par][4] = t1.x; ct[par][5] = t1.y; ct[par][6] = t1.z; ct[par][7] = t1.w;
+                }
+                mbar_wait(&bar_full[stage], phase);
+                uint8_t* sa = sm + (size_t)stage * Cfg::STAGE_BYTES + (w * 32 + (lane >> 3)) * 128 + pc * 16;
+                uint4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(sa + i * 512);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int par = i & 1;
                     float2 f;
-                    f = unpack_bf16x2(v.x);
-                    v.x = pack_bf16x2(fmaxf(fmaf(f.x, s0.x, t0.x), 0.f), fmaxf(fmaf(f.y, s0.y, t0.y), 0.f));
-                    f = unpack_bf16x2(v.y);
-                    v.y = pack_bf16x2(fmaxf(fmaf(f.x, s0.z, t0.z), 0.f), fmaxf(fmaf(f.y, s0.w, t0.w), 0.f));
-                    f = unpack_bf16x2(v.z);
-                    v.z = pack_bf16x2(fmaxf(fmaf(f.x, s1.x, t1.x), 0.f), fmaxf(fmaf(f.y, s1.y, t1.y), 0.f));
-                    f = unpack_bf16x2(v.w);
-                    v.w = pack_bf16x2(fmaxf(fmaf(f.x, s1.z, t1.z), 0.f), fmaxf(fmaf(f.y, s1.w, t1.w), 0.f));
-                    *ptr = v;
+                    f = unpack_bf16x2(v[i].x);
+                    v[i].x = pack_bf16x2(fmaxf(fmaf(f.x, cs[par][0], ct[par][0]), 0.f), fmaxf(fmaf(f.y, cs[par][1], ct[par][1]), 0.f));
+                    f = unpack_bf16x2(v[i].y);
+                    v[i].y = pack_bf16x2(fmaxf(fmaf(f.x, cs[par][2], ct[par][2]), 0.f), fmaxf(fmaf(f.y, cs[par][3], ct[par][3]), 0.f));
+                    f = unpack_bf16x2(v[i].z);
+                    v[i].z = pack_bf16x2(fmaxf(fmaf(f.x, cs[par][4], ct[par][4]), 0.f), fmaxf(fmaf(f.y, cs[par][5], ct[par][5]), 0.f));
+                    f = unpack_bf16x2(v[i].w);
+                    v[i].w = pack_bf16x2(fmaxf(fmaf(f.x, cs[par][6], ct[par][6]), 0.f), fmaxf(fmaf(f.y, cs[par][7], ct[par][7]), 0.f));
+                    *reinterpret_cast<uint4*>(sa + i * 512) = v[i];
                 }
                 fence_proxy_async_smem();
                 __syncwarp();

@@ -80,14 +80,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 int mb, nb, kb0, kb1;
                 decode(u, mb, nb, kb0, kb1);
+                const int ngroups = (min(TN_BN, p.No - nb * TN_BN) + 63) >> 6;      // 64-column groups of B that hold data
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     uint8_t* sa = sm + (size_t)stage * TN_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&bar_full[stage], TN_STAGE_BYTES);
+                    mbar_arrive_expect_tx(&bar_full[stage], TN_A_BYTES + ngroups * TN_GROUP_BYTES);
 #pragma unroll
                     for (int g = 0; g < 2; ++g) tma_load_2d(&tmA, &bar_full[stage], sa + g * TN_GROUP_BYTES, mb * TN_BM + g * 64, kb * TN_BK);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
+                    for (int g = 0; g < ngroups; ++g)
                         tma_load_2d(&tmB, &bar_full[stage], sa + TN_A_BYTES + g * TN_GROUP_BYTES, nb * TN_BN + g * 64, kb * TN_BK);
                     if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -95,7 +95,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = idesc_bf16(TN_BM, TN_BN, 1, 1);
             constexpr uint64_t tmpl = smem_desc_template(TN_GROUP_BYTES, 1024, LAYOUT_SW128);
             int stage = 0;
             uint32_t phase = 0;
@@ -107,6 +106,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(acc * TN_BN);
+                const uint32_t idesc = idesc_bf16(TN_BM, ((min(TN_BN, p.No - nb * TN_BN) + 63) >> 6) * 64, 1, 1);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(XFORM ? &bar_xf[stage] : &bar_full[stage], phase);
                     tc_fence_after();
@@ -136,8 +136,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int row = mb * TN_BM + g * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * TN_BN);
             if (kb1 > kb0) {
+                const int ncols_tile = ((min(TN_BN, p.No - nb * TN_BN) + 63) >> 6) * 64;
 #pragma unroll 1
-                for (int c0 = 0; c0 < TN_BN; c0 += 32) {
+                for (int c0 = 0; c0 < ncols_tile; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld32(taddr + c0, r);
                     tmem_ld_wait();
@@ -172,33 +173,45 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             int mb, nb, kb0, kb1;
             decode(u, mb, nb, kb0, kb1);
+            const int ngroups = (min(TN_BN, p.No - nb * TN_BN) + 63) >> 6;
+            const bool active = w < ngroups;
+            const int pc = lane & 7;
+            // row & 7 of the rows this lane touches is ((i & 1) * 4 + (lane >> 3)): two sets of 8 constants per unit
+            float cs[2][8], ct[2][8];
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+                const int n0 = nb * TN_BN + w * 64 + ((pc ^ (par * 4 + (lane >> 3))) << 3);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool ok = active && n0 + j < p.No;
+                    cs[par][j] = ok ? __ldg(p.xf_scale + n0 + j) : 0.f;
+                    ct[par][j] = ok ? __ldg(p.xf_shift + n0 + j) : 0.f;
+                }
+            }
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&bar_full[stage], phase);
-                uint8_t* sb = sm + (size_t)stage * TN_STAGE_BYTES + TN_A_BYTES;
-                // 256 rows-of-128B in the 4 groups; warp w owns group w; 16 iterations x (4 rows x 8 chunks)
-#pragma unroll 4
-                for (int i = 0; i < 16; ++i) {
-                    const int row = i * 4 + (lane >> 3);
-                    const int pc = lane & 7;
-                    const int n0 = nb * TN_BN + w * 64 + ((pc ^ (row & 7)) << 3);
-                    uint4* ptr = reinterpret_cast<uint4*>(sb + w * TN_GROUP_BYTES + row * 128 + pc * 16);
-                    uint4 v = *ptr;
-                    float sc[8], sh[8];
+                if (active) {
+                    uint8_t* sb = sm + (size_t)stage * TN_STAGE_BYTES + TN_A_BYTES + w * TN_GROUP_BYTES + (lane >> 3) * 128 + pc * 16;
+                    // 64 rows-of-128B of group w; 2 batches of 8 iterations x (4 rows x 8 chunks)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const bool ok = n0 + j < p.No;
-                        sc[j] = ok ? __ldg(p.xf_scale + n0 + j) : 0.f;
-                        sh[j] = ok ? __ldg(p.xf_shift + n0 + j) : 0.f;
-                    }
-                    uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
+                    for (int b = 0; b < 2; ++b) {
+                        uint4 v[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&vv[q]));
-                        __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(fmaf(f.x, sc[2 * q], sh[2 * q]), 0.f),
-                                                                  fmaxf(fmaf(f.y, sc[2 * q + 1], sh[2 * q + 1]), 0.f));
-                        vv[q] = *reinterpret_cast<uint32_t*>(&o);
+                        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(sb + (b * 8 + i) * 512);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int par = i & 1;
+                            uint32_t* vv = reinterpret_cast<uint32_t*>(&v[i]);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&vv[q]));
+                                __nv_bfloat162 o = __floats2bfloat162_rn(fmaxf(fmaf(f.x, cs[par][2 * q], ct[par][2 * q]), 0.f),
+                                                                          fmaxf(fmaf(f.y, cs[par][2 * q + 1], ct[par][2 * q + 1]), 0.f));
+                                vv[q] = *reinterpret_cast<uint32_t*>(&o);
+                            }
+                            *reinterpret_cast<uint4*>(sb + (b * 8 + i) * 512) = v[i];
+                        }
                     }
-                    *ptr = v;
                 }
                 fence_proxy_async_smem();
                 __syncwarp();

@@ -60,7 +60,7 @@ int gn_tmap_encode(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const 
         GN_REQUIRE((gs[i] & 15) == 0, GN_EALIGN, "TMA: stride %llu of dim %d is not a multiple of 16 bytes", (unsigned long long)gs[i], i + 1);
     }
     CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(gaddr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);   // 256B promotion over-fetches column slices of the concat buffers
     GN_REQUIRE(r == CUDA_SUCCESS, GN_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, box %u x %u)", (int)r,
                rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 1), box[0], rank > 1 ? box[1] : 1);
     return GN_OK;
