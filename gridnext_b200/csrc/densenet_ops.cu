@@ -127,22 +127,36 @@ __global__ void __launch_bounds__(256) maxpool3s2_fwd_kernel(const __nv_bfloat16
 
 // dZ0[pixel, c] = (sum of dPool over the windows whose arg-max is this pixel) * [act0 > 0] * s0[c]; BN0 column sums.
 // act0 is the ACTIVATED stem output: xhat = (act0 - beta) / gamma where act0 > 0.
+// Thread layout of the backward pooling kernels: a thread owns ONE group of 8 channels for its whole life (its BatchNorm
+// constants and column partial sums stay in registers) and walks pixels with 32-bit index arithmetic; blockDim = G * ppb.
+// Column sums: sum g and sum g*ref per channel; xhat is applied once at the end: p1 * (sum g*ref - p0 * sum g).
+__device__ __forceinline__ void colsum_thread_flush(float* s_sum, int C, int cg, const float (&sg)[8], const float (&sx)[8],
+                                                    const float* __restrict__ p0, const float* __restrict__ p1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+        atomicAdd(&s_sum[c], sg[j]);
+        atomicAdd(&s_sum[C + c], __ldg(p1 + c) * (sx[j] - __ldg(p0 + c) * sg[j]));
+    }
+}
+
 __global__ void __launch_bounds__(256) maxpool3s2_bnrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, long ldp,
                                                                     const unsigned char* __restrict__ idx,
                                                                     const __nv_bfloat16* __restrict__ act, long lda, int N, int Hi, int Wi,
                                                                     int C, const float* __restrict__ sc, const float* __restrict__ p0,
                                                                     const float* __restrict__ p1, __nv_bfloat16* __restrict__ dz, long ldz,
-                                                                    float* __restrict__ colsum, int ldsum) {
+                                                                    float* __restrict__ colsum, int ldsum, int G, int ppb) {
     extern __shared__ float s_sum[];
     colsum_block_begin(s_sum, C);
-    const int Ho = Hi / 2, Wo = Wi / 2, G = C / 8;
-    const long total = (long)N * Hi * Wi * G;
-    ColAcc ca; ca.init();
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(e % G);
-        const long ip = e / G;
-        const int ix = (int)(ip % Wi), iy = (int)((ip / Wi) % Hi), n = (int)(ip / ((long)Wi * Hi));
-        ca.select(cg, s_sum, C);
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    const int cg = threadIdx.x % G, pl = threadIdx.x / G;
+    const V8 s = ld_f32x8(sc + cg * 8);
+    float sg[8], sx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sx[j] = 0.f; }
+    const int npix = N * Hi * Wi;
+    for (int ip = blockIdx.x * ppb + pl; ip < npix; ip += gridDim.x * ppb) {
+        const int ix = ip % Wi, t = ip / Wi, iy = t % Hi, n = t / Hi;
         V8 g;
 #pragma unroll
         for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
@@ -157,24 +171,23 @@ __global__ void __launch_bounds__(256) maxpool3s2_bnrelu_bwd_kernel(const __nv_b
                 const V8 d = ld_bf16x8(dpool + op * ldp + cg * 8);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const unsigned b = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xff;
-                    if ((int)b == k) g.v[j] += d.v[j];
+                    const unsigned bsel = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xff;
+                    if ((int)bsel == k) g.v[j] += d.v[j];
                 }
             }
         }
-        const V8 a = ld_bf16x8(act + ip * lda + cg * 8);
+        const V8 a = ld_bf16x8(act + (long)ip * lda + cg * 8);
         V8 o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = cg * 8 + j;
             const float gg = a.v[j] > 0.f ? g.v[j] : 0.f;
-            ca.g[j] += gg;
-            ca.x[j] += gg * (a.v[j] - __ldg(p0 + c)) * __ldg(p1 + c);
-            o.v[j] = gg * __ldg(sc + c);
+            sg[j] += gg;
+            sx[j] += gg * a.v[j];
+            o.v[j] = gg * s.v[j];
         }
-        st_bf16x8(dz + ip * ldz + cg * 8, o);
+        st_bf16x8(dz + (long)ip * ldz + cg * 8, o);
     }
-    ca.flush(s_sum, C);
+    colsum_thread_flush(s_sum, C, cg, sg, sx, p0, p1);
     colsum_block_end(s_sum, C, colsum, ldsum);
 }
 
@@ -215,36 +228,47 @@ __global__ void __launch_bounds__(256) pool_bnrelu_bwd_kernel(const void* __rest
                                                                long ldr, int N, int H, int W, int C, const float* __restrict__ sc,
                                                                const float* __restrict__ sh, const float* __restrict__ p0,
                                                                const float* __restrict__ p1, __nv_bfloat16* __restrict__ dC, long ldc,
-                                                               float* __restrict__ colsum, int ldsum) {
+                                                               float* __restrict__ colsum, int ldsum, int G, int ppb) {
     extern __shared__ float s_sum[];
     colsum_block_begin(s_sum, C);
-    const int G = C / 8;
-    const long total = (long)N * H * W * G;
-    const float inv = GAP ? 1.f / (float)(H * W) : 0.25f;
-    ColAcc ca; ca.init();
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(e % G);
-        const long ip = e / G;
-        const int ix = (int)(ip % W), iy = (int)((ip / W) % H), n = (int)(ip / ((long)W * H));
-        ca.select(cg, s_sum, C);
-        V8 d;
-        if (GAP) d = ld_f32x8(reinterpret_cast<const float*>(dpool) + (long)n * ldp + cg * 8);
-        else d = ld_bf16x8(reinterpret_cast<const __nv_bfloat16*>(dpool) + (((long)n * (H / 2) + (iy >> 1)) * (W / 2) + (ix >> 1)) * ldp + cg * 8);
-        const V8 r = ld_bf16x8(raw + ip * ldr + cg * 8);
-        V8 o;
+    const int cg = threadIdx.x % G, pl = threadIdx.x / G;
+    const V8 s = ld_f32x8(sc + cg * 8), t = ld_f32x8(sh + cg * 8);
+    float sg[8], sx[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = cg * 8 + j;
-            const float s = __ldg(sc + c);
-            const float a = fmaf(r.v[j], s, __ldg(sh + c));
-            const float gg = a > 0.f ? d.v[j] * inv : 0.f;
-            ca.g[j] += gg;
-            ca.x[j] += gg * (r.v[j] - __ldg(p0 + c)) * __ldg(p1 + c);
-            o.v[j] = gg * s;
+    for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sx[j] = 0.f; }
+    const int Ho = H / 2, Wo = W / 2;
+    const int n_units = GAP ? N : N * Ho * Wo;           // one unit = one pooled value per channel
+    const int pix_per_unit = GAP ? H * W : 4;
+    const float inv = GAP ? 1.f / (float)(H * W) : 0.25f;
+    for (int u = blockIdx.x * ppb + pl; u < n_units; u += gridDim.x * ppb) {
+        V8 d;
+        long ip0;
+        if (GAP) {
+            d = ld_f32x8(reinterpret_cast<const float*>(dpool) + (long)u * ldp + cg * 8);
+            ip0 = (long)u * H * W;
+        } else {
+            d = ld_bf16x8(reinterpret_cast<const __nv_bfloat16*>(dpool) + (long)u * ldp + cg * 8);
+            const int ox = u % Wo, q = u / Wo, oy = q % Ho, n = q / Ho;
+            ip0 = ((long)n * H + 2 * oy) * W + 2 * ox;
         }
-        st_bf16x8(dC + ip * ldc + cg * 8, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] *= inv;
+        for (int pi = 0; pi < pix_per_unit; ++pi) {
+            const long ip = GAP ? ip0 + pi : ip0 + (pi >> 1) * W + (pi & 1);
+            const V8 r = ld_bf16x8(raw + ip * ldr + cg * 8);
+            V8 o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float a = fmaf(r.v[j], s.v[j], t.v[j]);
+                const float gg = a > 0.f ? d.v[j] : 0.f;
+                sg[j] += gg;
+                sx[j] += gg * r.v[j];
+                o.v[j] = gg * s.v[j];
+            }
+            st_bf16x8(dC + ip * ldc + cg * 8, o);
+        }
     }
-    ca.flush(s_sum, C);
+    colsum_thread_flush(s_sum, C, cg, sg, sx, p0, p1);
     colsum_block_end(s_sum, C, colsum, ldsum);
 }
 
@@ -386,9 +410,13 @@ GN_API int gn_maxpool3s2_bnrelu_bwd(const void* dpool, long ldp, const unsigned 
                                     cudaStream_t stream) {
     GN_REQUIRE(dpool && idx && act && sc && p0 && p1 && dz && colsum && N > 0 && C % 8 == 0 && C <= 2048, GN_EINVAL,
                "maxpool3s2_bnrelu_bwd: bad arguments");
-    const long total = (long)N * Hi * Wi * (C / 8);
-    maxpool3s2_bnrelu_bwd_kernel<<<grid_for_groups(total, 8, C / 8), 256, 2 * C * sizeof(float), stream>>>(
-        (const __nv_bfloat16*)dpool, ldp, idx, (const __nv_bfloat16*)act, lda, N, Hi, Wi, C, sc, p0, p1, (__nv_bfloat16*)dz, ldz, colsum, ldsum);
+    const int G = C / 8;
+    GN_REQUIRE(G <= 256 && (long)N * Hi * Wi < (1L << 31), GN_EUNSUPPORTED, "maxpool3s2_bnrelu_bwd: at most 2048 channels and 2^31 pixels");
+    const int ppb = 256 / G;
+    unsigned grid = (unsigned)gn_ceil_div((long)N * Hi * Wi, ppb);
+    if (grid > (unsigned)gn_num_sms() * 8) grid = gn_num_sms() * 8;
+    maxpool3s2_bnrelu_bwd_kernel<<<grid, G * ppb, 2 * C * sizeof(float), stream>>>(
+        (const __nv_bfloat16*)dpool, ldp, idx, (const __nv_bfloat16*)act, lda, N, Hi, Wi, C, sc, p0, p1, (__nv_bfloat16*)dz, ldz, colsum, ldsum, G, ppb);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -407,17 +435,21 @@ GN_API int gn_bnrelu_avgpool2_fwd(const void* in, long ldi, int N, int H, int W,
 GN_API int gn_pool_bnrelu_bwd(const void* dpool, long ldp, int gap, const void* raw, long ldr, int N, int H, int W, int C, const float* sc,
                               const float* sh, const float* p0, const float* p1, void* dC, long ldc, float* colsum, int ldsum,
                               cudaStream_t stream) {
-    GN_REQUIRE(dpool && raw && sc && sh && p0 && p1 && dC && colsum && N > 0 && C % 8 == 0 && C <= 4096, GN_EINVAL, "pool_bnrelu_bwd: bad arguments");
+    GN_REQUIRE(dpool && raw && sc && sh && p0 && p1 && dC && colsum && N > 0 && C % 8 == 0 && C <= 2048, GN_EINVAL, "pool_bnrelu_bwd: bad arguments");
     GN_REQUIRE(gap || (H % 2 == 0 && W % 2 == 0), GN_EINVAL, "pool_bnrelu_bwd: odd spatial size");
-    const long total = (long)N * H * W * (C / 8);
-    const unsigned grid = grid_for_groups(total, 8, C / 8);
+    const int G = C / 8;
+    GN_REQUIRE(G <= 256 && (long)N * H * W < (1L << 31), GN_EUNSUPPORTED, "pool_bnrelu_bwd: at most 2048 channels and 2^31 pixels");
+    const int ppb = 256 / G;
+    const long units = gap ? N : (long)N * (H / 2) * (W / 2);
+    unsigned grid = (unsigned)gn_ceil_div(units, ppb);
+    if (grid > (unsigned)gn_num_sms() * 8) grid = gn_num_sms() * 8;
     const size_t smem = 2 * C * sizeof(float);
     if (gap)
-        pool_bnrelu_bwd_kernel<true><<<grid, 256, smem, stream>>>(dpool, ldp, (const __nv_bfloat16*)raw, ldr, N, H, W, C, sc, sh, p0, p1,
-                                                                 (__nv_bfloat16*)dC, ldc, colsum, ldsum);
+        pool_bnrelu_bwd_kernel<true><<<grid, G * ppb, smem, stream>>>(dpool, ldp, (const __nv_bfloat16*)raw, ldr, N, H, W, C, sc, sh, p0, p1,
+                                                                     (__nv_bfloat16*)dC, ldc, colsum, ldsum, G, ppb);
     else
-        pool_bnrelu_bwd_kernel<false><<<grid, 256, smem, stream>>>(dpool, ldp, (const __nv_bfloat16*)raw, ldr, N, H, W, C, sc, sh, p0, p1,
-                                                                  (__nv_bfloat16*)dC, ldc, colsum, ldsum);
+        pool_bnrelu_bwd_kernel<false><<<grid, G * ppb, smem, stream>>>(dpool, ldp, (const __nv_bfloat16*)raw, ldr, N, H, W, C, sc, sh, p0, p1,
+                                                                      (__nv_bfloat16*)dC, ldc, colsum, ldsum, G, ppb);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -72,30 +72,65 @@ def densenet_block_config(sd):
     return tuple(cfg[b] for b in sorted(cfg))
 
 
-def densenet_forward(sd, x, classify=True):
-    """Eval-mode DenseNet-BC forward.  x: (N, 3, P, P) float."""
+class _RoundGradBf16(torch.autograd.Function):
+    """Identity whose gradient is rounded to bfloat16 (where the B200 path stores a bf16 gradient tensor)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _rb(t, on):
+    """Straight-through bfloat16 rounding of the forward value (gradient passes unrounded)."""
+    if not on:
+        return t
+    return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+
+
+def _rg(t, on):
+    return _RoundGradBf16.apply(t) if on else t
+
+
+def densenet_forward(sd, x, classify=True, emulate_bf16=False):
+    """Eval-mode DenseNet-BC forward.  x: (N, 3, P, P) float.
+
+    ``emulate_bf16``: same fp32 arithmetic, but every tensor the B200 path stores in bfloat16 (input, conv weights,
+    activated operands, conv outputs, pooled transition input, and the gradients dZ / dC) is rounded at that point,
+    and the transition pools BEFORE its 1x1 convolution (they commute; gridnext_b200/densenet.py).  This pins the
+    kernels far tighter than the fp32 comparison allows, because ReLU masks then agree."""
+    e = emulate_bf16
     small_inputs = 'features.norm0.weight' not in sd
-    w0 = sd['features.conv0.weight']
+    w0 = _rb(sd['features.conv0.weight'], e)
+    x = _rb(x, e)
     if small_inputs:
-        x = F.conv2d(x, w0, stride=1, padding=1)
+        x = _rb(F.conv2d(x, w0, stride=1, padding=1), e)
     else:
-        x = F.conv2d(x, w0, stride=2, padding=3)
-        x = torch.relu(_bn_eval(sd, 'features.norm0.', x))
+        x = _rg(F.conv2d(x, w0, stride=2, padding=3), e)
+        x = _rb(torch.relu(_bn_eval(sd, 'features.norm0.', x)), e)
         x = F.max_pool2d(x, 3, stride=2, padding=1)
     cfg = densenet_block_config(sd)
     for bi, nl in enumerate(cfg, start=1):
+        x = _rg(x, e)
         for li in range(1, nl + 1):
             p = 'features.denseblock%d.denselayer%d.' % (bi, li)
-            h = torch.relu(_bn_eval(sd, p + 'norm1.', x))
-            h = F.conv2d(h, sd[p + 'conv1.weight'])
-            h = torch.relu(_bn_eval(sd, p + 'norm2.', h))
-            h = F.conv2d(h, sd[p + 'conv2.weight'], padding=1)
+            h = _rb(torch.relu(_bn_eval(sd, p + 'norm1.', x)), e)
+            h = _rg(F.conv2d(h, _rb(sd[p + 'conv1.weight'], e)), e)
+            h = _rb(torch.relu(_bn_eval(sd, p + 'norm2.', h)), e)
+            h = _rg(_rb(F.conv2d(h, _rb(sd[p + 'conv2.weight'], e), padding=1), e), e)
             x = torch.cat((x, h), 1)
         if bi != len(cfg):
             p = 'features.transition%d.' % bi
             x = torch.relu(_bn_eval(sd, p + 'norm.', x))
-            x = F.conv2d(x, sd[p + 'conv.weight'])
-            x = F.avg_pool2d(x, 2, stride=2)
+            if e:
+                x = _rg(_rb(F.avg_pool2d(x, 2, stride=2), e), e)
+                x = _rb(F.conv2d(x, _rb(sd[p + 'conv.weight'], e)), e)
+            else:
+                x = F.conv2d(x, sd[p + 'conv.weight'])
+                x = F.avg_pool2d(x, 2, stride=2)
     x = torch.relu(_bn_eval(sd, 'features.norm_final.', x))
     x = x.mean((2, 3))
     if classify:

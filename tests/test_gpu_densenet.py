@@ -57,7 +57,33 @@ def test_densenet_matches_reference_golden(tag):
             got = params[k[5:]].grad.cpu()
             cos = float(torch.nn.functional.cosine_similarity(got.flatten().double(), ref.flatten().double(), dim=0))
             assert cos > 0.98, (k, cos)              # 120 layers of bf16 backward: noise grows towards the stem
-            assert relmax(got, ref) < 0.2, k
+            assert relmax(got, ref) < 0.3, k                 # fp32 reference vs bf16 path; the tight check is the bf16-emulating oracle below
+
+
+@pytest.mark.parametrize('kw,P,N', [(dict(growth_rate=8, block_config=(2, 2), num_init_features=16, bn_size=2), 32, 5),
+                                     (dict(growth_rate=32, block_config=(6, 12, 24, 16), num_init_features=64, bn_size=4), 64, 3),
+                                     (dict(growth_rate=16, block_config=(3, 4), num_init_features=32, bn_size=4), 48, 4)])
+def test_densenet_matches_bf16_emulating_oracle(kw, P, N):
+    """Kernel parity proper: the oracle rounds to bfloat16 exactly where the B200 path stores bf16 (operands, activations,
+    dZ / dC), so ReLU masks agree and what is left is fp32 summation order: logits 5e-3, every parameter gradient 3e-2
+    of its max-norm (an order of magnitude tighter than the fp32 comparison above)."""
+    net, sd = build(kw, 91)
+    g = torch.Generator(); g.manual_seed(17)
+    x = torch.randn(N, 3, P, P, generator=g)
+    dy = torch.randn(N, 7, generator=g)
+    sd_r = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v) for k, v in sd.items()}
+    ref = R.densenet_forward(sd_r, x, emulate_bf16=True)
+    (ref * dy).sum().backward()
+    logits = net(x.cuda())
+    (logits * dy.cuda()).sum().backward()
+    assert relmax(logits, ref.detach()) < 5e-3
+    worst = ('', 0.0)
+    for k, p in net.named_parameters():
+        r = sd_r[k].grad
+        err = relmax(p.grad, r)
+        if err > worst[1]:
+            worst = (k, err)
+    assert worst[1] < 3e-2, worst
 
 
 def test_densenet121_p128_matches_oracle_and_argmax():
