@@ -35,6 +35,11 @@ _SIGS = {
     'gn_normalize_u8': [vp, vp, cl, ci, vp, vp, vp, ci, vp],
     'gn_gemm_tn_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, vp, vp, vp],
     'gn_im2col7x7s2': [vp, ci, ci, ci, vp, ci, vp],
+    'gn_stem_pack_input': [vp, ci, ci, ci, vp, vp],
+    'gn_stem_pack_weight': [vp, ci, vp, vp],
+    'gn_stem_conv_fwd': [vp, ci, ci, vp, ci, vp, vp, ci, vp, cl, vp],
+    'gn_stem_conv_wgrad': [vp, ci, ci, vp, cl, ci, vp, vp],
+    'gn_stem_unpack_wgrad': [vp, ci, vp, vp],
     'gn_maxpool3s2_fwd': [vp, cl, ci, ci, ci, ci, vp, cl, vp, vp],
     'gn_maxpool3s2_bnrelu_bwd': [vp, cl, vp, vp, cl, ci, ci, ci, ci, vp, vp, vp, vp, cl, vp, ci, vp],
     'gn_bnrelu_avgpool2_fwd': [vp, cl, ci, ci, ci, ci, vp, vp, vp, cl, vp],

@@ -139,8 +139,8 @@ def _check_supported(net):
     if net.small_inputs:
         raise NotImplementedError('DenseNet (B200): small_inputs=True (3x3 stem) is not on the GridNet hot path')
     f = net.features
-    if f.conv0.out_channels % 8:
-        raise NotImplementedError('DenseNet (B200): num_init_features must be a multiple of 8')
+    if f.conv0.out_channels % 8 or f.conv0.out_channels > 128:
+        raise NotImplementedError('DenseNet (B200): num_init_features must be a multiple of 8, at most 128')
     for name, m in f.named_children():
         if name.startswith('denseblock'):
             for l in m.children():
@@ -161,16 +161,13 @@ def _forward_chunk(net, geo, cst, x, save):
     n, P, dev = x.shape[0], geo.P, x.device
     f = net.features
     bf = torch.bfloat16
-    # ---- stem: conv0 (7x7/2) as im2col + GEMM with norm0+ReLU epilogue, then 3x3/2 max-pool into block 1's buffer
-    M0 = n * geo.H0 * geo.H0
-    a0 = torch.empty((M0, 160), device=dev, dtype=bf)
-    call('gn_im2col7x7s2', ptr(x), 1 if x.dtype == bf else 0, n, P, ptr(a0), 160, stream())
-    w0 = torch.zeros((f.conv0.out_channels, 160), device=dev, dtype=bf)
-    w0[:, :147] = f.conv0.weight.detach().reshape(f.conv0.out_channels, 147).to(bf)
+    # ---- stem: conv0 (7x7/2) read straight from the NHWC4 patch by the tensor core (no im2col buffer), norm0+ReLU in the
+    # epilogue, then 3x3/2 max-pool into block 1's buffer
+    xq = tc.stem_pack_input(x)
     b0 = cst.of(f.norm0)
     c0 = f.conv0.out_channels
-    act0 = tc.gemm_bf16(a0, w0, scale=b0['sc'], shift=b0['sh'], relu=True)
-    saved = dict(a0=a0, act0=act0, blocks=[]) if save else None
+    act0 = tc.stem_conv_fwd(xq, tc.stem_pack_weight(f.conv0.weight.detach()), scale=b0['sc'], shift=b0['sh'], relu=True)
+    saved = dict(xq=xq, act0=act0, blocks=[]) if save else None
     blk0 = geo.blocks[0]
     M = n * blk0['H'] * blk0['H']
     C = torch.empty((M, blk0['c_tot']), device=dev, dtype=bf)
@@ -325,8 +322,7 @@ def _backward_chunk(net, geo, cst, saved, dout, grads):
             dz0 = torch.empty((M0, c0), device=dev, dtype=bf)
             call('gn_maxpool3s2_bnrelu_bwd', ptr(dC), blk['c_tot'], ptr(saved['idx0']), ptr(saved['act0']), c0, n, geo.H0, geo.H0, c0,
                  ptr(k0['sc']), ptr(k0['beta']), ptr(k0['inv_gamma']), ptr(dz0), c0, ptr(colsum_of(k0)), tot, stream())
-            dw0 = grads.buf(f.conv0.weight, (c0, 160))
-            tc.gemm_tn_bf16(dz0, saved['a0'], dw0)
+            grads.acc(f.conv0.weight, tc.stem_conv_wgrad(saved['xq'], dz0, c0))
 
 
 class _DenseNetFn(torch.autograd.Function):
@@ -382,8 +378,6 @@ class _DenseNetFn(torch.autograd.Function):
                 out.append(bn_of_param[id(p)].clone())
             elif id(p) in grads.w:
                 gpar = grads.w[id(p)]
-                if p is net.features.conv0.weight:
-                    gpar = gpar[:, :147]
                 out.append(gpar.reshape(p.shape).contiguous())
             else:
                 out.append(None)

@@ -96,3 +96,47 @@ def conv3x3_wgrad_bf16(x2d, dy2d, Nimg, H, W, CI, CO):
     dw = torch.empty((CO, CI, 3, 3), device=x2d.device, dtype=torch.float32)
     call('gn_conv3x3_unpack_grad', ptr(dwp), CO, CI, ptr(dw), stream())
     return dw
+
+
+# ---- stem (conv0 7x7 / stride 2 / pad 3 + norm0 + relu0) without an im2col buffer -----------------------------------
+def stem_pack_input(x):
+    """(N, 3, P, P) fp32 | bf16 -> NHWC4 bf16 (N, P, P, 4): RGB + a zero channel, 8 bytes per pixel."""
+    _lib.require_cuda(x)
+    N, _, P, _ = x.shape
+    xq = torch.empty((N, P, P, 4), device=x.device, dtype=torch.bfloat16)
+    call('gn_stem_pack_input', ptr(x), 1 if x.dtype == torch.bfloat16 else 0, N, P, ptr(xq), stream())
+    return xq
+
+
+def stem_pack_weight(w):
+    """fp32 (CO, 3, 7, 7) -> bf16 [7, CO, 32] (per kernel row: 8 pixel slots x 4 channels, slot 0 and channel 3 zero)."""
+    _lib.require_cuda(w)
+    CO = int(w.shape[0])
+    wq = torch.empty((7, CO, 32), device=w.device, dtype=torch.bfloat16)
+    call('gn_stem_pack_weight', ptr(w.contiguous().float()), CO, ptr(wq), stream())
+    return wq
+
+
+def stem_conv_fwd(xq, wq, scale=None, shift=None, relu=False, out=None):
+    """out[(n, oy, ox), co] = [relu](conv7x7s2(x)[n, co, oy, ox] * scale[co] + shift[co]), bf16 rows of CO channels."""
+    _lib.require_cuda(xq, wq)
+    N, P = int(xq.shape[0]), int(xq.shape[1])
+    CO = int(wq.shape[1])
+    Ho = P // 2
+    if out is None:
+        out = torch.empty((N * Ho * Ho, CO), device=xq.device, dtype=torch.bfloat16)
+    _, _, ldo = _rows_pitch(out)
+    call('gn_stem_conv_fwd', ptr(xq), N, P, ptr(wq), CO, ptr(scale), ptr(shift), 1 if relu else 0, ptr(out), ldo, stream())
+    return out
+
+
+def stem_conv_wgrad(xq, dz, CO):
+    """-> fp32 (CO, 3, 7, 7) weight gradient from NHWC4 patches and dz [(n, oy, ox), >=CO] bf16."""
+    _lib.require_cuda(xq, dz)
+    N, P = int(xq.shape[0]), int(xq.shape[1])
+    _, _, ldz = _rows_pitch(dz)
+    dwq = torch.zeros((CO, 7 * 32), device=xq.device, dtype=torch.float32)
+    call('gn_stem_conv_wgrad', ptr(xq), N, P, ptr(dz), ldz, CO, ptr(dwq), stream())
+    dw = torch.empty((CO, 3, 7, 7), device=xq.device, dtype=torch.float32)
+    call('gn_stem_unpack_wgrad', ptr(dwq), CO, ptr(dw), stream())
+    return dw

@@ -115,6 +115,15 @@ int gn_conv3x3_unpack_grad(const float* dwp, int CO, int CI, float* dw, gn_strea
  * ops of the cited densenet.py lines.  colsum is fp32 [2][ldsum]: row 0 += sum g (d beta), row 1 += sum g*xhat (d gamma). */
 /* conv0 operand: A0[m, c*49+ky*7+kx] for the 7x7 / stride 2 / pad 3 stem (densenet.py:107) from NCHW fp32|bf16 patches */
 int gn_im2col7x7s2(const void* x, int x_is_bf16, int N, int P, void* a0, int ldk, gn_stream_t stream);
+/* Stem without an im2col buffer (densenet.py:107-109): the patch is repacked once to NHWC4 bf16 (RGB + zero channel), the
+ * 7x7 / stride 2 convolution reads its overlapping operand rows straight from the image rows through a no-swizzle UMMA
+ * descriptor; norm0 + relu0 run in the epilogue.  wq: [7][CO][32] bf16 (gn_stem_pack_weight), dwq: [CO][224] fp32. */
+int gn_stem_pack_input(const void* x, int x_is_bf16, int N, int P, void* xq, gn_stream_t stream);
+int gn_stem_pack_weight(const float* w, int CO, void* wq, gn_stream_t stream);
+int gn_stem_conv_fwd(const void* xq, int N, int P, const void* wq, int CO, const float* scale, const float* shift, int relu, void* out,
+                     long ldo, gn_stream_t stream);
+int gn_stem_conv_wgrad(const void* xq, int N, int P, const void* dz, long ldz, int CO, float* dwq, gn_stream_t stream);
+int gn_stem_unpack_wgrad(const float* dwq, int CO, float* dw, gn_stream_t stream);
 /* pool0: MaxPool2d(3, 2, 1) (densenet.py:111-112); idx keeps the arg-max tap for the backward */
 int gn_maxpool3s2_fwd(const void* in, long ldi, int N, int Hi, int Wi, int C, void* out, long ldo, unsigned char* idx, gn_stream_t stream);
 int gn_maxpool3s2_bnrelu_bwd(const void* dpool, long ldp, const unsigned char* idx, const void* act, long lda, int N, int Hi, int Wi, int C,

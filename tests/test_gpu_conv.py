@@ -79,3 +79,31 @@ def test_conv3x3_weight_gradient(Nimg, H, W, CI, CO):
     dbuf = torch.zeros((M, CO + 200), dtype=torch.bfloat16, device='cuda'); dbuf[:, 96:96 + CO] = dy.reshape(M, CO).cuda()
     dw = conv3x3_wgrad_bf16(xbuf[:, :CI], dbuf[:, 96:96 + CO], Nimg, H, W, CI, CO)
     assert rel(dw.cpu(), w.grad) < 1e-4
+
+
+@pytest.mark.parametrize('N,P,CO', [(3, 128, 64), (5, 64, 64), (4, 32, 16), (2, 224, 64), (7, 48, 32), (2, 128, 96), (3, 40, 24)])
+def test_stem_conv7x7s2_forward_and_weight_gradient(N, P, CO):
+    """conv0 + norm0 + relu0 (densenet.py:107-109) and the conv0 weight gradient, read from NHWC4 patches without im2col."""
+    from gridnext_b200 import tc
+    x = rnd((N, 3, P, P), 31).to(torch.bfloat16)
+    w = rnd((CO, 3, 7, 7), 32, (2.0 / 147) ** 0.5)
+    g = torch.Generator(); g.manual_seed(33)
+    sc, sh = torch.rand(CO, generator=g) + 0.5, torch.randn(CO, generator=g) * 0.3
+    wr = w.to(torch.bfloat16).float()
+    conv = F.conv2d(x.float(), wr, stride=2, padding=3)
+    ref = torch.relu(conv * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)).permute(0, 2, 3, 1).reshape(-1, CO)
+    xq = tc.stem_pack_input(x.cuda())
+    assert torch.equal(xq[..., :3].cpu(), x.permute(0, 2, 3, 1)) and float(xq[..., 3].abs().max()) == 0
+    out = tc.stem_conv_fwd(xq, tc.stem_pack_weight(w.cuda()), scale=sc.cuda(), shift=sh.cuda(), relu=True)
+    assert rel(out.float().cpu(), ref) < 1e-2
+    # fp32 input takes the same path
+    xq32 = tc.stem_pack_input(x.float().cuda())
+    assert torch.equal(xq32, xq)
+    # weight gradient: dz is a column slice of a wider buffer
+    Ho = P // 2
+    dz = rnd((N * Ho * Ho, CO), 34).to(torch.bfloat16)
+    wz = torch.zeros((CO, 3, 7, 7), requires_grad=True)
+    F.conv2d(x.float(), wz, stride=2, padding=3).backward(dz.float().reshape(N, Ho, Ho, CO).permute(0, 3, 1, 2))
+    dbuf = torch.zeros((N * Ho * Ho, CO + 16), dtype=torch.bfloat16, device='cuda'); dbuf[:, 8:8 + CO] = dz.cuda()
+    dw = tc.stem_conv_wgrad(xq, dbuf[:, 8:8 + CO], CO)
+    assert rel(dw.cpu(), wz.grad) < 2e-5

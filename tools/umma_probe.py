@@ -182,6 +182,25 @@ def main():
     A, B = ints(128, 32), ints(32, 32)
     out.append(run_case('kmaj_sw64_bf16', A, B, kmajor_sw(2, 64), kmajor_sw(2, 64), desc(0, 512, SW64), desc(0, 512, SW64), idesc(128, 32), 2, 32, 32, False))
 
+
+    # 8. OVERLAPPING rows ("Toeplitz" operand for the strided 7x7 stem): A[r, k] = S[8 r + k], i.e. row pitch 16 B, K chunk pitch 16 B.
+    #    K-major no-swizzle with LBO = 16 (K-adjacent core matrices), SBO = 128 (8-row groups).
+    S = rng.integers(-4, 5, 128 * 8 + 64 + 64).astype(np.float32)
+    A = np.stack([S[8 * r: 8 * r + 64] for r in range(128)])
+    B = ints(64, 64)
+    out.append(run_case('toeplitz_kmaj_A_lbo16_sbo128', A, B, lambda r, k: (8 * r + k) * 2, kmajor_sw(2), desc(16, 128, SW_NONE), desc(0, 1024, SW128),
+                        idesc(128, 64), 4, 32, 32, False))
+    # 8b. the same overlapping window as the MN-major B operand of the stem weight gradient: B[n, k] = S[8 k + n] (n contiguous, k pitch 16 B),
+    #     SBO = 16 (MN-adjacent core matrices), LBO = 128 (8-k groups); one MMA step = 16 k = 256 B.
+    Bt = np.stack([S[8 * np.arange(64) + n] for n in range(32)])         # [N=32, K=64]
+    A2 = ints(128, 64)
+    out.append(run_case('toeplitz_mnmaj_B_sbo16_lbo128', A2, Bt, kmajor_sw(2), lambda n, k: (8 * k + n) * 2, desc(0, 1024, SW128), desc(128, 16, SW_NONE),
+                        idesc(128, 32, b_mn=1), 4, 32, 256, False))
+    # 8c. MN-major SW128 A whose two 64-wide groups alias (LBO = 0): D rows 64..127 must repeat rows 0..63
+    A3, B3 = ints(64, 64), ints(32, 64)
+    out.append(run_case('A_mnmaj_sw128_alias_lbo0', np.concatenate([A3, A3]), B3, lambda mn, k: k * 128 + ((((mn % 64) * 2 // 16) ^ (k % 8)) * 16) + ((mn % 64) * 2) % 16,
+                        kmajor_sw(2), desc(0, 1024, SW128), desc(0, 1024, SW128), idesc(128, 32, a_mn=1), 4, 2048, 32, False))
+
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump(out, open('gpurun_out/umma_probe.json', 'w'), indent=1)
     print('PASS %d / %d' % (sum(r['ok'] for r in out), len(out)))
