@@ -319,8 +319,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                                         const float ref = u ? rf.y : rf.x;
                                         const float sc = cst[e];
                                         const float a = is_raw ? fmaf(ref, sc, cst[C3_MAX_CO + e]) : ref;
-                                        const float gg = (valid && a > 0.f) ? __uint_as_float(r[e]) : 0.f;
-                                        gx[e] = gg * ref;          // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
+                                        const bool on = valid && a > 0.f;       // dropped rows hold stale shared memory: select, never multiply
+                                        const float gg = on ? __uint_as_float(r[e]) : 0.f;
+                                        gx[e] = on ? gg * ref : 0.f;            // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
                                         v[e] = gg;
                                         o2[u] = gg * sc;
                                     }
