@@ -33,6 +33,8 @@ _SIGS = {
     'gn_spot_table': [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp],
     'gn_patch_gather': [vp, cl, ci, ci, vp, ci, ci, vp, vp, vp, ci, vp],
     'gn_normalize_u8': [vp, vp, cl, ci, vp, vp, vp, ci, vp],
+    'gn_cast_f32_bf16': [vp, vp, cl, vp],
+    'gn_rows_affine_bf16': [vp, cl, vp, vp, ci, vp, cl, cl, ci, ci, vp],
     'gn_gemm_tn_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, vp, vp, vp],
     'gn_im2col7x7s2': [vp, ci, ci, ci, vp, ci, vp],
     'gn_stem_pack_input': [vp, ci, ci, ci, vp, vp],

@@ -148,7 +148,9 @@ class GridNetHexOddr(GridNetHex):
             fast = _fast_f(self.patch_classifier)
             if fast is not None and x.is_cuda and self.atonce_patch_limit is None:
                 # count slab (B, G, H, W) consumed directly: no permute/reshape copy (K2 in SURVEY 2.2)
-                return fast.forward_grid(x, self.f_dim)
+                out = fast.forward_grid(x, self.f_dim)
+                if out is not None:
+                    return out
             return super(GridNetHexOddr, self).patch_predictions(x.permute((0, 2, 3, 1)))
         return super(GridNetHexOddr, self).patch_predictions(x)
 

@@ -87,6 +87,12 @@ int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M, int N,
                  const float* bn_p1, float* bn_colsum, int bn_ldsum, int bn_rmw, gn_stream_t stream);
 /* bn_ref != NULL selects the BN+ReLU-backward epilogue of gn_conv3x3_bf16 (bf16 out; bn_rmw: out += g * bn_sc). */
 
+/* count MLP glue (notebooks/Tutorial_visium_count.ipynb cell 12): fp32 count slab -> bf16 (consumed in place by gn_gemm_tn_bf16, so
+ * the permute+reshape copy of gridnet_models.py:168,83 never happens); fp32 rows -> [relu](x*scale+shift) -> bf16 rows, pad columns zero */
+int gn_cast_f32_bf16(const float* in, void* out, long n, gn_stream_t stream);
+int gn_rows_affine_bf16(const float* in, long ldi, const float* scale, const float* shift, int relu, void* out, long ldo, long N, int C,
+                        int Cpad, gn_stream_t stream);
+
 /* Weight-gradient GEMM: out[Mo, No] (fp32, pitch ldo) += a[Kp, Mo]^T * op(b)[Kp, No]; rows of a and b are the
  * reduction index (pixels / spots).  op(b) = relu(b * xf_scale[n] + xf_shift[n]) when given.  Split over the
  * reduction dimension with vector atomics: the caller zeroes (or pre-loads) out.  Replaces the weight gradient

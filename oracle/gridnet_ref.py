@@ -30,13 +30,24 @@ def sub(sd, prefix):
 
 
 # ----------------------------------------------------------------------------- count MLP f
-def mlp_forward(sd, x, spec=COUNT_MLP_SPEC, training=False, stats_out=None):
+def mlp_forward(sd, x, spec=COUNT_MLP_SPEC, training=False, stats_out=None, emulate_bf16=False):
     """x: (N, G).  BatchNorm1d uses running stats unless ``training`` (GridNetHexMM quirk,
-    training.py:126 only puts ``patch_classifier`` in eval)."""
+    training.py:126 only puts ``patch_classifier`` in eval).
+
+    ``emulate_bf16``: same fp32 arithmetic with the input, the Linear weights and every stored activation (after a Linear
+    that is not followed by BatchNorm, and after each ReLU) rounded to bfloat16 where the B200 path stores bf16, so ReLU
+    masks agree with the kernels (see densenet_forward)."""
+    e = emulate_bf16
+    x = _rb(x, e)
+    last = len(spec) - 1
     for i, kind in enumerate(spec):
         p = '%d.' % i
         if kind == 'L':
-            x = F.linear(x, sd[p + 'weight'], sd[p + 'bias'])
+            x = F.linear(x, _rb(sd[p + 'weight'], e), sd[p + 'bias'])
+            if i != last and spec[i + 1] != 'B':
+                x = _rg(_rb(x, e), e)
+            elif i != last:
+                x = _rg(x, e)
         elif kind == 'B':
             if training:
                 mean = x.mean(0)
@@ -49,7 +60,7 @@ def mlp_forward(sd, x, spec=COUNT_MLP_SPEC, training=False, stats_out=None):
                 mean, var = sd[p + 'running_mean'], sd[p + 'running_var']
             x = (x - mean) / torch.sqrt(var + BN_EPS) * sd[p + 'weight'] + sd[p + 'bias']
         elif kind == 'R':
-            x = torch.relu(x)
+            x = _rb(torch.relu(x), e)
         else:
             raise ValueError(kind)
     return x
@@ -191,9 +202,9 @@ def grid_from_spots(p, B, H, W):
     return p.reshape(B, H, W, -1).permute(0, 3, 1, 2)
 
 
-def gridnet_count_forward(sd, x, use_bn=True, training=True, stats_out=None, f_training=False):
+def gridnet_count_forward(sd, x, use_bn=True, training=True, stats_out=None, f_training=False, emulate_bf16=False):
     B, G, H, W = x.shape
-    f = mlp_forward(sub(sd, 'patch_classifier.'), spots_from_counts(x), training=f_training)
+    f = mlp_forward(sub(sd, 'patch_classifier.'), spots_from_counts(x), training=f_training, emulate_bf16=emulate_bf16)
     return corrector_forward(sub(sd, 'corrector.'), grid_from_spots(f, B, H, W), use_bn, training, stats_out)
 
 
