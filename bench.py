@@ -252,11 +252,13 @@ def main():
 
     # ---- instrumented step: time share of every C-ABI entry point
     roof = None
+    # every rank runs the instrumented step (it contains the gradient all-reduce); only rank 0 records it
+    torch.cuda.synchronize()
     if rank == 0:
-        torch.cuda.synchronize()
         _lib.PROFILE = {}
-        step_resident()
-        torch.cuda.synchronize()
+    step_resident()
+    torch.cuda.synchronize()
+    if rank == 0:
         prof, _lib.PROFILE = _lib.PROFILE, None
         table = {k: dict(calls=len(v), ms=sum(a.elapsed_time(b) for a, b, _ in v)) for k, v in prof.items()}
         total = sum(t['ms'] for t in table.values())
