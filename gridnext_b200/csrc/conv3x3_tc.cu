@@ -37,7 +37,7 @@ struct Conv3Params {
 };
 
 #define C3_SUB_BYTES 16384
-#define C3_MAX_ESTAGES 4
+#define C3_MAX_ESTAGES 8
 #define C3_EPI_WARPS 8
 #define C3_MAX_CO 256
 
@@ -96,6 +96,7 @@ __device__ __forceinline__ void c3_issue_tile(uint32_t d, uint64_t descA, uint64
 //   warp 2: epilogue feeder (TMA loads of the BN reference tile, one box per padded row)
 //   warp 3: TMEM allocator + epilogue drain (TMA row stores; border positions fall outside the tensor map and are dropped)
 //   warps 4-11: epilogue (tcgen05.ld -> math -> swizzled st.shared in place)
+template <int EPI_MODE>
 __global__ void __launch_bounds__(384, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmRef, const Conv3Params p) {
@@ -118,8 +119,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     uint8_t* s_slots = s_a + (size_t)p.stages * stage_bytes;
     float* s_epi = reinterpret_cast<float*>(s_slots + (size_t)p.e_stages * C3_SUB_BYTES);      // [4][C3_MAX_CO]
 
-    if (p.epi_mode == 1) {
+    float* s_cs = s_epi + 4 * C3_MAX_CO;                                                        // [2][C3_MAX_CO] column sums of this CTA
+    if (EPI_MODE == 1) {
         for (int i = threadIdx.x; i < C3_MAX_CO; i += blockDim.x) {
+            s_cs[i] = 0.f;
+            s_cs[C3_MAX_CO + i] = 0.f;
             const bool in = i < p.CO;
             s_epi[i] = in ? p.bn.sc[i] : 0.f;
             s_epi[C3_MAX_CO + i] = (in && p.bn.sh) ? p.bn.sh[i] : 0.f;
@@ -131,7 +135,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmOut);
-        if (p.epi_mode == 1) tma_prefetch_desc(&tmRef);
+        if (EPI_MODE == 1) tma_prefetch_desc(&tmRef);
         mbar_init(&bar_w, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bar_full[s], 1);
@@ -216,7 +220,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 const int Rg0 = tile * R;
                 for (int j = 0; j < p.nsub; ++j) {
                     mbar_wait(&bar_eempty[es], eph ^ 1);
-                    if (p.epi_mode == 1) {
+                    if (EPI_MODE == 1) {
                         uint8_t* slot = s_slots + (size_t)es * C3_SUB_BYTES;
                         mbar_arrive_expect_tx(&bar_efull[es], (uint32_t)(R * W2 * 128));
                         int n, yp;
@@ -273,10 +277,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         uint32_t acc_phase = 0;
         int es = 0;
         uint32_t eph = 0;
-        float cs_g[4], cs_x[4];       // per-lane column partial sums, channel j*64 + h*32 + lane
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { cs_g[i] = 0.f; cs_x[i] = 0.f; }
-        const bool want_sums = p.epi_mode == 1 && p.bn.colsum != nullptr;
+        const bool want_sums = EPI_MODE == 1 && p.bn.colsum != nullptr;
         const bool is_raw = p.bn.ref_is_raw != 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(&bar_tfull[acc], acc_phase);
@@ -285,61 +286,68 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             c3_row_coords(tile * R + r_loc, total_rows, H2, p.Nimg, n, yp);
             const bool valid = r_loc < R && n >= 0 && n < p.Nimg && yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * 256);
+#pragma unroll 1
+            for (int j = 0; j < p.nsub; ++j) {
+                mbar_wait(&bar_efull[es], eph);
+                uint8_t* rowp = s_slots + (size_t)es * C3_SUB_BYTES + trow * 128;
+                const int c0 = j * 64 + h * 32;
+                __syncwarp();
+                if (c0 < p.NP) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+                    const float* cst = s_epi + c0;
+                    float v[32], gx[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < p.nsub) {
-                    mbar_wait(&bar_efull[es], eph);
-                    uint8_t* rowp = s_slots + (size_t)es * C3_SUB_BYTES + trow * 128;
-                    const int c0 = j * 64 + h * 32;
-                    __syncwarp();
-                    if (c0 < p.NP) {
-                        uint32_t r[32];
-                        tmem_ld32(taddr + c0, r);
-                        tmem_ld_wait();
-                        const float* cst = s_epi + c0;
-                        float v[32], gx[32];
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t off = (((uint32_t)(h * 4 + q)) ^ sw) << 4;
+                        uint32_t res[4];
+                        if (EPI_MODE == 0) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t off = (((uint32_t)(h * 4 + q)) ^ sw) << 4;
-                            uint32_t res[4];
-                            if (p.epi_mode == 0) {
-#pragma unroll
-                                for (int e2 = 0; e2 < 4; ++e2)
-                                    res[e2] = c3_pack_bf16x2(__uint_as_float(r[8 * q + 2 * e2]), __uint_as_float(r[8 * q + 2 * e2 + 1]));
-                            } else {
-                                const uint4 rv = *reinterpret_cast<const uint4*>(rowp + off);
-                                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                                for (int e2 = 0; e2 < 4; ++e2) {
-                                    const float2 rf = c3_unpack_bf16x2(rw[e2]);
-                                    float o2[2];
-#pragma unroll
-                                    for (int u = 0; u < 2; ++u) {
-                                        const int e = 8 * q + 2 * e2 + u;
-                                        const float ref = u ? rf.y : rf.x;
-                                        const float sc = cst[e];
-                                        const float a = is_raw ? fmaf(ref, sc, cst[C3_MAX_CO + e]) : ref;
-                                        const bool on = valid && a > 0.f;       // dropped rows hold stale shared memory: select, never multiply
-                                        const float gg = on ? __uint_as_float(r[e]) : 0.f;
-                                        gx[e] = on ? gg * ref : 0.f;            // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
-                                        v[e] = gg;
-                                        o2[u] = gg * sc;
-                                    }
-                                    res[e2] = c3_pack_bf16x2(o2[0], o2[1]);
-                                }
+                            for (int e2 = 0; e2 < 4; ++e2)
+                                res[e2] = c3_pack_bf16x2(__uint_as_float(r[8 * q + 2 * e2]), __uint_as_float(r[8 * q + 2 * e2 + 1]));
+                        } else {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(rowp + off);
+                            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+                            const float4 sc0 = *reinterpret_cast<const float4*>(cst + 8 * q), sc1 = *reinterpret_cast<const float4*>(cst + 8 * q + 4);
+                            const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                            float shv[8];
+                            if (is_raw) {
+                                const float4 sh0 = *reinterpret_cast<const float4*>(cst + C3_MAX_CO + 8 * q),
+                                             sh1 = *reinterpret_cast<const float4*>(cst + C3_MAX_CO + 8 * q + 4);
+                                shv[0] = sh0.x; shv[1] = sh0.y; shv[2] = sh0.z; shv[3] = sh0.w; shv[4] = sh1.x; shv[5] = sh1.y; shv[6] = sh1.z; shv[7] = sh1.w;
                             }
-                            *reinterpret_cast<uint4*>(rowp + off) = make_uint4(res[0], res[1], res[2], res[3]);
+#pragma unroll
+                            for (int e2 = 0; e2 < 4; ++e2) {
+                                const float2 rf = c3_unpack_bf16x2(rw[e2]);
+                                float o2[2];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const int e = 8 * q + 2 * e2 + u;
+                                    const float ref = u ? rf.y : rf.x;
+                                    const float sc = scv[2 * e2 + u];
+                                    const float a = is_raw ? fmaf(ref, sc, shv[2 * e2 + u]) : ref;
+                                    const bool on = valid && a > 0.f;       // dropped rows hold stale shared memory: select, never multiply
+                                    const float gg = on ? __uint_as_float(r[e]) : 0.f;
+                                    gx[e] = on ? gg * ref : 0.f;            // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
+                                    v[e] = gg;
+                                    o2[u] = gg * sc;
+                                }
+                                res[e2] = c3_pack_bf16x2(o2[0], o2[1]);
+                            }
                         }
-                        if (want_sums) {
-                            cs_g[j] += gn_warp_colsum32(v, lane);
-                            cs_x[j] += gn_warp_colsum32(gx, lane);
-                        }
+                        *reinterpret_cast<uint4*>(rowp + off) = make_uint4(res[0], res[1], res[2], res[3]);
                     }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_eready[es]);
-                    if (++es == p.e_stages) { es = 0; eph ^= 1; }
+                    if (want_sums) {
+                        const float sg = gn_warp_colsum32(v, lane), sx = gn_warp_colsum32(gx, lane);
+                        atomicAdd(&s_cs[c0 + lane], sg);
+                        atomicAdd(&s_cs[C3_MAX_CO + c0 + lane], sx);
+                    }
                 }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_eready[es]);
+                if (++es == p.e_stages) { es = 0; eph ^= 1; }
             }
             tc_fence_before();
             __syncwarp();
@@ -348,13 +356,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             if (acc == 0) acc_phase ^= 1;
         }
         if (want_sums) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int col = j * 64 + h * 32 + lane;
-                if (j < p.nsub && col < p.CO) {
-                    atomicAdd(p.bn.colsum + col, cs_g[j]);
-                    atomicAdd(p.bn.colsum + p.bn.ldsum + col, __ldg(p.bn.p1 + col) * (cs_x[j] - __ldg(p.bn.p0 + col) * cs_g[j]));
-                }
+            named_bar_sync(1, C3_EPI_WARPS * 32);          // every epilogue warp has added its last partial sums
+            for (int col = threadIdx.x - 4 * 32; col < p.CO; col += C3_EPI_WARPS * 32) {
+                const float sg = s_cs[col], sx = s_cs[C3_MAX_CO + col];
+                atomicAdd(p.bn.colsum + col, sg);
+                atomicAdd(p.bn.colsum + p.bn.ldsum + col, __ldg(p.bn.p1 + col) * (sx - __ldg(p.bn.p0 + col) * sg));
             }
         }
     }
@@ -424,7 +430,7 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     }
     const int w_bytes = ((9 * p.kblocks * p.NP * p.w_row_bytes + 1023) / 1024) * 1024;
     const int stage_bytes = p.kblocks * p.a_rows * 128;
-    const int epi_fixed = 4 * C3_MAX_CO * 4;
+    const int epi_fixed = 6 * C3_MAX_CO * 4;
     const int budget = 227 * 1024 - 1024 - 512;
     GN_REQUIRE(w_bytes + stage_bytes + 2 * C3_SUB_BYTES + epi_fixed <= budget, GN_EUNSUPPORTED,
                "conv3x3: tile does not fit shared memory (weights %d B + stage %d B)", w_bytes, stage_bytes);
@@ -464,13 +470,15 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
         int rc = gn_tmap_encode(&tmRef, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, bn_ref, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    static int max_set = 0;
-    if ((int)smem > max_set) {
-        GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        max_set = (int)smem;
+    static int max_set[2] = {0, 0};
+    if ((int)smem > max_set[p.epi_mode]) {
+        if (p.epi_mode) GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set[p.epi_mode] = (int)smem;
     }
     const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
-    conv3x3_kernel<<<grid, 384, smem, stream>>>(tmX, tmW, tmOut, tmRef, p);
+    if (p.epi_mode) conv3x3_kernel<1><<<grid, 384, smem, stream>>>(tmX, tmW, tmOut, tmRef, p);
+    else conv3x3_kernel<0><<<grid, 384, smem, stream>>>(tmX, tmW, tmOut, tmRef, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

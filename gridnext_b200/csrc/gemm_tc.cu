@@ -38,7 +38,7 @@ using namespace gnptx;
 #define GEMM_EPI_MAX_N 1024
 #define GEMM_SUB_BYTES 16384      // one epilogue sub-tile: 128 rows x 64 bf16 (128-byte rows, SWIZZLE_128B)
 #define GEMM_MAX_STAGES 8
-#define GEMM_MAX_ESTAGES 6
+#define GEMM_MAX_ESTAGES 8
 #define GEMM_EPI_WARPS 8
 #define GEMM_EPI_THREADS (GEMM_EPI_WARPS * 32)
 
@@ -60,7 +60,7 @@ struct GemmParams {
     BnBwdEpi bn;
     int stages;                // main-loop ring depth
     int e_stages;              // epilogue sub-tile ring depth (TMA epilogues)
-    int slot_bytes;            // GEMM_SUB_BYTES, or 2x for read-modify-write (reference tile + old/new output tile)
+    int slot_bytes;            // GEMM_SUB_BYTES
 };
 
 template <int BN> struct GemmCfg {
@@ -135,6 +135,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int STAGES = p.stages;
     uint8_t* s_slots = sm + (size_t)STAGES * Cfg::STAGE_BYTES;                                   // e_stages x slot_bytes
     float* s_epi = reinterpret_cast<float*>(s_slots + (EPI == EPI_DIRECT ? 0 : (size_t)p.e_stages * p.slot_bytes));   // [4][GEMM_EPI_MAX_N]
+    float* s_cs = s_epi + 2 * GEMM_EPI_MAX_N;                                                     // [2][GEMM_EPI_MAX_N] column sums (EPI_BNBWD; reuses the p0/p1 rows)
     float* s_xf = s_epi + (EPI == EPI_DIRECT ? 0 : 4 * GEMM_EPI_MAX_N);                           // [2][GEMM_MAX_XF_K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -156,8 +157,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else {
                 s_epi[i] = in ? p.bn.sc[i] : 0.f;
                 s_epi[GEMM_EPI_MAX_N + i] = (in && p.bn.sh) ? p.bn.sh[i] : 0.f;
-                s_epi[2 * GEMM_EPI_MAX_N + i] = in ? p.bn.p0[i] : 0.f;
-                s_epi[3 * GEMM_EPI_MAX_N + i] = in ? p.bn.p1[i] : 0.f;
+                s_epi[2 * GEMM_EPI_MAX_N + i] = 0.f;          // s_cs: sum g
+                s_epi[3 * GEMM_EPI_MAX_N + i] = 0.f;          // s_cs: sum g * ref
             }
         }
     }
@@ -250,7 +251,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         uint8_t* slot = s_slots + (size_t)es * p.slot_bytes;
                         mbar_arrive_expect_tx(&bar_efull[es], (uint32_t)p.slot_bytes);
                         tma_load_2d(&tmRef, &bar_efull[es], slot, nb * BN + j * 64, mb * GEMM_BM);
-                        if (p.bn.rmw) tma_load_2d(&tmOut, &bar_efull[es], slot + GEMM_SUB_BYTES, nb * BN + j * 64, mb * GEMM_BM);
                     } else {
                         mbar_arrive(&bar_efull[es]);
                     }
@@ -268,7 +268,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int nsub = (min(BN, p.N - nb * BN) + 63) >> 6;
                 for (int j = 0; j < nsub; ++j) {
                     mbar_wait(&bar_eready[es], eph);
-                    tma_store_2d(&tmOut, s_slots + (size_t)es * p.slot_bytes + (p.slot_bytes - GEMM_SUB_BYTES), nb * BN + j * 64, mb * GEMM_BM);
+                    if (EPI == EPI_BNBWD && p.bn.rmw) tma_reduce_add_2d(&tmOut, s_slots + (size_t)es * p.slot_bytes, nb * BN + j * 64, mb * GEMM_BM);
+                    else tma_store_2d(&tmOut, s_slots + (size_t)es * p.slot_bytes, nb * BN + j * 64, mb * GEMM_BM);
                     tma_store_commit();
                     if (prev_es >= 0) {
                         tma_store_wait_read<1>();          // the previous sub-tile's store has drained its slot
@@ -293,14 +294,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int cur_nb = -1;
         const bool want_sums = (EPI == EPI_BNBWD || (EPI == EPI_DIRECT && p.epi_mode == 1)) && p.bn.colsum != nullptr;
         auto flush_colsums = [&]() {
-            if (want_sums && cur_nb >= 0) {
+            if (EPI == EPI_DIRECT && want_sums && cur_nb >= 0) {
 #pragma unroll
                 for (int j = 0; j < NSUB; ++j) {
                     const int col = cur_nb * BN + j * 64 + h * 32 + lane;
                     if (col < p.N) {
                         atomicAdd(p.bn.colsum + col, cs_g[j]);
-                        const float sx = EPI == EPI_BNBWD ? __ldg(p.bn.p1 + col) * (cs_x[j] - __ldg(p.bn.p0 + col) * cs_g[j]) : cs_x[j];
-                        atomicAdd(p.bn.colsum + p.bn.ldsum + col, sx);
+                        atomicAdd(p.bn.colsum + p.bn.ldsum + col, cs_x[j]);
                     }
                     cs_g[j] = 0.f; cs_x[j] = 0.f;
                 }
@@ -366,77 +366,69 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             } else {
                 const int nsub = (min(BN, p.N - nb * BN) + 63) >> 6;
-#pragma unroll
-                for (int j = 0; j < NSUB; ++j) {
-                    if (j < nsub) {
-                        mbar_wait(&bar_efull[es], eph);
-                        uint8_t* slot = s_slots + (size_t)es * p.slot_bytes;
-                        uint8_t* ref_row = slot + trow * 128;
-                        uint8_t* out_row = ref_row + (p.slot_bytes - GEMM_SUB_BYTES);     // same tile unless read-modify-write
-                        __syncwarp();
-                        if (active) {
+#pragma unroll 1
+                for (int j = 0; j < nsub; ++j) {
+                    mbar_wait(&bar_efull[es], eph);
+                    uint8_t* row_p = s_slots + (size_t)es * p.slot_bytes + trow * 128;      // results replace the staged tile in place
+                    __syncwarp();
+                    if (active) {
                         uint32_t r[32];
                         tmem_ld32(taddr + j * 64 + h * 32, r);
                         tmem_ld_wait();
-                        const float* cst = s_epi + nb * BN + j * 64 + h * 32;
-                        if (EPI == EPI_STORE) {
+                        const int col0 = nb * BN + j * 64 + h * 32;
+                        const float* cst = s_epi + col0;
+                        float v[32], gx[32];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                float o[8];
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t off = (((uint32_t)(h * 4 + q)) ^ sw) << 4;
+                            const float4 c0a = *reinterpret_cast<const float4*>(cst + 8 * q), c0b = *reinterpret_cast<const float4*>(cst + 8 * q + 4);
+                            const float4 c1a = *reinterpret_cast<const float4*>(cst + GEMM_EPI_MAX_N + 8 * q),
+                                         c1b = *reinterpret_cast<const float4*>(cst + GEMM_EPI_MAX_N + 8 * q + 4);
+                            const float k0[8] = {c0a.x, c0a.y, c0a.z, c0a.w, c0b.x, c0b.y, c0b.z, c0b.w};     // scale
+                            const float k1[8] = {c1a.x, c1a.y, c1a.z, c1a.w, c1b.x, c1b.y, c1b.z, c1b.w};     // shift
+                            uint32_t res[4];
+                            if (EPI == EPI_STORE) {
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const float x = fmaf(__uint_as_float(r[8 * q + e]), cst[8 * q + e], cst[GEMM_EPI_MAX_N + 8 * q + e]);
-                                    o[e] = p.relu ? fmaxf(x, 0.f) : x;
+                                for (int e2 = 0; e2 < 4; ++e2) {
+                                    float x0 = fmaf(__uint_as_float(r[8 * q + 2 * e2]), k0[2 * e2], k1[2 * e2]);
+                                    float x1 = fmaf(__uint_as_float(r[8 * q + 2 * e2 + 1]), k0[2 * e2 + 1], k1[2 * e2 + 1]);
+                                    if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                                    res[e2] = pack_bf16x2(x0, x1);
                                 }
-                                uint4 t;
-                                t.x = pack_bf16x2(o[0], o[1]); t.y = pack_bf16x2(o[2], o[3]);
-                                t.z = pack_bf16x2(o[4], o[5]); t.w = pack_bf16x2(o[6], o[7]);
-                                *reinterpret_cast<uint4*>(out_row + ((((uint32_t)(h * 4 + q)) ^ sw) << 4)) = t;
-                            }
-                        } else {
-                            float v[32], gx[32];
-                            const bool rmw = p.bn.rmw != 0, is_raw = p.bn.ref_is_raw != 0;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint32_t off = (((uint32_t)(h * 4 + q)) ^ sw) << 4;
-                                const uint4 rv = *reinterpret_cast<const uint4*>(ref_row + off);
-                                uint4 ov = make_uint4(0u, 0u, 0u, 0u);
-                                if (rmw) ov = *reinterpret_cast<const uint4*>(out_row + off);
+                            } else {
+                                const bool is_raw = p.bn.ref_is_raw != 0;
+                                const uint4 rv = *reinterpret_cast<const uint4*>(row_p + off);
                                 const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-                                const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
-                                uint32_t res[4];
 #pragma unroll
                                 for (int e2 = 0; e2 < 4; ++e2) {
                                     const float2 rf = unpack_bf16x2(rw[e2]);
-                                    const float2 of = unpack_bf16x2(ow[e2]);
                                     float o2[2];
 #pragma unroll
                                     for (int u = 0; u < 2; ++u) {
                                         const int e = 8 * q + 2 * e2 + u;
                                         const float ref = u ? rf.y : rf.x;
-                                        const float old = u ? of.y : of.x;
-                                        const float sc = cst[e];
-                                        const float a = is_raw ? fmaf(ref, sc, cst[GEMM_EPI_MAX_N + e]) : ref;
+                                        const float sc = k0[2 * e2 + u];
+                                        const float a = is_raw ? fmaf(ref, sc, k1[2 * e2 + u]) : ref;
                                         const float gg = a > 0.f ? __uint_as_float(r[e]) : 0.f;
-                                        gx[e] = gg * ref;          // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
+                                        gx[e] = gg * ref;             // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
                                         v[e] = gg;
-                                        o2[u] = rmw ? fmaf(gg, sc, old) : gg * sc;
+                                        o2[u] = gg * sc;              // += (read-modify-write) is done by the TMA reduction in L2
                                     }
                                     res[e2] = pack_bf16x2(o2[0], o2[1]);
                                 }
-                                *reinterpret_cast<uint4*>(out_row + off) = make_uint4(res[0], res[1], res[2], res[3]);
                             }
-                            if (want_sums) {
-                                cs_g[j] += gn_warp_colsum32(v, lane);
-                                cs_x[j] += gn_warp_colsum32(gx, lane);
-                            }
+                            *reinterpret_cast<uint4*>(row_p + off) = make_uint4(res[0], res[1], res[2], res[3]);
                         }
+                        if (EPI == EPI_BNBWD && want_sums) {
+                            const float sg = gn_warp_colsum32(v, lane), sx = gn_warp_colsum32(gx, lane);
+                            atomicAdd(&s_cs[col0 + lane], sg);
+                            atomicAdd(&s_cs[GEMM_EPI_MAX_N + col0 + lane], sx);
                         }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_eready[es]);
-                        if (++es == p.e_stages) { es = 0; eph ^= 1; }
                     }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_eready[es]);
+                    if (++es == p.e_stages) { es = 0; eph ^= 1; }
                 }
             }
             tc_fence_before();
@@ -446,6 +438,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (acc == 0) acc_phase ^= 1;
         }
         flush_colsums();
+        if (EPI == EPI_BNBWD && want_sums) {
+            named_bar_sync(1, GEMM_EPI_THREADS);            // every epilogue warp has added its last partial sums
+            for (int col = threadIdx.x - 4 * 32; col < p.N; col += GEMM_EPI_THREADS) {
+                const float sg = s_cs[col], sx = s_cs[GEMM_EPI_MAX_N + col];
+                atomicAdd(p.bn.colsum + col, sg);
+                atomicAdd(p.bn.colsum + p.bn.ldsum + col, __ldg(p.bn.p1 + col) * (sx - __ldg(p.bn.p0 + col) * sg));
+            }
+        }
     } else if (XFORM && warp >= 12) {
         // ===================== operand transform: A <- relu(A * scale[k] + shift[k]) in place =====================
         const int w = warp - 12;
@@ -506,8 +506,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     const int budget = 227 * 1024 - 1024 - 512;        // dynamic shared memory minus alignment slack and static barriers
     int fixed = XFORM ? 2 * GEMM_MAX_XF_K * 4 : 0;
     if (EPI != EPI_DIRECT) {
-        p.slot_bytes = (EPI == EPI_BNBWD && p.bn.rmw) ? 2 * GEMM_SUB_BYTES : GEMM_SUB_BYTES;
-        p.e_stages = p.slot_bytes == GEMM_SUB_BYTES ? 4 : 3;
+        p.slot_bytes = GEMM_SUB_BYTES;       // read-modify-write goes through the TMA reduction: no old-output tile in shared memory
+        p.e_stages = EPI == EPI_BNBWD ? 6 : 4;
         fixed += 4 * GEMM_EPI_MAX_N * 4 + p.e_stages * p.slot_bytes;
     } else {
         p.slot_bytes = 0;

@@ -96,6 +96,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+// TMA reduction (shared -> global += ...): the add happens in L2 with the tensor map's element type (bf16 here), so a
+// read-modify-write epilogue never has to bring the old output tile into the SM
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still have to READ their shared-memory source
 template <int N>
