@@ -13,6 +13,8 @@
 // memory with 16-byte loads, then every thread turns 4 pixels x 3 channels into three vector
 // stores, one per NCHW channel plane.  HBM-bound: 3*P*P bytes in, 3*P*P*sizeof(out) bytes out per spot.
 #include "gn_common.cuh"
+#include "gn_ptx.cuh"
+#include "gn_tma.cuh"
 
 // cells[n] = {cx, cy, valid} for grid cell n = y_ind * w_st + x_ind
 __global__ void spot_table_kernel(const unsigned char* __restrict__ in_tissue, const int* __restrict__ array_row,
@@ -57,8 +59,8 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) patch_gather_kernel(const unsigned char* __restrict__ img, long pitch, long img_bytes, int H, int W,
                                                            const int* __restrict__ cells, int P, int rpc, int row_buf,
                                                            const float* __restrict__ mean, const float* __restrict__ stdv,
-                                                           OutT* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char sm[];
+                                                           OutT* __restrict__ out, int only_rest) {
+    extern __shared__ __align__(128) unsigned char sm[];
     float* lut = reinterpret_cast<float*>(sm);                 // [3][256]
     unsigned char* rows = sm + 3 * 256 * sizeof(float);        // [rpc][row_buf]
     __shared__ int s_off[64];                                  // byte offset of the staged segment inside its row buffer
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const unsigned char* 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cx = cells[3 * cell + 0], cy = cells[3 * cell + 1], valid = cells[3 * cell + 2];
     const int hw = P / 2;
+    if (only_rest && valid && cx - hw >= 0 && cx - hw + P <= W && cy - hw >= 0 && cy - hw + P <= H) return;   // the TMA kernel owns this cell
     OutT* ocell = out + (long)cell * 3 * P * P;
     const int nrows = min(rpc, P - r0);
     const int groups = P / 4;
@@ -139,6 +142,72 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const unsigned char* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA path for cells whose window lies inside the image (all but the few spots within P/2 of a border).  TMA boxes must
+// start on a 16-byte boundary of the innermost dimension (a misaligned start faults -- measured), so the image is viewed as
+// rows of uint32 and the box starts at the 16-byte boundary below the window's first byte; the byte offset d (0..15, the
+// same for every row of a cell) is removed with funnel shifts when a thread unpacks its 4 pixels (12 bytes).  Border / out-of-tissue cells are left to the generic kernel above (`only_rest` = 1).
+#define PG_RPC 32            // patch rows per CTA
+
+__device__ __forceinline__ bool pg_interior(int cx, int cy, int hw, int P, int H, int W) {
+    return cx - hw >= 0 && cx - hw + P <= W && cy - hw >= 0 && cy - hw + P <= H;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) patch_gather_tma_kernel(const __grid_constant__ CUtensorMap tmImg, int H, int W, const int* __restrict__ cells,
+                                                               int P, int row_bytes, const float* __restrict__ mean,
+                                                               const float* __restrict__ stdv, OutT* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    __shared__ __align__(8) uint64_t bar;
+    const int cell = blockIdx.x, r0 = blockIdx.y * PG_RPC;
+    const int cx = cells[3 * cell + 0], cy = cells[3 * cell + 1], valid = cells[3 * cell + 2];
+    const int hw = P / 2;
+    if (!valid || !pg_interior(cx, cy, hw, P, H, W)) return;
+    const int tid = threadIdx.x;
+    float* lut = reinterpret_cast<float*>(sm);                        // [3][256]
+    unsigned char* rows = sm + 3 * 256 * sizeof(float);               // [PG_RPC][row_bytes] (+ 16 bytes of slack)
+    const int b0 = 3 * (cx - hw);                                     // first byte of the window in its image row
+    const int a0 = b0 & ~15, d = b0 - a0;
+    if (tid == 0) {
+        gnptx::mbar_init(&bar, 1);
+        gnptx::fence_barrier_init();
+        gnptx::mbar_arrive_expect_tx(&bar, (uint32_t)(PG_RPC * row_bytes));
+        gnptx::tma_load_2d(&tmImg, &bar, rows, a0 >> 2, cy - hw + r0);
+    }
+    // value table: raw u8 -> float, or ((v / 255) - mean) / std in IEEE fp32 like ToTensor + Normalize
+    for (int e = tid; e < 3 * 256; e += 256) {
+        const int c = e >> 8, v = e & 255;
+        float f = (float)v;
+        if (mean != nullptr) f = __fdiv_rn(__fsub_rn(__fdiv_rn(f, 255.0f), mean[c]), stdv[c]);
+        lut[e] = f;
+    }
+    __syncthreads();
+    gnptx::mbar_wait(&bar, 0);
+    // thread = 4 pixels (12 bytes): four 4-byte shared loads from the word holding the first byte, one funnel shift per word
+    // (the byte phase (d & 3) is uniform), 12 table look-ups, and one 8/16-byte store per channel -- consecutive lanes write
+    // consecutive addresses of the output row.
+    const int groups = P / 4;
+    const int sh = (d & 3) * 8;
+    OutT* ocell = out + (long)cell * 3 * P * P;
+    for (int e = tid; e < PG_RPC * groups; e += 256) {
+        const int r = e / groups, g = e - r * groups;
+        const unsigned* src = reinterpret_cast<const unsigned*>(rows + (size_t)r * row_bytes + ((12 * g + d) & ~3));
+        const unsigned i0 = src[0], i1 = src[1], i2 = src[2], i3 = src[3];
+        const unsigned w[3] = {__funnelshift_r(i0, i1, sh), __funnelshift_r(i1, i2, sh), __funnelshift_r(i2, i3, sh)};
+        float v[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int byte = 3 * j + c;
+                v[c][j] = lut[c * 256 + ((w[byte >> 2] >> (8 * (byte & 3))) & 0xff)];
+            }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            Pack4<OutT>::store(ocell + ((long)c * P + r0 + r) * P + 4 * g, v[c][0], v[c][1], v[c][2], v[c][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 GN_API int gn_spot_table(const unsigned char* in_tissue, const int* array_row, const int* array_col, const double* pxl_row,
                          const double* pxl_col, int n_spots, int h_st, int w_st, int* cells /* [h_st*w_st][3] */,
                          int* n_dropped /* [1] */, cudaStream_t stream) {
@@ -169,12 +238,34 @@ GN_API int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, c
     GN_REQUIRE(rpc >= 1, GN_EUNSUPPORTED, "patch_gather: patch too wide");
     const size_t smem = 3 * 256 * sizeof(float) + (size_t)rpc * row_buf;
     const long img_bytes = (long)(H - 1) * pitch + 3L * W;
+    // interior cells go through TMA when the image can be described by a tensor map of uint32 rows (16-byte pitch)
+    const int row_bytes = ((3 * P + 16 + 15) / 16) * 16;          // window + up to 15 bytes of lead-in, a whole number of 16-byte units
+    const bool use_tma = (P % 32 == 0) && (row_bytes / 4 <= 256) && (pitch % 16 == 0) && (W % 4 == 0) && H >= P && W >= P;
+    if (use_tma) {
+        CUtensorMap tm;
+        uint64_t dims[2] = {(uint64_t)(3 * W / 4), (uint64_t)H};       // rows as uint32; the lead-out past 3*W is out of bounds = zero-filled, never read
+        uint64_t strides[1] = {(uint64_t)pitch};
+        uint32_t box[2] = {(uint32_t)(row_bytes / 4), PG_RPC};
+        int rc = gn_tmap_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, img, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        const size_t smem_t = 3 * 256 * sizeof(float) + (size_t)PG_RPC * row_bytes + 16;
+        dim3 grid_t(n_cells, P / PG_RPC);
+        if (out_bf16) {
+            GN_CUDA(cudaFuncSetAttribute(patch_gather_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+            patch_gather_tma_kernel<__nv_bfloat16><<<grid_t, 256, smem_t, stream>>>(tm, H, W, cells, P, row_bytes, mean, stdv, (__nv_bfloat16*)out);
+        } else {
+            GN_CUDA(cudaFuncSetAttribute(patch_gather_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+            patch_gather_tma_kernel<float><<<grid_t, 256, smem_t, stream>>>(tm, H, W, cells, P, row_bytes, mean, stdv, (float*)out);
+        }
+        GN_LAUNCH_CHECK();
+    }
     dim3 grid(n_cells, gn_ceil_div(P, rpc));
     if (out_bf16)
         patch_gather_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(img, pitch, img_bytes, H, W, cells, P, rpc, row_buf, mean, stdv,
-                                                                        (__nv_bfloat16*)out);
+                                                                        (__nv_bfloat16*)out, use_tma ? 1 : 0);
     else
-        patch_gather_kernel<float><<<grid, 256, smem, stream>>>(img, pitch, img_bytes, H, W, cells, P, rpc, row_buf, mean, stdv, (float*)out);
+        patch_gather_kernel<float><<<grid, 256, smem, stream>>>(img, pitch, img_bytes, H, W, cells, P, rpc, row_buf, mean, stdv, (float*)out,
+                                                               use_tma ? 1 : 0);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -44,6 +44,21 @@ def _normalize_params(preprocess_xform):
     raise NotImplementedError("grid_from_wsi_visium on B200 supports preprocess_xform=None or a torchvision Normalize")
 
 
+_CONST_CACHE = {}
+
+
+def _dev_const(values, device):
+    """Per-channel constants as a cached device tensor (no host->device copy per call; keeps the step graph-capturable)."""
+    if values is None:
+        return None
+    key = (tuple(float(v) for v in values), str(device))
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(key[0], device=device, dtype=torch.float32)
+        _CONST_CACHE[key] = t
+    return t
+
+
 def spot_table(in_tissue, array_row, array_col, pxl_row, pxl_col, device, h_st=VISIUM_H_ST, w_st=VISIUM_W_ST):
     """Device table cells[h_st*w_st][3] = (cx, cy, valid) from a Visium position table.  Returns (cells, n_dropped)."""
     dev = torch.device(device)
@@ -70,8 +85,7 @@ def gather_patches(img, cells, patch_size, mean=None, std=None, out_dtype=torch.
     P = int(patch_size)
     if out is None:
         out = torch.empty((h_st, w_st, 3, P, P), device=img.device, dtype=out_dtype)
-    m = torch.tensor(mean, device=img.device, dtype=torch.float32) if mean is not None else None
-    s = torch.tensor(std, device=img.device, dtype=torch.float32) if std is not None else None
+    m, s = _dev_const(mean, img.device), _dev_const(std, img.device)
     call('gn_patch_gather', ptr(img), 3 * W, H, W, ptr(cells), h_st * w_st, P, ptr(m), ptr(s), ptr(out),
          1 if out_dtype == torch.bfloat16 else 0, stream())
     return out
@@ -85,8 +99,7 @@ def normalize_patches(patches_u8, mean=None, std=None, out_dtype=torch.float32, 
     P = int(patches_u8.shape[-1])
     n_cells = patches_u8.numel() // (3 * P * P)
     out = torch.empty(patches_u8.shape, device=patches_u8.device, dtype=out_dtype)
-    m = torch.tensor(mean, device=out.device, dtype=torch.float32) if mean is not None else None
-    s = torch.tensor(std, device=out.device, dtype=torch.float32) if std is not None else None
+    m, s = _dev_const(mean, out.device), _dev_const(std, out.device)
     call('gn_normalize_u8', ptr(patches_u8), ptr(valid), n_cells, P, ptr(m), ptr(s), ptr(out), 1 if out_dtype == torch.bfloat16 else 0, stream())
     return out
 

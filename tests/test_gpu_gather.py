@@ -32,7 +32,8 @@ def test_gather_matches_reference_golden():
     assert np.array_equal(nrm.cpu().numpy()[::11, ::9], gold['nrm_sub'])        # bit-exact fp32
 
 
-@pytest.mark.parametrize('P,Himg,Wimg,seed', [(128, 1500, 1700, 1), (32, 400, 377, 2), (64, 333, 1001, 3), (256, 700, 900, 4)])
+@pytest.mark.parametrize('P,Himg,Wimg,seed', [(128, 1500, 1700, 1), (32, 400, 377, 2), (64, 333, 1001, 3), (256, 700, 900, 4),
+                                              (128, 1500, 1600, 5), (64, 500, 1024, 6), (256, 800, 1008, 7)])   # 16-byte pitch: TMA path
 def test_gather_matches_oracle_bit_exact(P, Himg, Wimg, seed):
     # pitch chosen so that spots hang over all four image borders (edge clamp) and odd byte alignments occur
     pos = synth.synth_positions(pitch_col=Wimg / 130.0, pitch_row=Himg / 79.0, org_row=1.0, org_col=1.5)
