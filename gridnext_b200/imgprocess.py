@@ -91,14 +91,17 @@ def gather_patches(img, cells, patch_size, mean=None, std=None, out_dtype=torch.
     return out
 
 
-def normalize_patches(patches_u8, mean=None, std=None, out_dtype=torch.float32, valid=None):
+def normalize_patches(patches_u8, mean=None, std=None, out_dtype=torch.float32, valid=None, out=None):
     """uint8 (..., 3, P, P) CUDA patch grid -> ToTensor + Normalize on the device (absent cells stay 0)."""
     _lib.require_cuda(patches_u8)
     if patches_u8.dtype != torch.uint8 or not patches_u8.is_contiguous() or patches_u8.shape[-3] != 3:
         raise ValueError('normalize_patches: expected a contiguous uint8 (..., 3, P, P) tensor')
     P = int(patches_u8.shape[-1])
     n_cells = patches_u8.numel() // (3 * P * P)
-    out = torch.empty(patches_u8.shape, device=patches_u8.device, dtype=out_dtype)
+    if out is None:
+        out = torch.empty(patches_u8.shape, device=patches_u8.device, dtype=out_dtype)
+    elif out.dtype != out_dtype or out.numel() != patches_u8.numel() or not out.is_contiguous():
+        raise ValueError('normalize_patches: out must be a contiguous %s tensor of the input size' % out_dtype)
     m, s = _dev_const(mean, out.device), _dev_const(std, out.device)
     call('gn_normalize_u8', ptr(patches_u8), ptr(valid), n_cells, P, ptr(m), ptr(s), ptr(out), 1 if out_dtype == torch.bfloat16 else 0, stream())
     return out
