@@ -10,6 +10,9 @@ shifted down; inside ``GridNetHex*`` the corrector runs through ``corrector.run_
 in the Visium layout instead, without any re-indexing copies.
 """
 import math
+import ctypes
+import os
+
 import torch
 import torch.nn as nn
 
@@ -38,9 +41,29 @@ def pack_weights(ks, ksize, cin, cout, mode):
     return wp
 
 
+# 'auto': tensor cores once the convolution is throughput-bound (>= 16 Visium arrays' worth of cells); below that the g network
+# is launch-latency-bound and the exact-fp32 FMA kernel costs the same.  '1' / '0' force one path (tests, benchmarks).
+TENSOR_CORE_MODE = os.environ.get('GRIDNEXT_B200_HEX_TC', 'auto')
+TENSOR_CORE_MIN_CELLS = 16 * 78 * 64
+
+
+def _use_tc(B, cin, cout, H, W, ksize):
+    if TENSOR_CORE_MODE == '0' or not _lib.load().gn_hexconv_tc_supported(cin, cout, H, W, ksize):
+        return False
+    return TENSOR_CORE_MODE == '1' or B * H * W >= TENSOR_CORE_MIN_CELLS
+
+
 def hexconv_fwd(x, wp, bias, cout, ksize, in_scale=None, in_shift=None, stats=None):
+    """y = hexconv(x') + bias.  kernel_size 1 with <= 32 channels runs on tcgen05 (bf16 x 3 split, fp32 accumulate: the
+    7-tap, 32-channel convolution is far above the FP32-FMA ridge); everything else on the FP32-FMA kernel."""
     B, cin, H, W = x.shape
     y = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
+    if _use_tc(B, cin, cout, H, W, ksize):
+        ws = torch.empty((int(_lib.load().gn_hexconv_tc_workspace_bytes(B, H, W)) + 1024,), device=x.device, dtype=torch.uint8)
+        off = (-ws.data_ptr()) % 1024
+        call('gn_hexconv_fwd_tc', ptr(x), ptr(wp), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(y), ptr(stats), B, cin, cout, H, W,
+             ctypes.c_void_p(ws.data_ptr() + off), stream())
+        return y
     call('gn_hexconv_fwd', ptr(x), ptr(wp), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(y), ptr(stats),
          B, cin, cout, H, W, ksize, stream())
     return y

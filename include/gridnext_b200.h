@@ -41,6 +41,12 @@ int gn_hexconv_unpack_grad(const float* dwp, float* dk0, float* dk1, float* dk2,
  * zeroes) accumulates per-channel sum and sum of squares of y for the next BatchNorm2d. */
 int gn_hexconv_fwd(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift,
                    float* y, double* stats, int B, int cin, int cout, int H, int W, int ksize, gn_stream_t stream);
+/* Tensor-core variant of gn_hexconv_fwd for kernel_size 1 and <= 32 channels (tcgen05, bf16 x 3 split, fp32 accumulate): same
+ * contract; `workspace` is caller-owned scratch of gn_hexconv_tc_workspace_bytes(B, H, W) bytes, 1024-byte aligned. */
+int gn_hexconv_tc_supported(int cin, int cout, int H, int W, int ksize);
+long gn_hexconv_tc_workspace_bytes(int B, int H, int W);
+int gn_hexconv_fwd_tc(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
+                      double* stats, int B, int cin, int cout, int H, int W, void* workspace, gn_stream_t stream);
 /* dwp[T][cin][cout] += sum dY * x' ; dbias[cout] += sum dY  (caller zeroes both). */
 int gn_hexconv_wgrad(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp,
                      float* dbias, int B, int cin, int cout, int H, int W, int ksize, gn_stream_t stream);

@@ -57,6 +57,74 @@ def test_hexconv_fwd_bwd_matches_oracle(k, cfg):
         assert rel_err(a.grad, r.grad) < TOL
 
 
+@pytest.mark.parametrize('cfg', [(7, 32, 2, 78, 64), (32, 32, 3, 78, 64), (32, 7, 2, 78, 64), (3, 5, 2, 7, 9), (4, 4, 1, 4, 4), (14, 32, 1, 9, 70),
+                                 (32, 32, 17, 78, 64), (20, 12, 3, 11, 33)])
+def test_hexconv_tensor_core_path_matches_oracle(cfg, monkeypatch):
+    """kernel_size 1, <= 32 channels on tcgen05 (bf16 x 3 split): forward and data gradient still within 1e-5 of the fp64 oracle."""
+    from gridnext_b200 import hexagdly as hx
+    monkeypatch.setattr(hx, 'TENSOR_CORE_MODE', '1')
+    cin, cout, B, H, W = cfg
+    ks, b, x, dy = rand_hex(cin, cout, 1, B, H, W, seed=77 + cin + H)
+    ks_r = [t.clone().double().requires_grad_(True) for t in ks]
+    b_r = b.clone().double().requires_grad_(True)
+    x_r = x.clone().double().requires_grad_(True)
+    y_r = hexconv_visium(x_r, ks_r, b_r)
+    y_r.backward(dy.double())
+    ks_g = [t.clone().to(dev()).requires_grad_(True) for t in ks]
+    b_g = b.clone().to(dev()).requires_grad_(True)
+    x_g = x.clone().to(dev()).requires_grad_(True)
+    y_g = hx.hexconv_visium(x_g, ks_g, b_g)
+    y_g.backward(dy.to(dev()))
+    assert rel_err(y_g, y_r) < TOL
+    assert rel_err(x_g.grad, x_r.grad) < TOL
+    for a, r in zip(ks_g, ks_r):
+        assert rel_err(a.grad, r.grad) < TOL
+
+
+@pytest.mark.parametrize('B', [3, 20])
+def test_fused_corrector_on_tensor_cores(B, monkeypatch):
+    """The 5-layer corrector with every hex layer on the tensor-core path: each layer is within 1e-5, the composition of five
+    (with two train-mode BatchNorms in between) within 2e-5 of the fp64 oracle; B = 20 also takes this path in 'auto' mode."""
+    from gridnext_b200 import hexagdly as hx
+    from gridnext_b200.gridnet_models import GridNetHexOddr
+    import torch.nn as nn
+    monkeypatch.setattr(hx, 'TENSOR_CORE_MODE', '1' if B < 16 else 'auto')
+    net = GridNetHexOddr(nn.Identity(), (7,), (78, 64), 7).to(dev()).train()
+    sd = {k: v.detach().cpu() for k, v in net.corrector.state_dict().items()}
+    g = torch.Generator(); g.manual_seed(3)
+    x = torch.randn(B, 7, 78, 64, generator=g)
+    dy = torch.randn(B, 7, 78, 64, generator=g)
+    sd_r = {k: (v.double().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v) for k, v in sd.items()}
+    x_r = x.double().requires_grad_(True)
+    y_r = R.corrector_forward(sd_r, x_r, use_bn=True, training=True)
+    y_r.backward(dy.double())
+    x_g = x.to(dev()).requires_grad_(True)
+    y_g = net._correct_visium(x_g)
+    y_g.backward(dy.to(dev()))
+    assert rel_err(y_g, y_r) < 2e-5
+
+    # Gradients: a 5e-6 difference in a pre-ReLU activation flips the ReLU mask of the few cells that sit that close to zero.
+    # Each flip changes its own gradient entries by O(1) and, through the train-mode BatchNorm backward (which subtracts batch
+    # means), every other entry by ~1/N.  The fp32-FMA path has the same discontinuity (it flips ~10x fewer cells).  The kernels
+    # themselves are pinned at 1e-5 per layer above; here the composed gradient must agree in L2 (1 %); a flipped cell may move its own entry by up to 25 % of the max-norm.
+    def close(got, ref, name):
+        got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+        l2 = float((got - ref).norm() / max(float(ref.norm()), 1e-3 * ref.numel() ** 0.5))
+        mx = float((got - ref).abs().max() / max(float(ref.abs().max()), 1e-3))
+        assert l2 < 1e-2 and mx < 0.25, (name, l2, mx)
+    close(x_g.grad, x_r.grad, 'dx')
+    params = dict(net.corrector.named_parameters())
+    for name, p in params.items():
+        ref = sd_r[name].grad
+        if float(ref.abs().max()) < 1e-9:
+            # bias in front of a train-mode BatchNorm: its gradient is exactly zero in theory (sum of mean-free terms); what is
+            # left is summation noise, which must be negligible against the gradient of the same layer's kernel
+            sib = params[name.replace('bias_tensor', 'kernel0')].grad
+            assert float(p.grad.abs().max()) < 1e-2 * float(sib.abs().max()), name
+            continue
+        close(p.grad, ref, name)
+
+
 def test_hexagdly_module_layout_matches_upstream_composition():
     import gridnext_b200.hexagdly as hx
     torch.manual_seed(3)
