@@ -312,3 +312,173 @@ GN_API int gn_hexconv_fwd_tc(const float* x, const float* wp, const float* bias,
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
+
+// ================================================================================================
+// Weight gradient on tensor cores:  dWp[t][ci][co] += sum_s X'[s + off_t, ci] * dY[s, co]  over both parity planes.
+// Both operands are "MN-major" (rows = positions = the reduction index): A = the X' window started at the tap's row
+// (64 columns = hi | lo of ci, the second 64-column group aliased: LBO = 0), B = the dY tile (64 columns = hi | lo of co).
+// All four cross terms hi/lo x hi/lo land in the 64 x 64 accumulator of the tap; the seven accumulators (448 TMEM
+// columns) live for the whole persistent CTA and are folded and added to global memory once at the end.
+struct HexTcWgParams {
+    int B, H, W, Cin, Cout, Q, WP, PS, tiles_per_img, n_tiles, win_rows;
+    float* dwp;                  // [7][Cin][Cout] fp32, +=
+    int row_off[2][HTC_TAPS];
+    int src[2][HTC_TAPS];
+};
+
+__global__ void __launch_bounds__(192, 1)
+hexconv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const HexTcWgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_done;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int win_bytes = ((p.win_rows * 128 + 1023) / 1024) * 1024;
+    const int stage_bytes = 2 * win_bytes + 2 * 16384;            // X' windows (even, odd) + dY tiles (even, odd)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmDY);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const bool has_work = (int)blockIdx.x < p.n_tiles;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const int b = tile / p.tiles_per_img, s0 = (tile - b * p.tiles_per_img) * 128;
+                mbar_wait(&bar_empty[stage], phase ^ 1);
+                uint8_t* st = sm + (size_t)stage * stage_bytes;
+                mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(2 * p.win_rows * 128 + 2 * 16384));
+                tma_load_3d(&tmX, &bar_full[stage], st, 0, s0 - 1, 2 * b);
+                tma_load_3d(&tmX, &bar_full[stage], st + win_bytes, 0, s0 - p.WP - 1, 2 * b + 1);
+                tma_load_3d(&tmDY, &bar_full[stage], st + 2 * win_bytes, 0, s0, 2 * b);
+                tma_load_3d(&tmDY, &bar_full[stage], st + 2 * win_bytes + 16384, 0, s0, 2 * b + 1);
+                stage ^= 1;
+                if (stage == 0) phase ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = idesc_bf16(128, 64, 1, 1);
+            const uint64_t tmplA = smem_desc_template(0, 1024, LAYOUT_SW128);      // MN-major, the two 64-wide groups aliased
+            const uint64_t tmplB = smem_desc_template(0, 1024, LAYOUT_SW128);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t started = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(&bar_full[stage], phase);
+                tc_fence_after();
+                const uint32_t st = smem_u32(sm + (size_t)stage * stage_bytes);
+                const uint64_t descX[2] = {smem_desc(tmplA, st), smem_desc(tmplA, st + win_bytes)};
+#pragma unroll
+                for (int par = 0; par < 2; ++par) {
+                    const uint64_t descDY = smem_desc(tmplB, st + 2 * win_bytes + par * 16384);
+#pragma unroll
+                    for (int t = 0; t < HTC_TAPS; ++t) {
+                        const uint64_t da = descX[p.src[par][t]] + (uint64_t)(p.row_off[par][t] * 8);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {        // 128 positions = 8 x 16 reduction rows (2048 B each)
+                            umma_bf16(tmem_base + (uint32_t)(t * 64), da + (uint64_t)(k * 128), descDY + (uint64_t)(k * 128), idesc, (started >> t) & 1u);
+                            started |= 1u << t;
+                        }
+                    }
+                }
+                umma_commit(&bar_empty[stage]);
+                stage ^= 1;
+                if (stage == 0) phase ^= 1;
+            }
+            umma_commit(&bar_done);
+        }
+    } else if (has_work) {
+        const int g = warp & 3;
+        if (g < 2) {                                   // accumulator rows 0..31 = x_hi[ci], 32..63 = x_lo[ci]
+            mbar_wait(&bar_done, 0);
+            tc_fence_after();
+            const int ci = lane;
+            for (int t = 0; t < HTC_TAPS; ++t) {
+                uint32_t r0[32], r1[32];
+                __syncwarp();
+                tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(t * 64), r0);          // x dY_hi[co]
+                tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(t * 64 + 32), r1);     // x dY_lo[co]
+                tmem_ld_wait();
+                if (ci < p.Cin) {
+                    float* o = p.dwp + ((long)t * p.Cin + ci) * p.Cout;
+                    for (int co = 0; co < p.Cout; ++co) atomicAdd(o + co, __uint_as_float(r0[co]) + __uint_as_float(r1[co]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+GN_API long gn_hexconv_tc_wgrad_workspace_bytes(int B, int H, int W) { return 2 * (((htc_planes_bytes(B, H, W) + 1023) / 1024) * 1024) + 1024; }
+
+// dwp[7][cin][cout] += sum dY * x'   (x' = in_scale ? relu(x*in_scale+in_shift) : x); same contract as gn_hexconv_wgrad except
+// that the bias gradient is not produced here (it is a plain channel sum of dY: gn_bn_stats).
+GN_API int gn_hexconv_wgrad_tc(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, int B, int cin,
+                               int cout, int H, int W, void* workspace, cudaStream_t stream) {
+    GN_REQUIRE(x && dy && dwp && workspace && B > 0, GN_EINVAL, "hexconv_wgrad_tc: bad arguments");
+    GN_REQUIRE(gn_hexconv_tc_supported(cin, cout, H, W, 1), GN_EUNSUPPORTED, "hexconv_wgrad_tc: needs kernel_size 1, <= 32 channels, W <= 122");
+    GN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), GN_EINVAL, "hexconv_wgrad_tc: in_scale/in_shift must come together");
+    GN_REQUIRE(B <= 32767 && ((uintptr_t)workspace & 1023) == 0, GN_EALIGN, "hexconv_wgrad_tc: workspace must be 1024-byte aligned, batch <= 32767");
+    HexTcWgParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = H; p.W = W; p.Cin = cin; p.Cout = cout;
+    p.Q = (H + 1) / 2; p.WP = W + 2; p.PS = p.Q * p.WP;
+    p.tiles_per_img = gn_ceil_div(p.PS, 128);
+    p.n_tiles = B * p.tiles_per_img;
+    p.win_rows = 128 + p.WP + 2;
+    p.dwp = dwp;
+    static const int dy_[HTC_TAPS] = {0, 0, 0, -1, -1, 1, 1};
+    static const int dxe[HTC_TAPS] = {-1, 0, 1, -1, 0, -1, 0};
+    static const int dxo[HTC_TAPS] = {-1, 0, 1, 0, 1, 0, 1};
+    for (int t = 0; t < HTC_TAPS; ++t) {
+        if (dy_[t] == 0) { p.src[0][t] = 0; p.row_off[0][t] = dxe[t] + 1; }
+        else { p.src[0][t] = 1; p.row_off[0][t] = (dy_[t] < 0 ? -p.WP : 0) + dxe[t] + p.WP + 1; }
+        if (dy_[t] == 0) { p.src[1][t] = 1; p.row_off[1][t] = dxo[t] + p.WP + 1; }
+        else { p.src[1][t] = 0; p.row_off[1][t] = (dy_[t] > 0 ? p.WP : 0) + dxo[t] + 1; }
+    }
+    const long pb = ((htc_planes_bytes(B, H, W) + 1023) / 1024) * 1024;
+    __nv_bfloat16* px = (__nv_bfloat16*)workspace;
+    __nv_bfloat16* pdy = (__nv_bfloat16*)((uint8_t*)workspace + pb);
+    dim3 cgrid(2 * p.Q, B);
+    hex_to_planes_kernel<<<cgrid, p.WP <= 96 ? 96 : 128, 0, stream>>>(x, in_scale, in_shift, cin, H, W, p.Q, p.WP, px);
+    GN_LAUNCH_CHECK();
+    hex_to_planes_kernel<<<cgrid, p.WP <= 96 ? 96 : 128, 0, stream>>>(dy, nullptr, nullptr, cout, H, W, p.Q, p.WP, pdy);
+    GN_LAUNCH_CHECK();
+    CUtensorMap tmX, tmDY;
+    {
+        uint64_t dims[3] = {64, (uint64_t)p.PS, (uint64_t)2 * B};
+        uint64_t strides[2] = {128, (uint64_t)p.PS * 128};
+        uint32_t box[3] = {64, (uint32_t)p.win_rows, 1};
+        int rc = gn_tmap_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, px, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        uint32_t box2[3] = {64, 128, 1};
+        rc = gn_tmap_encode(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, pdy, dims, strides, box2, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    const int win_bytes = ((p.win_rows * 128 + 1023) / 1024) * 1024;
+    const size_t smem = (size_t)2 * (2 * win_bytes + 2 * 16384) + 1024;
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        GN_CUDA(cudaFuncSetAttribute(hexconv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
+    }
+    const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
+    hexconv_tc_wgrad_kernel<<<grid, 192, smem, stream>>>(tmX, tmDY, p);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}

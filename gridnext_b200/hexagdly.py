@@ -59,20 +59,32 @@ def hexconv_fwd(x, wp, bias, cout, ksize, in_scale=None, in_shift=None, stats=No
     B, cin, H, W = x.shape
     y = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
     if _use_tc(B, cin, cout, H, W, ksize):
-        ws = torch.empty((int(_lib.load().gn_hexconv_tc_workspace_bytes(B, H, W)) + 1024,), device=x.device, dtype=torch.uint8)
-        off = (-ws.data_ptr()) % 1024
-        call('gn_hexconv_fwd_tc', ptr(x), ptr(wp), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(y), ptr(stats), B, cin, cout, H, W,
-             ctypes.c_void_p(ws.data_ptr() + off), stream())
+        ws, wptr = _aligned_workspace(_lib.load().gn_hexconv_tc_workspace_bytes(B, H, W), x.device)
+        call('gn_hexconv_fwd_tc', ptr(x), ptr(wp), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(y), ptr(stats), B, cin, cout, H, W, wptr, stream())
         return y
     call('gn_hexconv_fwd', ptr(x), ptr(wp), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(y), ptr(stats),
          B, cin, cout, H, W, ksize, stream())
     return y
 
 
+def _aligned_workspace(nbytes, device):
+    ws = torch.empty((int(nbytes) + 1024,), device=device, dtype=torch.uint8)
+    return ws, ctypes.c_void_p(ws.data_ptr() + (-ws.data_ptr()) % 1024)
+
+
 def hexconv_wgrad(x, dy, ksize, in_scale=None, in_shift=None, want_bias=True):
     B, cin, H, W = x.shape
     cout = dy.shape[1]
     dwp = torch.zeros((n_taps(ksize), cin, cout), device=x.device, dtype=torch.float32)
+    if _use_tc(B, cin, cout, H, W, ksize):
+        ws, wptr = _aligned_workspace(_lib.load().gn_hexconv_tc_wgrad_workspace_bytes(B, H, W), x.device)
+        call('gn_hexconv_wgrad_tc', ptr(x), ptr(in_scale), ptr(in_shift), ptr(dy), ptr(dwp), B, cin, cout, H, W, wptr, stream())
+        db = None
+        if want_bias:
+            st = torch.zeros(2 * cout, device=x.device, dtype=torch.float64)
+            call('gn_bn_stats', ptr(dy), ptr(st), B, cout, H * W, stream())
+            db = st[:cout].float()
+        return dwp, db
     db = torch.zeros((cout,), device=x.device, dtype=torch.float32) if want_bias else None
     call('gn_hexconv_wgrad', ptr(x), ptr(in_scale), ptr(in_shift), ptr(dy), ptr(dwp), ptr(db), B, cin, cout, H, W, ksize, stream())
     return dwp, db

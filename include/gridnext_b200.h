@@ -47,6 +47,10 @@ int gn_hexconv_tc_supported(int cin, int cout, int H, int W, int ksize);
 long gn_hexconv_tc_workspace_bytes(int B, int H, int W);
 int gn_hexconv_fwd_tc(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
                       double* stats, int B, int cin, int cout, int H, int W, void* workspace, gn_stream_t stream);
+/* Tensor-core weight gradient (same shapes as gn_hexconv_fwd_tc); dbias is not produced: it is gn_bn_stats' channel sum of dY. */
+long gn_hexconv_tc_wgrad_workspace_bytes(int B, int H, int W);
+int gn_hexconv_wgrad_tc(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, int B, int cin,
+                        int cout, int H, int W, void* workspace, gn_stream_t stream);
 /* dwp[T][cin][cout] += sum dY * x' ; dbias[cout] += sum dY  (caller zeroes both). */
 int gn_hexconv_wgrad(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp,
                      float* dbias, int B, int cin, int cout, int H, int W, int ksize, gn_stream_t stream);
