@@ -39,7 +39,6 @@ _SIGS = {
     'gn_cast_f32_bf16': [vp, vp, cl, vp],
     'gn_rows_affine_bf16': [vp, cl, vp, vp, ci, vp, cl, cl, ci, ci, vp],
     'gn_gemm_tn_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, vp, vp, vp],
-    'gn_im2col7x7s2': [vp, ci, ci, ci, vp, ci, vp],
     'gn_stem_pack_input': [vp, ci, ci, ci, vp, vp],
     'gn_stem_pack_weight': [vp, ci, vp, vp],
     'gn_stem_conv_fwd': [vp, ci, ci, vp, ci, vp, vp, ci, vp, cl, vp],

@@ -1,5 +1,5 @@
 // Memory-bound pieces of the DenseNet-BC f network in NHWC bf16 (everything that is not a GEMM / 3x3 conv):
-// stem im2col + max-pool, transition BN-ReLU-avgpool, head BN-ReLU-global-average-pool + classifier, and their
+// stem max-pool, transition BN-ReLU-avgpool, head BN-ReLU-global-average-pool + classifier, and their
 // backward passes with the BatchNorm parameter-gradient column sums fused in.
 //
 // Reference: /root/reference/gridnext/densenet.py  conv0/norm0/relu0/pool0 (:103-112), _Transition (:47-54),
@@ -72,34 +72,16 @@ __device__ __forceinline__ void colsum_block_end(float* s_sum, int C, float* col
     }
 }
 
-// ------------------------------------------------------------------------------------------------ stem
-// A0[m, c*49 + ky*7 + kx] = x[n, c, 2*oy - 3 + ky, 2*ox - 3 + kx]  (0 outside), columns >= 147 zero
-template <typename InT>
-__global__ void __launch_bounds__(256) im2col7x7s2_kernel(const InT* __restrict__ x, int N, int P, int Ho, __nv_bfloat16* __restrict__ a0, int ldk) {
-    const long total = (long)N * Ho * Ho * ldk;
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int k = (int)(e % ldk);
-        const long m = e / ldk;
-        float v = 0.f;
-        if (k < 147) {
-            const int ox = (int)(m % Ho), oy = (int)((m / Ho) % Ho), n = (int)(m / ((long)Ho * Ho));
-            const int c = k / 49, ky = (k % 49) / 7, kx = k % 7;
-            const int iy = 2 * oy - 3 + ky, ix = 2 * ox - 3 + kx;
-            if (iy >= 0 && iy < P && ix >= 0 && ix < P) v = (float)x[(((long)n * 3 + c) * P + iy) * P + ix];
-        }
-        a0[e] = __float2bfloat16_rn(v);
-    }
-}
-
+// ------------------------------------------------------------------------------------------------ stem (pool0; conv0 lives in stem_conv.cu)
 // 3x3 / stride 2 / pad 1 max pool, NHWC; idx = ky*3+kx of the first maximum (PyTorch tie rule)
 __global__ void __launch_bounds__(256) maxpool3s2_fwd_kernel(const __nv_bfloat16* __restrict__ in, long ldi, int N, int Hi, int Wi, int C,
                                                               __nv_bfloat16* __restrict__ out, long ldo, unsigned char* __restrict__ idx) {
     const int Ho = Hi / 2, Wo = Wi / 2, G = C / 8;
-    const long total = (long)N * Ho * Wo * G;
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(e % G);
-        const long op = e / G;
-        const int ox = (int)(op % Wo), oy = (int)((op / Wo) % Ho), n = (int)(op / ((long)Wo * Ho));
+    const int total = N * Ho * Wo * G;                     // < 2^31 (checked by the launcher): 32-bit index arithmetic
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int op = e / G, cg = e - op * G;
+        const int q = op / Wo, ox = op - q * Wo;
+        const int n = q / Ho, oy = q - n * Ho;
         V8 best; unsigned char bi[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { best.v[j] = -INFINITY; bi[j] = 0; }
@@ -117,11 +99,11 @@ __global__ void __launch_bounds__(256) maxpool3s2_fwd_kernel(const __nv_bfloat16
                     if (v.v[j] > best.v[j]) { best.v[j] = v.v[j]; bi[j] = (unsigned char)(ky * 3 + kx); }
             }
         }
-        st_bf16x8(out + op * ldo + cg * 8, best);
+        st_bf16x8(out + (long)op * ldo + cg * 8, best);
         uint2 pk;
         pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
         pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
-        *reinterpret_cast<uint2*>(idx + op * C + cg * 8) = pk;
+        *reinterpret_cast<uint2*>(idx + (long)op * C + cg * 8) = pk;
     }
 }
 
@@ -197,11 +179,11 @@ __global__ void __launch_bounds__(256) bnrelu_avgpool2_fwd_kernel(const __nv_bfl
                                                                    const float* __restrict__ sc, const float* __restrict__ sh,
                                                                    __nv_bfloat16* __restrict__ out, long ldo) {
     const int Ho = H / 2, Wo = W / 2, G = C / 8;
-    const long total = (long)N * Ho * Wo * G;
-    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        const int cg = (int)(e % G);
-        const long op = e / G;
-        const int ox = (int)(op % Wo), oy = (int)((op / Wo) % Ho), n = (int)(op / ((long)Wo * Ho));
+    const int total = N * Ho * Wo * G;                     // < 2^31 (checked by the launcher)
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int op = e / G, cg = e - op * G;
+        const int q = op / Wo, ox = op - q * Wo;
+        const int n = q / Ho, oy = q - n * Ho;
         const V8 s = ld_f32x8(sc + cg * 8), t = ld_f32x8(sh + cg * 8);
         V8 acc;
 #pragma unroll
@@ -216,7 +198,7 @@ __global__ void __launch_bounds__(256) bnrelu_avgpool2_fwd_kernel(const __nv_bfl
             }
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc.v[j] *= 0.25f;
-        st_bf16x8(out + op * ldo + cg * 8, acc);
+        st_bf16x8(out + (long)op * ldo + cg * 8, acc);
     }
 }
 
@@ -382,24 +364,12 @@ static inline unsigned grid_for_groups(long items, int mult, int G) {
     return g;
 }
 
-GN_API int gn_im2col7x7s2(const void* x, int x_is_bf16, int N, int P, void* a0, int ldk, cudaStream_t stream) {
-    GN_REQUIRE(x && a0 && N > 0 && P >= 8 && P % 2 == 0, GN_EINVAL, "im2col7x7s2: bad arguments (P must be even)");
-    GN_REQUIRE(ldk >= 147 && ldk % 8 == 0, GN_EALIGN, "im2col7x7s2: ldk must be >= 147 and a multiple of 8");
-    const int Ho = P / 2;
-    const long total = (long)N * Ho * Ho * ldk;
-    if (x_is_bf16)
-        im2col7x7s2_kernel<__nv_bfloat16><<<grid_for(total, 16), 256, 0, stream>>>((const __nv_bfloat16*)x, N, P, Ho, (__nv_bfloat16*)a0, ldk);
-    else
-        im2col7x7s2_kernel<float><<<grid_for(total, 16), 256, 0, stream>>>((const float*)x, N, P, Ho, (__nv_bfloat16*)a0, ldk);
-    GN_LAUNCH_CHECK();
-    return GN_OK;
-}
-
 GN_API int gn_maxpool3s2_fwd(const void* in, long ldi, int N, int Hi, int Wi, int C, void* out, long ldo, unsigned char* idx,
                              cudaStream_t stream) {
     GN_REQUIRE(in && out && idx && N > 0 && Hi % 2 == 0 && Wi % 2 == 0 && C % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0, GN_EINVAL,
                "maxpool3s2_fwd: bad arguments");
     const long total = (long)N * (Hi / 2) * (Wi / 2) * (C / 8);
+    GN_REQUIRE(total < (1L << 31), GN_EUNSUPPORTED, "maxpool3s2_fwd: too many elements for 32-bit indexing");
     maxpool3s2_fwd_kernel<<<grid_for(total, 16), 256, 0, stream>>>((const __nv_bfloat16*)in, ldi, N, Hi, Wi, C, (__nv_bfloat16*)out, ldo, idx);
     GN_LAUNCH_CHECK();
     return GN_OK;
@@ -426,6 +396,7 @@ GN_API int gn_bnrelu_avgpool2_fwd(const void* in, long ldi, int N, int H, int W,
     GN_REQUIRE(in && out && sc && sh && N > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0, GN_EINVAL,
                "bnrelu_avgpool2_fwd: bad arguments");
     const long total = (long)N * (H / 2) * (W / 2) * (C / 8);
+    GN_REQUIRE(total < (1L << 31), GN_EUNSUPPORTED, "bnrelu_avgpool2_fwd: too many elements for 32-bit indexing");
     bnrelu_avgpool2_fwd_kernel<<<grid_for(total, 16), 256, 0, stream>>>((const __nv_bfloat16*)in, ldi, N, H, W, C, sc, sh, (__nv_bfloat16*)out, ldo);
     GN_LAUNCH_CHECK();
     return GN_OK;

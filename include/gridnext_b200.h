@@ -129,8 +129,6 @@ int gn_conv3x3_unpack_grad(const float* dwp, int CO, int CI, float* dw, gn_strea
 
 /* ---- memory-bound DenseNet pieces (NHWC bf16, eval-mode BatchNorm folded to scale/shift); each replaces the ATen
  * ops of the cited densenet.py lines.  colsum is fp32 [2][ldsum]: row 0 += sum g (d beta), row 1 += sum g*xhat (d gamma). */
-/* conv0 operand: A0[m, c*49+ky*7+kx] for the 7x7 / stride 2 / pad 3 stem (densenet.py:107) from NCHW fp32|bf16 patches */
-int gn_im2col7x7s2(const void* x, int x_is_bf16, int N, int P, void* a0, int ldk, gn_stream_t stream);
 /* Stem without an im2col buffer (densenet.py:107-109): the patch is repacked once to NHWC4 bf16 (RGB + zero channel), the
  * 7x7 / stride 2 convolution reads its overlapping operand rows straight from the image rows through a no-swizzle UMMA
  * descriptor; norm0 + relu0 run in the epilogue.  wq: [7][CO][32] bf16 (gn_stem_pack_weight), dwq: [CO][224] fp32. */
