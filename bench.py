@@ -384,8 +384,13 @@ def main():
                              ms_per_step=ms_e2e / args.steps, host_input='uint8 patch grid (78,64,3,128,128) + int64 labels, pinned'),
                     roofline=roof, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
+    # Leave without tearing the process group down: destroying an NCCL communicator whose collectives were captured into
+    # CUDA graphs that are still alive hung at exit (observed at N = 2); process exit releases everything.
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == '__main__':
