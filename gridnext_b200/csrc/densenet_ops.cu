@@ -122,6 +122,8 @@ __device__ __forceinline__ void colsum_thread_flush(float* s_sum, int C, int cg,
     }
 }
 
+// Work unit = the 2x2 input quad {2a, 2a+1} x {2b, 2b+1}: it touches exactly the four windows (a, b), (a, b+1), (a+1, b),
+// (a+1, b+1), so every pooled gradient / arg-max byte is loaded once per quad instead of once per input pixel.
 __global__ void __launch_bounds__(256) maxpool3s2_bnrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, long ldp,
                                                                     const unsigned char* __restrict__ idx,
                                                                     const __nv_bfloat16* __restrict__ act, long lda, int N, int Hi, int Wi,
@@ -136,38 +138,58 @@ __global__ void __launch_bounds__(256) maxpool3s2_bnrelu_bwd_kernel(const __nv_b
     float sg[8], sx[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sx[j] = 0.f; }
-    const int npix = N * Hi * Wi;
-    for (int ip = blockIdx.x * ppb + pl; ip < npix; ip += gridDim.x * ppb) {
-        const int ix = ip % Wi, t = ip / Wi, iy = t % Hi, n = t / Hi;
-        V8 g;
+    const int nquads = N * Ho * Wo;
+    for (int qd = blockIdx.x * ppb + pl; qd < nquads; qd += gridDim.x * ppb) {
+        const int b = qd % Wo, t = qd / Wo, a = t % Ho, n = t / Ho;
+        // the four windows; w = wy*2 + wx with (wy, wx) = window offset from (a, b)
+        V8 d[4];
+        uint2 pk[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
-        for (int oy = iy >> 1; oy <= ((iy + 1) >> 1); ++oy) {
-            if (oy >= Ho) continue;
-            const int ky = iy - (2 * oy - 1);
-            for (int ox = ix >> 1; ox <= ((ix + 1) >> 1); ++ox) {
-                if (ox >= Wo) continue;
-                const int k = ky * 3 + (ix - (2 * ox - 1));
+        for (int w = 0; w < 4; ++w) {
+            const int oy = a + (w >> 1), ox = b + (w & 1);
+            if (oy < Ho && ox < Wo) {
                 const long op = ((long)n * Ho + oy) * Wo + ox;
-                const uint2 pk = *reinterpret_cast<const uint2*>(idx + op * C + cg * 8);
-                const V8 d = ld_bf16x8(dpool + op * ldp + cg * 8);
+                pk[w] = *reinterpret_cast<const uint2*>(idx + op * C + cg * 8);
+                d[w] = ld_bf16x8(dpool + op * ldp + cg * 8);
+            } else {
+                pk[w] = make_uint2(0xffffffffu, 0xffffffffu);          // tap 255 never matches
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const unsigned bsel = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xff;
-                    if ((int)bsel == k) g.v[j] += d.v[j];
-                }
+                for (int j = 0; j < 8; ++j) d[w].v[j] = 0.f;
             }
         }
-        const V8 a = ld_bf16x8(act + (long)ip * lda + cg * 8);
-        V8 o;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float gg = a.v[j] > 0.f ? g.v[j] : 0.f;
-            sg[j] += gg;
-            sx[j] += gg * a.v[j];
-            o.v[j] = gg * s.v[j];
-        }
-        st_bf16x8(dz + (long)ip * ldz + cg * 8, o);
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                const int iy = 2 * a + py, ix = 2 * b + px;
+                const long ip = ((long)n * Hi + iy) * Wi + ix;
+                V8 g;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+                // pixel (2a+py, 2b+px) lies in window (a+wy, b+wx) at tap ky = py + 1 - 2 wy, kx = px + 1 - 2 wx (wy <= py, wx <= px)
+#pragma unroll
+                for (int wy = 0; wy <= py; ++wy)
+#pragma unroll
+                    for (int wx = 0; wx <= px; ++wx) {
+                        const int w = wy * 2 + wx;
+                        const unsigned k = (unsigned)((py + 1 - 2 * wy) * 3 + (px + 1 - 2 * wx));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const unsigned bsel = ((j < 4 ? pk[w].x : pk[w].y) >> (8 * (j & 3))) & 0xff;
+                            if (bsel == k) g.v[j] += d[w].v[j];
+                        }
+                    }
+                const V8 av = ld_bf16x8(act + ip * lda + cg * 8);
+                V8 o;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float gg = av.v[j] > 0.f ? g.v[j] : 0.f;
+                    sg[j] += gg;
+                    sx[j] += gg * av.v[j];
+                    o.v[j] = gg * s.v[j];
+                }
+                st_bf16x8(dz + ip * ldz + cg * 8, o);
+            }
     }
     colsum_thread_flush(s_sum, C, cg, sg, sx, p0, p1);
     colsum_block_end(s_sum, C, colsum, ldsum);
@@ -383,7 +405,8 @@ GN_API int gn_maxpool3s2_bnrelu_bwd(const void* dpool, long ldp, const unsigned 
     const int G = C / 8;
     GN_REQUIRE(G <= 256 && (long)N * Hi * Wi < (1L << 31), GN_EUNSUPPORTED, "maxpool3s2_bnrelu_bwd: at most 2048 channels and 2^31 pixels");
     const int ppb = 256 / G;
-    unsigned grid = (unsigned)gn_ceil_div((long)N * Hi * Wi, ppb);
+    GN_REQUIRE(Hi % 2 == 0 && Wi % 2 == 0, GN_EINVAL, "maxpool3s2_bnrelu_bwd: odd spatial size");
+    unsigned grid = (unsigned)gn_ceil_div((long)N * (Hi / 2) * (Wi / 2), ppb);
     if (grid > (unsigned)gn_num_sms() * 8) grid = gn_num_sms() * 8;
     maxpool3s2_bnrelu_bwd_kernel<<<grid, G * ppb, 2 * C * sizeof(float), stream>>>(
         (const __nv_bfloat16*)dpool, ldp, idx, (const __nv_bfloat16*)act, lda, N, Hi, Wi, C, sc, p0, p1, (__nv_bfloat16*)dz, ldz, colsum, ldsum, G, ppb);
