@@ -39,6 +39,9 @@ _SIGS = {
     'gn_cast_f32_bf16': [vp, vp, cl, vp],
     'gn_rows_affine_bf16': [vp, cl, vp, vp, ci, vp, cl, cl, ci, ci, vp],
     'gn_gemm_tn_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, vp, vp, vp],
+    'gn_prep_job_bytes': [],
+    'gn_prepare_weights': [vp, ci, cl, vp, vp],
+    'gn_unpack_gradients': [vp, ci, cl, vp, vp],
     'gn_stem_pack_input': [vp, ci, ci, ci, vp, vp],
     'gn_stem_pack_weight': [vp, ci, vp, vp],
     'gn_stem_conv_fwd': [vp, ci, ci, vp, ci, vp, vp, ci, vp, cl, vp],
@@ -107,7 +110,7 @@ def check(rc, what=''):
 
 
 # kernels launched per C-ABI call (for the benchmark's gpu_launches count); default 1
-KERNELS_PER_CALL = {'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0,
+KERNELS_PER_CALL = {'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0, 'gn_prep_job_bytes': 0,
                     'gn_device_sm_count': 0, 'gn_hexconv_n_taps': 0}
 LAUNCHES = [0]
 PROFILE = None      # when a dict: name -> [n_calls, [cuda event pairs]]

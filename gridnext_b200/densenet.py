@@ -101,9 +101,131 @@ class _Consts:
         return self.bn[id(bn)]
 
 
-def _w2d_bf16(conv):
-    w = conv.weight.detach()
-    return w.reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+_JOB_DTYPE = [('src', '<u8'), ('dst', '<i8'), ('start', '<i8'), ('kind', '<i4'), ('a', '<i4'), ('b', '<i4'), ('ld', '<i4')]
+_CAST, _TRANSPOSE, _C3PACK0, _C3PACK1, _STEM, _UNPACK_C3, _UNPACK_STEM = range(7)
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class _Plan:
+    """Derived-weight and gradient workspaces of one DenseNet on one device, laid out once.
+
+    ``prepare()`` fills ONE flat bf16 buffer with every copy the tensor-core kernels consume (1x1 weights cast and
+    transposed, 3x3 weights packed for the forward and the data gradient, the stem window order) in a single launch driven
+    by a device-resident job table; ``Grads`` hands out views of ONE flat fp32 accumulator (a single fill per step) and a
+    second table turns the packed 3x3 / stem accumulators back into parameter layout in a single launch.  Parameter
+    addresses are stable across optimizer steps, so the tables are built once (and rebuilt if a parameter moves)."""
+
+    def __init__(self, net):
+        import numpy as np
+        assert _lib.load().gn_prep_job_bytes() == np.dtype(_JOB_DTYPE).itemsize
+        self.key = _Plan.key_of(net)
+        dev = net.classifier.weight.device
+        f = net.features
+        jobs, self.wviews, self.wshapes = [], {}, {}
+        off = [0, 0]          # [bf16 weight elements, job items]
+
+        def add_w(name, param, kind, a, b, ld, rows):
+            n = rows * ld
+            jobs.append((param.data_ptr(), off[0], off[1], kind, a, b, ld))
+            self.wshapes[name] = (off[0], rows, ld)
+            off[0] += _pad8(n) + 56      # keep every view 128-byte aligned (TMA needs 16)
+            off[0] = (off[0] + 63) // 64 * 64
+            off[1] += n
+
+        c0 = f.conv0.out_channels
+        add_w(('stem',), f.conv0.weight, _STEM, c0, 0, 32, 7 * c0)
+        for name, m in f.named_children():
+            if name.startswith('denseblock'):
+                for layer in m.children():
+                    bott, cin = layer.conv1.out_channels, layer.conv1.in_channels
+                    g = layer.conv2.out_channels
+                    add_w(('w1', id(layer)), layer.conv1.weight, _CAST, bott, cin, _pad8(cin), bott)              # [bott, cin]
+                    add_w(('w1t', id(layer)), layer.conv1.weight, _TRANSPOSE, bott, cin, _pad8(bott), cin)        # [cin, bott]
+                    add_w(('wp2', id(layer)), layer.conv2.weight, _C3PACK0, g, bott, _pad8(bott), 9 * g)          # [9*g, bott]
+                    add_w(('wp2t', id(layer)), layer.conv2.weight, _C3PACK1, g, bott, _pad8(g), 9 * bott)         # [9*bott, g]
+            elif name.startswith('transition'):
+                co, ci = m.conv.out_channels, m.conv.in_channels
+                add_w(('wt', id(m)), m.conv.weight, _CAST, co, ci, _pad8(ci), co)
+                add_w(('wtt', id(m)), m.conv.weight, _TRANSPOSE, co, ci, _pad8(co), ci)
+        self.n_w_items = off[1]
+        self.wbuf = torch.zeros(off[0], device=dev, dtype=torch.bfloat16)
+        self.wjobs = torch.from_numpy(np.array(jobs, dtype=_JOB_DTYPE).view(np.uint8).copy()).to(dev)
+        self.n_wjobs = len(jobs)
+
+        # ---- gradient accumulators (fp32): [conv0 dwq][per layer: dw1, dwp2][per transition: dwt][classifier w, b]
+        goff = [0]
+        self.gslots = {}
+
+        def add_g(name, numel):
+            self.gslots[name] = (goff[0], numel)
+            goff[0] += (numel + 3) // 4 * 4
+
+        ujobs, uoff = [], [0, 0]
+        self.uslots = {}
+
+        def add_u(param, kind, a, b, gname):
+            n = param.numel()
+            ujobs.append((gname, uoff[0], uoff[1], kind, a, b, 0))
+            self.uslots[id(param)] = (uoff[0], tuple(param.shape))
+            uoff[0] += (n + 3) // 4 * 4
+            uoff[1] += n
+
+        add_g(('stem',), c0 * 224)
+        add_u(f.conv0.weight, _UNPACK_STEM, c0, 0, ('stem',))
+        for name, m in f.named_children():
+            if name.startswith('denseblock'):
+                for layer in m.children():
+                    bott, cin, g = layer.conv1.out_channels, layer.conv1.in_channels, layer.conv2.out_channels
+                    add_g(('dw1', id(layer)), bott * cin)
+                    add_g(('dwp2', id(layer)), 9 * bott * g)
+                    add_u(layer.conv2.weight, _UNPACK_C3, g, bott, ('dwp2', id(layer)))
+            elif name.startswith('transition'):
+                add_g(('dwt', id(m)), m.conv.out_channels * m.conv.in_channels)
+        J, Cf = net.classifier.out_features, net.classifier.in_features
+        add_g(('cls_w',), J * Cf)
+        add_g(('cls_b',), J)
+        self.g_total = goff[0]
+        self.u_total_items = uoff[1]
+        self.u_numel = uoff[0]
+        self.n_ujobs = len(ujobs)
+        self.dev = dev
+        # persistent accumulator (stable address: the un-pack table can live on the device, and the step stays graph-capturable)
+        self.gflat = torch.zeros(self.g_total, device=dev, dtype=torch.float32)
+        rows = [(self.gflat.data_ptr() + 4 * self.gslots[gname][0], dst, start, kind, a, b, ld) for gname, dst, start, kind, a, b, ld in ujobs]
+        self.ujobs = torch.from_numpy(np.array(rows, dtype=_JOB_DTYPE).view(np.uint8).copy()).to(dev)
+
+    @staticmethod
+    def key_of(net):
+        return tuple(p.data_ptr() for p in net.parameters()) + (str(net.classifier.weight.device),)
+
+    @staticmethod
+    def of(net):
+        plan = getattr(net, '_b200_plan', None)
+        if plan is None or plan.key != _Plan.key_of(net):
+            plan = _Plan(net)
+            object.__setattr__(net, '_b200_plan', plan)
+        return plan
+
+    def prepare(self):
+        call('gn_prepare_weights', ptr(self.wjobs), self.n_wjobs, self.n_w_items, ptr(self.wbuf), stream())
+
+    def w(self, *name):
+        o, rows, ld = self.wshapes[name]
+        return self.wbuf[o:o + rows * ld].view(rows, ld)
+
+    def g(self, name, shape):
+        o, n = self.gslots[name]
+        return self.gflat[o:o + n].view(shape)
+
+    def finish(self):
+        """-> (copy of the flat accumulator, flat buffer with the conv2 / conv0 gradients in parameter layout): fresh tensors, so
+        the gradients handed to autograd do not alias the persistent workspace."""
+        out = torch.empty(self.u_numel, device=self.dev, dtype=torch.float32)
+        call('gn_unpack_gradients', ptr(self.ujobs), self.n_ujobs, self.u_total_items, ptr(out), stream())
+        return self.gflat.clone(), out
 
 
 class _Geometry:
@@ -156,7 +278,7 @@ def _check_supported(net):
                                   'train-mode f is not implemented')
 
 
-def _forward_chunk(net, geo, cst, x, save):
+def _forward_chunk(net, geo, cst, plan, x, save):
     """x: (n, 3, P, P) fp32|bf16 CUDA.  Returns (out, saved | None)."""
     n, P, dev = x.shape[0], geo.P, x.device
     f = net.features
@@ -166,7 +288,7 @@ def _forward_chunk(net, geo, cst, x, save):
     xq = tc.stem_pack_input(x)
     b0 = cst.of(f.norm0)
     c0 = f.conv0.out_channels
-    act0 = tc.stem_conv_fwd(xq, tc.stem_pack_weight(f.conv0.weight.detach()), scale=b0['sc'], shift=b0['sh'], relu=True)
+    act0 = tc.stem_conv_fwd(xq, plan.w('stem').view(7, c0, 32), scale=b0['sc'], shift=b0['sh'], relu=True)
     saved = dict(xq=xq, act0=act0, blocks=[]) if save else None
     blk0 = geo.blocks[0]
     M = n * blk0['H'] * blk0['H']
@@ -186,10 +308,9 @@ def _forward_chunk(net, geo, cst, x, save):
             k1, k2 = cst.of(layer.norm1), cst.of(layer.norm2)
             if save or a2 is None:
                 a2 = torch.empty((M, bott), device=dev, dtype=bf)
-            tc.gemm_bf16(C[:, :cin], _w2d_bf16(layer.conv1), out=a2, scale=k2['sc'], shift=k2['sh'], relu=True,
+            tc.gemm_bf16(C[:, :cin], plan.w('w1', id(layer))[:, :cin], out=a2, scale=k2['sc'], shift=k2['sh'], relu=True,
                          xf_scale=k1['sc'], xf_shift=k1['sh'])
-            wp = tc.conv3x3_pack(layer.conv2.weight.detach(), 0)
-            tc.conv3x3_bf16(a2, n, H, H, bott, wp, g, C[:, cin:cin + g])
+            tc.conv3x3_bf16(a2, n, H, H, bott, plan.w('wp2', id(layer)), g, C[:, cin:cin + g])
             if save:
                 a2s.append(a2)
             cin += g
@@ -202,7 +323,7 @@ def _forward_chunk(net, geo, cst, x, save):
             call('gn_bnrelu_avgpool2_fwd', ptr(C), ct, n, H, H, ct, ptr(kt['sc']), ptr(kt['sh']), ptr(pooled), ct, stream())
             nxt = geo.blocks[bi + 1]
             Cn = torch.empty((M // 4, nxt['c_tot']), device=dev, dtype=bf)
-            tc.gemm_bf16(pooled, _w2d_bf16(tr.conv), out=Cn[:, :nxt['c_in']])
+            tc.gemm_bf16(pooled, plan.w('wt', id(tr))[:, :ct], out=Cn[:, :nxt['c_in']])
             rec['pooled'] = pooled
             if save:
                 saved['blocks'].append(rec)
@@ -228,28 +349,16 @@ def _forward_chunk(net, geo, cst, x, save):
 
 
 class _Grads:
-    """fp32 gradient accumulators keyed like the module's parameters."""
+    """Gradient accumulators of one backward pass: BatchNorm column sums + the plan's flat fp32 workspace (zeroed here)."""
 
-    def __init__(self, net, cst):
+    def __init__(self, net, cst, plan):
         dev = net.classifier.weight.device
         self.bn_colsum = torch.zeros((2, cst.bn_total), device=dev, dtype=torch.float32)   # row 0: d beta, row 1: d gamma
-        self.w = {}
-
-    def acc(self, param, g):
-        k = id(param)
-        if k in self.w:
-            self.w[k] += g
-        else:
-            self.w[k] = g
-
-    def buf(self, param, shape):
-        k = id(param)
-        if k not in self.w:
-            self.w[k] = torch.zeros(shape, device=param.device, dtype=torch.float32)
-        return self.w[k]
+        self.plan = plan
+        plan.gflat.zero_()
 
 
-def _backward_chunk(net, geo, cst, saved, dout, grads):
+def _backward_chunk(net, geo, cst, plan, saved, dout, grads):
     n, dev, bf = saved['n'], dout.device, torch.bfloat16
     f = net.features
     last = geo.blocks[-1]
@@ -264,8 +373,8 @@ def _backward_chunk(net, geo, cst, saved, dout, grads):
     if net.classify:
         J = net.classifier.out_features
         dfeat = torch.empty((n, Cf), device=dev, dtype=torch.float32)
-        dw = grads.buf(net.classifier.weight, (J, Cf))
-        db = grads.buf(net.classifier.bias, (J,))
+        dw = plan.g(('cls_w',), (J, Cf))
+        db = plan.g(('cls_b',), (J,))
         call('gn_linear_small_bwd', ptr(dout), ptr(saved['feat']), Cf, ptr(net.classifier.weight.detach().float().contiguous()), n, Cf, J,
              ptr(dfeat), Cf, ptr(dw), ptr(db), stream())
     else:
@@ -290,14 +399,11 @@ def _backward_chunk(net, geo, cst, saved, dout, grads):
             k1, k2 = cst.of(layer.norm1), cst.of(layer.norm2)
             a2 = rec['a2'][li]
             dY = dC[:, cin:cin + g]
-            grads.acc(layer.conv2.weight, tc.conv3x3_wgrad_bf16(a2, dY, n, H, H, bott, g))
-            wpt = tc.conv3x3_pack(layer.conv2.weight.detach(), 1)
-            tc.conv3x3_bf16(dY, n, H, H, g, wpt, bott, dz,
+            tc.conv3x3_wgrad_into(a2, dY, n, H, H, bott, g, plan.g(('dwp2', id(layer)), (9, bott, g)))
+            tc.conv3x3_bf16(dY, n, H, H, g, plan.w('wp2t', id(layer)), bott, dz,
                             bn=dict(ref=a2, ref_is_raw=False, sc=k2['sc'], sh=None, p0=k2['beta'], p1=k2['inv_gamma'], colsum=colsum_of(k2)))
-            dw1 = grads.buf(layer.conv1.weight, (bott, cin))
-            tc.gemm_tn_bf16(dz, C[:, :cin], dw1, k1['sc'], k1['sh'])
-            w1t = layer.conv1.weight.detach().reshape(bott, cin).t().contiguous().to(bf)      # [cin, bott]
-            tc.gemm_bf16(dz, w1t, out=dC[:, :cin],
+            tc.gemm_tn_bf16(dz, C[:, :cin], plan.g(('dw1', id(layer)), (bott, cin)), k1['sc'], k1['sh'])
+            tc.gemm_bf16(dz, plan.w('w1t', id(layer))[:, :bott], out=dC[:, :cin],
                          bn=dict(ref=C[:, :cin], ref_is_raw=True, sc=k1['sc'], sh=k1['sh'], p0=k1['mean'], p1=k1['invstd'],
                                  colsum=colsum_of(k1), rmw=True))
         if bi > 0:
@@ -306,10 +412,8 @@ def _backward_chunk(net, geo, cst, saved, dout, grads):
             kt = cst.of(tr.norm)
             ctp, c_in = prev['c_tot'], blk['c_in']
             d_out = dC[:, :c_in]
-            dwt = grads.buf(tr.conv.weight, (c_in, ctp))
-            tc.gemm_tn_bf16(d_out, prec['pooled'], dwt)
-            wtt = tr.conv.weight.detach().reshape(c_in, ctp).t().contiguous().to(bf)          # [ctp, c_in]
-            dP = tc.gemm_bf16(d_out, wtt)
+            tc.gemm_tn_bf16(d_out, prec['pooled'], plan.g(('dwt', id(tr)), (c_in, ctp)))
+            dP = tc.gemm_bf16(d_out, plan.w('wtt', id(tr))[:, :c_in])
             Hp = prev['H']
             dCp = torch.empty((n * Hp * Hp, ctp), device=dev, dtype=bf)
             call('gn_pool_bnrelu_bwd', ptr(dP), ctp, 0, ptr(prec['C']), ctp, n, Hp, Hp, ctp, ptr(kt['sc']), ptr(kt['sh']), ptr(kt['mean']),
@@ -322,7 +426,7 @@ def _backward_chunk(net, geo, cst, saved, dout, grads):
             dz0 = torch.empty((M0, c0), device=dev, dtype=bf)
             call('gn_maxpool3s2_bnrelu_bwd', ptr(dC), blk['c_tot'], ptr(saved['idx0']), ptr(saved['act0']), c0, n, geo.H0, geo.H0, c0,
                  ptr(k0['sc']), ptr(k0['beta']), ptr(k0['inv_gamma']), ptr(dz0), c0, ptr(colsum_of(k0)), tot, stream())
-            grads.acc(f.conv0.weight, tc.stem_conv_wgrad(saved['xq'], dz0, c0))
+            tc.stem_conv_wgrad_into(saved['xq'], dz0, c0, plan.g(('stem',), (c0, 224)))
 
 
 class _DenseNetFn(torch.autograd.Function):
@@ -337,50 +441,67 @@ class _DenseNetFn(torch.autograd.Function):
         x = x.contiguous()
         geo = _Geometry(net, int(x.shape[2]))
         cst = _Consts(net)
+        plan = _Plan.of(net)
+        plan.prepare()
         N = x.shape[0]
         need_grad = any(ctx.needs_input_grad[2:])
-        ctx.net, ctx.geo, ctx.cst = net, geo, cst
+        ctx.net, ctx.geo, ctx.cst, ctx.plan = net, geo, cst, plan
         ctx.plist = list(net.parameters())
         assert len(ctx.plist) == len(params)
         if N <= MAX_SPOTS_RESIDENT:
-            out, saved = _forward_chunk(net, geo, cst, x, need_grad)
+            out, saved = _forward_chunk(net, geo, cst, plan, x, need_grad)
             ctx.saved, ctx.x = saved, None
         else:
-            outs = [_forward_chunk(net, geo, cst, x[i:i + MAX_SPOTS_RESIDENT], False)[0] for i in range(0, N, MAX_SPOTS_RESIDENT)]
+            outs = [_forward_chunk(net, geo, cst, plan, x[i:i + MAX_SPOTS_RESIDENT], False)[0] for i in range(0, N, MAX_SPOTS_RESIDENT)]
             out = torch.cat(outs, 0)
             ctx.saved, ctx.x = None, (x if need_grad else None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        net, geo, cst = ctx.net, ctx.geo, ctx.cst
+        net, geo, cst, plan = ctx.net, ctx.geo, ctx.cst, ctx.plan
         dout = dout.contiguous().float()
-        grads = _Grads(net, cst)
+        grads = _Grads(net, cst, plan)
         if ctx.saved is not None:
-            _backward_chunk(net, geo, cst, ctx.saved, dout, grads)
+            _backward_chunk(net, geo, cst, plan, ctx.saved, dout, grads)
             ctx.saved = None
         else:
             x = ctx.x
             for i in range(0, x.shape[0], MAX_SPOTS_RESIDENT):
-                _, saved = _forward_chunk(net, geo, cst, x[i:i + MAX_SPOTS_RESIDENT], True)
-                _backward_chunk(net, geo, cst, saved, dout[i:i + MAX_SPOTS_RESIDENT].contiguous(), grads)
+                _, saved = _forward_chunk(net, geo, cst, plan, x[i:i + MAX_SPOTS_RESIDENT], True)
+                _backward_chunk(net, geo, cst, plan, saved, dout[i:i + MAX_SPOTS_RESIDENT].contiguous(), grads)
                 del saved
             ctx.x = None
-        # map accumulated gradients onto the parameter list
-        out = []
-        bn_of_param = {}
+        # map accumulated gradients onto the parameter list: views of two fresh flat buffers
+        gret, gunp = plan.finish()
+        bn_grads = grads.bn_colsum
+        by_param = {}
         for b in cst.bns:
             k = cst.of(b)
-            bn_of_param[id(b.weight)] = grads.bn_colsum[1, k['off']:k['off'] + k['n']]
-            bn_of_param[id(b.bias)] = grads.bn_colsum[0, k['off']:k['off'] + k['n']]
+            by_param[id(b.weight)] = bn_grads[1, k['off']:k['off'] + k['n']]
+            by_param[id(b.bias)] = bn_grads[0, k['off']:k['off'] + k['n']]
+        f = net.features
+        for nm, m in f.named_children():
+            if nm.startswith('denseblock'):
+                for layer in m.children():
+                    o, nel = plan.gslots[('dw1', id(layer))]
+                    by_param[id(layer.conv1.weight)] = gret[o:o + nel]
+            elif nm.startswith('transition'):
+                o, nel = plan.gslots[('dwt', id(m))]
+                by_param[id(m.conv.weight)] = gret[o:o + nel]
+        o, nel = plan.gslots[('cls_w',)]
+        by_param[id(net.classifier.weight)] = gret[o:o + nel]
+        o, nel = plan.gslots[('cls_b',)]
+        by_param[id(net.classifier.bias)] = gret[o:o + nel]
+        for pid, (o, shape) in plan.uslots.items():
+            nel = 1
+            for d in shape:
+                nel *= d
+            by_param[pid] = gunp[o:o + nel]
+        out = []
         for p in ctx.plist:
-            if id(p) in bn_of_param:
-                out.append(bn_of_param[id(p)].clone())
-            elif id(p) in grads.w:
-                gpar = grads.w[id(p)]
-                out.append(gpar.reshape(p.shape).contiguous())
-            else:
-                out.append(None)
+            gp = by_param.get(id(p))
+            out.append(None if gp is None else gp.view(p.shape))
         return (None, None) + tuple(out)
 
 

@@ -84,6 +84,17 @@ def conv3x3_bf16(x2d, Nimg, H, W, CI, wp, CO, out2d, bn=None):
     return out2d
 
 
+def conv3x3_wgrad_into(x2d, dy2d, Nimg, H, W, CI, CO, dwp):
+    """dwp [9, CI, CO] fp32 (+=): packed weight gradient of the 3x3 convolution (un-packed later in one batched launch)."""
+    _lib.require_cuda(x2d, dy2d, dwp)
+    M, _, ldx = _rows_pitch(x2d)
+    M2, _, ldy = _rows_pitch(dy2d)
+    if M != Nimg * H * W or M2 != M or tuple(dwp.shape) != (9, CI, CO) or not dwp.is_contiguous():
+        raise ValueError('conv3x3_wgrad_into: shape mismatch')
+    call('gn_conv3x3_wgrad_bf16', ptr(x2d), ldx, ptr(dy2d), ldy, Nimg, H, W, CI, CO, ptr(dwp), stream())
+    return dwp
+
+
 def conv3x3_wgrad_bf16(x2d, dy2d, Nimg, H, W, CI, CO):
     """-> fp32 (CO, CI, 3, 3) weight gradient of the 3x3 convolution from activations x2d [M, >=CI] and dy2d [M, >=CO]."""
     _lib.require_cuda(x2d, dy2d)
@@ -128,6 +139,15 @@ def stem_conv_fwd(xq, wq, scale=None, shift=None, relu=False, out=None):
     _, _, ldo = _rows_pitch(out)
     call('gn_stem_conv_fwd', ptr(xq), N, P, ptr(wq), CO, ptr(scale), ptr(shift), 1 if relu else 0, ptr(out), ldo, stream())
     return out
+
+
+def stem_conv_wgrad_into(xq, dz, CO, dwq):
+    """dwq [CO, 224] fp32 (+=): packed conv0 weight gradient."""
+    _lib.require_cuda(xq, dz, dwq)
+    N, P = int(xq.shape[0]), int(xq.shape[1])
+    _, _, ldz = _rows_pitch(dz)
+    call('gn_stem_conv_wgrad', ptr(xq), N, P, ptr(dz), ldz, CO, ptr(dwq), stream())
+    return dwq
 
 
 def stem_conv_wgrad(xq, dz, CO):

@@ -129,6 +129,14 @@ int gn_conv3x3_unpack_grad(const float* dwp, int CO, int CI, float* dw, gn_strea
 
 /* ---- memory-bound DenseNet pieces (NHWC bf16, eval-mode BatchNorm folded to scale/shift); each replaces the ATen
  * ops of the cited densenet.py lines.  colsum is fp32 [2][ldsum]: row 0 += sum g (d beta), row 1 += sum g*xhat (d gamma). */
+/* Batched derivation of the bf16 / packed weight copies the tensor-core kernels consume (one launch for the whole network) and the
+ * inverse for the packed gradient accumulators.  jobs: device array of n_jobs records {const float* src; long dst_off; long start;
+ * int kind, a, b, ld;} (gn_prep_job_bytes() each), kinds: 0 cast [a,b]->[a,ld]; 1 transpose [a,b]->[b,ld]; 2/3 3x3 pack for the
+ * forward / data gradient (what gn_conv3x3_pack does); 4 stem pack (gn_stem_pack_weight); 5 3x3 gradient un-pack; 6 stem un-pack. */
+int gn_prep_job_bytes(void);
+int gn_prepare_weights(const void* jobs, int n_jobs, long total_items, void* dst_bf16, gn_stream_t stream);
+int gn_unpack_gradients(const void* jobs, int n_jobs, long total_items, float* dst, gn_stream_t stream);
+
 /* Stem without an im2col buffer (densenet.py:107-109): the patch is repacked once to NHWC4 bf16 (RGB + zero channel), the
  * 7x7 / stride 2 convolution reads its overlapping operand rows straight from the image rows through a no-swizzle UMMA
  * descriptor; norm0 + relu0 run in the epilogue.  wq: [7][CO][32] bf16 (gn_stem_pack_weight), dwq: [CO][224] fp32. */
