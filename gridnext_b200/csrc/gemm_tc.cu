@@ -119,6 +119,25 @@ __device__ __forceinline__ void epi_store_row(const GemmParams& p, int row, int 
     }
 }
 
+// The it-th tile of this CTA -> (n-block, m-block); false when the CTA is done.  The TMA epilogues keep their column sums in
+// shared memory for ALL columns, so tiles are ordered m-major (the n-blocks of one m-block are consecutive tile numbers and
+// run on neighbouring CTAs at the same time): the A tile (dZ, shared by every n-block) comes from L2 instead of HBM.  The
+// host picks a grid size coprime with the number of n-blocks so that every CTA sees all n-blocks (the last one is narrow).
+// The register-accumulating direct epilogue flushes on every n-block change and keeps the n-major order.
+template <int EPI>
+__device__ __forceinline__ bool gemm_next_tile(int it, const GemmParams& p, int& nb, int& mb) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    if (tile >= p.num_m_blocks * p.num_n_blocks) return false;
+    if (EPI == EPI_DIRECT) {
+        nb = tile / p.num_m_blocks;
+        mb = tile - nb * p.num_m_blocks;
+    } else {
+        mb = tile / p.num_n_blocks;
+        nb = tile - mb * p.num_n_blocks;
+    }
+    return true;
+}
+
 template <int BN, bool XFORM, int EPI>
 __global__ void __launch_bounds__(XFORM ? 512 : 384, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -196,8 +215,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int nb = tile / p.num_m_blocks, mb = tile % p.num_m_blocks;
+            for (int it = 0;; ++it) {
+                int nb, mb;
+                if (!gemm_next_tile<EPI>(it, p, nb, mb)) break;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     uint8_t* sa = sm + (size_t)stage * Cfg::STAGE_BYTES;
@@ -217,7 +237,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int it = 0;; ++it) {
+                int nb_, mb_;
+                if (!gemm_next_tile<EPI>(it, p, nb_, mb_)) break;
                 mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(acc * BN);
@@ -242,8 +264,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (EPI != EPI_DIRECT && elect_one()) {
             int es = 0;
             uint32_t eph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int nb = tile / p.num_m_blocks, mb = tile % p.num_m_blocks;
+            for (int it = 0;; ++it) {
+                int nb, mb;
+                if (!gemm_next_tile<EPI>(it, p, nb, mb)) break;
                 const int nsub = (min(BN, p.N - nb * BN) + 63) >> 6;
                 for (int j = 0; j < nsub; ++j) {
                     mbar_wait(&bar_eempty[es], eph ^ 1);
@@ -263,8 +286,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (EPI != EPI_DIRECT && elect_one()) {
             int es = 0, prev_es = -1;
             uint32_t eph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int nb = tile / p.num_m_blocks, mb = tile % p.num_m_blocks;
+            for (int it = 0;; ++it) {
+                int nb, mb;
+                if (!gemm_next_tile<EPI>(it, p, nb, mb)) break;
                 const int nsub = (min(BN, p.N - nb * BN) + 63) >> 6;
                 for (int j = 0; j < nsub; ++j) {
                     mbar_wait(&bar_eready[es], eph);
@@ -311,8 +335,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool active = (BN >= 64) || h == 0;       // BN = 32: the upper half-warps have no accumulator columns
         const int trow = g * 32 + lane;                 // row of the tile owned by this thread
         const uint32_t sw = (uint32_t)(trow & 7);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int nb = tile / p.num_m_blocks, mb = tile % p.num_m_blocks;
+        for (int it = 0;; ++it) {
+            int nb, mb;
+            if (!gemm_next_tile<EPI>(it, p, nb, mb)) break;
             if (nb != cur_nb) { flush_colsums(); cur_nb = nb; }
             mbar_wait(&bar_tfull[acc], acc_phase);
             tc_fence_after();
@@ -451,7 +476,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int w = warp - 12;
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int it = 0;; ++it) {
+            int nb_, mb_;
+            if (!gemm_next_tile<EPI>(it, p, nb_, mb_)) break;
             for (int kb = 0; kb < nkb; ++kb) {
                 // row & 7 of the rows this lane touches is ((i & 1) * 4 + (lane >> 3)): two sets of 8 constants per k-block
                 const int pc = lane & 7;                            // physical 16-byte chunk in the 128-byte row
@@ -525,7 +552,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
         attr_set = smem;
     }
     const int tiles = p.num_m_blocks * p.num_n_blocks;
-    const int grid = tiles < gn_num_sms() ? tiles : gn_num_sms();
+    int grid = tiles < gn_num_sms() ? tiles : gn_num_sms();
+    if (EPI != EPI_DIRECT && p.num_n_blocks > 1 && grid > 1)
+        while (grid % 2 == 0 && p.num_n_blocks % 2 == 0 || grid % 3 == 0 && p.num_n_blocks % 3 == 0) --grid;      // coprime with the n-block count
     gemm_bf16_kernel<BN, XFORM, EPI><<<grid, XFORM ? 512 : 384, smem, stream>>>(tmA, tmB, tmOut, tmRef, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
