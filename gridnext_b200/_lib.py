@@ -38,6 +38,11 @@ _SIGS = {
     'gn_normalize_u8': [vp, vp, cl, ci, vp, vp, vp, ci, vp],
     'gn_cast_f32_bf16': [vp, vp, cl, vp],
     'gn_rows_affine_bf16': [vp, cl, vp, vp, ci, vp, cl, cl, ci, ci, vp],
+    'gn_colstats_bf16': [vp, cl, cl, ci, vp, vp, vp],
+    'gn_bn_train_coeffs': [vp, vp, cl, vp, vp, cf, cf, vp, vp, vp, vp, vp, vp, ci, vp],
+    'gn_affine_relu_bf16': [vp, cl, vp, cl, cl, ci, vp, vp, ci, vp],
+    'gn_bn_train_fix_coeffs': [vp, vp, vp, vp, vp, cl, ci, vp, vp, ci, vp],
+    'gn_bn_train_fix_bf16': [vp, cl, vp, cl, cl, ci, vp, vp, vp],
     'gn_gemm_tn_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, vp, vp, vp],
     'gn_prep_job_bytes': [],
     'gn_prepare_weights': [vp, ci, cl, vp, vp],

@@ -14,8 +14,11 @@ Underneath (B200-first, not a translation of the module graph):
   * conv2 (3x3) = padded-position implicit GEMM with the nine taps as descriptor offsets into one TMA-loaded tile;
   * backward = the mirrored kernels with BatchNorm/ReLU backward and BN parameter gradients fused into the
     data-gradient epilogues; weight gradients are split-K tcgen05 GEMMs.
-BatchNorm is evaluated with running statistics: f is always in eval mode on the grid-wise hot path
-(/root/reference/gridnext/training.py:126).  Train-mode BN of f (train_spotwise) is not implemented here.
+On the grid-wise hot path f is always in eval mode (/root/reference/gridnext/training.py:126): BatchNorm is a per-channel
+affine from the running statistics.  In train mode (f pre-training, training.py:11-98) the SAME kernels run with constants
+derived from batch statistics (csrc/bn_train.cu): the statistics of a concat channel are computed once, when it is produced,
+and shared by every layer that normalises it; the mean/variance terms of the BatchNorm gradient are a per-channel correction
+dx -= c0 + c1*x applied once per channel after all of its consumers have accumulated into the gradient buffer.
 """
 import math
 from collections import OrderedDict
@@ -273,9 +276,11 @@ def _check_supported(net):
                     raise NotImplementedError('DenseNet (B200): dropout in training mode is not implemented')
         if name.startswith('transition') and m.conv.out_channels % 8:
             raise NotImplementedError('DenseNet (B200): transition widths must be multiples of 8')
-    if any(b.training for b in _bn_list(net)):
-        raise NotImplementedError('DenseNet (B200): BatchNorm must be in eval mode (train_gridwise puts f in eval, training.py:126); '
-                                  'train-mode f is not implemented')
+    modes = set(bool(b.training) for b in _bn_list(net))
+    if len(modes) != 1:
+        raise NotImplementedError('DenseNet (B200): BatchNorm layers must be all in train mode or all in eval mode')
+    if any(not b.track_running_stats for b in _bn_list(net)):
+        raise NotImplementedError('DenseNet (B200): BatchNorm without running statistics is not supported')
 
 
 def _forward_chunk(net, geo, cst, plan, x, save):
@@ -429,6 +434,239 @@ def _backward_chunk(net, geo, cst, plan, saved, dout, grads):
             tc.stem_conv_wgrad_into(saved['xq'], dz0, c0, plan.g(('stem',), (c0, 224)))
 
 
+class _TrainConsts:
+    """Train-mode counterpart of _Consts: the same per-BN views (sc, sh, mean, invstd, beta, inv_gamma), but sc / sh / mean /
+    invstd are filled layer by layer from batch statistics (``fill``) as the forward pass produces the data."""
+
+    def __init__(self, net):
+        bns = _bn_list(net)
+        dev = net.classifier.weight.device
+        sizes = [b.num_features for b in bns]
+        tot = sum(sizes)
+        g = torch.cat([b.weight.detach() for b in bns]).float()
+        be = torch.cat([b.bias.detach() for b in bns]).float().contiguous()
+        ig = torch.where(g != 0, 1.0 / g, torch.zeros_like(g)).contiguous()
+        buf = torch.empty((4, tot), device=dev, dtype=torch.float32)
+        self.bn = {}
+        off = 0
+        for b, n in zip(bns, sizes):
+            self.bn[id(b)] = dict(sc=buf[0, off:off + n], sh=buf[1, off:off + n], mean=buf[2, off:off + n], invstd=buf[3, off:off + n],
+                                  beta=be[off:off + n], inv_gamma=ig[off:off + n], off=off, n=n)
+            off += n
+        self.bn_total = tot
+        self.bns = bns
+
+    def of(self, bn):
+        return self.bn[id(bn)]
+
+    def fill(self, bn, ssum, ssq, M):
+        """Batch statistics (fp64 sums over M rows) -> this BN's constants; running statistics updated as nn.BatchNorm2d does."""
+        if M < 2:
+            raise ValueError('Expected more than 1 value per channel when training, got %d' % M)
+        k = self.of(bn)
+        mom = bn.momentum if bn.momentum is not None else 1.0 / (int(bn.num_batches_tracked.item()) + 1)
+        call('gn_bn_train_coeffs', ptr(ssum), ptr(ssq), M, ptr(bn.weight.detach()), ptr(bn.bias.detach()), float(bn.eps), float(mom),
+             ptr(bn.running_mean), ptr(bn.running_var), ptr(k['sc']), ptr(k['sh']), ptr(k['mean']), ptr(k['invstd']), k['n'], stream())
+        return k
+
+    def finish(self):
+        torch._foreach_add_([b.num_batches_tracked for b in self.bns], 1)
+
+
+def _colstats(x2d, C, ssum, ssq):
+    call('gn_colstats_bf16', ptr(x2d), x2d.stride(0), x2d.shape[0], C, ptr(ssum), ptr(ssq), stream())
+
+
+def _affine_relu(x2d, y2d, C, k):
+    call('gn_affine_relu_bf16', ptr(x2d), x2d.stride(0), ptr(y2d), y2d.stride(0), x2d.shape[0], C, ptr(k['sc']), ptr(k['sh']), 1, stream())
+
+
+def _fix_coeffs(colsum2, k, M, accumulate, F, C):
+    """F[0] (c0), F[1] (c1) (+)= the BatchNorm mean/variance gradient terms of one BN from its column sums (d_beta, d_gamma)."""
+    call('gn_bn_train_fix_coeffs', ptr(colsum2[0]), ptr(colsum2[1]), ptr(k['sc']), ptr(k['invstd']), ptr(k['mean']), M, 1 if accumulate else 0,
+         ptr(F[0]), ptr(F[1]), C, stream())
+
+
+def _fix(dx2d, x2d, C, F0, F1):
+    call('gn_bn_train_fix_bf16', ptr(dx2d), dx2d.stride(0), ptr(x2d), x2d.stride(0), dx2d.shape[0], C, ptr(F0), ptr(F1), stream())
+
+
+def _forward_train(net, geo, cst, plan, x, save):
+    """Train-mode forward of one batch (batch statistics span the whole batch: no chunking).  Returns (out, saved | None)."""
+    n, dev = x.shape[0], x.device
+    f = net.features
+    bf = torch.bfloat16
+    # fp64 (sum, sum of squares) slots: conv0 | per block: the concat channels, then one bottleneck slot per layer
+    slots = f.conv0.out_channels + sum(b['c_tot'] + len(b['layers']) * b['bott'] for b in geo.blocks)
+    st = torch.zeros((2, slots), device=dev, dtype=torch.float64)
+    so = [0]
+
+    def take(nch):
+        v = st[:, so[0]:so[0] + nch]
+        so[0] += nch
+        return v
+
+    # ---- stem: raw conv0, statistics, norm0 + ReLU as a pass, max-pool
+    xq = tc.stem_pack_input(x)
+    c0 = f.conv0.out_channels
+    z0 = tc.stem_conv_fwd(xq, plan.w('stem').view(7, c0, 32))
+    M0 = n * geo.H0 * geo.H0
+    s0 = take(c0)
+    _colstats(z0, c0, s0[0], s0[1])
+    k0 = cst.fill(f.norm0, s0[0], s0[1], M0)
+    act0 = torch.empty_like(z0)
+    _affine_relu(z0, act0, c0, k0)
+    saved = dict(xq=xq, z0=z0, act0=act0, blocks=[]) if save else None
+    blk0 = geo.blocks[0]
+    M = n * blk0['H'] * blk0['H']
+    C = torch.empty((M, blk0['c_tot']), device=dev, dtype=bf)
+    idx0 = torch.empty((M, c0), device=dev, dtype=torch.uint8)
+    call('gn_maxpool3s2_fwd', ptr(act0), c0, n, geo.H0, geo.H0, c0, ptr(C), blk0['c_tot'], ptr(idx0), stream())
+    if save:
+        saved['idx0'] = idx0
+    stats = None
+    for bi, blk in enumerate(geo.blocks):
+        H, g, bott = blk['H'], blk['growth'], blk['bott']
+        M = n * H * H
+        cin = blk['c_in']
+        stats = take(blk['c_tot'])
+        _colstats(C, cin, stats[0], stats[1])
+        a2 = torch.empty((M, bott), device=dev, dtype=bf)
+        zs = []
+        z = None
+        for layer in blk['layers']:
+            k1 = cst.fill(layer.norm1, stats[0], stats[1], M)
+            if save or z is None:
+                z = torch.empty((M, bott), device=dev, dtype=bf)
+            tc.gemm_bf16(C[:, :cin], plan.w('w1', id(layer))[:, :cin], out=z, xf_scale=k1['sc'], xf_shift=k1['sh'])
+            s2 = take(bott)
+            _colstats(z, bott, s2[0], s2[1])
+            k2 = cst.fill(layer.norm2, s2[0], s2[1], M)
+            _affine_relu(z, a2, bott, k2)
+            tc.conv3x3_bf16(a2, n, H, H, bott, plan.w('wp2', id(layer)), g, C[:, cin:cin + g])
+            _colstats(C[:, cin:cin + g], g, stats[0, cin:], stats[1, cin:])
+            if save:
+                zs.append(z)
+            cin += g
+        rec = dict(C=C, z=zs)
+        if blk['trans'] is not None:
+            tr = blk['trans']
+            ct = blk['c_tot']
+            kt = cst.fill(tr.norm, stats[0], stats[1], M)
+            pooled = torch.empty((M // 4, ct), device=dev, dtype=bf)
+            call('gn_bnrelu_avgpool2_fwd', ptr(C), ct, n, H, H, ct, ptr(kt['sc']), ptr(kt['sh']), ptr(pooled), ct, stream())
+            nxt = geo.blocks[bi + 1]
+            Cn = torch.empty((M // 4, nxt['c_tot']), device=dev, dtype=bf)
+            tc.gemm_bf16(pooled, plan.w('wt', id(tr))[:, :ct], out=Cn[:, :nxt['c_in']])
+            rec['pooled'] = pooled
+            if save:
+                saved['blocks'].append(rec)
+            C = Cn
+        elif save:
+            saved['blocks'].append(rec)
+    last = geo.blocks[-1]
+    kf = cst.fill(f.norm_final, stats[0], stats[1], n * last['H'] * last['H'])
+    feat = torch.empty((n, geo.c_final), device=dev, dtype=torch.float32)
+    call('gn_bnrelu_gap_fwd', ptr(C), last['c_tot'], n, last['H'] * last['H'], geo.c_final, ptr(kf['sc']), ptr(kf['sh']), ptr(feat), geo.c_final, stream())
+    if net.classify:
+        J = net.classifier.out_features
+        out = torch.empty((n, J), device=dev, dtype=torch.float32)
+        call('gn_linear_small_fwd', ptr(feat), geo.c_final, ptr(net.classifier.weight.detach().float().contiguous()),
+             ptr(net.classifier.bias.detach().float().contiguous()), n, geo.c_final, J, ptr(out), stream())
+    else:
+        out = feat
+    if save:
+        saved['feat'] = feat
+        saved['n'] = n
+    cst.finish()
+    return out, saved
+
+
+def _backward_train(net, geo, cst, plan, saved, dout, grads):
+    """Train-mode backward: the eval-mode kernel sequence plus the per-channel mean/variance corrections (module docstring)."""
+    n, dev, bf = saved['n'], dout.device, torch.bfloat16
+    f = net.features
+    last = geo.blocks[-1]
+    cs = grads.bn_colsum
+    tot = cst.bn_total
+
+    def colsum_of(k):
+        return cs[:, k['off']:k['off'] + k['n']]
+
+    Cf = geo.c_final
+    if net.classify:
+        J = net.classifier.out_features
+        dfeat = torch.empty((n, Cf), device=dev, dtype=torch.float32)
+        call('gn_linear_small_bwd', ptr(dout), ptr(saved['feat']), Cf, ptr(net.classifier.weight.detach().float().contiguous()), n, Cf, J,
+             ptr(dfeat), Cf, ptr(plan.g(('cls_w',), (J, Cf))), ptr(plan.g(('cls_b',), (J,))), stream())
+    else:
+        dfeat = dout
+    kf = cst.of(f.norm_final)
+    C = saved['blocks'][-1]['C']
+    M = n * last['H'] * last['H']
+    dC = torch.empty((M, last['c_tot']), device=dev, dtype=bf)
+    call('gn_pool_bnrelu_bwd', ptr(dfeat), Cf, 1, ptr(C), last['c_tot'], n, last['H'], last['H'], Cf, ptr(kf['sc']), ptr(kf['sh']),
+         ptr(kf['mean']), ptr(kf['invstd']), ptr(dC), last['c_tot'], ptr(colsum_of(kf)), tot, stream())
+    F = torch.zeros((2, last['c_tot']), device=dev, dtype=torch.float32)      # (c0, c1) of the block's concat channels
+    _fix_coeffs(colsum_of(kf), kf, M, True, F, Cf)
+    for bi in range(len(geo.blocks) - 1, -1, -1):
+        blk, rec = geo.blocks[bi], saved['blocks'][bi]
+        H, g, bott = blk['H'], blk['growth'], blk['bott']
+        C = rec['C']
+        M = n * H * H
+        dz = torch.empty((M, bott), device=dev, dtype=bf)
+        a2 = torch.empty((M, bott), device=dev, dtype=bf)
+        Fz = torch.empty((2, bott), device=dev, dtype=torch.float32)
+        cin = blk['c_tot']
+        for li in range(len(blk['layers']) - 1, -1, -1):
+            layer = blk['layers'][li]
+            cin -= g
+            k1, k2 = cst.of(layer.norm1), cst.of(layer.norm2)
+            z = rec['z'][li]
+            dY = dC[:, cin:cin + g]
+            _fix(dY, C[:, cin:cin + g], g, F[0, cin:], F[1, cin:])          # every consumer of these channels has accumulated
+            _affine_relu(z, a2, bott, k2)
+            tc.conv3x3_wgrad_into(a2, dY, n, H, H, bott, g, plan.g(('dwp2', id(layer)), (9, bott, g)))
+            tc.conv3x3_bf16(dY, n, H, H, g, plan.w('wp2t', id(layer)), bott, dz,
+                            bn=dict(ref=z, ref_is_raw=True, sc=k2['sc'], sh=k2['sh'], p0=k2['mean'], p1=k2['invstd'], colsum=colsum_of(k2)))
+            _fix_coeffs(colsum_of(k2), k2, M, False, Fz, bott)
+            _fix(dz, z, bott, Fz[0], Fz[1])
+            tc.gemm_tn_bf16(dz, C[:, :cin], plan.g(('dw1', id(layer)), (bott, cin)), k1['sc'], k1['sh'])
+            tc.gemm_bf16(dz, plan.w('w1t', id(layer))[:, :bott], out=dC[:, :cin],
+                         bn=dict(ref=C[:, :cin], ref_is_raw=True, sc=k1['sc'], sh=k1['sh'], p0=k1['mean'], p1=k1['invstd'],
+                                 colsum=colsum_of(k1), rmw=True))
+            _fix_coeffs(colsum_of(k1), k1, M, True, F, cin)
+        c_in = blk['c_in']
+        _fix(dC[:, :c_in], C[:, :c_in], c_in, F[0], F[1])
+        if bi > 0:
+            prev, prec = geo.blocks[bi - 1], saved['blocks'][bi - 1]
+            tr = prev['trans']
+            kt = cst.of(tr.norm)
+            ctp = prev['c_tot']
+            d_out = dC[:, :c_in]
+            tc.gemm_tn_bf16(d_out, prec['pooled'], plan.g(('dwt', id(tr)), (c_in, ctp)))
+            dP = tc.gemm_bf16(d_out, plan.w('wtt', id(tr))[:, :c_in])
+            Hp = prev['H']
+            Mp = n * Hp * Hp
+            dCp = torch.empty((Mp, ctp), device=dev, dtype=bf)
+            call('gn_pool_bnrelu_bwd', ptr(dP), ctp, 0, ptr(prec['C']), ctp, n, Hp, Hp, ctp, ptr(kt['sc']), ptr(kt['sh']), ptr(kt['mean']),
+                 ptr(kt['invstd']), ptr(dCp), ctp, ptr(colsum_of(kt)), tot, stream())
+            F = torch.empty((2, ctp), device=dev, dtype=torch.float32)
+            _fix_coeffs(colsum_of(kt), kt, Mp, False, F, ctp)
+            dC = dCp
+        else:
+            c0 = f.conv0.out_channels
+            k0 = cst.of(f.norm0)
+            M0 = n * geo.H0 * geo.H0
+            dz0 = torch.empty((M0, c0), device=dev, dtype=bf)
+            call('gn_maxpool3s2_bnrelu_bwd', ptr(dC), blk['c_tot'], ptr(saved['idx0']), ptr(saved['act0']), c0, n, geo.H0, geo.H0, c0,
+                 ptr(k0['sc']), ptr(k0['beta']), ptr(k0['inv_gamma']), ptr(dz0), c0, ptr(colsum_of(k0)), tot, stream())
+            F0 = torch.empty((2, c0), device=dev, dtype=torch.float32)
+            _fix_coeffs(colsum_of(k0), k0, M0, False, F0, c0)
+            _fix(dz0, saved['z0'], c0, F0[0], F0[1])
+            tc.stem_conv_wgrad_into(saved['xq'], dz0, c0, plan.g(('stem',), (c0, 224)))
+
+
 class _DenseNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, net, *params):
@@ -440,15 +678,21 @@ class _DenseNetFn(torch.autograd.Function):
             x = x.float()
         x = x.contiguous()
         geo = _Geometry(net, int(x.shape[2]))
-        cst = _Consts(net)
+        train_bn = bool(net.features.norm_final.training)
+        cst = _TrainConsts(net) if train_bn else _Consts(net)
         plan = _Plan.of(net)
         plan.prepare()
         N = x.shape[0]
         need_grad = any(ctx.needs_input_grad[2:])
-        ctx.net, ctx.geo, ctx.cst, ctx.plan = net, geo, cst, plan
+        ctx.net, ctx.geo, ctx.cst, ctx.plan, ctx.train_bn = net, geo, cst, plan, train_bn
         ctx.plist = list(net.parameters())
         assert len(ctx.plist) == len(params)
-        if N <= MAX_SPOTS_RESIDENT:
+        if train_bn:
+            if N > MAX_SPOTS_RESIDENT:
+                raise ValueError('DenseNet (B200): a train-mode batch is limited to %d spots (batch statistics span the whole batch)' % MAX_SPOTS_RESIDENT)
+            out, saved = _forward_train(net, geo, cst, plan, x, need_grad)
+            ctx.saved, ctx.x = saved, None
+        elif N <= MAX_SPOTS_RESIDENT:
             out, saved = _forward_chunk(net, geo, cst, plan, x, need_grad)
             ctx.saved, ctx.x = saved, None
         else:
@@ -462,7 +706,10 @@ class _DenseNetFn(torch.autograd.Function):
         net, geo, cst, plan = ctx.net, ctx.geo, ctx.cst, ctx.plan
         dout = dout.contiguous().float()
         grads = _Grads(net, cst, plan)
-        if ctx.saved is not None:
+        if ctx.train_bn:
+            _backward_train(net, geo, cst, plan, ctx.saved, dout, grads)
+            ctx.saved = None
+        elif ctx.saved is not None:
             _backward_chunk(net, geo, cst, plan, ctx.saved, dout, grads)
             ctx.saved = None
         else:

@@ -28,8 +28,23 @@ def _to_device(inputs, device):
     return inputs.to(device, non_blocking=True)
 
 
+def _spot_forward(model, inputs):
+    """f on one spot batch: the count MLP pattern goes through the tensor-core path (count_mlp.forward_spots), a
+    gridnext_b200 DenseNet runs its own kernels in either BatchNorm mode, anything else is called as is."""
+    if inputs.is_cuda and inputs.dim() == 2 and isinstance(model, torch.nn.Sequential):
+        from .count_mlp import compile_count_mlp
+        fast = compile_count_mlp(model)
+        if fast is not None:
+            out = fast.forward_spots(inputs)
+            if out is not None:
+                return out
+    return model(inputs)
+
+
 def train_spotwise(model, dataloaders, criterion, optimizer, num_epochs=10, outfile=None, display=False):
-    """Spot classifier (f) pre-training loop; library ops only (row f3 of SURVEY.md section 8)."""
+    """Spot classifier (f) pre-training loop (/root/reference/gridnext/training.py:11-98; row f3 of SURVEY.md section 8):
+    same phases, metrics, best-weights bookkeeping and return triple; f runs with train-mode BatchNorm in the train phase
+    (batch statistics + running-stat update, csrc/bn_train.cu) and eval-mode BatchNorm in the val phase."""
     since = time.time()
     val_acc_history, train_acc_history = [], []
     best_model_wts = copy.deepcopy(model.state_dict())
@@ -48,7 +63,7 @@ def train_spotwise(model, dataloaders, criterion, optimizer, num_epochs=10, outf
                 labels = labels.to(device)
                 optimizer.zero_grad()
                 with torch.set_grad_enabled(phase == 'train'):
-                    outputs = model(inputs)
+                    outputs = _spot_forward(model, inputs)
                     loss = criterion(outputs, labels)
                     _, preds = torch.max(outputs, 1)
                     if phase == 'train':

@@ -165,6 +165,23 @@ int gn_linear_small_bwd(const float* dlog, const float* feat, long ldf, const fl
 int gn_bn_eval_consts(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int C, float* scale,
                       float* shift, float* invstd, float* inv_gamma, gn_stream_t stream);
 
+/* Train-mode BatchNorm around the same tensor-core kernels (f pre-training, training.py:11-98; the count f that training.py:126
+ * leaves in train mode inside GridNetHexMM).  Forward: batch statistics of bf16 rows (fp64 sums; caller zeroes them) -> the
+ * per-channel constants (scale, shift, mean, invstd) the kernels above consume, with nn.BatchNorm's running-stat update
+ * (running_* nullable; running_var gets the unbiased variance); y = [relu](x*sc+sh) as a pass of its own, because a GEMM cannot
+ * normalise its own output.  Backward: the BN-backward epilogues return dx_eval = g*scale and the column sums (d_beta, d_gamma);
+ * dx = dx_eval - (c0 + c1*x) with c1 = scale*invstd*d_gamma/M, c0 = scale*d_beta/M - c1*mean (accumulate: several DenseNet
+ * layers normalise the same concat channel).  C and pitches are multiples of 8, pointers 16-byte aligned. */
+int gn_colstats_bf16(const void* x, long ld, long M, int C, double* sum, double* sumsq, gn_stream_t stream);
+int gn_bn_train_coeffs(const double* sum, const double* sumsq, long M, const float* gamma, const float* beta, float eps, float momentum,
+                       float* running_mean, float* running_var, float* sc, float* sh, float* mean, float* invstd, int C,
+                       gn_stream_t stream);
+int gn_affine_relu_bf16(const void* x, long ldx, void* y, long ldy, long M, int C, const float* sc, const float* sh, int relu,
+                        gn_stream_t stream);
+int gn_bn_train_fix_coeffs(const float* dbeta, const float* dgamma, const float* sc, const float* invstd, const float* mean, long M,
+                           int accumulate, float* c0, float* c1, int C, gn_stream_t stream);
+int gn_bn_train_fix_bf16(void* dx, long lddx, const void* x, long ldx, long M, int C, const float* c0, const float* c1, gn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

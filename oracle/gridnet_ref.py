@@ -48,6 +48,8 @@ def mlp_forward(sd, x, spec=COUNT_MLP_SPEC, training=False, stats_out=None, emul
                 x = _rg(_rb(x, e), e)
             elif i != last:
                 x = _rg(x, e)
+                if training:
+                    x = _rb(x, e)       # train-mode BN: the raw Linear output is stored (bf16) before its statistics exist
         elif kind == 'B':
             if training:
                 mean = x.mean(0)
@@ -106,14 +108,32 @@ def _rg(t, on):
     return _RoundGradBf16.apply(t) if on else t
 
 
-def densenet_forward(sd, x, classify=True, emulate_bf16=False):
-    """Eval-mode DenseNet-BC forward.  x: (N, 3, P, P) float.
+def _bn2d(sd, p, x, training, stats_out):
+    """nn.BatchNorm2d of the reference's DenseNet (densenet.py:24-29,50,134): running statistics in eval mode, batch statistics
+    (biased variance; running stats updated with momentum 0.1 and the unbiased variance) in train mode."""
+    if not training:
+        return _bn_eval(sd, p, x)
+    mean = x.mean((0, 2, 3))
+    var = x.var((0, 2, 3), unbiased=False)
+    if stats_out is not None:
+        n = x.numel() // x.shape[1]
+        stats_out[p + 'running_mean'] = (1 - BN_MOMENTUM) * sd[p + 'running_mean'] + BN_MOMENTUM * mean.detach()
+        stats_out[p + 'running_var'] = (1 - BN_MOMENTUM) * sd[p + 'running_var'] + BN_MOMENTUM * var.detach() * n / (n - 1)
+    xh = (x - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + BN_EPS)
+    return xh * sd[p + 'weight'].view(1, -1, 1, 1) + sd[p + 'bias'].view(1, -1, 1, 1)
+
+
+def densenet_forward(sd, x, classify=True, emulate_bf16=False, training=False, stats_out=None):
+    """DenseNet-BC forward (densenet.py:152-159).  x: (N, 3, P, P) float.  ``training``: train-mode BatchNorm (f pre-training,
+    training.py:11-98); eval mode is what the grid-wise hot path uses (training.py:126).
 
     ``emulate_bf16``: same fp32 arithmetic, but every tensor the B200 path stores in bfloat16 (input, conv weights,
-    activated operands, conv outputs, pooled transition input, and the gradients dZ / dC) is rounded at that point,
-    and the transition pools BEFORE its 1x1 convolution (they commute; gridnext_b200/densenet.py).  This pins the
-    kernels far tighter than the fp32 comparison allows, because ReLU masks then agree."""
+    activated operands, conv outputs, pooled transition input, and the gradients dZ / dC; in train mode also the raw conv0 /
+    conv1 outputs, which must exist before their statistics do) is rounded at that point, and the transition pools BEFORE
+    its 1x1 convolution (they commute; gridnext_b200/densenet.py).  This pins the kernels far tighter than the fp32
+    comparison allows, because ReLU masks then agree."""
     e = emulate_bf16
+    t = training
     small_inputs = 'features.norm0.weight' not in sd
     w0 = _rb(sd['features.conv0.weight'], e)
     x = _rb(x, e)
@@ -121,28 +141,30 @@ def densenet_forward(sd, x, classify=True, emulate_bf16=False):
         x = _rb(F.conv2d(x, w0, stride=1, padding=1), e)
     else:
         x = _rg(F.conv2d(x, w0, stride=2, padding=3), e)
-        x = _rb(torch.relu(_bn_eval(sd, 'features.norm0.', x)), e)
+        x = _rb(x, e and t)
+        x = _rb(torch.relu(_bn2d(sd, 'features.norm0.', x, t, stats_out)), e)
         x = F.max_pool2d(x, 3, stride=2, padding=1)
     cfg = densenet_block_config(sd)
     for bi, nl in enumerate(cfg, start=1):
         x = _rg(x, e)
         for li in range(1, nl + 1):
             p = 'features.denseblock%d.denselayer%d.' % (bi, li)
-            h = _rb(torch.relu(_bn_eval(sd, p + 'norm1.', x)), e)
+            h = _rb(torch.relu(_bn2d(sd, p + 'norm1.', x, t, stats_out)), e)
             h = _rg(F.conv2d(h, _rb(sd[p + 'conv1.weight'], e)), e)
-            h = _rb(torch.relu(_bn_eval(sd, p + 'norm2.', h)), e)
+            h = _rb(h, e and t)
+            h = _rb(torch.relu(_bn2d(sd, p + 'norm2.', h, t, stats_out)), e)
             h = _rg(_rb(F.conv2d(h, _rb(sd[p + 'conv2.weight'], e), padding=1), e), e)
             x = torch.cat((x, h), 1)
         if bi != len(cfg):
             p = 'features.transition%d.' % bi
-            x = torch.relu(_bn_eval(sd, p + 'norm.', x))
+            x = torch.relu(_bn2d(sd, p + 'norm.', x, t, stats_out))
             if e:
                 x = _rg(_rb(F.avg_pool2d(x, 2, stride=2), e), e)
                 x = _rb(F.conv2d(x, _rb(sd[p + 'conv.weight'], e)), e)
             else:
                 x = F.conv2d(x, sd[p + 'conv.weight'])
                 x = F.avg_pool2d(x, 2, stride=2)
-    x = torch.relu(_bn_eval(sd, 'features.norm_final.', x))
+    x = torch.relu(_bn2d(sd, 'features.norm_final.', x, t, stats_out))
     x = x.mean((2, 3))
     if classify:
         x = F.linear(x, sd['classifier.weight'], sd['classifier.bias'])

@@ -198,6 +198,7 @@ def main():
                         x_ind=xy[:, 0].astype(np.int16), y_ind=xy[:, 1].astype(np.int16))
     manifest['t1_template_positions'] = dict(n=len(df), n_in_tissue=int(df['in_tissue'].sum()))
 
+    extras(manifest, (gm, dn, tr, ip))
     with open(os.path.join(OUT, 'state_dict_keys.json'), 'w') as fh:
         json.dump(KEYS, fh, sort_keys=True)
     with open(os.path.join(OUT, 'manifest.json'), 'w') as fh:
@@ -205,5 +206,33 @@ def main():
     print(json.dumps(manifest, indent=1))
 
 
+def extras(manifest, mods):
+    """Vectors added after the first set (``python -m oracle.make_golden --extras`` regenerates only these)."""
+    gm, dn, tr, ip = mods
+    # ---- D3: tiny DenseNet in TRAIN mode (f pre-training, training.py:11-98): batch-stat BatchNorm, running-stat update
+    tag, kw, P, N, seed = 'd3_densenet_tiny_train', dict(growth_rate=8, block_config=(2, 3), num_init_features=16, bn_size=2), 32, 6, 33
+    net = dn.DenseNet(num_classes=7, small_inputs=False, efficient=False, drop_rate=0, **kw)
+    load_synth(net, seed)
+    net.train()
+    gx = torch.Generator(); gx.manual_seed(seed + 100)
+    x = torch.randn(N, 3, P, P, generator=gx)
+    logits = net(x)
+    gy = torch.Generator(); gy.manual_seed(seed + 200)
+    dy = torch.randn(logits.shape, generator=gy)
+    (logits * dy).sum().backward()
+    g = grads_of(net)
+    after = {k: v for k, v in net.state_dict().items() if 'running' in k or 'num_batches' in k}
+    np.savez_compressed(os.path.join(OUT, tag + '.npz'), logits=logits.detach().numpy(),
+                        **{'grad.' + k: v.numpy() for k, v in g.items()}, **{'after.' + k: v.numpy() for k, v in after.items()})
+    manifest[tag] = dict(P=P, N=N, seed_w=seed, seed_x=seed + 100, seed_dy=seed + 200, **{k: list(v) if isinstance(v, tuple) else v for k, v in kw.items()})
+
+
 if __name__ == '__main__':
-    main()
+    if '--extras' in sys.argv:
+        man = json.load(open(os.path.join(OUT, 'manifest.json')))
+        torch.set_num_threads(os.cpu_count())
+        extras(man, import_reference())
+        with open(os.path.join(OUT, 'manifest.json'), 'w') as fh:
+            json.dump(man, fh, indent=1, sort_keys=True)
+    else:
+        main()

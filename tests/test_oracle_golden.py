@@ -135,6 +135,32 @@ def test_densenet_matches_reference(golden, tag):
             assert np.allclose(sd[k[5:]].grad.numpy(), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max()), k  # fp32 noise through 121 layers
 
 
+def test_densenet_train_mode_matches_reference(golden):
+    """Train-mode BatchNorm of f (training.py:11-98 pre-training): logits, every parameter gradient and the updated running
+    statistics of the reference's DenseNet in .train()."""
+    tag = 'd3_densenet_tiny_train'
+    m = MAN[tag]
+    gold = golden(tag)
+    sd = make_sd(S.densenet_shapes(m['growth_rate'], tuple(m['block_config']), m['num_init_features'], m['bn_size']), m['seed_w'])
+    g = torch.Generator(); g.manual_seed(m['seed_x'])
+    x = torch.randn(m['N'], 3, m['P'], m['P'], generator=g)
+    stats = {}
+    logits = R.densenet_forward(sd, x, training=True, stats_out=stats)
+    assert np.allclose(logits.detach().numpy(), gold['logits'], rtol=1e-4, atol=1e-5)
+    g = torch.Generator(); g.manual_seed(m['seed_dy'])
+    dy = torch.randn(logits.shape, generator=g)
+    (logits * dy).sum().backward()
+    n = 0
+    for k in gold.files:
+        if k.startswith('grad.'):
+            ref = gold[k]
+            assert np.allclose(sd[k[5:]].grad.numpy(), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max()), k
+            n += 1
+        elif k.startswith('after.') and 'running' in k:
+            assert np.allclose(stats[k[6:]].numpy(), gold[k], rtol=1e-5, atol=1e-6), k
+    assert n == len([k for k in sd if sd[k].requires_grad])
+
+
 def test_multimodal_matches_reference(golden):
     m = MAN['m1_multimodal_4x4']
     gold = golden('m1_multimodal_4x4')
