@@ -27,6 +27,10 @@ _SIGS = {
     'gn_hexconv_tc_supported': [ci, ci, ci, ci, ci],
     'gn_hexconv_wgrad_tc': [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp],
     'gn_hexconv_wgrad': [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
+    'gn_sqconv_pack': [vp, ci, ci, ci, ci, vp, vp],
+    'gn_sqconv_unpack_grad': [vp, vp, ci, ci, ci, vp],
+    'gn_sqconv_fwd': [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
+    'gn_sqconv_wgrad': [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
     'gn_bn_finalize': [vp, vp, vp, vp, vp, cf, cf, cd, vp, vp, vp, ci, ci, vp],
     'gn_bn_eval_affine': [vp, vp, vp, vp, cf, vp, vp, vp, ci, vp],
     'gn_bn_stats': [vp, vp, ci, ci, cl, vp],

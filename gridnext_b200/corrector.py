@@ -1,10 +1,13 @@
-"""Fused execution of the hexagonal g corrector (forward + backward) in the Visium layout.
+"""Fused execution of the g corrector (forward + backward): hexagonal in the Visium layout, or the base GridNet's Cartesian one.
 
 Runs the ``nn.Sequential`` built by ``GridNetHex._init_corrector``
 (/root/reference/gridnext/gridnet_models.py:128-148: hex hex [BN] ReLU hex hex [BN] ReLU hex) as ONE
 autograd node: BatchNorm statistics come out of the preceding hexconv's epilogue, BatchNorm-apply +
 ReLU is the next hexconv's prologue (the activated tensor is never materialised), and the rot90/flip
 re-indexing of gridnet_models.py:177-185 is gone because the kernels take the row parity directly.
+
+The base ``GridNet``'s Cartesian corrector (gridnet_models.py:51-66: Conv2d 3x3, 5x5, 5x5, 3x3 with [BN] ReLU in between) runs
+through the same node: a K x K window is a parity-independent tap table of the same tile kernels (csrc/hexconv.cu, gn_sqconv_*).
 """
 import torch
 import torch.nn as nn
@@ -14,15 +17,24 @@ from ._lib import ptr, stream, call
 from . import hexagdly as hx
 
 
-def parse_corrector(seq):
-    """-> list of stages [(hex_module, bn_module | None, relu_before: bool)] or None if not fusable.
+def _is_square_conv(m):
+    if not isinstance(m, nn.Conv2d):
+        return False
+    K = m.kernel_size[0]
+    return (m.kernel_size == (K, K) and K in (1, 3, 5) and m.stride == (1, 1) and m.padding == (K // 2, K // 2) and m.dilation == (1, 1)
+            and m.groups == 1 and m.padding_mode == 'zeros')
 
-    Stage j = optional (BatchNorm2d, ReLU | ReLU) applied to the running tensor, then a hex conv."""
+
+def parse_corrector(seq):
+    """-> list of stages [(conv_module, bn_module | None, relu_before: bool)] or None if not fusable.
+
+    Stage j = optional (BatchNorm2d, ReLU | ReLU) applied to the running tensor, then a hex conv (hexagdly.Conv2d) or a
+    Cartesian one (nn.Conv2d K x K, stride 1, 'same' zero padding)."""
     if not isinstance(seq, nn.Sequential):
         return None
     stages, bn, relu = [], None, False
     for m in seq:
-        if isinstance(m, hx.Conv2d):
+        if isinstance(m, hx.Conv2d) or _is_square_conv(m):
             if bn is not None and not relu:
                 return None           # BN without ReLU before a conv: not a pattern we fuse
             stages.append((m, bn, relu))
@@ -75,11 +87,11 @@ class _CorrectorFn(torch.autograd.Function):
             elif st['relu']:
                 C = st['cin']
                 scale = torch.ones(C, device=dev); shift = torch.zeros(C, device=dev)
-            wp = hx.pack_weights(ks, st['ksize'], st['cin'], st['cout'], 0)
+            wp = hx.pack_weights(ks, st['ksize'], st['cin'], st['cout'], 0, st['kind'])
             nxt = meta[j + 1] if j + 1 < len(meta) else None
             want_stats = nxt is not None and nxt['bn'] is not None and nxt['bn']['training']
             stats = torch.zeros(2 * st['cout'], device=dev, dtype=torch.float64) if want_stats else None
-            out = hx.hexconv_fwd(cur, wp, bias, st['cout'], st['ksize'], scale, shift, stats)
+            out = hx.hexconv_fwd(cur, wp, bias, st['cout'], st['ksize'], scale, shift, stats, st['kind'])
             saved.append((cur, scale, shift, mi))
             per_stage_params.append((ks, bias, gamma, beta))
             cur, cur_stats = out, stats
@@ -100,13 +112,13 @@ class _CorrectorFn(torch.autograd.Function):
             st = meta[j]
             inp, scale, shift, mi = saved[j]
             ks, bias, gamma, beta = sp[j]
-            dwp, db = hx.hexconv_wgrad(inp, grad, st['ksize'], scale, shift, want_bias=bias is not None)
-            gks = hx.unpack_grad(dwp, [k.shape for k in ks], st['ksize'], st['cin'], st['cout'])
+            dwp, db = hx.hexconv_wgrad(inp, grad, st['ksize'], scale, shift, want_bias=bias is not None, kind=st['kind'])
+            gks = hx.unpack_grad(dwp, [k.shape for k in ks], st['ksize'], st['cin'], st['cout'], st['kind'])
             dgamma = dbeta = None
             need_dx = j > 0 or ctx.needs_input_grad[0]
             if need_dx:
-                wpt = hx.pack_weights(ks, st['ksize'], st['cin'], st['cout'], 1)
-                dA = hx.hexconv_fwd(grad, wpt, None, st['cin'], st['ksize'])
+                wpt = hx.pack_weights(ks, st['ksize'], st['cin'], st['cout'], 1, st['kind'])
+                dA = hx.hexconv_fwd(grad, wpt, None, st['cin'], st['ksize'], kind=st['kind'])
                 if scale is not None:
                     C = st['cin']
                     dH = torch.empty_like(dA)
@@ -142,11 +154,19 @@ def run_corrector(stages, x, training):
     """x: (B, f_dim, H, W) Visium layout -> (B, n_out, H, W)."""
     meta, params = [], []
     for (hexm, bn, relu) in stages:
-        k = hexm.hexbase_size
-        m = dict(ksize=k, cin=hexm.in_channels, cout=hexm.out_channels, nk=k + 1, has_bias=hexm.bias_tensor is not None, bn=None, relu=relu)
-        params.extend(getattr(hexm, 'kernel%d' % i) for i in range(k + 1))
-        if hexm.bias_tensor is not None:
-            params.append(hexm.bias_tensor)
+        if isinstance(hexm, nn.Conv2d):
+            m = dict(kind='sq', ksize=hexm.kernel_size[0], cin=hexm.in_channels, cout=hexm.out_channels, nk=1, has_bias=hexm.bias is not None,
+                     bn=None, relu=relu)
+            params.append(hexm.weight)
+            if hexm.bias is not None:
+                params.append(hexm.bias)
+        else:
+            k = hexm.hexbase_size
+            m = dict(kind='hex', ksize=k, cin=hexm.in_channels, cout=hexm.out_channels, nk=k + 1, has_bias=hexm.bias_tensor is not None, bn=None,
+                     relu=relu)
+            params.extend(getattr(hexm, 'kernel%d' % i) for i in range(k + 1))
+            if hexm.bias_tensor is not None:
+                params.append(hexm.bias_tensor)
         if bn is not None:
             bn_train = bool(training and bn.training)
             if bn_train and bn.momentum is None:

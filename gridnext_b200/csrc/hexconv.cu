@@ -26,6 +26,7 @@
 struct HexTaps {
     int n;
     int k;
+    int square;                      // 1: Cartesian K x K window (K = 2k+1), one weight tensor (Cout, Cin, K, K)
     signed char dy[HEX_MAX_TAPS];
     signed char dxe[HEX_MAX_TAPS];
     signed char dxo[HEX_MAX_TAPS];
@@ -55,6 +56,27 @@ static HexTaps make_taps(int k) {
     return t;
 }
 
+// Cartesian K x K, stride 1, padding K/2 (the base GridNet corrector's nn.Conv2d layers, gridnet_models.py:51-66): the same
+// tile kernels with a parity-independent tap table; the weight tensor plays the role of kernel_0 with (a, side) = (row, col).
+static HexTaps make_square_taps(int K) {
+    HexTaps t;
+    memset(&t, 0, sizeof(t));
+    t.k = K / 2;
+    t.square = 1;
+    int n = 0;
+    for (int r = 0; r < K; ++r)
+        for (int c = 0; c < K; ++c) {
+            t.dy[n] = (signed char)(r - K / 2);
+            t.dxe[n] = t.dxo[n] = (signed char)(c - K / 2);
+            t.ki[n] = 0;
+            t.ka[n] = (signed char)r;
+            t.kside[n] = (signed char)c;
+            ++n;
+        }
+    t.n = n;
+    return t;
+}
+
 struct HexKernelPtrs {
     const float* k[HEX_MAX_K + 1];
 };
@@ -72,7 +94,7 @@ __global__ void hex_pack_kernel(HexKernelPtrs kp, HexTaps taps, int Cin, int Cou
         int t = (int)(e / ((long)Cin * Cout));
         int r = (int)(e % ((long)Cin * Cout));
         int i = taps.ki[t], a = taps.ka[t], side = taps.kside[t];
-        int na = 2 * taps.k + 1 - i, ns = (i == 0) ? 1 : 2;
+        int na = 2 * taps.k + 1 - i, ns = taps.square ? na : ((i == 0) ? 1 : 2);
         int co, ci;
         if (mode == 0) {
             ci = r / Cout; co = r % Cout;
@@ -93,7 +115,7 @@ __global__ void hex_unpack_grad_kernel(const float* __restrict__ dwp, HexTaps ta
         int r = (int)(e % ((long)Cin * Cout));
         int ci = r / Cout, co = r % Cout;
         int i = taps.ki[t], a = taps.ka[t], side = taps.kside[t];
-        int na = 2 * taps.k + 1 - i, ns = (i == 0) ? 1 : 2;
+        int na = 2 * taps.k + 1 - i, ns = taps.square ? na : ((i == 0) ? 1 : 2);
         kp.k[i][(((long)co * Cin + ci) * na + a) * ns + side] = dwp[e];
     }
 }
@@ -380,25 +402,27 @@ static int launch_fwd(const float* x, const float* wp, const float* bias, const 
     return GN_OK;
 }
 
-GN_API int gn_hexconv_fwd(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
-                          double* stats, int B, int cin, int cout, int H, int W, int ksize, cudaStream_t stream) {
-    GN_REQUIRE(ksize >= 1 && ksize <= HEX_MAX_K, GN_EUNSUPPORTED, "hexconv: kernel_size %d not in 1..3", ksize);
+static int conv_fwd_impl(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
+                         double* stats, int B, int cin, int cout, int H, int W, const HexTaps& taps, cudaStream_t stream) {
     GN_REQUIRE(x && wp && y && B > 0 && cin > 0 && cout > 0 && H > 0 && W > 0, GN_EINVAL, "hexconv_fwd: bad arguments");
     GN_REQUIRE(B <= 65535, GN_EUNSUPPORTED, "hexconv_fwd: batch %d > 65535", B);
     GN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), GN_EINVAL, "hexconv_fwd: in_scale/in_shift must come together");
-    HexTaps taps = make_taps(ksize);
     if (cout <= 8) return launch_fwd<8>(x, wp, bias, in_scale, in_shift, y, stats, B, cin, cout, H, W, taps, stream);
     if (cout <= 16) return launch_fwd<16>(x, wp, bias, in_scale, in_shift, y, stats, B, cin, cout, H, W, taps, stream);
     return launch_fwd<32>(x, wp, bias, in_scale, in_shift, y, stats, B, cin, cout, H, W, taps, stream);
 }
 
-GN_API int gn_hexconv_wgrad(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, float* dbias,
-                            int B, int cin, int cout, int H, int W, int ksize, cudaStream_t stream) {
+GN_API int gn_hexconv_fwd(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
+                          double* stats, int B, int cin, int cout, int H, int W, int ksize, cudaStream_t stream) {
     GN_REQUIRE(ksize >= 1 && ksize <= HEX_MAX_K, GN_EUNSUPPORTED, "hexconv: kernel_size %d not in 1..3", ksize);
+    return conv_fwd_impl(x, wp, bias, in_scale, in_shift, y, stats, B, cin, cout, H, W, make_taps(ksize), stream);
+}
+
+static int conv_wgrad_impl(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, float* dbias,
+                           int B, int cin, int cout, int H, int W, const HexTaps& taps, cudaStream_t stream) {
     GN_REQUIRE(x && dy && dwp && B > 0 && cin > 0 && cout > 0 && H > 0 && W > 0, GN_EINVAL, "hexconv_wgrad: bad arguments");
     GN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), GN_EINVAL, "hexconv_wgrad: in_scale/in_shift must come together");
-    HexTaps taps = make_taps(ksize);
-    const int k = ksize;
+    const int k = taps.k;
     size_t smem = ((size_t)HEX_CC * (HEX_TR + 2 * k) * (HEX_TW + 2 * k) + (size_t)HEX_TR * HEX_TW * HEXW_CO) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -414,4 +438,48 @@ GN_API int gn_hexconv_wgrad(const float* x, const float* in_scale, const float* 
     hexconv_wgrad_kernel<<<grid, HEX_THREADS, smem, stream>>>(x, in_scale, in_shift, dy, dwp, dbias, B, cin, cout, H, W, taps);
     GN_LAUNCH_CHECK();
     return GN_OK;
+}
+
+GN_API int gn_hexconv_wgrad(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, float* dbias,
+                            int B, int cin, int cout, int H, int W, int ksize, cudaStream_t stream) {
+    GN_REQUIRE(ksize >= 1 && ksize <= HEX_MAX_K, GN_EUNSUPPORTED, "hexconv: kernel_size %d not in 1..3", ksize);
+    return conv_wgrad_impl(x, in_scale, in_shift, dy, dwp, dbias, B, cin, cout, H, W, make_taps(ksize), stream);
+}
+
+// ---- Cartesian K x K (K in {1, 3, 5}), stride 1, zero padding K/2: nn.Conv2d of the base GridNet corrector
+// (/root/reference/gridnext/gridnet_models.py:51-66).  Same packed layout Wp[t = r*K + c][cin][cout], same fusions.
+#define SQ_OK(K) ((K) == 1 || (K) == 3 || (K) == 5)
+
+GN_API int gn_sqconv_pack(const float* w, int K, int cin, int cout, int mode, float* wp, cudaStream_t stream) {
+    GN_REQUIRE(SQ_OK(K), GN_EUNSUPPORTED, "sqconv: kernel size %d not in {1, 3, 5}", K);
+    GN_REQUIRE(cin > 0 && cout > 0 && wp && w, GN_EINVAL, "sqconv_pack: bad arguments");
+    HexKernelPtrs kp = {{w, nullptr, nullptr, nullptr}};
+    HexTaps taps = make_square_taps(K);
+    long total = (long)taps.n * cin * cout;
+    hex_pack_kernel<<<gn_ceil_div(total, 256) > 1024 ? 1024 : gn_ceil_div(total, 256), 256, 0, stream>>>(kp, taps, cin, cout, mode, wp);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+GN_API int gn_sqconv_unpack_grad(const float* dwp, float* dw, int K, int cin, int cout, cudaStream_t stream) {
+    GN_REQUIRE(SQ_OK(K), GN_EUNSUPPORTED, "sqconv: kernel size %d not in {1, 3, 5}", K);
+    GN_REQUIRE(cin > 0 && cout > 0 && dwp && dw, GN_EINVAL, "sqconv_unpack_grad: bad arguments");
+    HexKernelPtrsMut kp = {{dw, nullptr, nullptr, nullptr}};
+    HexTaps taps = make_square_taps(K);
+    long total = (long)taps.n * cin * cout;
+    hex_unpack_grad_kernel<<<gn_ceil_div(total, 256) > 1024 ? 1024 : gn_ceil_div(total, 256), 256, 0, stream>>>(dwp, taps, cin, cout, kp);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+GN_API int gn_sqconv_fwd(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
+                         double* stats, int B, int cin, int cout, int H, int W, int K, cudaStream_t stream) {
+    GN_REQUIRE(SQ_OK(K), GN_EUNSUPPORTED, "sqconv: kernel size %d not in {1, 3, 5}", K);
+    return conv_fwd_impl(x, wp, bias, in_scale, in_shift, y, stats, B, cin, cout, H, W, make_square_taps(K), stream);
+}
+
+GN_API int gn_sqconv_wgrad(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, float* dbias,
+                           int B, int cin, int cout, int H, int W, int K, cudaStream_t stream) {
+    GN_REQUIRE(SQ_OK(K), GN_EUNSUPPORTED, "sqconv: kernel size %d not in {1, 3, 5}", K);
+    return conv_wgrad_impl(x, in_scale, in_shift, dy, dwp, dbias, B, cin, cout, H, W, make_square_taps(K), stream);
 }

@@ -36,7 +36,8 @@ def _fast_f(module):
 
 
 class GridNet(nn.Module):
-    """Base class: Cartesian grids, square-conv corrector (library convs; not on the hex hot path)."""
+    """Base class: Cartesian grids; the square-conv corrector (gridnet_models.py:51-66) runs on the same tile kernels as the
+    hexagonal one (a K x K window is a parity-independent tap table), BatchNorm/ReLU fused the same way."""
 
     def __init__(self, patch_classifier, patch_shape, grid_shape, n_classes,
                  use_bn=True, atonce_patch_limit=None, f_dim=None):
@@ -100,7 +101,11 @@ class GridNet(nn.Module):
         return patch_pred_grid.permute((0, 3, 1, 2))
 
     def forward(self, x):
-        return self.corrector(self.patch_predictions(x))
+        ppg = self.patch_predictions(x)
+        stages = parse_corrector(self.corrector) if ppg.is_cuda else None
+        if stages is not None:
+            return run_corrector(stages, ppg, self.training)
+        return self.corrector(ppg)       # user-defined corrector: module by module, like the reference
 
 
 class GridNetHex(GridNet):

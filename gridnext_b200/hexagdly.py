@@ -33,11 +33,15 @@ def _kptrs(ks):
     return p + [None] * (4 - len(p))
 
 
-def pack_weights(ks, ksize, cin, cout, mode):
-    """[T][cin][cout] (mode 0) or reflected/transposed [T][cout][cin] (mode 1) packed copy."""
-    wp = torch.empty((n_taps(ksize), cin, cout) if mode == 0 else (n_taps(ksize), cout, cin),
-                     device=ks[0].device, dtype=torch.float32)
-    call('gn_hexconv_pack', *_kptrs(ks), ksize, cin, cout, mode, ptr(wp), stream())
+def pack_weights(ks, ksize, cin, cout, mode, kind='hex'):
+    """[T][cin][cout] (mode 0) or reflected/transposed [T][cout][cin] (mode 1) packed copy.
+    kind 'sq': Cartesian ksize x ksize window (nn.Conv2d of the base GridNet corrector), ks = [weight (Cout, Cin, K, K)]."""
+    T = ksize * ksize if kind == 'sq' else n_taps(ksize)
+    wp = torch.empty((T, cin, cout) if mode == 0 else (T, cout, cin), device=ks[0].device, dtype=torch.float32)
+    if kind == 'sq':
+        call('gn_sqconv_pack', ptr(ks[0]), ksize, cin, cout, mode, ptr(wp), stream())
+    else:
+        call('gn_hexconv_pack', *_kptrs(ks), ksize, cin, cout, mode, ptr(wp), stream())
     return wp
 
 
@@ -53,11 +57,14 @@ def _use_tc(B, cin, cout, H, W, ksize):
     return TENSOR_CORE_MODE == '1' or B * H * W >= TENSOR_CORE_MIN_CELLS
 
 
-def hexconv_fwd(x, wp, bias, cout, ksize, in_scale=None, in_shift=None, stats=None):
+def hexconv_fwd(x, wp, bias, cout, ksize, in_scale=None, in_shift=None, stats=None, kind='hex'):
     """y = hexconv(x') + bias.  kernel_size 1 with <= 32 channels runs on tcgen05 (bf16 x 3 split, fp32 accumulate: the
     7-tap, 32-channel convolution is far above the FP32-FMA ridge); everything else on the FP32-FMA kernel."""
     B, cin, H, W = x.shape
     y = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
+    if kind == 'sq':
+        call('gn_sqconv_fwd', ptr(x), ptr(wp), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(y), ptr(stats), B, cin, cout, H, W, ksize, stream())
+        return y
     if _use_tc(B, cin, cout, H, W, ksize):
         ws, wptr = _aligned_workspace(_lib.load().gn_hexconv_tc_workspace_bytes(B, H, W), x.device)
         call('gn_hexconv_fwd_tc', ptr(x), ptr(wp), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(y), ptr(stats), B, cin, cout, H, W, wptr, stream())
@@ -72,9 +79,14 @@ def _aligned_workspace(nbytes, device):
     return ws, ctypes.c_void_p(ws.data_ptr() + (-ws.data_ptr()) % 1024)
 
 
-def hexconv_wgrad(x, dy, ksize, in_scale=None, in_shift=None, want_bias=True):
+def hexconv_wgrad(x, dy, ksize, in_scale=None, in_shift=None, want_bias=True, kind='hex'):
     B, cin, H, W = x.shape
     cout = dy.shape[1]
+    if kind == 'sq':
+        dwp = torch.zeros((ksize * ksize, cin, cout), device=x.device, dtype=torch.float32)
+        db = torch.zeros((cout,), device=x.device, dtype=torch.float32) if want_bias else None
+        call('gn_sqconv_wgrad', ptr(x), ptr(in_scale), ptr(in_shift), ptr(dy), ptr(dwp), ptr(db), B, cin, cout, H, W, ksize, stream())
+        return dwp, db
     dwp = torch.zeros((n_taps(ksize), cin, cout), device=x.device, dtype=torch.float32)
     if _use_tc(B, cin, cout, H, W, ksize):
         ws, wptr = _aligned_workspace(_lib.load().gn_hexconv_tc_wgrad_workspace_bytes(B, H, W), x.device)
@@ -90,9 +102,12 @@ def hexconv_wgrad(x, dy, ksize, in_scale=None, in_shift=None, want_bias=True):
     return dwp, db
 
 
-def unpack_grad(dwp, shapes, ksize, cin, cout):
+def unpack_grad(dwp, shapes, ksize, cin, cout, kind='hex'):
     gs = [torch.empty(s, device=dwp.device, dtype=torch.float32) for s in shapes]
-    call('gn_hexconv_unpack_grad', ptr(dwp), *_kptrs(gs), ksize, cin, cout, stream())
+    if kind == 'sq':
+        call('gn_sqconv_unpack_grad', ptr(dwp), ptr(gs[0]), ksize, cin, cout, stream())
+    else:
+        call('gn_hexconv_unpack_grad', ptr(dwp), *_kptrs(gs), ksize, cin, cout, stream())
     return gs
 
 

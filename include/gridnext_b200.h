@@ -165,6 +165,16 @@ int gn_linear_small_bwd(const float* dlog, const float* feat, long ldf, const fl
 int gn_bn_eval_consts(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int C, float* scale,
                       float* shift, float* invstd, float* inv_gamma, gn_stream_t stream);
 
+/* Cartesian K x K convolution (K in {1, 3, 5}), stride 1, zero padding K/2: nn.Conv2d of the base GridNet corrector
+ * (gridnet_models.py:51-66: 3x3, 5x5, 5x5, 3x3).  Same tile kernels, packed layout Wp[r*K + c][cin][cout], BN/ReLU prologue and
+ * BN-statistics epilogue as gn_hexconv_*; w / dw: (Cout, Cin, K, K) fp32.  pack mode 1 = reflected + transposed (data gradient). */
+int gn_sqconv_pack(const float* w, int K, int cin, int cout, int mode, float* wp, gn_stream_t stream);
+int gn_sqconv_unpack_grad(const float* dwp, float* dw, int K, int cin, int cout, gn_stream_t stream);
+int gn_sqconv_fwd(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
+                  double* stats, int B, int cin, int cout, int H, int W, int K, gn_stream_t stream);
+int gn_sqconv_wgrad(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, float* dbias,
+                    int B, int cin, int cout, int H, int W, int K, gn_stream_t stream);
+
 /* Train-mode BatchNorm around the same tensor-core kernels (f pre-training, training.py:11-98; the count f that training.py:126
  * leaves in train mode inside GridNetHexMM).  Forward: batch statistics of bf16 rows (fp64 sums; caller zeroes them) -> the
  * per-channel constants (scale, shift, mean, invstd) the kernels above consume, with nn.BatchNorm's running-stat update

@@ -212,6 +212,31 @@ def corrector_forward(sd, x, use_bn=True, training=True, stats_out=None, ksize=1
     return hexl(hex_idx[4], h)
 
 
+def cartesian_corrector_forward(sd, x, use_bn=True, training=True, stats_out=None):
+    """Base GridNet corrector (gridnet_models.py:51-66): Conv2d 3x3, [BN], ReLU, Conv2d 5x5, [BN], ReLU, Conv2d 5x5, [BN], ReLU,
+    Conv2d 3x3, all n_classes wide with 'same' zero padding.  sd keys '<idx>.weight' ... of the nn.Sequential."""
+    step = 3 if use_bn else 2
+    h, idx = x, 0
+    for K in (3, 5, 5):
+        h = F.conv2d(h, sd['%d.weight' % idx], sd['%d.bias' % idx], padding=K // 2)
+        if use_bn:
+            p = '%d.' % (idx + 1)
+            if training:
+                mean = h.mean((0, 2, 3))
+                var = h.var((0, 2, 3), unbiased=False)
+                if stats_out is not None:
+                    n = h.numel() // h.shape[1]
+                    stats_out[p + 'running_mean'] = (1 - BN_MOMENTUM) * sd[p + 'running_mean'] + BN_MOMENTUM * mean.detach()
+                    stats_out[p + 'running_var'] = (1 - BN_MOMENTUM) * sd[p + 'running_var'] + BN_MOMENTUM * var.detach() * n / (n - 1)
+            else:
+                mean, var = sd[p + 'running_mean'], sd[p + 'running_var']
+            h = (h - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + BN_EPS)
+            h = h * sd[p + 'weight'].view(1, -1, 1, 1) + sd[p + 'bias'].view(1, -1, 1, 1)
+        h = torch.relu(h)
+        idx += step
+    return F.conv2d(h, sd['%d.weight' % idx], sd['%d.bias' % idx], padding=1)
+
+
 # ----------------------------------------------------------------------------- composite
 def spots_from_counts(x):
     """(B, G, H, W) -> (B*H*W, G), spot order n = b*H*W + y*W + x (gridnet_models.py:168,83)."""

@@ -226,6 +226,27 @@ def extras(manifest, mods):
                         **{'grad.' + k: v.numpy() for k, v in g.items()}, **{'after.' + k: v.numpy() for k, v in after.items()})
     manifest[tag] = dict(P=P, N=N, seed_w=seed, seed_x=seed + 100, seed_dy=seed + 200, **{k: list(v) if isinstance(v, tuple) else v for k, v in kw.items()})
 
+    # ---- C1 / C2: base (Cartesian) GridNet, corrector = Conv2d 3x3, 5x5, 5x5, 3x3 (gridnet_models.py:51-66), with / without BN
+    for tag, use_bn, seed in (('c1_cartesian_bn', True, 51), ('c2_cartesian_nobn', False, 52)):
+        n_cls, f_dim, B, H, W = 5, 6, 3, 9, 11
+        model = gm.GridNet(nn.Linear(4, f_dim), (4,), (H, W), n_cls, use_bn=use_bn, f_dim=f_dim)
+        load_synth(model, seed, tag)
+        gx = torch.Generator(); gx.manual_seed(seed + 100)
+        x = torch.randn(B, H, W, 4, generator=gx)
+        from oracle import synth
+        y = synth.synth_labels(B, n_cls, H, W, seed=seed + 200)
+        out, loss, ncorr, nfg = step_like_train_gridwise(model, x, y)
+        g = grads_of(model)
+        after = {k: v for k, v in model.state_dict().items() if 'running' in k}
+        np.savez_compressed(os.path.join(OUT, tag + '.npz'), x=x.numpy(), y=y.numpy(), out=out.numpy(), loss=loss.numpy(), ncorr=ncorr, nfg=nfg,
+                            **{'grad.' + k: v.numpy() for k, v in g.items()}, **{'after.' + k: v.numpy() for k, v in after.items()})
+        manifest[tag] = dict(n_cls=n_cls, f_dim=f_dim, B=B, H=H, W=W, seed_w=seed, use_bn=use_bn)
+    keys_path = os.path.join(OUT, 'state_dict_keys.json')
+    if os.path.exists(keys_path):
+        old = json.load(open(keys_path))
+        old.update(KEYS)
+        KEYS.update(old)
+
 
 if __name__ == '__main__':
     if '--extras' in sys.argv:
@@ -234,5 +255,7 @@ if __name__ == '__main__':
         extras(man, import_reference())
         with open(os.path.join(OUT, 'manifest.json'), 'w') as fh:
             json.dump(man, fh, indent=1, sort_keys=True)
+        with open(os.path.join(OUT, 'state_dict_keys.json'), 'w') as fh:
+            json.dump(KEYS, fh, sort_keys=True)
     else:
         main()

@@ -69,6 +69,28 @@ def with_prefix(prefix, shapes):
     return {prefix + k: v for k, v in shapes.items()}
 
 
+def cartesian_corrector_shapes(f_dim, n_cls, use_bn=True):
+    """nn.Sequential of the base GridNet (gridnet_models.py:51-66)."""
+    s, idx = {}, 0
+    for cin, K in ((f_dim, 3), (n_cls, 5), (n_cls, 5)):
+        s['%d.weight' % idx] = (n_cls, cin, K, K)
+        s['%d.bias' % idx] = (n_cls,)
+        if use_bn:
+            for k, shp in (('weight', (n_cls,)), ('bias', (n_cls,)), ('running_mean', (n_cls,)), ('running_var', (n_cls,)), ('num_batches_tracked', ())):
+                s['%d.%s' % (idx + 1, k)] = shp
+        idx += 3 if use_bn else 2
+    s['%d.weight' % idx] = (n_cls, n_cls, 3, 3)
+    s['%d.bias' % idx] = (n_cls,)
+    return s
+
+
+def cartesian_gridnet_shapes(f_shapes, f_dim, n_cls, use_bn=True):
+    s = {'bg_const': (1, f_dim), 'dummy_tensor': (1,)}
+    s.update(with_prefix('patch_classifier.', f_shapes))
+    s.update(with_prefix('corrector.', cartesian_corrector_shapes(f_dim, n_cls, use_bn)))
+    return s
+
+
 def gridnet_shapes(f_shapes, f_dim, n_cls, use_bn=True):
     s = {'bg_const': (1, f_dim), 'dummy_tensor': (1,)}
     s.update(with_prefix('patch_classifier.', f_shapes))

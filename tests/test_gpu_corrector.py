@@ -245,3 +245,67 @@ def test_count_gridnet_step_matches_reference_golden():
                 assert cos > 0.98 and err < 0.3, (k, cos, err)
             n += 1
     assert n >= 30
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Base (Cartesian) GridNet: square-conv corrector on the same tile kernels
+@pytest.mark.parametrize('K', [1, 3, 5])
+@pytest.mark.parametrize('cfg', [(6, 5, 3, 9, 11), (7, 7, 2, 78, 64), (32, 7, 1, 20, 70), (3, 40, 2, 8, 130), (16, 16, 1, 4, 4)])
+def test_square_conv_fwd_bwd_matches_conv2d(K, cfg):
+    """gn_sqconv_* == F.conv2d(stride 1, padding K//2): forward, data gradient, weight and bias gradients (fp32, 1e-5)."""
+    import torch.nn.functional as F
+    from gridnext_b200 import hexagdly as hx
+    cin, cout, B, H, W = cfg
+    g = torch.Generator(); g.manual_seed(100 * K + cin)
+    w = torch.randn(cout, cin, K, K, generator=g) / (cin * K * K) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    x = torch.randn(B, cin, H, W, generator=g)
+    dy = torch.randn(B, cout, H, W, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=K // 2)
+    (ref * dy).sum().backward()
+    xd, wd, bd, dyd = x.cuda(), w.cuda(), b.cuda(), dy.cuda()
+    y = hx.hexconv_fwd(xd, hx.pack_weights([wd], K, cin, cout, 0, 'sq'), bd, cout, K, kind='sq')
+    assert rel_err(y, ref) < TOL
+    dx = hx.hexconv_fwd(dyd, hx.pack_weights([wd], K, cin, cout, 1, 'sq'), None, cin, K, kind='sq')
+    assert rel_err(dx, xr.grad) < TOL
+    dwp, db = hx.hexconv_wgrad(xd, dyd, K, kind='sq')
+    dw = hx.unpack_grad(dwp, [w.shape], K, cin, cout, 'sq')[0]
+    assert rel_err(dw, wr.grad) < TOL and rel_err(db, br.grad) < TOL
+
+
+@pytest.mark.parametrize('tag', ['c1_cartesian_bn', 'c2_cartesian_nobn'])
+def test_cartesian_gridnet_step_matches_reference_golden(tag):
+    """gridnext_b200.GridNet (base class, gridnet_models.py:24-109) against the reference's own GridNet: output, loss, every
+    gradient and the BatchNorm running statistics after one train_gridwise iteration."""
+    import torch.nn as nn
+    from gridnext_b200.gridnet_models import GridNet
+    from gridnext_b200.training import gridwise_step
+    from gridnext_b200.corrector import parse_corrector
+    m = MAN[tag]
+    gold = np.load(os.path.join(GOLDEN, tag + '.npz'))
+    net = GridNet(nn.Linear(4, m['f_dim']), (4,), (m['H'], m['W']), m['n_cls'], use_bn=m['use_bn'], f_dim=m['f_dim'])
+    sd = synth.synth_state_dict(S.cartesian_gridnet_shapes({'weight': (m['f_dim'], 4), 'bias': (m['f_dim'],)}, m['f_dim'], m['n_cls'], m['use_bn']), m['seed_w'])
+    assert set(net.state_dict().keys()) == set(sd.keys())
+    net.load_state_dict(sd)
+    net.cuda()
+    assert parse_corrector(net.corrector) is not None
+    net.train(); net.patch_classifier.eval()
+    x, y = torch.from_numpy(gold['x']).cuda(), torch.from_numpy(gold['y']).cuda()
+    out = net(x)
+    assert rel_err(out, torch.from_numpy(gold['out'])) < 1e-4
+    net.load_state_dict(sd)       # undo the running-stat update of the probe above
+    loss, acc, _ = gridwise_step(net, x, y, nn.CrossEntropyLoss(), 1, True)
+    assert abs(float(loss.detach()) - float(gold['loss'])) < 1e-5
+    assert (int(acc.tolist()[2]), int(acc.tolist()[1])) == (int(gold['ncorr']), int(gold['nfg']))
+    params = dict(net.named_parameters())
+    got_sd = net.state_dict()
+    zero_theory = ('corrector.0.bias', 'corrector.3.bias', 'corrector.6.bias') if m['use_bn'] else ()   # a bias in front of train-mode BN
+    for k in gold.files:
+        if k.startswith('grad.') and k[5:] in zero_theory:
+            scale = float(np.abs(gold['grad.' + k[5:-4] + 'weight']).sum((1, 2, 3)).max())
+            assert float(params[k[5:]].grad.abs().max()) < 1e-5 * scale, k
+        elif k.startswith('grad.'):
+            assert rel_err(params[k[5:]].grad, torch.from_numpy(gold[k])) < 1e-3, k
+        elif k.startswith('after.'):
+            assert rel_err(got_sd[k[6:]], torch.from_numpy(gold[k])) < 1e-5, k

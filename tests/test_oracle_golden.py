@@ -114,6 +114,30 @@ def test_small_grid_nobn_matches_reference(golden):
             assert np.allclose(sd[k[5:]].grad.numpy(), gold[k], rtol=1e-3, atol=1e-6), k
 
 
+@pytest.mark.parametrize('tag', ['c1_cartesian_bn', 'c2_cartesian_nobn'])
+def test_cartesian_gridnet_matches_reference(golden, tag):
+    """Base GridNet (square-conv corrector, gridnet_models.py:51-66) through the reference's own class."""
+    m = MAN[tag]
+    gold = golden(tag)
+    sd = make_sd(S.cartesian_gridnet_shapes({'weight': (m['f_dim'], 4), 'bias': (m['f_dim'],)}, m['f_dim'], m['n_cls'], m['use_bn']), m['seed_w'])
+    assert set(sd) == set(json.load(open(os.path.join(GOLDEN, 'state_dict_keys.json')))[tag])
+    x, y = t(gold['x']), t(gold['y'])
+    B, H, W, _ = x.shape
+    f = torch.nn.functional.linear(x.reshape(-1, 4), sd['patch_classifier.weight'], sd['patch_classifier.bias'])
+    stats = {}
+    out = R.cartesian_corrector_forward(R.sub(sd, 'corrector.'), R.grid_from_spots(f, B, H, W), use_bn=m['use_bn'], stats_out=stats)
+    loss, ncorr, nfg = R.masked_ce(out, y)
+    loss.backward()
+    assert np.allclose(out.detach().numpy(), gold['out'], rtol=1e-4, atol=1e-5)
+    assert abs(float(loss) - float(gold['loss'])) < 1e-5
+    assert (ncorr, nfg) == (int(gold['ncorr']), int(gold['nfg']))
+    for k in gold.files:
+        if k.startswith('grad.'):
+            assert np.allclose(sd[k[5:]].grad.numpy(), gold[k], rtol=1e-3, atol=1e-6), k
+        elif k.startswith('after.corrector.'):
+            assert np.allclose(stats[k[len('after.corrector.'):]].numpy(), gold[k], rtol=1e-5, atol=1e-6), k
+
+
 @pytest.mark.parametrize('tag', ['d1_densenet121_p64', 'd2_densenet_tiny_p32'])
 def test_densenet_matches_reference(golden, tag):
     m = MAN[tag]
