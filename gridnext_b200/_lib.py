@@ -27,6 +27,11 @@ _SIGS = {
     'gn_hexconv_tc_supported': [ci, ci, ci, ci, ci],
     'gn_hexconv_wgrad_tc': [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp],
     'gn_hexconv_wgrad': [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
+    'gn_cell_inverse': [vp, ci, vp, ci, vp],
+    'gn_grid_gather_rows': [vp, cl, vp, vp, cl, cl, cl, vp],
+    'gn_grid_gather_cols': [vp, cl, vp, vp, cl, ci, ci, vp],
+    'gn_grid_labels': [vp, vp, vp, ci, vp],
+    'gn_mm_fg_consistency': [vp, cl, vp, cl, ci, vp, vp, ci, vp],
     'gn_sqconv_pack': [vp, ci, ci, ci, ci, vp, vp],
     'gn_sqconv_unpack_grad': [vp, vp, ci, ci, ci, vp],
     'gn_sqconv_fwd': [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
@@ -119,7 +124,7 @@ def check(rc, what=''):
 
 
 # kernels launched per C-ABI call (for the benchmark's gpu_launches count); default 1
-KERNELS_PER_CALL = {'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0, 'gn_prep_job_bytes': 0,
+KERNELS_PER_CALL = {'gn_cell_inverse': 2, 'gn_mm_fg_consistency': 2, 'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0, 'gn_prep_job_bytes': 0,
                     'gn_device_sm_count': 0, 'gn_hexconv_n_taps': 0}
 LAUNCHES = [0]
 PROFILE = None      # when a dict: name -> [n_calls, [cuda event pairs]]

@@ -165,6 +165,19 @@ int gn_linear_small_bwd(const float* dlog, const float* feat, long ldf, const fl
 int gn_bn_eval_consts(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int C, float* scale,
                       float* shift, float* invstd, float* inv_gamma, gn_stream_t stream);
 
+/* Dataset tensor assembly (utils.py:144-166 read_annotated_starray, image_datasets.py:205-232 PatchGridDataset item,
+ * multimodal_datasets.py:237-244): inverse spot->cell map (last spot wins, cell < 0 drops the spot), then one pass over the
+ * OUTPUT grid: rows (patches), columns (genes x spots -> channels-first count slab), labels (+1, 0 = background), and the
+ * multimodal foreground-consistency rule in place (flags: n_cells bytes of workspace). */
+int gn_cell_inverse(const int* cell, int n_rows, int* inv, int n_cells, gn_stream_t stream);
+int gn_grid_gather_rows(const void* src, long src_pitch_bytes, const int* inv, void* dst, long dst_pitch_bytes, long n_cells,
+                        long row_bytes, gn_stream_t stream);
+int gn_grid_gather_cols(const float* src, long src_pitch, const int* inv, float* dst, long dst_pitch, int G, int n_cells,
+                        gn_stream_t stream);
+int gn_grid_labels(const long long* labels, const int* inv, long long* annots, int n_cells, gn_stream_t stream);
+int gn_mm_fg_consistency(float* patch, long F, float* counts, long counts_pitch, int G, long long* annots, unsigned char* flags,
+                         int n_cells, gn_stream_t stream);
+
 /* Cartesian K x K convolution (K in {1, 3, 5}), stride 1, zero padding K/2: nn.Conv2d of the base GridNet corrector
  * (gridnet_models.py:51-66: 3x3, 5x5, 5x5, 3x3).  Same tile kernels, packed layout Wp[r*K + c][cin][cout], BN/ReLU prologue and
  * BN-statistics epilogue as gn_hexconv_*; w / dw: (Cout, Cin, K, K) fp32.  pack mode 1 = reflected + transposed (data gradient). */

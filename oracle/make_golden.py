@@ -241,6 +241,36 @@ def extras(manifest, mods):
         np.savez_compressed(os.path.join(OUT, tag + '.npz'), x=x.numpy(), y=y.numpy(), out=out.numpy(), loss=loss.numpy(), ncorr=ncorr, nfg=nfg,
                             **{'grad.' + k: v.numpy() for k, v in g.items()}, **{'after.' + k: v.numpy() for k, v in after.items()})
         manifest[tag] = dict(n_cls=n_cls, f_dim=f_dim, B=B, H=H, W=W, seed_w=seed, use_bn=use_bn)
+    # ---- A1: read_annotated_starray (utils.py:87-166) on synthetic Splotch-format files with a one-hot annotation matrix run
+    # through the reference's own read_annotfile (incl. its row filter, utils.py:239).  (annot_file=None raises
+    # UnboundLocalError in the reference, utils.py:164, so there is no un-annotated vector.)
+    import gridnext.utils as ut
+    rng = np.random.RandomState(61)
+    G, n_spots, n_cls = 12, 300, 6
+    all_xy = [(c, r) for r in range(78) for c in range(r % 2, 128, 2)]
+    sel = rng.choice(len(all_xy), n_spots, replace=False)
+    coords = np.array([all_xy[i] for i in sel], dtype=np.int32)
+    cstrs = ['%d_%d' % (c, r) for c, r in coords]
+    cmat = rng.poisson(2.0, (G, n_spots)).astype(np.float64) * rng.rand(G, n_spots).round(3)
+    lbl = rng.randint(0, n_cls, n_spots)
+    lbl[:3] = [n_cls, n_cls + 1, n_cls + 2]                    # three classes that occur exactly once survive the row filter
+    onehot = np.zeros((n_cls + 3, n_spots), dtype=int)
+    annotated = rng.rand(n_spots) < 0.8
+    annotated[:3] = True
+    for j in range(n_spots):
+        if annotated[j]:
+            onehot[lbl[j], j] = 1
+    with tempfile.TemporaryDirectory() as td:
+        import pandas as pd
+        cf, af = os.path.join(td, 'counts.tsv'), os.path.join(td, 'annots.tsv')
+        pd.DataFrame(cmat, index=['g%d' % i for i in range(G)], columns=cstrs).to_csv(cf, sep='\t')
+        pd.DataFrame(onehot, index=['c%d' % i for i in range(n_cls + 3)], columns=cstrs).to_csv(af, sep='\t')
+        cg1, ag1 = ut.read_annotated_starray(cf, af)
+        a_coords, a_lbls = ut.read_annotfile(af, Visium=False, afile_delim='\t')
+    np.savez_compressed(os.path.join(OUT, 'a1_starray.npz'), cmat=cmat.astype(np.float32), coords=coords,
+                        counts_annot=np.transpose(cg1, (2, 0, 1)).astype(np.float32), annots_annot=ag1.astype(np.int64),
+                        annot_coords=np.array(list(a_coords)), annot_lbls=np.asarray(a_lbls).astype(np.int64))
+    manifest['a1_starray'] = dict(G=G, n_spots=n_spots, n_annot_rows=int(len(a_coords)))
     keys_path = os.path.join(OUT, 'state_dict_keys.json')
     if os.path.exists(keys_path):
         old = json.load(open(keys_path))

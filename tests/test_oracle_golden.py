@@ -239,3 +239,20 @@ def test_template_positions_index_math(golden):
     assert tab.shape == (4525, 4)
     assert tab[:, 0].max() == 63 and tab[:, 1].max() <= 77
     assert gather_ref.spot_table([1, 1, 1], [0, 0, 0], [0, 0, 0], [0.5, 1.5, 2.5], [2.5, 3.5, -0.5])[:, 2:].tolist() == [[2, 0], [4, 2], [0, 2]]
+
+
+def test_dataset_assembly_oracle_matches_reference(golden):
+    """oracle/datasets_ref.count_grid == the reference's read_annotated_starray run on synthetic files (utils.py:87-166)."""
+    from oracle import datasets_ref as D
+    gold = golden('a1_starray')
+    cstrs = ['%d_%d' % (c, r) for c, r in gold['coords']]
+    adict = dict(zip(gold['annot_coords'].tolist(), gold['annot_lbls'].tolist()))
+    counts, annots = D.count_grid(gold['cmat'].astype(np.float64), cstrs, adict)
+    assert np.array_equal(counts, gold['counts_annot'])
+    assert np.array_equal(annots, gold['annots_annot'])
+    # the rule of multimodal_datasets.py:237-244 on a hand-checkable case
+    c = np.ones((2, 2, 2), np.float32); p = np.ones((2, 2, 3), np.float32); a = np.array([[1, 0], [2, 3]])
+    p[1, 0] = 0                       # no image data -> loses label and counts
+    c2, p2, a2 = D.mm_fg_consistency(c, p, a)
+    assert a2.tolist() == [[1, 0], [0, 3]] and c2[:, 1, 0].tolist() == [0, 0] and c2[:, 0, 1].tolist() == [1, 1]
+    assert p2[0, 1].tolist() == [0, 0, 0] and p2[1, 1].tolist() == [1, 1, 1]
