@@ -33,6 +33,7 @@ struct Conv3Params {
     int nsub;             // 64-channel output sub-tiles per tile
     int e_stages;         // epilogue sub-tile ring depth
     int epi_mode;         // 0 plain store, 1 BnBwdEpi (reference tile fetched by TMA)
+    int stack;            // 1: the three kx taps of a kernel row are stacked along UMMA N (3 MMAs chains of N = 3*CO instead of 9 of N = CO)
     BnBwdEpi bn;
 };
 
@@ -91,6 +92,43 @@ __device__ __forceinline__ void c3_issue_tile(uint32_t d, uint64_t descA, uint64
     }
 }
 
+// N-stacked variant for narrow outputs (CO <= 32: the forward conv2, 128 -> 32).  A UMMA with N = 32 costs the same ~45 cycles
+// as one with N = 96 (the A-operand fetch from shared memory, 128 B/clk, sets the floor: tools/umma_rate), so the three kx
+// taps of one kernel row share ONE MMA: B = the 3*CO packed weight rows (kx, co) of that ky -- contiguous in the packed
+// layout -- and A = the tile shifted by (ky-1) padded rows only.  Accumulator column block kx of row q then holds
+//   E_kx[q] = sum_ky X[q + (ky-1)(W+2)] . W[ky, kx]     and     out[p] = E_0[p-1] + E_1[p] + E_2[p+1],
+// a neighbour-lane sum the epilogue does with two warp shuffles per channel (rows p-1 / p+1 live in adjacent TMEM lanes;
+// a tile is whole padded rows, so both neighbours of every interior position are inside the tile).  24 MMAs per tile
+// instead of 72.
+template <int KB_T, int K16_T>
+__device__ __forceinline__ void c3_issue_tile_stacked(uint32_t d, uint64_t descA, uint64_t descW, uint32_t idesc, int W2, int kb_buf16,
+                                                      int w_tile16, int kblocks, int CI) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const uint64_t da = descA + (uint64_t)(int64_t)(ky * W2 * 8);
+        if (KB_T > 0) {
+            const uint64_t dw = descW + (uint64_t)(ky * KB_T * w_tile16);
+#pragma unroll
+            for (int kb = 0; kb < KB_T; ++kb)
+#pragma unroll
+                for (int k = 0; k < K16_T; ++k) {
+                    umma_bf16(d, da + (uint64_t)(kb * kb_buf16 + k * 2), dw + (uint64_t)(kb * w_tile16 + k * 2), idesc, acc);
+                    acc = 1;
+                }
+        } else {
+            const uint64_t dw = descW + (uint64_t)(ky * kblocks * w_tile16);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int k16n = (min(64, CI - kb * 64) + 15) >> 4;
+                for (int k = 0; k < k16n; ++k) {
+                    umma_bf16(d, da + (uint64_t)(kb * kb_buf16 + k * 2), dw + (uint64_t)(kb * w_tile16 + k * 2), idesc, acc);
+                    acc = 1;
+                }
+            }
+        }
+    }
+}
+
 // Tile = R consecutive PADDED image rows (R * (W+2) <= 128 positions, accumulator row i = position i of the tile).
 //   warp 0: TMA producer (R+2 padded rows per k-block)      warp 1: MMA issuer (9 taps x kblocks x k16)
 //   warp 2: epilogue feeder (TMA loads of the BN reference tile, one box per padded row)
@@ -98,26 +136,31 @@ __device__ __forceinline__ void c3_issue_tile(uint32_t d, uint64_t descA, uint64
 //   warps 4-11: epilogue (tcgen05.ld -> math -> swizzled st.shared in place)
 template <int EPI_MODE>
 __global__ void __launch_bounds__(384, 1)
-conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
-               const __grid_constant__ CUtensorMap tmRef, const Conv3Params p) {
+conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXb, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRef, const Conv3Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_w, bar_full[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
     __shared__ __align__(8) uint64_t bar_efull[C3_MAX_ESTAGES], bar_eready[C3_MAX_ESTAGES], bar_eempty[C3_MAX_ESTAGES];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_xchg[2][4][2][32];                 // stacked forward: boundary lanes' E_0 / E_2 rows between epilogue warps
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int W2 = p.W + 2, H2 = p.H + 2, R = p.R;
     const int total_rows = p.Nimg * H2;
-    const int w_tile_bytes = p.NP * p.w_row_bytes;                       // one (tap, k-block) weight tile (rows beyond CO: next tap / zero fill, never stored)
-    const int w_bytes = ((9 * p.kblocks * w_tile_bytes + 1023) / 1024) * 1024;
+    const bool stack = EPI_MODE == 0 && p.stack;
+    const int w_groups = stack ? 3 : 9;                                  // weight tiles per k-block: kernel rows (stacked) or taps
+    const int w_tile_bytes = (stack ? 3 * p.CO : p.NP) * p.w_row_bytes;  // one (group, k-block) weight tile (rows beyond CO: next tap / zero fill, never stored)
+    const int w_bytes = ((w_groups * p.kblocks * w_tile_bytes + 1023) / 1024) * 1024;
     const int kb_buf_bytes = p.a_rows * 128;                             // one k-block of one stage
     const int stage_bytes = p.kblocks * kb_buf_bytes;
     uint8_t* s_w = sm;
     uint8_t* s_a = sm + w_bytes;
     uint8_t* s_slots = s_a + (size_t)p.stages * stage_bytes;
-    float* s_epi = reinterpret_cast<float*>(s_slots + (size_t)p.e_stages * C3_SUB_BYTES);      // [4][C3_MAX_CO]
+    const int slot_bytes = stack ? C3_SUB_BYTES / 2 : C3_SUB_BYTES;      // stacked forward: 128 positions x 64 B (<= 32 channels, SWIZZLE_64B)
+    const int slot_row = stack ? 64 : 128;
+    float* s_epi = reinterpret_cast<float*>(s_slots + (size_t)p.e_stages * slot_bytes);         // [4][C3_MAX_CO]
 
     float* s_cs = s_epi + 4 * C3_MAX_CO;                                                        // [2][C3_MAX_CO] column sums of this CTA
     if (EPI_MODE == 1) {
@@ -133,6 +176,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmXb);
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmOut);
         if (EPI_MODE == 1) tma_prefetch_desc(&tmRef);
@@ -159,10 +203,10 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (warp == 0) {
         if (elect_one()) {
             // resident weights: 9 * kblocks boxes of {row bytes / 2 channels, CO rows}
-            mbar_arrive_expect_tx(&bar_w, 9 * p.kblocks * w_tile_bytes);
-            for (int t = 0; t < 9; ++t)
+            mbar_arrive_expect_tx(&bar_w, w_groups * p.kblocks * w_tile_bytes);
+            for (int t = 0; t < w_groups; ++t)
                 for (int kb = 0; kb < p.kblocks; ++kb)
-                    tma_load_2d(&tmW, &bar_w, s_w + (t * p.kblocks + kb) * w_tile_bytes, kb * 64, t * p.CO);
+                    tma_load_2d(&tmW, &bar_w, s_w + (t * p.kblocks + kb) * w_tile_bytes, kb * 64, t * (stack ? 3 : 1) * p.CO);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -172,19 +216,26 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 c3_row_coords(Rg0 - 1, total_rows, H2, p.Nimg, n, yp);
                 mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)((R + 2) * W2 * 128 * p.kblocks));
                 uint8_t* dst = s_a + (size_t)stage * stage_bytes + 1024;
-                for (int lr = 0; lr < R + 2; ++lr) {
-                    const int nn = n < p.Nimg ? n : p.Nimg;     // past the last image: any out-of-bounds index (zero fill)
+                if (n >= 0 && yp + R + 1 < H2) {
+                    // all R + 2 padded rows lie in one image: ONE box per k-block (a TMA instruction costs the issuing thread
+                    // ~80 cycles; ten per tile kept the two-stage ring from covering the DRAM latency)
                     for (int kb = 0; kb < p.kblocks; ++kb)
-                        tma_load_4d(&tmX, &bar_full[stage], dst + (size_t)kb * kb_buf_bytes, kb * 64, -1, yp - 1, nn);
-                    dst += W2 * 128;
-                    c3_row_next(H2, n, yp);
+                        tma_load_4d(&tmXb, &bar_full[stage], dst + (size_t)kb * kb_buf_bytes, kb * 64, -1, yp - 1, n);
+                } else {
+                    for (int lr = 0; lr < R + 2; ++lr) {
+                        const int nn = n < p.Nimg ? n : p.Nimg;     // past the last image: any out-of-bounds index (zero fill)
+                        for (int kb = 0; kb < p.kblocks; ++kb)
+                            tma_load_4d(&tmX, &bar_full[stage], dst + (size_t)kb * kb_buf_bytes, kb * 64, -1, yp - 1, nn);
+                        dst += W2 * 128;
+                        c3_row_next(H2, n, yp);
+                    }
                 }
                 if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = idesc_bf16(128, p.NP, 0, 0);
+            const uint32_t idesc = idesc_bf16(128, stack ? 3 * p.CO : p.NP, 0, 0);
             const uint64_t tmplA = smem_desc_template(0, 1024, LAYOUT_SW128);
             const uint64_t tmplW = p.w_row_bytes == 128 ? smem_desc_template(0, 1024, LAYOUT_SW128) : smem_desc_template(0, 512, LAYOUT_SW64);
             mbar_wait(&bar_w, 0);
@@ -201,7 +252,10 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 const uint64_t descA = smem_desc(tmplA, smem_u32(s_a + (size_t)stage * stage_bytes) + 1024);   // buffer row 0 = local padded row -1, x' = 0
                 const uint64_t descW = smem_desc(tmplW, w_base);
                 const int kb_buf16 = kb_buf_bytes >> 4, w_tile16 = w_tile_bytes >> 4;
-                if (p.CI == 128) c3_issue_tile<2, 4>(d, descA, descW, idesc, W2, kb_buf16, w_tile16, p.kblocks, p.CI);
+                if (stack) {
+                    if (p.CI == 128) c3_issue_tile_stacked<2, 4>(d, descA, descW, idesc, W2, kb_buf16, w_tile16, p.kblocks, p.CI);
+                    else c3_issue_tile_stacked<0, 0>(d, descA, descW, idesc, W2, kb_buf16, w_tile16, p.kblocks, p.CI);
+                } else if (p.CI == 128) c3_issue_tile<2, 4>(d, descA, descW, idesc, W2, kb_buf16, w_tile16, p.kblocks, p.CI);
                 else if (p.CI == 32) c3_issue_tile<1, 2>(d, descA, descW, idesc, W2, kb_buf16, w_tile16, p.kblocks, p.CI);
                 else c3_issue_tile<0, 0>(d, descA, descW, idesc, W2, kb_buf16, w_tile16, p.kblocks, p.CI);
                 umma_commit(&bar_empty[stage]);
@@ -212,25 +266,21 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
         }
     } else if (warp == 2) {
-        // ---- epilogue feeder
-        if (elect_one()) {
+        // ---- epilogue feeder (BN-backward epilogue only; the plain epilogue waits for the drain's release itself: one hop less)
+        if (EPI_MODE == 1 && elect_one()) {
             int es = 0;
             uint32_t eph = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 const int Rg0 = tile * R;
                 for (int j = 0; j < p.nsub; ++j) {
                     mbar_wait(&bar_eempty[es], eph ^ 1);
-                    if (EPI_MODE == 1) {
-                        uint8_t* slot = s_slots + (size_t)es * C3_SUB_BYTES;
-                        mbar_arrive_expect_tx(&bar_efull[es], (uint32_t)(R * W2 * 128));
-                        int n, yp;
-                        c3_row_coords(Rg0, total_rows, H2, p.Nimg, n, yp);
-                        for (int r = 0; r < R; ++r) {
-                            tma_load_4d(&tmRef, &bar_efull[es], slot + (size_t)r * W2 * 128, j * 64, -1, yp - 1, n < p.Nimg ? n : p.Nimg);
-                            c3_row_next(H2, n, yp);
-                        }
-                    } else {
-                        mbar_arrive(&bar_efull[es]);
+                    uint8_t* slot = s_slots + (size_t)es * slot_bytes;
+                    mbar_arrive_expect_tx(&bar_efull[es], (uint32_t)(R * W2 * 128));
+                    int n, yp;
+                    c3_row_coords(Rg0, total_rows, H2, p.Nimg, n, yp);
+                    for (int r = 0; r < R; ++r) {
+                        tma_load_4d(&tmRef, &bar_efull[es], slot + (size_t)r * W2 * 128, j * 64, -1, yp - 1, n < p.Nimg ? n : p.Nimg);
+                        c3_row_next(H2, n, yp);
                     }
                     if (++es == p.e_stages) { es = 0; eph ^= 1; }
                 }
@@ -247,11 +297,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 c3_row_coords(Rg0, total_rows, H2, p.Nimg, n0, yp0);
                 for (int j = 0; j < p.nsub; ++j) {
                     mbar_wait(&bar_eready[es], eph);
-                    const uint8_t* slot = s_slots + (size_t)es * C3_SUB_BYTES;
+                    const uint8_t* slot = s_slots + (size_t)es * slot_bytes;
                     int n = n0, yp = yp0;
                     for (int r = 0; r < R; ++r) {
                         if (n < p.Nimg && yp >= 1 && yp <= p.H)
-                            tma_store_4d(&tmOut, slot + ((size_t)r * W2 + 1) * 128, j * 64, 0, yp - 1, n);   // skip the x' = 0 border position
+                            tma_store_4d(&tmOut, slot + ((size_t)r * W2 + 1 + (stack ? 1 : 0)) * slot_row, j * 64, 0, yp - 1, n);   // skip the x' = 0 border position
                         c3_row_next(H2, n, yp);
                     }
                     tma_store_commit();
@@ -288,11 +338,67 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * 256);
 #pragma unroll 1
             for (int j = 0; j < p.nsub; ++j) {
-                mbar_wait(&bar_efull[es], eph);
-                uint8_t* rowp = s_slots + (size_t)es * C3_SUB_BYTES + trow * 128;
+                if (EPI_MODE == 1) mbar_wait(&bar_efull[es], eph);
+                else mbar_wait(&bar_eempty[es], eph ^ 1);
+                // stacked forward: 64-byte rows, stored one row down so that the TMA store source (position r*W2 + 1, W even) stays 128-byte aligned
+                uint8_t* rowp = s_slots + (size_t)es * slot_bytes + (trow + (stack ? 1 : 0)) * slot_row;
                 const int c0 = j * 64 + h * 32;
                 __syncwarp();
-                if (c0 < p.NP) {
+                if (EPI_MODE == 0 && stack) {
+                    // out[p] = E_0[p-1] + E_1[p] + E_2[p+1]: the neighbours' rows come from the adjacent lanes (and, at the warp
+                    // boundaries, from the adjacent epilogue warp through s_xchg; one named barrier per tile, double-buffered)
+                    // warp (g, h): rows 32g..32g+31, channels 16h..16h+15
+                    uint32_t r0[16], r1[16], r2[16];
+                    tmem_ld16(taddr + 16 * h, r0);
+                    tmem_ld16(taddr + p.CO + 16 * h, r1);
+                    tmem_ld16(taddr + 2 * p.CO + 16 * h, r2);
+                    tmem_ld_wait();
+                    float4* xw = reinterpret_cast<float4*>(&s_xchg[acc][g][0][16 * h]);
+                    if (lane == 31) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            xw[q] = make_float4(__uint_as_float(r0[4 * q]), __uint_as_float(r0[4 * q + 1]), __uint_as_float(r0[4 * q + 2]),
+                                                __uint_as_float(r0[4 * q + 3]));
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            xw[8 + q] = make_float4(__uint_as_float(r2[4 * q]), __uint_as_float(r2[4 * q + 1]), __uint_as_float(r2[4 * q + 2]),
+                                                    __uint_as_float(r2[4 * q + 3]));
+                    }
+                    named_bar_sync(2, C3_EPI_WARPS * 32);
+                    float v[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[e]), 1);
+                        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[e]), 1);
+                        v[e] = __uint_as_float(r1[e]) + (lane > 0 ? up : 0.f) + (lane < 31 ? dn : 0.f);
+                    }
+                    if (lane == 0 && g > 0) {
+                        const float4* xr = reinterpret_cast<const float4*>(&s_xchg[acc][g - 1][0][16 * h]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 t = xr[q];
+                            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                        }
+                    }
+                    if (lane == 31 && g < 3) {
+                        const float4* xr = reinterpret_cast<const float4*>(&s_xchg[acc][g + 1][1][16 * h]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 t = xr[q];
+                            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                        }
+                    }
+                    const uint32_t sw64 = (uint32_t)(((trow + 1) >> 1) & 3);   // SWIZZLE_64B: 16-byte chunk index ^= address bits [8:7]
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (trow == 127) break;                                // never an interior position; its shifted row would leave the slot
+                        const uint32_t off = (((uint32_t)(2 * h + q)) ^ sw64) << 4;
+                        *reinterpret_cast<uint4*>(rowp + off) = make_uint4(c3_pack_bf16x2(v[8 * q], v[8 * q + 1]), c3_pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                                           c3_pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), c3_pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                    }
+                } else if (c0 < p.NP) {
                     uint32_t r[32];
                     tmem_ld32(taddr + c0, r);
                     tmem_ld_wait();
@@ -421,6 +527,7 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     p.n_tiles = (int)((total_rows + p.R - 1) / p.R);
     p.nsub = (CO + 63) / 64;
     p.epi_mode = bn_ref != nullptr ? 1 : 0;
+    p.stack = (p.epi_mode == 0 && CO <= 32 && (3 * CO) % 16 == 0 && W % 2 == 0) ? 1 : 0;
     GN_REQUIRE(((uintptr_t)out & 15) == 0 && ldo % 8 == 0, GN_EALIGN, "conv3x3: output view must be 16-byte aligned with a pitch that is a multiple of 8");
     if (p.epi_mode == 1) {
         GN_REQUIRE(bn_sc && bn_p0 && bn_p1 && (!bn_ref_is_raw || bn_sh), GN_EINVAL, "conv3x3: incomplete BN-backward epilogue arguments");
@@ -428,18 +535,19 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
         p.bn.ref = (const __nv_bfloat16*)bn_ref; p.bn.ldref = bn_ldref; p.bn.ref_is_raw = bn_ref_is_raw;
         p.bn.sc = bn_sc; p.bn.sh = bn_sh; p.bn.p0 = bn_p0; p.bn.p1 = bn_p1; p.bn.colsum = bn_colsum; p.bn.ldsum = bn_ldsum; p.bn.rmw = 0;
     }
-    const int w_bytes = ((9 * p.kblocks * p.NP * p.w_row_bytes + 1023) / 1024) * 1024;
+    const int w_bytes = (((p.stack ? 3 * 3 * CO : 9 * p.NP) * p.kblocks * p.w_row_bytes + 1023) / 1024) * 1024;
     const int stage_bytes = p.kblocks * p.a_rows * 128;
     const int epi_fixed = 6 * C3_MAX_CO * 4;
-    const int budget = 227 * 1024 - 1024 - 512;
-    GN_REQUIRE(w_bytes + stage_bytes + 2 * C3_SUB_BYTES + epi_fixed <= budget, GN_EUNSUPPORTED,
+    const int budget = 227 * 1024 - 1024 - 512 - 2048;      // static shared memory: barriers + the stacked epilogue's exchange rows
+    const int slot_bytes = p.stack ? C3_SUB_BYTES / 2 : C3_SUB_BYTES;
+    GN_REQUIRE(w_bytes + stage_bytes + 2 * slot_bytes + epi_fixed <= budget, GN_EUNSUPPORTED,
                "conv3x3: tile does not fit shared memory (weights %d B + stage %d B)", w_bytes, stage_bytes);
-    p.stages = (w_bytes + 2 * stage_bytes + 2 * C3_SUB_BYTES + epi_fixed <= budget) ? 2 : 1;
-    p.e_stages = (budget - w_bytes - p.stages * stage_bytes - epi_fixed) / C3_SUB_BYTES;
+    p.stages = (w_bytes + 2 * stage_bytes + 2 * slot_bytes + epi_fixed <= budget) ? 2 : 1;
+    p.e_stages = (budget - w_bytes - p.stages * stage_bytes - epi_fixed) / slot_bytes;
     if (p.e_stages > C3_MAX_ESTAGES) p.e_stages = C3_MAX_ESTAGES;
-    const size_t smem = (size_t)w_bytes + (size_t)p.stages * stage_bytes + (size_t)p.e_stages * C3_SUB_BYTES + epi_fixed + 1024;
+    const size_t smem = (size_t)w_bytes + (size_t)p.stages * stage_bytes + (size_t)p.e_stages * slot_bytes + epi_fixed + 1024;
 
-    CUtensorMap tmX, tmW, tmOut, tmRef;
+    CUtensorMap tmX, tmXb, tmW, tmOut, tmRef;
     memset(&tmRef, 0, sizeof(tmRef));
     {
         uint64_t dims[4] = {(uint64_t)CI, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
@@ -447,11 +555,14 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
         uint32_t box[4] = {64, (uint32_t)W2, 1, 1};
         int rc = gn_tmap_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
+        box[2] = (uint32_t)(p.R + 2);                         // the whole halo tile of one k-block when it lies inside one image
+        rc = gn_tmap_encode(&tmXb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
     }
     {
         uint64_t dims[2] = {(uint64_t)CI, (uint64_t)9 * CO};
         uint64_t strides[1] = {(uint64_t)ldw * 2};
-        uint32_t box[2] = {(uint32_t)(p.w_row_bytes / 2), (uint32_t)p.NP};
+        uint32_t box[2] = {(uint32_t)(p.w_row_bytes / 2), (uint32_t)(p.stack ? 3 * CO : p.NP)};
         int rc = gn_tmap_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wp, dims, strides, box,
                                 p.w_row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
@@ -459,8 +570,9 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     {
         uint64_t dims[4] = {(uint64_t)CO, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t strides[3] = {(uint64_t)ldo * 2, (uint64_t)W * ldo * 2, (uint64_t)H * W * ldo * 2};
-        uint32_t box[4] = {64, (uint32_t)W, 1, 1};        // stores may not start at a negative coordinate (tools/tma_store_probe)
-        int rc = gn_tmap_encode(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        uint32_t box[4] = {p.stack ? 32u : 64u, (uint32_t)W, 1, 1};        // stores may not start at a negative coordinate (tools/tma_store_probe)
+        int rc = gn_tmap_encode(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box,
+                                p.stack ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
     if (p.epi_mode == 1) {
@@ -477,8 +589,8 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
         max_set[p.epi_mode] = (int)smem;
     }
     const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
-    if (p.epi_mode) conv3x3_kernel<1><<<grid, 384, smem, stream>>>(tmX, tmW, tmOut, tmRef, p);
-    else conv3x3_kernel<0><<<grid, 384, smem, stream>>>(tmX, tmW, tmOut, tmRef, p);
+    if (p.epi_mode) conv3x3_kernel<1><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
+    else conv3x3_kernel<0><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
