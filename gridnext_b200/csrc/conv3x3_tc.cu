@@ -608,6 +608,7 @@ struct Conv3WgParams {
     int a_rows, b_rows;             // buffer rows (positions) per stage for X halo and dY
     int n_tiles;
     int stages;
+    int stack;                      // 1 (CO <= 32): the three kx taps share one MMA, B = dY shifted by +1 / 0 / -1 positions stacked along N
     float* dwp;                     // [9][CI][CO] fp32
 };
 
@@ -622,7 +623,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int W2 = p.W + 2, H2 = p.H + 2, HALO = p.W + 3;
     const int a_group_bytes = p.a_rows * 128;
     const int a_bytes = 2 * a_group_bytes;
-    const int b_bytes = p.b_rows * 128;
+    const int b_row_bytes = p.stack ? 64 : 128;      // stacked: dY as [position][32 channels] SWIZZLE_64B, so that a 32-channel group is one MN atom
+    const int b_ext = p.stack ? 1 : 0;               // ... and positions P0-1 .. P0+128 are needed
+    const int b_bytes = p.b_rows * b_row_bytes;
     const int stage_bytes = a_bytes + b_bytes;
 
     if (warp == 0 && lane == 0) {
@@ -654,9 +657,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 const int R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
                 const int R1 = (P0 + 127 + HALO) / W2;
                 const int nr = (int)(R1 - R0 + 1);
-                const int Q0 = P0 / W2, Q1 = (P0 + 127) / W2;
+                const int Q0 = P0 - b_ext >= 0 ? (P0 - b_ext) / W2 : -1, Q1 = (P0 + 127 + b_ext) / W2;
                 const int nq = (int)(Q1 - Q0 + 1);
-                mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)((2 * nr + nq) * W2 * 128));
+                mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(2 * nr * W2 * 128 + nq * W2 * b_row_bytes));
                 for (int r = 0; r < nr; ++r) {
                     const int R = R0 + r;
                     int n, yp;
@@ -666,7 +669,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 }
                 for (int r = 0; r < nq; ++r) {
                     const int R = Q0 + r;
-                    tma_load_4d(&tmDY, &bar_full[stage], sa + a_bytes + (size_t)r * W2 * 128, 0, -1, R % H2 - 1, R / H2);
+                    int n, yp;
+                    if (R >= 0) { n = R / H2; yp = R - n * H2; } else { n = -1; yp = 0; }
+                    tma_load_4d(&tmDY, &bar_full[stage], sa + a_bytes + (size_t)r * W2 * b_row_bytes, 0, -1, yp - 1, n);
                 }
                 if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
             }
@@ -676,6 +681,8 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             const uint32_t idesc = idesc_bf16(128, p.NP, 1, 1);
             const uint64_t tmplA = smem_desc_template((uint32_t)a_group_bytes, 1024, LAYOUT_SW128);
             const uint64_t tmplB = smem_desc_template(0, 1024, LAYOUT_SW128);
+            const uint32_t idesc_s = idesc_bf16(128, 96, 1, 1);
+            const uint64_t tmplBs = smem_desc_template(64, 512, LAYOUT_SW64);
             int stage = 0;
             uint32_t phase = 0;
             bool first_tile = true;
@@ -686,16 +693,33 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 const int lo = P0 - HALO;
                 const int R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
                 const int a_row0 = (int)(P0 - R0 * W2);
-                const int b_row0 = (int)(P0 - (P0 / W2) * W2);
                 const uint32_t a_base = smem_u32(sm + (size_t)stage * stage_bytes);
-                const uint32_t b_base = a_base + a_bytes + b_row0 * 128;
-                for (int t = 0; t < 9; ++t) {
-                    const uint32_t a_addr = a_base + (a_row0 + (t / 3 - 1) * W2 + (t % 3 - 1)) * 128;
-                    const uint32_t d = tmem_base + (uint32_t)(t * p.NP);
+                if (p.stack) {
+                    // D_ky[ci, (j, co)] += sum_q X[q + (ky-1)W2][ci] * dY[q - 1 + j][co],  j = 2 - kx: the three N groups are the SAME dY
+                    // buffer starting one position (64 B = LBO) later each -- overlapping MN atoms, legal because the swizzle is a
+                    // function of the absolute shared-memory address
+                    const int Q0 = P0 - 1 >= 0 ? (P0 - 1) / W2 : -1;
+                    const uint32_t b_base = a_base + a_bytes + (uint32_t)(P0 - 1 - Q0 * W2) * 64;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)    // 128 positions = 8 x 16 reduction rows
-                        umma_bf16(d, smem_desc(tmplA, a_addr + k * 2048), smem_desc(tmplB, b_base + k * 2048), idesc,
-                                  (uint32_t)(!first_tile || k != 0));
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t a_addr = a_base + (a_row0 + (ky - 1) * W2) * 128;
+                        const uint32_t d = tmem_base + (uint32_t)(ky * 96);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_bf16(d, smem_desc(tmplA, a_addr + k * 2048), smem_desc(tmplBs, b_base + k * 1024), idesc_s,
+                                      (uint32_t)(!first_tile || k != 0));
+                    }
+                } else {
+                    const int b_row0 = (int)(P0 - (P0 / W2) * W2);
+                    const uint32_t b_base = a_base + a_bytes + b_row0 * 128;
+                    for (int t = 0; t < 9; ++t) {
+                        const uint32_t a_addr = a_base + (a_row0 + (t / 3 - 1) * W2 + (t % 3 - 1)) * 128;
+                        const uint32_t d = tmem_base + (uint32_t)(t * p.NP);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)    // 128 positions = 8 x 16 reduction rows
+                            umma_bf16(d, smem_desc(tmplA, a_addr + k * 2048), smem_desc(tmplB, b_base + k * 2048), idesc,
+                                      (uint32_t)(!first_tile || k != 0));
+                    }
                 }
                 umma_commit(&bar_empty[stage]);
                 first_tile = false;
@@ -711,7 +735,8 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int t = 0; t < 9; ++t) {
             for (int c0 = 0; c0 < p.NP; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(t * p.NP + c0), r);
+                const uint32_t col = p.stack ? (uint32_t)((t / 3) * 96 + (2 - t % 3) * 32) : (uint32_t)(t * p.NP + c0);
+                tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + col, r);
                 tmem_ld_wait();
                 if (c < p.CI) {
                     float* o = p.dwp + ((long)t * p.CI + c) * p.CO + c0;
@@ -759,10 +784,11 @@ GN_API int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long l
     p.Nimg = Nimg; p.H = H; p.W = W; p.CI = CI; p.CO = CO; p.NP = ((CO + 15) / 16) * 16;
     const int W2 = W + 2, HALO = W + 3;
     p.a_rows = ((127 + 2 * HALO) / W2 + 2) * W2;
-    p.b_rows = (127 / W2 + 2) * W2;
+    p.stack = (CO <= 32 && W % 2 == 0 && !getenv("GN_C3_WG_NOSTACK")) ? 1 : 0;     // 64-byte dY rows: TMA destinations stay 128-byte aligned only for even W + 2
+    p.b_rows = ((127 + 2 * p.stack) / W2 + 2) * W2;
     p.n_tiles = (int)(((long)(H + 2) * W2 * Nimg + 127) / 128);
     p.dwp = dwp;
-    const size_t stage_b = (size_t)(2 * p.a_rows + p.b_rows) * 128;
+    const size_t stage_b = (size_t)(2 * p.a_rows) * 128 + (size_t)p.b_rows * (p.stack ? 64 : 128);
     p.stages = (2 * stage_b + 1024 <= 227 * 1024 - 256) ? 2 : 1;
     const size_t smem = p.stages * stage_b + 1024;
     GN_REQUIRE(smem <= 227 * 1024 - 256, GN_EUNSUPPORTED, "conv3x3_wgrad: tile does not fit shared memory (%zu B)", smem);
@@ -777,8 +803,9 @@ GN_API int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long l
     {
         uint64_t dims[4] = {(uint64_t)CO, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t strides[3] = {(uint64_t)ldy * 2, (uint64_t)W * ldy * 2, (uint64_t)H * W * ldy * 2};
-        uint32_t box[4] = {64, (uint32_t)W2, 1, 1};
-        int rc = gn_tmap_encode(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        uint32_t box[4] = {p.stack ? 32u : 64u, (uint32_t)W2, 1, 1};
+        int rc = gn_tmap_encode(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy, dims, strides, box,
+                                p.stack ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
     static int max_set = 0;
