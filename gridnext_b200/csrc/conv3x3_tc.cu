@@ -134,8 +134,14 @@ __device__ __forceinline__ void c3_issue_tile_stacked(uint32_t d, uint64_t descA
 //   warp 2: epilogue feeder (TMA loads of the BN reference tile, one box per padded row)
 //   warp 3: TMEM allocator + epilogue drain (TMA row stores; border positions fall outside the tensor map and are dropped)
 //   warps 4-11: epilogue (tcgen05.ld -> math -> swizzled st.shared in place)
-template <int EPI_MODE>
-__global__ void __launch_bounds__(384, 1)
+//   EPI_WARPS = 16 (BN-backward epilogue with <= 128 output channels): warp (g, cb) owns accumulator rows 32g..32g+31 and the
+//   FIXED 32-column block cb for the whole kernel, so the BN column sums (sum g, sum g*ref) stay in 64 registers per thread
+//   across all tiles and are reduced over the 32 rows ONCE at the end.  (With 8 warps each sub-tile paid two 31-step shuffle
+//   butterflies -- 57 % of the epilogue's instructions -- and two resident warps per scheduler could not hide their latency:
+//   the data-gradient convolution was bound by its epilogue at 2.9 TB/s.)  The two sub-tiles of a tile are processed
+//   concurrently by the two halves of the epilogue.
+template <int EPI_MODE, int EPI_WARPS>
+__global__ void __launch_bounds__((4 + EPI_WARPS) * 32, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXb, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRef, const Conv3Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -185,7 +191,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
             mbar_init(&bar_tfull[s], 1);
-            mbar_init(&bar_tempty[s], C3_EPI_WARPS);
+            mbar_init(&bar_tempty[s], EPI_WARPS);
         }
         for (int s = 0; s < C3_MAX_ESTAGES; ++s) {
             mbar_init(&bar_efull[s], 1);
@@ -316,6 +322,86 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             tma_store_wait_all<0>();
         }
         __syncwarp();
+    } else if (EPI_WARPS == 16) {
+        // ---- epilogue, register-accumulating form (see the kernel comment): warp (g, cb), sub-tile j = cb / 2, half h = cb % 2
+        const int g = warp & 3;
+        const int cb = (warp - 4) >> 2;
+        const int j = cb >> 1, h = cb & 1;
+        const int trow = g * 32 + lane;
+        const uint32_t sw = (uint32_t)(trow & 7);
+        const int r_loc = trow / W2, xp = trow % W2;
+        const bool active = j < p.nsub;
+        const bool is_raw = p.bn.ref_is_raw != 0;
+        float sg[32], sx[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sg[e] = sx[e] = 0.f;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int es = j % p.e_stages;
+        uint32_t eph = (uint32_t)((j / p.e_stages) & 1);
+        const float* cst = s_epi + cb * 32;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(&bar_tfull[acc], acc_phase);
+            tc_fence_after();
+            if (active) {
+                int n, yp;
+                c3_row_coords(tile * R + r_loc, total_rows, H2, p.Nimg, n, yp);
+                const bool valid = r_loc < R && n >= 0 && n < p.Nimg && yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
+                const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * 256 + cb * 32);
+                mbar_wait(&bar_efull[es], eph);
+                uint8_t* rowp = s_slots + (size_t)es * slot_bytes + trow * 128;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {                               // eight 4-column chunks (register budget: 96 per thread, 64 of them sums)
+                    uint32_t r[4];
+                    tmem_ld4(taddr + 4 * ch, r);
+                    const uint32_t off = ((((uint32_t)(h * 4 + (ch >> 1))) ^ sw) << 4) + (uint32_t)((ch & 1) * 8);
+                    const uint2 rv = *reinterpret_cast<const uint2*>(rowp + off);
+                    const uint32_t rw[2] = {rv.x, rv.y};
+                    tmem_ld_wait();
+                    uint32_t res[2];
+#pragma unroll
+                    for (int e2 = 0; e2 < 2; ++e2) {
+                        const float2 rf = c3_unpack_bf16x2(rw[e2]);
+                        const float2 sc2 = *reinterpret_cast<const float2*>(cst + 4 * ch + 2 * e2);
+                        float2 sh2 = make_float2(0.f, 0.f);
+                        if (is_raw) sh2 = *reinterpret_cast<const float2*>(cst + C3_MAX_CO + 4 * ch + 2 * e2);
+                        float o2[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int e = 4 * ch + 2 * e2 + u;
+                            const float ref = u ? rf.y : rf.x;
+                            const float sc = u ? sc2.y : sc2.x;
+                            const float a = is_raw ? fmaf(ref, sc, u ? sh2.y : sh2.x) : ref;
+                            const bool on = valid && a > 0.f;               // dropped rows hold stale shared memory: select, never multiply
+                            const float gg = on ? __uint_as_float(r[2 * e2 + u]) : 0.f;
+                            sg[e] += gg;
+                            sx[e] += on ? gg * ref : 0.f;                   // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
+                            o2[u] = gg * sc;
+                        }
+                        res[e2] = c3_pack_bf16x2(o2[0], o2[1]);
+                    }
+                    *reinterpret_cast<uint2*>(rowp + off) = make_uint2(res[0], res[1]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_eready[es]);
+                es += p.nsub;
+                while (es >= p.e_stages) { es -= p.e_stages; eph ^= 1; }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (active && p.bn.colsum != nullptr) {
+            const float tg = gn_warp_colsum32(sg, lane), tx = gn_warp_colsum32(sx, lane);
+            const int col = cb * 32 + lane;
+            if (col < p.CO) {
+                atomicAdd(p.bn.colsum + col, tg);
+                atomicAdd(p.bn.colsum + p.bn.ldsum + col, __ldg(p.bn.p1 + col) * (tx - __ldg(p.bn.p0 + col) * tg));
+            }
+        }
     } else {
         // ---- epilogue: thread = (accumulator row, 32-channel half of each 64-channel sub-tile)
         const int g = warp & 3;
@@ -584,13 +670,16 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     }
     static int max_set[2] = {0, 0};
     if ((int)smem > max_set[p.epi_mode]) {
-        if (p.epi_mode) GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (p.epi_mode) {
+            GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         max_set[p.epi_mode] = (int)smem;
     }
     const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
-    if (p.epi_mode) conv3x3_kernel<1><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
-    else conv3x3_kernel<0><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
+    if (p.epi_mode && p.nsub <= 2 && p.e_stages >= 2 && !getenv("GN_C3_EPI8")) conv3x3_kernel<1, 16><<<grid, 640, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
+    else if (p.epi_mode) conv3x3_kernel<1, 8><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
+    else conv3x3_kernel<0, 8><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
