@@ -698,6 +698,9 @@ struct Conv3WgParams {
     int n_tiles;
     int stages;
     int stack;                      // 1 (CO <= 32): the three kx taps share one MMA, B = dY shifted by +1 / 0 / -1 positions stacked along N
+    int img;                        // > 0: small images -- a tile is img WHOLE padded images (img * (H+2) * (W+2) <= 128 positions), one TMA box per
+                                    // image and operand: no halo rows from neighbouring images and 3 * img TMA instructions per tile instead of ~47
+    int k16;                        // reduction steps of 16 positions per tile
     float* dwp;                     // [9][CI][CO] fp32
 };
 
@@ -727,12 +730,22 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_init(&bar_done, 1);
         fence_barrier_init();
     }
+    if (p.img > 0) {
+        // positions between the images' data and the next multiple of 16, and the slack rows the shifted taps reach, are never
+        // written by TMA: they must hold zeros (dY) / finite values (X) for the whole kernel
+        uint4* z = reinterpret_cast<uint4*>(sm);
+        const int n16 = p.stages * stage_bytes / 16;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+    }
     if (warp == 1) tmem_alloc<512>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     const bool has_work = (int)blockIdx.x < p.n_tiles;
+    const int img_pos = H2 * W2;                 // positions of one padded image
+    const int img_front = W2 + 1;                // slack rows in front of the first image of a tile (tap (0, 0) reaches back W2 + 1 positions)
 
     if (warp == 0) {
         if (elect_one()) {
@@ -741,6 +754,17 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 mbar_wait(&bar_empty[stage], phase ^ 1);
                 uint8_t* sa = sm + (size_t)stage * stage_bytes;
+                if (p.img > 0) {
+                    mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(3 * p.img * img_pos * 128));
+                    for (int i = 0; i < p.img; ++i) {
+                        const int n = tile * p.img + i;           // past the last image: out of bounds = zero fill
+                        for (int g = 0; g < 2; ++g)
+                            tma_load_4d(&tmX, &bar_full[stage], sa + (size_t)g * a_group_bytes + (size_t)(img_front + i * img_pos) * 128, g * 64, -1, -1, n);
+                        tma_load_4d(&tmDY, &bar_full[stage], sa + a_bytes + (size_t)(i * img_pos) * 128, 0, -1, -1, n);
+                    }
+                    if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
+                    continue;
+                }
                 const int P0 = tile * 128;
                 const int lo = P0 - HALO;
                 const int R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
@@ -781,9 +805,18 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 const int P0 = tile * 128;
                 const int lo = P0 - HALO;
                 const int R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
-                const int a_row0 = (int)(P0 - R0 * W2);
+                const int a_row0 = p.img > 0 ? img_front : (int)(P0 - R0 * W2);
                 const uint32_t a_base = smem_u32(sm + (size_t)stage * stage_bytes);
-                if (p.stack) {
+                if (p.img > 0) {
+                    const uint32_t b_base = a_base + a_bytes;
+                    for (int t = 0; t < 9; ++t) {
+                        const uint32_t a_addr = a_base + (a_row0 + (t / 3 - 1) * W2 + (t % 3 - 1)) * 128;
+                        const uint32_t d = tmem_base + (uint32_t)(t * p.NP);
+                        for (int k = 0; k < p.k16; ++k)
+                            umma_bf16(d, smem_desc(tmplA, a_addr + k * 2048), smem_desc(tmplB, b_base + k * 2048), idesc,
+                                      (uint32_t)(!first_tile || k != 0));
+                    }
+                } else if (p.stack) {
                     // D_ky[ci, (j, co)] += sum_q X[q + (ky-1)W2][ci] * dY[q - 1 + j][co],  j = 2 - kx: the three N groups are the SAME dY
                     // buffer starting one position (64 B = LBO) later each -- overlapping MN atoms, legal because the swizzle is a
                     // function of the absolute shared-memory address
@@ -873,9 +906,16 @@ GN_API int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long l
     p.Nimg = Nimg; p.H = H; p.W = W; p.CI = CI; p.CO = CO; p.NP = ((CO + 15) / 16) * 16;
     const int W2 = W + 2, HALO = W + 3;
     p.a_rows = ((127 + 2 * HALO) / W2 + 2) * W2;
-    p.stack = (CO <= 32 && W % 2 == 0 && !getenv("GN_C3_WG_NOSTACK")) ? 1 : 0;     // 64-byte dY rows: TMA destinations stay 128-byte aligned only for even W + 2
+    p.img = (H + 2) * (W + 2) <= 128 ? 128 / ((H + 2) * (W + 2)) : 0;
+    p.k16 = p.img > 0 ? (p.img * (H + 2) * (W + 2) + 15) / 16 : 8;
+    p.stack = (p.img == 0 && CO <= 32 && W % 2 == 0 && W >= 24) ? 1 : 0;   // measured: pays for the 32-pixel rows of block 1 only     // 64-byte dY rows: TMA destinations stay 128-byte aligned only for even W + 2
     p.b_rows = ((127 + 2 * p.stack) / W2 + 2) * W2;
     p.n_tiles = (int)(((long)(H + 2) * W2 * Nimg + 127) / 128);
+    if (p.img > 0) {
+        p.a_rows = ((W2 + 1) + 128 + (W2 + 1) + 7) / 8 * 8;
+        p.b_rows = 128;
+        p.n_tiles = (Nimg + p.img - 1) / p.img;
+    }
     p.dwp = dwp;
     const size_t stage_b = (size_t)(2 * p.a_rows) * 128 + (size_t)p.b_rows * (p.stack ? 64 : 128);
     p.stages = (2 * stage_b + 1024 <= 227 * 1024 - 256) ? 2 : 1;
@@ -885,14 +925,14 @@ GN_API int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long l
     {
         uint64_t dims[4] = {(uint64_t)CI, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t strides[3] = {(uint64_t)ldx * 2, (uint64_t)W * ldx * 2, (uint64_t)H * W * ldx * 2};
-        uint32_t box[4] = {64, (uint32_t)W2, 1, 1};
+        uint32_t box[4] = {64, (uint32_t)W2, p.img > 0 ? (uint32_t)(H + 2) : 1u, 1};
         int rc = gn_tmap_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
     {
         uint64_t dims[4] = {(uint64_t)CO, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t strides[3] = {(uint64_t)ldy * 2, (uint64_t)W * ldy * 2, (uint64_t)H * W * ldy * 2};
-        uint32_t box[4] = {p.stack ? 32u : 64u, (uint32_t)W2, 1, 1};
+        uint32_t box[4] = {p.stack ? 32u : 64u, (uint32_t)W2, p.img > 0 ? (uint32_t)(H + 2) : 1u, 1};
         int rc = gn_tmap_encode(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy, dims, strides, box,
                                 p.stack ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
