@@ -33,6 +33,7 @@ struct Conv3Params {
     int nsub;             // 64-channel output sub-tiles per tile
     int e_stages;         // epilogue sub-tile ring depth
     int epi_mode;         // 0 plain store, 1 BnBwdEpi (reference tile fetched by TMA)
+    int img;              // > 0: small feature maps -- R = img * (H+2): a tile is img whole padded images, loaded with one TMA box per image
     int stack;            // 1: the three kx taps of a kernel row are stacked along UMMA N (3 MMAs chains of N = 3*CO instead of 9 of N = CO)
     BnBwdEpi bn;
 };
@@ -220,8 +221,18 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 const int Rg0 = tile * R;
                 int n, yp;
                 c3_row_coords(Rg0 - 1, total_rows, H2, p.Nimg, n, yp);
-                mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)((R + 2) * W2 * 128 * p.kblocks));
                 uint8_t* dst = s_a + (size_t)stage * stage_bytes + 1024;
+                if (p.img > 0) {
+                    // whole images: the halo rows above / below a tile belong to other images and only feed dropped border outputs
+                    mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(R * W2 * 128 * p.kblocks));
+                    for (int i = 0; i < p.img; ++i)
+                        for (int kb = 0; kb < p.kblocks; ++kb)
+                            tma_load_4d(&tmXb, &bar_full[stage], dst + (size_t)kb * kb_buf_bytes + (size_t)(1 + i * H2) * W2 * 128, kb * 64, -1, -1,
+                                        tile * p.img + i);
+                    if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
+                    continue;
+                }
+                mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)((R + 2) * W2 * 128 * p.kblocks));
                 if (n >= 0 && yp + R + 1 < H2) {
                     // all R + 2 padded rows lie in one image: ONE box per k-block (a TMA instruction costs the issuing thread
                     // ~80 cycles; ten per tile kept the two-stage ring from covering the DRAM latency)
@@ -282,11 +293,16 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                     mbar_wait(&bar_eempty[es], eph ^ 1);
                     uint8_t* slot = s_slots + (size_t)es * slot_bytes;
                     mbar_arrive_expect_tx(&bar_efull[es], (uint32_t)(R * W2 * 128));
-                    int n, yp;
-                    c3_row_coords(Rg0, total_rows, H2, p.Nimg, n, yp);
-                    for (int r = 0; r < R; ++r) {
-                        tma_load_4d(&tmRef, &bar_efull[es], slot + (size_t)r * W2 * 128, j * 64, -1, yp - 1, n < p.Nimg ? n : p.Nimg);
-                        c3_row_next(H2, n, yp);
+                    if (p.img > 0) {
+                        for (int i = 0; i < p.img; ++i)
+                            tma_load_4d(&tmRef, &bar_efull[es], slot + (size_t)(i * H2) * W2 * 128, j * 64, -1, -1, tile * p.img + i);
+                    } else {
+                        int n, yp;
+                        c3_row_coords(Rg0, total_rows, H2, p.Nimg, n, yp);
+                        for (int r = 0; r < R; ++r) {
+                            tma_load_4d(&tmRef, &bar_efull[es], slot + (size_t)r * W2 * 128, j * 64, -1, yp - 1, n < p.Nimg ? n : p.Nimg);
+                            c3_row_next(H2, n, yp);
+                        }
                     }
                     if (++es == p.e_stages) { es = 0; eph ^= 1; }
                 }
@@ -608,6 +624,8 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     const int W2 = W + 2;
     GN_REQUIRE(W2 <= 128, GN_EUNSUPPORTED, "conv3x3: width %d too large (W + 2 must fit one 128-position tile)", W);
     p.R = 128 / W2;
+    p.img = ((H + 2) * W2 <= 128 && !getenv("GN_C3_NOIMG")) ? 128 / ((H + 2) * W2) : 0;
+    if (p.img > 0) p.R = p.img * (H + 2);
     p.a_rows = ((2 * W2 + 137 + 7) / 8) * 8;
     const long total_rows = (long)(H + 2) * Nimg;
     p.n_tiles = (int)((total_rows + p.R - 1) / p.R);
@@ -641,7 +659,7 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
         uint32_t box[4] = {64, (uint32_t)W2, 1, 1};
         int rc = gn_tmap_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
-        box[2] = (uint32_t)(p.R + 2);                         // the whole halo tile of one k-block when it lies inside one image
+        box[2] = p.img > 0 ? (uint32_t)(H + 2) : (uint32_t)(p.R + 2);   // a whole padded image | the whole halo tile of one k-block when it lies inside one image
         rc = gn_tmap_encode(&tmXb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
@@ -664,7 +682,7 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     if (p.epi_mode == 1) {
         uint64_t dims[4] = {(uint64_t)CO, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t strides[3] = {(uint64_t)bn_ldref * 2, (uint64_t)W * bn_ldref * 2, (uint64_t)H * W * bn_ldref * 2};
-        uint32_t box[4] = {64, (uint32_t)W2, 1, 1};
+        uint32_t box[4] = {64, (uint32_t)W2, p.img > 0 ? (uint32_t)(H + 2) : 1u, 1};
         int rc = gn_tmap_encode(&tmRef, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, bn_ref, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
