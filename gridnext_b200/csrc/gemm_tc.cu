@@ -138,8 +138,14 @@ __device__ __forceinline__ bool gemm_next_tile(int it, const GemmParams& p, int&
     return true;
 }
 
+// Operand-transform warps: 4, or 8 in two groups that take alternate k-blocks (EPI_STORE: the forward conv1).  One warp per
+// scheduler cannot hide the LDS -> FMA -> STS latency of a 16 KB tile inside the ~760 cycles HBM needs to deliver it; with two
+// groups every group has two k-block periods per tile.
+template <bool XFORM, int EPI>
+struct GemmThreads { static constexpr int XF_WARPS = XFORM ? (EPI == EPI_STORE ? 8 : 4) : 0; static constexpr int N = (12 + XF_WARPS) * 32; };
+
 template <int BN, bool XFORM, int EPI>
-__global__ void __launch_bounds__(XFORM ? 512 : 384, 1)
+__global__ void __launch_bounds__(GemmThreads<XFORM, EPI>::N, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                  const __grid_constant__ CUtensorMap tmRef, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
@@ -473,13 +479,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (XFORM && warp >= 12) {
         // ===================== operand transform: A <- relu(A * scale[k] + shift[k]) in place =====================
-        const int w = warp - 12;
-        int stage = 0;
+        const int w = (warp - 12) & 3;
+        const int grp = (warp - 12) >> 2;                           // which of the alternating k-block groups this warp belongs to
+        constexpr int NGRP = GemmThreads<XFORM, EPI>::XF_WARPS / 4;
+        int stage = 0, cnt = 0;
         uint32_t phase = 0;
         for (int it = 0;; ++it) {
             int nb_, mb_;
             if (!gemm_next_tile<EPI>(it, p, nb_, mb_)) break;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+                if (NGRP == 2 && (cnt & 1) != grp) {
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 // row & 7 of the rows this lane touches is ((i & 1) * 4 + (lane >> 3)): two sets of 8 constants per k-block
                 const int pc = lane & 7;                            // physical 16-byte chunk in the 128-byte row
                 float cs[2][8], ct[2][8];
@@ -555,7 +567,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     int grid = tiles < gn_num_sms() ? tiles : gn_num_sms();
     if (EPI != EPI_DIRECT && p.num_n_blocks > 1 && grid > 1)
         while (grid % 2 == 0 && p.num_n_blocks % 2 == 0 || grid % 3 == 0 && p.num_n_blocks % 3 == 0) --grid;      // coprime with the n-block count
-    gemm_bf16_kernel<BN, XFORM, EPI><<<grid, XFORM ? 512 : 384, smem, stream>>>(tmA, tmB, tmOut, tmRef, p);
+    gemm_bf16_kernel<BN, XFORM, EPI><<<grid, GemmThreads<XFORM, EPI>::N, smem, stream>>>(tmA, tmB, tmOut, tmRef, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
