@@ -624,7 +624,7 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     const int W2 = W + 2;
     GN_REQUIRE(W2 <= 128, GN_EUNSUPPORTED, "conv3x3: width %d too large (W + 2 must fit one 128-position tile)", W);
     p.R = 128 / W2;
-    p.img = ((H + 2) * W2 <= 128 && !getenv("GN_C3_NOIMG")) ? 128 / ((H + 2) * W2) : 0;
+    p.img = ((H + 2) * W2 <= 128) ? 128 / ((H + 2) * W2) : 0;
     if (p.img > 0) p.R = p.img * (H + 2);
     p.a_rows = ((2 * W2 + 137 + 7) / 8) * 8;
     const long total_rows = (long)(H + 2) * Nimg;
@@ -695,7 +695,7 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
         max_set[p.epi_mode] = (int)smem;
     }
     const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
-    if (p.epi_mode && p.nsub <= 2 && p.e_stages >= 2 && !getenv("GN_C3_EPI8")) conv3x3_kernel<1, 16><<<grid, 640, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
+    if (p.epi_mode && p.nsub <= 2 && p.e_stages >= 2) conv3x3_kernel<1, 16><<<grid, 640, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
     else if (p.epi_mode) conv3x3_kernel<1, 8><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
     else conv3x3_kernel<0, 8><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
     GN_LAUNCH_CHECK();
