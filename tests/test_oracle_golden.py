@@ -256,3 +256,18 @@ def test_dataset_assembly_oracle_matches_reference(golden):
     c2, p2, a2 = D.mm_fg_consistency(c, p, a)
     assert a2.tolist() == [[1, 0], [0, 3]] and c2[:, 1, 0].tolist() == [0, 0] and c2[:, 0, 1].tolist() == [1, 1]
     assert p2[0, 1].tolist() == [0, 0, 0] and p2[1, 1].tolist() == [1, 1, 1]
+
+
+def test_spot_cells_host_logic_matches_reference_indexing():
+    """gridnext_b200.datasets.spot_cells (host side of the on-device assembly): pseudo-hex -> odd-r cells as utils.py:64-70,
+    rint for Cartesian coordinates (utils.py:153-154), IndexError where indexing the reference's grid would raise."""
+    from gridnext_b200.datasets import spot_cells
+    from oracle import datasets_ref as D
+    xs, ys = [0, 1, 3, 126, 127, 64], [0, 1, 77, 0, 77, 10]
+    cells = spot_cells(xs, ys).tolist()
+    for c, x, y in zip(cells, xs, ys):
+        ox, oy = D.pseudo_hex_to_oddr(x, y)
+        assert c == oy * 64 + ox
+    assert spot_cells([1.4, 2.5, 3.5], [0.6, 1.5, 2.5], visium=False, h_st=9, w_st=11).tolist() == [1 * 11 + 1, 2 * 11 + 2, 2 * 11 + 4]
+    with pytest.raises(IndexError):
+        spot_cells([400], [3])
