@@ -147,6 +147,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a captured CUDA graph')
+    ap.add_argument('--fused-adam', action='store_true',
+                    help='torch.optim.Adam(fused=True): a few fused launches instead of ~750 for-each / single-tensor kernels per step '
+                         '(DESIGN.md section 8 item 1; off by default until it has been run on a GPU)')
     ap.add_argument('--profile-out', default=None, help='write the per-kernel time table of the instrumented step to this JSON file')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -175,7 +178,7 @@ def main():
     model.to(dev)
     model.train(); model.patch_classifier.eval()          # training.py:120-126
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-4, capturable=True)
+    opt = torch.optim.Adam(params, lr=1e-4, capturable=True, fused=True if args.fused_adam else None)
     bucket = parallel.GradBucket(params) if world > 1 else None
     crit = nn.CrossEntropyLoss()
 
