@@ -169,7 +169,7 @@ def main():
     from gridnext_b200.densenet import DenseNet
     from gridnext_b200.gridnet_models import GridNetHexOddr
     from gridnext_b200.training import gridwise_step
-    from oracle import synth, shapes as S     # seeded synthetic weights / inputs only (not on the compute path)
+    from synthdata import synth, shapes as S   # seeded synthetic weights / inputs (data generators; nothing from oracle/ on this arm)
 
     # ---- model: reference constructor surface, synthetic weights
     f = DenseNet(num_classes=N_CLS, small_inputs=False, efficient=False, drop_rate=0, **DENSENET_KW)
