@@ -1,3 +1,4 @@
+# checker script: compares the CUDA path with oracle/, like the tests; not part of the product path
 import sys, json, os
 sys.path.insert(0, '.')
 import numpy as np, torch

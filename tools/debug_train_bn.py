@@ -1,4 +1,4 @@
-"""Per-parameter gradient error of the train-mode DenseNet path against the bf16-emulating oracle, in execution order."""
+"""[checker script: compares the CUDA path with oracle/, like the tests; not part of the product path] Per-parameter gradient error of the train-mode DenseNet path against the bf16-emulating oracle, in execution order."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

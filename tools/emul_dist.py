@@ -1,3 +1,4 @@
+# checker script: compares the CUDA path with oracle/, like the tests; not part of the product path
 import sys; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import torch
 from oracle import synth, shapes as S, gridnet_ref as R

@@ -1,3 +1,4 @@
+# checker script: compares the CUDA path with oracle/, like the tests; not part of the product path
 import sys; sys.path.insert(0,'/root/repo')
 import torch
 from gridnext_b200 import hexagdly as hx

@@ -85,7 +85,7 @@ def bench_ce():
 
 
 def bench_gather():
-    from oracle import synth
+    from synthdata import synth
     tis, rows, cols, pr, pc = synth.synth_positions(all_in_tissue=True)
     img = torch.randint(0, 256, (16512, 16000, 3), device=dev, dtype=torch.uint8)
     cells, _ = ip.spot_table(tis, rows, cols, pr, pc, torch.device(dev))

@@ -1,3 +1,4 @@
+# checker script: compares the CUDA path with oracle/, like the tests; not part of the product path
 import sys; sys.path.insert(0,'/root/repo')
 import torch, torch.nn as nn
 from oracle import synth, shapes as S, gridnet_ref as R
