@@ -271,6 +271,38 @@ def extras(manifest, mods):
                         counts_annot=np.transpose(cg1, (2, 0, 1)).astype(np.float32), annots_annot=ag1.astype(np.int64),
                         annot_coords=np.array(list(a_coords)), annot_lbls=np.asarray(a_lbls).astype(np.int64))
     manifest['a1_starray'] = dict(G=G, n_spots=n_spots, n_annot_rows=int(len(a_coords)))
+    # ---- A2: PatchGridDataset.__getitem__ (image_datasets.py:190-232) on synthetic patch files (lossless PNG), Loupe-format
+    # annotations + a Spaceranger-v2 position file: the patch grid and label grid the reference hands to GridNet
+    import gridnext.image_datasets as idt
+    from PIL import Image as PILImage
+    rng = np.random.RandomState(71)
+    n_p, hp = 140, 6
+    sel = rng.choice(len(all_xy), n_p, replace=False)
+    pcoords = np.array([all_xy[i] for i in sel], dtype=np.int32)                 # (array_col, array_row) pseudo-hex
+    ppatches = rng.randint(0, 256, (n_p, hp, hp, 3)).astype(np.uint8)
+    names = ['tumor', 'stroma', 'immune', 'necrosis']
+    plabel = rng.randint(0, len(names), n_p)
+    annotated = rng.rand(n_p) < 0.75
+    with tempfile.TemporaryDirectory() as td:
+        idir = os.path.join(td, 'arr0'); os.makedirs(idir)
+        for i in range(n_p):
+            PILImage.fromarray(ppatches[i]).save(os.path.join(idir, 'spot_%d_%d.png' % (pcoords[i, 0], pcoords[i, 1])))
+        pf, af = os.path.join(td, 'tissue_positions.csv'), os.path.join(td, 'annots.csv')
+        with open(pf, 'w') as fh:
+            fh.write('barcode,in_tissue,array_row,array_col,pxl_row_in_fullres,pxl_col_in_fullres\n')
+            for i in range(n_p):
+                fh.write('BC%04d-1,1,%d,%d,%d,%d\n' % (i, pcoords[i, 1], pcoords[i, 0], 100 + i, 200 + i))
+        with open(af, 'w') as fh:
+            fh.write('Barcode,annotation\n')
+            for i in range(n_p):
+                if annotated[i]:
+                    fh.write('BC%04d-1,%s\n' % (i, names[plabel[i]]))
+        ds = idt.PatchGridDataset([idir], [af], [pf], Visium=True, img_ext='png')
+        pg, ag = ds[0]
+        classes = list(ds.classes)
+    np.savez_compressed(os.path.join(OUT, 'a2_patchgrid.npz'), patches=ppatches, coords=pcoords, label=plabel, annotated=annotated,
+                        classes=np.array(classes), patch_grid=pg.numpy(), annots_grid=ag.numpy())
+    manifest['a2_patchgrid'] = dict(n=n_p, hp=hp, classes=classes)
     keys_path = os.path.join(OUT, 'state_dict_keys.json')
     if os.path.exists(keys_path):
         old = json.load(open(keys_path))

@@ -271,3 +271,19 @@ def test_spot_cells_host_logic_matches_reference_indexing():
     assert spot_cells([1.4, 2.5, 3.5], [0.6, 1.5, 2.5], visium=False, h_st=9, w_st=11).tolist() == [1 * 11 + 1, 2 * 11 + 2, 2 * 11 + 4]
     with pytest.raises(IndexError):
         spot_cells([400], [3])
+
+
+def test_patch_grid_oracle_matches_reference_dataset(golden):
+    """oracle/datasets_ref.patch_grid == the reference's PatchGridDataset.__getitem__ (image_datasets.py:190-232) run on synthetic
+    PNG patch files with Loupe annotations: ToTensor()'d patches placed at odd-r cells, labels + 1 (LabelEncoder order), 0 elsewhere."""
+    from oracle import datasets_ref as D
+    gold = golden('a2_patchgrid')
+    classes = gold['classes'].tolist()
+    assert classes == sorted(classes)                                   # LabelEncoder sorts the annotation names
+    names = ['tumor', 'stroma', 'immune', 'necrosis']
+    coords = [tuple(int(v) for v in c) for c in gold['coords']]
+    adict = {'%d_%d' % c: classes.index(names[l]) for c, l, a in zip(coords, gold['label'], gold['annotated']) if a}
+    patches = gold['patches'].transpose(0, 3, 1, 2).astype(np.float32) / 255.0          # ToTensor()
+    grid, annots = D.patch_grid(patches, coords, adict)
+    assert np.array_equal(annots, gold['annots_grid'])
+    assert grid.shape == gold['patch_grid'].shape and np.array_equal(grid, gold['patch_grid'])
