@@ -18,10 +18,11 @@ from .corrector import parse_corrector, run_corrector
 
 
 def init_weights(m):
-    if type(m) == nn.Conv2d or type(m) == nn.Linear:
+    """Xavier-uniform weights / zero biases for Conv2d and Linear, unit-gamma BatchNorm2d (reference gridnet_models.py:14-20)."""
+    if type(m) in (nn.Conv2d, nn.Linear):
         nn.init.xavier_uniform_(m.weight)
         nn.init.zeros_(m.bias)
-    if type(m) == nn.BatchNorm2d:
+    elif type(m) is nn.BatchNorm2d:
         nn.init.ones_(m.weight)
         nn.init.zeros_(m.bias)
 
@@ -41,19 +42,14 @@ class GridNet(nn.Module):
 
     def __init__(self, patch_classifier, patch_shape, grid_shape, n_classes,
                  use_bn=True, atonce_patch_limit=None, f_dim=None):
-        super(GridNet, self).__init__()
-        self.patch_shape = patch_shape
-        self.grid_shape = grid_shape
-        self.n_classes = n_classes
+        super().__init__()
         self.patch_classifier = patch_classifier
-        self.use_bn = use_bn
-        self.atonce_patch_limit = atonce_patch_limit
-        if f_dim is None:
-            f_dim = n_classes
-        self.f_dim = f_dim
+        self.patch_shape, self.grid_shape = patch_shape, grid_shape
+        self.n_classes, self.use_bn, self.atonce_patch_limit = n_classes, use_bn, atonce_patch_limit
+        self.f_dim = n_classes if f_dim is None else f_dim
         self.corrector = self._init_corrector()
-        # state-dict keys of the reference (gridnet_models.py:44-48)
-        self.bg = torch.zeros((1, f_dim), requires_grad=True)
+        # the two buffers below exist only for state-dict compatibility with the reference (gridnet_models.py:44-48)
+        self.bg = torch.zeros((1, self.f_dim), requires_grad=True)
         self.register_buffer("bg_const", self.bg)
         self.dummy = torch.ones(1, dtype=torch.float32, requires_grad=True)
         self.register_buffer("dummy_tensor", self.dummy)
@@ -78,21 +74,19 @@ class GridNet(nn.Module):
         return self.patch_classifier(patch_list)
 
     def _f_on_spots(self, patch_list):
-        """f over a flat spot list (N, ...) with the reference's chunking/checkpointing contract."""
-        if self.atonce_patch_limit is None:
+        """f over a flat spot list (N, ...).  ``atonce_patch_limit`` keeps the reference's contract (gridnet_models.py:88-104):
+        chunks of that many spots, each under activation checkpointing when f is being trained."""
+        limit = self.atonce_patch_limit
+        if limit is None:
             return self._ppl(patch_list, self.dummy_tensor)
-        chunks, count, n = [], 0, len(patch_list)
-        needs_grad = any(p.requires_grad for _, p in self.patch_classifier.named_parameters())
-        while count < n:
-            length = min(self.atonce_patch_limit, n - count)
-            tmp = patch_list.narrow(0, count, length)
-            if needs_grad and torch.is_grad_enabled():
-                chunk = cp.checkpoint(self._ppl, tmp, self.dummy_tensor, use_reentrant=True)
+        recompute = torch.is_grad_enabled() and any(p.requires_grad for p in self.patch_classifier.parameters())
+        outs = []
+        for chunk in patch_list.split(limit, dim=0):
+            if recompute:
+                outs.append(cp.checkpoint(self._ppl, chunk, self.dummy_tensor, use_reentrant=True))
             else:
-                chunk = self._ppl(tmp, self.dummy_tensor)
-            chunks.append(chunk)
-            count += self.atonce_patch_limit
-        return torch.cat(chunks, 0)
+                outs.append(self._ppl(chunk, self.dummy_tensor))
+        return torch.cat(outs, 0)
 
     def patch_predictions(self, x):
         patch_list = torch.reshape(x, (-1,) + tuple(self.patch_shape))
@@ -117,18 +111,20 @@ class GridNetHex(GridNet):
                                          use_bn, atonce_patch_limit, f_dim)
 
     def _init_corrector(self):
-        layers = [hexagdly.Conv2d(in_channels=self.f_dim, out_channels=32, kernel_size=1, stride=1, bias=True),
-                  hexagdly.Conv2d(in_channels=32, out_channels=32, kernel_size=1, stride=1, bias=True)]
-        if self.use_bn:
-            layers.append(nn.BatchNorm2d(32))
-        layers.append(nn.ReLU())
-        layers += [hexagdly.Conv2d(in_channels=32, out_channels=32, kernel_size=1, stride=1, bias=True),
-                   hexagdly.Conv2d(in_channels=32, out_channels=32, kernel_size=1, stride=1, bias=True)]
-        if self.use_bn:
-            layers.append(nn.BatchNorm2d(32))
-        layers.append(nn.ReLU())
-        layers.append(hexagdly.Conv2d(in_channels=32, out_channels=self.n_classes, kernel_size=1, stride=1, bias=True))
-        return nn.Sequential(*layers)
+        # hex hex [BN] ReLU | hex hex [BN] ReLU | hex, 32 channels wide (module order = the reference's state-dict indices)
+        width = 32
+
+        def hexl(cin, cout):
+            return hexagdly.Conv2d(in_channels=cin, out_channels=cout, kernel_size=1, stride=1, bias=True)
+
+        seq = []
+        for cin in (self.f_dim, width):
+            seq += [hexl(cin, width), hexl(width, width)]
+            if self.use_bn:
+                seq.append(nn.BatchNorm2d(width))
+            seq.append(nn.ReLU())
+        seq.append(hexl(width, self.n_classes))
+        return nn.Sequential(*seq)
 
     def _correct_visium(self, grid):
         """Apply the corrector to a (B, C, H, W) tensor whose hex parity is on the row index."""
@@ -170,36 +166,27 @@ class GridNetHexMM(GridNetHexOddr):
 
     def __init__(self, image_classifier, count_classifier, image_shape, count_shape, grid_shape, n_classes,
                  use_bn=True, atonce_patch_limit=None, image_f_dim=None, count_f_dim=None):
-        if image_f_dim is None:
-            image_f_dim = n_classes
-        if count_f_dim is None:
-            count_f_dim = n_classes
-        super(GridNetHexMM, self).__init__(image_classifier, image_shape, grid_shape, n_classes,
-                                           use_bn, atonce_patch_limit, image_f_dim + count_f_dim)
-        self.image_classifier = image_classifier
-        self.count_classifier = count_classifier
-        self.image_shape = image_shape
-        self.count_shape = count_shape
-        self.image_f_dim = image_f_dim
-        self.count_f_dim = count_f_dim
+        image_f_dim = n_classes if image_f_dim is None else image_f_dim
+        count_f_dim = n_classes if count_f_dim is None else count_f_dim
+        super().__init__(image_classifier, image_shape, grid_shape, n_classes, use_bn, atonce_patch_limit, image_f_dim + count_f_dim)
+        self.image_classifier, self.count_classifier = image_classifier, count_classifier
+        self.image_shape, self.count_shape = image_shape, count_shape
+        self.image_f_dim, self.count_f_dim = image_f_dim, count_f_dim
 
     def _set_mode(self, mode):
-        if mode == 'image':
-            self.patch_classifier = self.image_classifier
-            self.patch_shape = self.image_shape
-            self.f_dim = self.image_f_dim
-        elif mode == 'count':
-            self.patch_classifier = self.count_classifier
-            self.patch_shape = self.count_shape
-            self.f_dim = self.count_f_dim
+        """Point patch_classifier / patch_shape / f_dim at one modality ('image' | 'count'), or restore the concatenated width."""
+        if mode in ('image', 'count'):
+            self.patch_classifier = getattr(self, mode + '_classifier')
+            self.patch_shape = getattr(self, mode + '_shape')
+            self.f_dim = getattr(self, mode + '_f_dim')
         else:
             self.f_dim = self.count_f_dim + self.image_f_dim
 
     def patch_predictions(self, x):
         x_image, x_count = x
-        self._set_mode('count')
-        ppg_count = super(GridNetHexMM, self).patch_predictions(x_count)
-        self._set_mode('image')
-        ppg_image = super(GridNetHexMM, self).patch_predictions(x_image)
+        grids = []
+        for mode, x_mode in (('count', x_count), ('image', x_image)):          # concatenation order of the reference: [count | image]
+            self._set_mode(mode)
+            grids.append(super().patch_predictions(x_mode))
         self._set_mode('concat')
-        return torch.cat((ppg_count, ppg_image), dim=1)
+        return torch.cat(grids, dim=1)
