@@ -31,7 +31,7 @@ def _to_device(inputs, device):
 def _spot_forward(model, inputs):
     """f on one spot batch: the count MLP pattern goes through the tensor-core path (count_mlp.forward_spots), a
     gridnext_b200 DenseNet runs its own kernels in either BatchNorm mode, anything else is called as is."""
-    if inputs.is_cuda and inputs.dim() == 2 and isinstance(model, torch.nn.Sequential):
+    if torch.is_tensor(inputs) and inputs.is_cuda and inputs.dim() == 2 and isinstance(model, torch.nn.Sequential):
         from .count_mlp import compile_count_mlp
         fast = compile_count_mlp(model)
         if fast is not None:
@@ -42,51 +42,57 @@ def _spot_forward(model, inputs):
 
 
 def train_spotwise(model, dataloaders, criterion, optimizer, num_epochs=10, outfile=None, display=False):
-    """Spot classifier (f) pre-training loop (/root/reference/gridnext/training.py:11-98; row f3 of SURVEY.md section 8):
-    same phases, metrics, best-weights bookkeeping and return triple; f runs with train-mode BatchNorm in the train phase
-    (batch statistics + running-stat update, csrc/bn_train.cu) and eval-mode BatchNorm in the val phase."""
+    """Spot classifier (f) pre-training loop (/root/reference/gridnext/training.py:11-98; row f3 of SURVEY.md section 8).
+
+    Same contract as the reference: phases 'train' / 'val' per epoch, per-epoch mean LOSS appended to the train / val histories,
+    the weights of the epoch with the lowest validation loss kept (and saved to ``outfile``) and loaded back at the end; returns
+    ``(model, val_history, train_history)``.  f runs with train-mode BatchNorm in the train phase (batch statistics +
+    running-stat update, csrc/bn_train.cu) and eval-mode BatchNorm in the val phase.  Running sums stay on the device: one host
+    read per phase instead of one ``loss.item()`` per batch."""
     since = time.time()
-    val_acc_history, train_acc_history = [], []
+    history = {'train': [], 'val': []}
     best_model_wts = copy.deepcopy(model.state_dict())
-    best_acc = 0.0
+    best_loss = np.inf
     device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
     model.to(device)
     for epoch in range(num_epochs):
         print('Epoch {}/{}'.format(epoch, num_epochs - 1), flush=True)
         print('-' * 10, flush=True)
-        for phase in ['train', 'val']:
-            model.train() if phase == 'train' else model.eval()
-            running_loss = torch.zeros((), device=device, dtype=torch.float64)
-            running_corrects = torch.zeros((), device=device, dtype=torch.float64)
-            for inputs, labels in dataloaders[phase]:
-                inputs = inputs.to(device)
+        for phase in ('train', 'val'):
+            training = phase == 'train'
+            model.train(training)
+            totals = torch.zeros(2, device=device, dtype=torch.float64)          # sum of loss * batch size, correct predictions
+            batches = dataloaders[phase]
+            if display:
+                from tqdm import tqdm
+                batches = tqdm(batches)
+            for inputs, labels in batches:
+                inputs = _to_device(inputs, device)
                 labels = labels.to(device)
                 optimizer.zero_grad()
-                with torch.set_grad_enabled(phase == 'train'):
+                with torch.set_grad_enabled(training):
                     outputs = _spot_forward(model, inputs)
                     loss = criterion(outputs, labels)
-                    _, preds = torch.max(outputs, 1)
-                    if phase == 'train':
+                    if training:
                         loss.backward()
                         optimizer.step()
-                running_loss += loss.detach().double() * inputs.size(0)
-                running_corrects += torch.sum(preds == labels.data)
+                totals[0] += loss.detach().double() * labels.size(0)
+                totals[1] += (outputs.detach().argmax(1) == labels).sum()
             n = len(dataloaders[phase].dataset)
-            epoch_loss = float(running_loss) / n
-            epoch_acc = float(running_corrects) / n
+            epoch_loss, epoch_acc = (totals / n).tolist()
             print('{} Loss: {:.4f} Acc: {:.4f}'.format(phase, epoch_loss, epoch_acc), flush=True)
-            if phase == 'val' and epoch_acc > best_acc:
-                best_acc = epoch_acc
+            if not training and epoch_loss < best_loss:
+                best_loss = epoch_loss
                 best_model_wts = copy.deepcopy(model.state_dict())
                 if outfile is not None:
                     torch.save(model.state_dict(), outfile)
-            (val_acc_history if phase == 'val' else train_acc_history).append(epoch_acc)
+            history[phase].append(epoch_loss)
         print()
     time_elapsed = time.time() - since
     print('Training complete in {:.0f}m {:.0f}s'.format(time_elapsed // 60, time_elapsed % 60), flush=True)
-    print('Best val Acc: {:4f}'.format(best_acc), flush=True)
+    print('Best val loss: {:4f}'.format(best_loss), flush=True)
     model.load_state_dict(best_model_wts)
-    return model, val_acc_history, train_acc_history
+    return model, history['val'], history['train']
 
 
 def gridwise_step(model, inputs, labels, criterion, accum_iters=1, train=True, n_fg_override=None):

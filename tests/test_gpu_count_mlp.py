@@ -151,10 +151,12 @@ def test_train_spotwise_runs_count_mlp_and_densenet(capsys):
     y = torch.randint(0, 3, (128,), generator=g)
     x = torch.rand(128, 40, generator=g) + 2.0 * torch.nn.functional.one_hot(y, 40).float()
     dl = {'train': DataLoader(TensorDataset(x, y), batch_size=32), 'val': DataLoader(TensorDataset(x, y), batch_size=64)}
+    torch.manual_seed(0)
     f = tutorial_mlp(40, 3)
     opt = torch.optim.Adam(f.parameters(), lr=3e-3)
     f, vh, th = train_spotwise(f, dl, nn.CrossEntropyLoss(), opt, num_epochs=6)
-    assert len(vh) == 6 and len(th) == 6 and vh[-1] > 0.8, (vh, th)
+    # histories are per-epoch mean LOSSES (training.py:83-86); fp32 CPU run of the same problem: val 0.80 -> 0.014
+    assert len(vh) == 6 and len(th) == 6 and vh[-1] < 0.2 and th[-1] < th[0], (vh, th)
     # DenseNet
     y = torch.randint(0, 2, (48,), generator=g)
     x = torch.randn(48, 3, 32, 32, generator=g) * 0.3 + (y.float() * 2 - 1).view(-1, 1, 1, 1)
@@ -162,7 +164,8 @@ def test_train_spotwise_runs_count_mlp_and_densenet(capsys):
     net = DenseNet(growth_rate=8, block_config=(2, 2), num_init_features=16, bn_size=2, num_classes=2, small_inputs=False)
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
     net, vh, th = train_spotwise(net, dl, nn.CrossEntropyLoss(), opt, num_epochs=4)
-    assert th[-1] > 0.9 and vh[-1] > 0.8, (vh, th)
+    # reference DenseNet on CPU, three seeds: val loss 0.44..0.73 -> 0.13..0.35 in four epochs
+    assert vh[-1] < vh[0] and th[-1] < th[0] and vh[-1] < 0.65, (vh, th)
     capsys.readouterr()
 
 

@@ -82,3 +82,64 @@ def test_multimodal_patch_predictions_cpu_match_reference(ref_models):
             for out in (po, pr):
                 with pytest.raises(RuntimeError, match='shapes cannot be multiplied'):
                     out.sum().backward()
+
+
+@pytest.mark.parametrize('accum_iters', [1, 2])
+def test_train_gridwise_loop_cpu_matches_reference(ref_models, accum_iters, capsys):
+    """training.train_gridwise against the reference's own loop (training.py:101-209) on CPU: same accumulate/step cadence
+    (step at batch_ind % accum_iters == 0, :162-169), same histories, same best-weights bookkeeping, same final parameters."""
+    import copy
+    import gridnext.training as ref_tr
+    from torch.utils.data import TensorDataset, DataLoader
+    from gridnext_b200.gridnet_models import GridNet
+    from gridnext_b200.training import train_gridwise
+    torch.manual_seed(11)
+    H, W, n_cls, f_dim = 5, 4, 3, 3
+    x = torch.randn(6, H, W, 7)
+    y = torch.randint(0, n_cls + 1, (6, H, W))
+    dl = {'train': DataLoader(TensorDataset(x, y), batch_size=2), 'val': DataLoader(TensorDataset(x[:4], y[:4]), batch_size=2)}
+    ref = ref_models.GridNet(nn.Linear(7, f_dim), (7,), (H, W), n_cls, use_bn=True, f_dim=f_dim)
+    ours = GridNet(nn.Linear(7, f_dim), (7,), (H, W), n_cls, use_bn=True, f_dim=f_dim)
+    _sync(ours, ref)
+    ref_dev = ref_tr.device if hasattr(ref_tr, 'device') else None
+    results = []
+    for model, fn in ((ours, train_gridwise), (ref, ref_tr.train_gridwise)):
+        opt = torch.optim.SGD(model.parameters(), lr=0.05)
+        m, vh, th = fn(model, dl, nn.CrossEntropyLoss(), opt, num_epochs=3, accum_iters=accum_iters)
+        results.append((copy.deepcopy(m.state_dict()), vh, th))
+    capsys.readouterr()
+    (sd_o, vh_o, th_o), (sd_r, vh_r, th_r) = results
+    assert len(vh_o) == len(vh_r) and len(th_o) == len(th_r)
+    assert all(abs(float(a) - float(b)) < 1e-6 for a, b in zip(vh_o, vh_r))
+    assert all(abs(float(a) - float(b)) < 1e-6 for a, b in zip(th_o, th_r))
+    for k in sd_r:
+        assert torch.allclose(sd_o[k].float().cpu(), sd_r[k].float().cpu(), atol=1e-6), k
+
+
+def test_train_spotwise_loop_cpu_matches_reference(ref_models, capsys):
+    """training.train_spotwise against the reference's loop (training.py:11-98) on CPU: histories, best-accuracy bookkeeping and
+    the returned (best) weights."""
+    import copy
+    import gridnext.training as ref_tr
+    from torch.utils.data import TensorDataset, DataLoader
+    from gridnext_b200.training import train_spotwise
+    torch.manual_seed(13)
+    x = torch.randn(48, 12)
+    y = (x[:, 0] > 0).long() + (x[:, 1] > 0.5).long()
+    dl = {'train': DataLoader(TensorDataset(x, y), batch_size=16), 'val': DataLoader(TensorDataset(x[:32], y[:32]), batch_size=16)}
+
+    def net():
+        torch.manual_seed(17)
+        return nn.Sequential(nn.Linear(12, 10), nn.BatchNorm1d(10), nn.ReLU(), nn.Linear(10, 3))
+
+    results = []
+    for fn in (train_spotwise, ref_tr.train_spotwise):
+        model = net()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+        m, vh, th = fn(model, dl, nn.CrossEntropyLoss(), opt, num_epochs=4)
+        results.append((copy.deepcopy(m.state_dict()), [float(v) for v in vh], [float(v) for v in th]))
+    capsys.readouterr()
+    (sd_o, vh_o, th_o), (sd_r, vh_r, th_r) = results
+    assert vh_o == pytest.approx(vh_r, abs=1e-6) and th_o == pytest.approx(th_r, abs=1e-6)
+    for k in sd_r:
+        assert torch.allclose(sd_o[k].float(), sd_r[k].float().cpu(), atol=1e-6), k
