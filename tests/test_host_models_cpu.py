@@ -19,9 +19,10 @@ def ref_models():
     warnings.filterwarnings('ignore', category=SyntaxWarning)
     from oracle import hexagdly_shim
     sys.modules.setdefault('hexagdly', hexagdly_shim)
-    for name in ('matplotlib', 'matplotlib.pyplot'):
+    for name in ('matplotlib', 'matplotlib.pyplot', 'mpl_toolkits', 'mpl_toolkits.axes_grid1'):
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    sys.modules['mpl_toolkits.axes_grid1'].make_axes_locatable = lambda *a, **k: None
     if REF not in sys.path:
         sys.path.insert(0, REF)
     import gridnext.gridnet_models as gm
@@ -143,3 +144,57 @@ def test_train_spotwise_loop_cpu_matches_reference(ref_models, capsys):
     assert vh_o == pytest.approx(vh_r, abs=1e-6) and th_o == pytest.approx(th_r, abs=1e-6)
     for k in sd_r:
         assert torch.allclose(sd_o[k].float(), sd_r[k].float().cpu(), atol=1e-6), k
+
+
+@pytest.mark.parametrize('f_only', [False, True])
+def test_all_fgd_predictions_cpu_matches_reference(ref_models, f_only):
+    """utils.all_fgd_predictions against the reference's evaluation loop (utils.py:20-57) on CPU, and the index helpers."""
+    import gridnext.utils as ref_ut
+    from torch.utils.data import TensorDataset, DataLoader
+    from gridnext_b200 import utils as our_ut
+    from gridnext_b200.gridnet_models import GridNet
+    torch.manual_seed(21)
+    H, W, n_cls = 5, 4, 3
+    x = torch.randn(5, H, W, 7)
+    y = torch.randint(0, n_cls + 1, (5, H, W))
+    dl = DataLoader(TensorDataset(x, y), batch_size=2)
+    ref = ref_models.GridNet(nn.Linear(7, n_cls), (7,), (H, W), n_cls, use_bn=True)
+    ours = GridNet(nn.Linear(7, n_cls), (7,), (H, W), n_cls, use_bn=True)
+    _sync(ours, ref)
+    got = our_ut.all_fgd_predictions(dl, ours, f_only=f_only)
+    exp = ref_ut.all_fgd_predictions(dl, ref, f_only=f_only)
+    assert (got[0] == exp[0]).all() and (got[1] == exp[1]).all()
+    assert got[2].shape == exp[2].shape and abs(got[2] - exp[2]).max() < 1e-6
+    for col, row in [(0, 0), (1, 1), (127, 77), (64, 10), (3, 5)]:
+        assert our_ut.pseudo_hex_to_oddr(col, row) == ref_ut.pseudo_hex_to_oddr(col, row)
+        ox, oy = our_ut.pseudo_hex_to_oddr(col, row)
+        assert our_ut.oddr_to_pseudo_hex(ox, oy) == ref_ut.oddr_to_pseudo_hex(ox, oy)
+        assert our_ut.pseudo_to_true_hex(col, row) == ref_ut.pseudo_to_true_hex(col, row)
+
+
+def test_position_file_reader_and_window_rule_match_reference(ref_models, tmp_path):
+    """imgprocess.read_positions / _window (host side of grid_from_wsi_visium) against utils.visium_get_positions
+    (utils.py:246-287) and the window rule of imgprocess.py:188-195, for both Spaceranger position-file generations."""
+    import numpy as np
+    import gridnext.utils as ref_ut
+    from gridnext_b200 import imgprocess as ours
+    rows = [('AAAC-1', 1, 0, 0, 1200, 1300), ('AAAG-1', 0, 1, 1, 1397, 1413), ('AAAT-1', 1, 77, 127, 16000, 15800)]
+    v2 = tmp_path / 'run_v2' / 'outs' / 'spatial'; v2.mkdir(parents=True)
+    with open(v2 / 'tissue_positions.csv', 'w') as fh:
+        fh.write('barcode,in_tissue,array_row,array_col,pxl_row_in_fullres,pxl_col_in_fullres\n')
+        fh.writelines('%s,%d,%d,%d,%d,%d\n' % r for r in rows)
+    v1 = tmp_path / 'run_v1' / 'spatial'; v1.mkdir(parents=True)
+    with open(v1 / 'tissue_positions_list.csv', 'w') as fh:
+        fh.writelines('%s,%d,%d,%d,%d,%d\n' % r for r in rows)
+    for d in (tmp_path / 'run_v2', tmp_path / 'run_v1'):
+        got, exp = ours.read_positions(str(d)), ref_ut.visium_get_positions(str(d))
+        for k in ('in_tissue', 'array_row', 'array_col', 'pxl_row_in_fullres', 'pxl_col_in_fullres'):
+            assert np.array_equal(got[k], exp[k].values), (d, k)
+    (tmp_path / 'empty').mkdir()
+    for fn in (ours.read_positions, ref_ut.visium_get_positions):
+        with pytest.raises(ValueError):
+            fn(str(tmp_path / 'empty'))
+    # window rule (imgprocess.py:188-195): None -> patch size, float -> fraction of the image WIDTH, int -> pixels, else ValueError
+    assert ours._window(224, None, 1000) == 224 and ours._window(224, 0.1, 1000) == 100 and ours._window(224, 96, 1000) == 96
+    with pytest.raises(ValueError):
+        ours._window(224, '96', 1000)
