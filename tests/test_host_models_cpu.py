@@ -198,3 +198,46 @@ def test_position_file_reader_and_window_rule_match_reference(ref_models, tmp_pa
     assert ours._window(224, None, 1000) == 224 and ours._window(224, 0.1, 1000) == 100 and ours._window(224, 96, 1000) == 96
     with pytest.raises(ValueError):
         ours._window(224, '96', 1000)
+
+
+@pytest.mark.parametrize('kw', [dict(growth_rate=8, block_config=(2, 3), num_init_features=16, bn_size=2, num_classes=5, small_inputs=False),
+                                dict(growth_rate=32, block_config=(6, 12, 24, 16), num_init_features=64, bn_size=4, num_classes=7, small_inputs=False),
+                                dict(growth_rate=12, block_config=(3, 3, 3), num_init_features=24, bn_size=4, num_classes=10, small_inputs=True,
+                                     compression=0.5)])
+def test_densenet_constructor_and_init_match_reference(ref_models, kw):
+    """DenseNet(...) builds the same module tree (state-dict keys, shapes) and -- from the same RNG state -- the same initial
+    parameters as the reference constructor (densenet.py:93-150: He-normal convolutions, unit BatchNorm, zero classifier bias)."""
+    import gridnext.densenet as ref_dn
+    from gridnext_b200.densenet import DenseNet
+    torch.manual_seed(1234)
+    ref = ref_dn.DenseNet(**kw)
+    torch.manual_seed(1234)
+    ours = DenseNet(**kw)
+    sr, so = ref.state_dict(), ours.state_dict()
+    assert list(sr.keys()) == list(so.keys())
+    for k in sr:
+        assert sr[k].shape == so[k].shape and torch.equal(sr[k], so[k]), k
+    assert [n for n, _ in ours.named_modules()] == [n for n, _ in ref.named_modules()]
+
+
+@pytest.mark.parametrize('use_bn', [True, False])
+def test_cartesian_gridnet_constructor_matches_reference(ref_models, use_bn):
+    """Same RNG state -> the same freshly initialised GridNet (key order, buffers bg_const / dummy_tensor, corrector weights),
+    and init_weights() applied through .apply() leaves both in the same state (gridnet_models.py:14-20)."""
+    from gridnext_b200 import gridnet_models as ours_gm
+
+    def build(gm):
+        torch.manual_seed(77)
+        return gm.GridNet(nn.Linear(6, 5), (6,), (7, 9), 4, use_bn=use_bn, atonce_patch_limit=3, f_dim=5)
+
+    ref, ours = build(ref_models), build(ours_gm)
+    sr, so = ref.state_dict(), ours.state_dict()
+    assert list(sr.keys()) == list(so.keys())
+    for k in sr:
+        assert torch.equal(sr[k], so[k]), k
+    for attr in ('patch_shape', 'grid_shape', 'n_classes', 'use_bn', 'atonce_patch_limit', 'f_dim'):
+        assert getattr(ours, attr) == getattr(ref, attr), attr
+    torch.manual_seed(5); ref.apply(ref_models.init_weights)
+    torch.manual_seed(5); ours.apply(ours_gm.init_weights)
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, ours.state_dict()[k]), k
