@@ -19,6 +19,12 @@ VISIUM_H_ST = 78
 VISIUM_W_ST = 64
 
 
+def pseudo_hex_to_cartesian(c):
+    """Visium pseudo-hex (col, row) -> Cartesian coordinates with unit neighbour distance (reference imgprocess.py:41-46)."""
+    x, y = c
+    return (x / 2, y * np.sqrt(3) / 2)
+
+
 def _window(patch_size, window_size, xdim):
     if window_size is None:
         w = patch_size

@@ -194,6 +194,10 @@ def test_position_file_reader_and_window_rule_match_reference(ref_models, tmp_pa
     for fn in (ours.read_positions, ref_ut.visium_get_positions):
         with pytest.raises(ValueError):
             fn(str(tmp_path / 'empty'))
+    import gridnext.imgprocess as ref_ip
+    for c in [(0, 0), (3, 1), (127, 77)]:
+        assert ours.pseudo_hex_to_cartesian(c) == ref_ip.pseudo_hex_to_cartesian(c)
+        assert ours.pseudo_hex_to_oddr(*c) == ref_ip.pseudo_hex_to_oddr(*c) and ours.oddr_to_pseudo_hex(*c) == ref_ip.oddr_to_pseudo_hex(*c)
     # window rule (imgprocess.py:188-195): None -> patch size, float -> fraction of the image WIDTH, int -> pixels, else ValueError
     assert ours._window(224, None, 1000) == 224 and ours._window(224, 0.1, 1000) == 100 and ours._window(224, 96, 1000) == 96
     with pytest.raises(ValueError):
