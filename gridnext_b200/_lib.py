@@ -41,6 +41,8 @@ _SIGS = {
     'gn_bn_stats': [vp, vp, ci, ci, cl, vp],
     'gn_bn_act_fwd': [vp, vp, vp, vp, ci, ci, cl, ci, vp],
     'gn_bn_act_bwd': [vp, vp, vp, vp, vp, vp, cd, ci, vp, vp, vp, ci, ci, cl, ci, vp],
+    'gn_bn_act_bwd_reduce': [vp, vp, vp, vp, vp, vp, ci, ci, cl, ci, vp],
+    'gn_bn_act_bwd_apply': [vp, vp, vp, vp, vp, vp, cd, ci, vp, vp, vp, ci, ci, cl, ci, vp],
     'gn_masked_ce': [vp, vp, vp, vp, vp, vp, cf, ci, ci, cl, vp],
     'gn_spot_table': [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp],
     'gn_patch_gather': [vp, cl, ci, ci, vp, ci, ci, vp, vp, vp, ci, vp],

@@ -15,6 +15,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import ptr, stream, call
 from . import hexagdly as hx
+from . import parallel
 
 
 def _is_square_conv(m):
@@ -79,14 +80,20 @@ class _CorrectorFn(torch.autograd.Function):
                 scale = torch.empty(C, device=dev); shift = torch.empty(C, device=dev); mi = torch.empty(2 * C, device=dev)
                 bn = st['bn']
                 if bn['training']:
+                    count = float(B * H * W)
+                    if bn['sync']:          # SyncBN: statistics over every rank's cells (equal per-rank batch sizes)
+                        parallel.allreduce_sum_(cur_stats)
+                        count *= parallel.world_size()
                     call('gn_bn_finalize', ptr(cur_stats), ptr(gamma), ptr(beta), ptr(bn['running_mean']), ptr(bn['running_var']),
-                         bn['momentum'], bn['eps'], float(B * H * W), ptr(scale), ptr(shift), ptr(mi), C, 1, stream())
+                         bn['momentum'], bn['eps'], count, ptr(scale), ptr(shift), ptr(mi), C, 1, stream())
                 else:
                     call('gn_bn_eval_affine', ptr(gamma), ptr(beta), ptr(bn['running_mean']), ptr(bn['running_var']), bn['eps'],
                          ptr(scale), ptr(shift), ptr(mi), C, stream())
             elif st['relu']:
                 C = st['cin']
                 scale = torch.ones(C, device=dev); shift = torch.zeros(C, device=dev)
+            if st.get('tr'):          # Cartesian conv inside a hexagonal model: the reference applies it in HexagDLy layout = transposed
+                ks = [ks[0].transpose(2, 3).contiguous()]
             wp = hx.pack_weights(ks, st['ksize'], st['cin'], st['cout'], 0, st['kind'])
             nxt = meta[j + 1] if j + 1 < len(meta) else None
             want_stats = nxt is not None and nxt['bn'] is not None and nxt['bn']['training']
@@ -114,6 +121,8 @@ class _CorrectorFn(torch.autograd.Function):
             ks, bias, gamma, beta = sp[j]
             dwp, db = hx.hexconv_wgrad(inp, grad, st['ksize'], scale, shift, want_bias=bias is not None, kind=st['kind'])
             gks = hx.unpack_grad(dwp, [k.shape for k in ks], st['ksize'], st['cin'], st['cout'], st['kind'])
+            if st.get('tr'):
+                gks = [gks[0].transpose(2, 3).contiguous()]
             dgamma = dbeta = None
             need_dx = j > 0 or ctx.needs_input_grad[0]
             if need_dx:
@@ -129,8 +138,17 @@ class _CorrectorFn(torch.autograd.Function):
                     else:
                         mi = torch.zeros(2 * C, device=dev); mi[C:] = 1.0
                         training = 0
-                    call('gn_bn_act_bwd', ptr(dA), ptr(inp), ptr(scale), ptr(shift), ptr(mi), ptr(sums), float(B * H * W), training,
-                         ptr(dH), ptr(dgamma), ptr(dbeta), B, C, H * W, 1, stream())
+                    if st['bn'] is not None and st['bn']['sync'] and training:
+                        # SyncBN backward: this rank's parameter gradients from ITS sums, the data gradient from the global ones
+                        call('gn_bn_act_bwd_reduce', ptr(dA), ptr(inp), ptr(scale), ptr(shift), ptr(mi), ptr(sums), B, C, H * W, 1, stream())
+                        dbeta.copy_(sums[:C])
+                        dgamma.copy_(sums[C:])
+                        parallel.allreduce_sum_(sums)
+                        call('gn_bn_act_bwd_apply', ptr(dA), ptr(inp), ptr(scale), ptr(shift), ptr(mi), ptr(sums),
+                             float(B * H * W) * parallel.world_size(), training, ptr(dH), None, None, B, C, H * W, 1, stream())
+                    else:
+                        call('gn_bn_act_bwd', ptr(dA), ptr(inp), ptr(scale), ptr(shift), ptr(mi), ptr(sums), float(B * H * W), training,
+                             ptr(dH), ptr(dgamma), ptr(dbeta), B, C, H * W, 1, stream())
                     grad = dH
                 else:
                     grad = dA
@@ -150,13 +168,15 @@ class _CorrectorFn(torch.autograd.Function):
         return (dx, None) + tuple(flat)
 
 
-def run_corrector(stages, x, training):
-    """x: (B, f_dim, H, W) Visium layout -> (B, n_out, H, W)."""
+def run_corrector(stages, x, training, sq_transposed=False):
+    """x: (B, f_dim, H, W) Visium layout -> (B, n_out, H, W).  ``sq_transposed``: Cartesian nn.Conv2d stages act on the
+    TRANSPOSED grid (a hexagonal model hands its corrector the HexagDLy layout, gridnet_models.py:177-185), i.e. with
+    their kernels' two spatial axes swapped."""
     meta, params = [], []
     for (hexm, bn, relu) in stages:
         if isinstance(hexm, nn.Conv2d):
             m = dict(kind='sq', ksize=hexm.kernel_size[0], cin=hexm.in_channels, cout=hexm.out_channels, nk=1, has_bias=hexm.bias is not None,
-                     bn=None, relu=relu)
+                     bn=None, relu=relu, tr=bool(sq_transposed))
             params.append(hexm.weight)
             if hexm.bias is not None:
                 params.append(hexm.bias)
@@ -172,7 +192,7 @@ def run_corrector(stages, x, training):
             if bn_train and bn.momentum is None:
                 raise NotImplementedError('BatchNorm2d(momentum=None) (cumulative average) is not supported')
             m['bn'] = dict(training=bn_train, momentum=float(bn.momentum if bn.momentum is not None else 0.1), eps=float(bn.eps),
-                           running_mean=bn.running_mean, running_var=bn.running_var)
+                           running_mean=bn.running_mean, running_var=bn.running_var, sync=bn_train and parallel.sync_bn_active())
             params.extend([bn.weight, bn.bias])
             if bn_train and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked += 1

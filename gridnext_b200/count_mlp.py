@@ -72,12 +72,26 @@ def _parse(module):
     return stages
 
 
+def tensor_core_mlp_enabled():
+    """GRIDNEXT_B200_MLP_TC=0 keeps a recognised count MLP on the generic fp32 module path (bit-for-bit what the reference's
+    modules compute on the GPU); the default runs it on the bf16 tensor-core GEMMs (2e-2 of the fp32 result, north_star)."""
+    import os
+    return os.environ.get('GRIDNEXT_B200_MLP_TC', '1') != '0'
+
+
 def compile_count_mlp(module):
-    """-> object with ``forward_grid(x, f_dim)`` or None when the module is not the Linear/BN1d(eval)/ReLU pattern."""
-    stages = _parse(module)
-    if stages is None:
+    """-> object with ``forward_grid(x, f_dim)`` or None when the module is not the Linear/BN1d(eval)/ReLU pattern (or the
+    tensor-core MLP path is switched off).  The parse is cached on the module and redone only when its children change."""
+    if not tensor_core_mlp_enabled() or not isinstance(module, nn.Sequential):
         return None
-    return _Compiled(module, stages)
+    key = tuple(id(m) for m in module)
+    cached = module.__dict__.get('_b200_compiled')
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    stages = _parse(module)
+    compiled = None if stages is None else _Compiled(module, stages)
+    module.__dict__['_b200_compiled'] = (key, compiled)
+    return compiled
 
 
 def _cast_bf16(x):

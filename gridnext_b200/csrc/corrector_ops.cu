@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const float* __re
 
 // ------------------------------------------------------------------------------------------------
 // masked cross-entropy over (B, C, H, W) logits and (B, H, W) int64 labels (0 = background)
-// acc[0] = sum of per-spot losses, acc[1] = n_foreground, acc[2] = n_correct   (fp64)
+// acc[0] = sum of per-spot losses, acc[1] = n_foreground, acc[2] = n_correct, acc[3] = labels > C (out of range)   (fp64)
 __global__ void __launch_bounds__(256) ce_count_kernel(const long long* __restrict__ labels, long n, double* __restrict__ acc) {
     int cnt = 0;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) cnt += labels[e] > 0;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) ce_main_kernel(const float* __restrict__ 
     const double nfg = n_fg_ptr[0];
     const float gs = nfg > 0 ? (float)(grad_scale / nfg) : 0.f;
     double loss = 0.0;
-    int correct = 0;
+    int correct = 0, bad = 0;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
         const long b = e / HW, p = e % HW;
         const float* lp = logits + b * C * HW + p;
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256) ce_main_kernel(const float* __restrict__ 
             const int cls = (int)lab - 1;
             const float lse = m + logf(se);
             if (cls < C) loss += (double)(lse - v[cls % CE_MAX_C]);
+            else ++bad;                      // nn.CrossEntropyLoss raises "Target out of bounds"; the host checks acc[3]
             correct += (am == cls);
             if (dlogits) {
                 const float inv = 1.f / se;
@@ -195,9 +196,11 @@ __global__ void __launch_bounds__(256) ce_main_kernel(const float* __restrict__ 
     }
     loss = gn_warp_sum(loss);
     correct = __reduce_add_sync(0xffffffffu, correct);
+    bad = __reduce_add_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0) {
         if (loss != 0.0) atomicAdd(acc + 0, loss);
         if (correct) atomicAdd(acc + 2, (double)correct);
+        if (bad) atomicAdd(acc + 3, (double)bad);
     }
 }
 
@@ -262,6 +265,28 @@ GN_API int gn_bn_act_bwd(const float* dA, const float* h, const float* scale, co
     dim3 grid(C, chunks_for((long)B * HW, C));
     bn_act_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(dA, h, scale, shift, mean_invstd, sums, B, C, HW, relu);
     GN_LAUNCH_CHECK();
+    bn_act_bwd_apply_kernel<<<grid, 256, 0, stream>>>(dA, h, scale, shift, mean_invstd, sums, count, training, dH, dgamma, dbeta, B, C,
+                                                      HW, relu);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+// The two halves of gn_bn_act_bwd as separate calls, so that a data-parallel SyncBN can all-reduce `sums` in between.
+GN_API int gn_bn_act_bwd_reduce(const float* dA, const float* h, const float* scale, const float* shift, const float* mean_invstd,
+                                double* sums /* [2C], zeroed here */, int B, int C, long HW, int relu, cudaStream_t stream) {
+    GN_REQUIRE(dA && h && scale && shift && mean_invstd && sums && B > 0 && C > 0 && HW > 0, GN_EINVAL, "bn_act_bwd_reduce: bad arguments");
+    GN_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), stream));
+    dim3 grid(C, chunks_for((long)B * HW, C));
+    bn_act_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(dA, h, scale, shift, mean_invstd, sums, B, C, HW, relu);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+GN_API int gn_bn_act_bwd_apply(const float* dA, const float* h, const float* scale, const float* shift, const float* mean_invstd,
+                               const double* sums, double count, int training, float* dH, float* dgamma, float* dbeta, int B, int C,
+                               long HW, int relu, cudaStream_t stream) {
+    GN_REQUIRE(dA && h && scale && shift && mean_invstd && sums && dH && B > 0 && C > 0 && HW > 0, GN_EINVAL, "bn_act_bwd_apply: bad arguments");
+    dim3 grid(C, chunks_for((long)B * HW, C));
     bn_act_bwd_apply_kernel<<<grid, 256, 0, stream>>>(dA, h, scale, shift, mean_invstd, sums, count, training, dH, dgamma, dbeta, B, C,
                                                       HW, relu);
     GN_LAUNCH_CHECK();

@@ -130,7 +130,9 @@ class GridNetHex(GridNet):
         """Apply the corrector to a (B, C, H, W) tensor whose hex parity is on the row index."""
         stages = parse_corrector(self.corrector)
         if stages is not None:
-            return run_corrector(stages, grid, self.training)
+            # nn.Conv2d stages of a user corrector (e.g. notebooks/register_concat.ipynb) see the HexagDLy layout in the
+            # reference, i.e. the transposed grid: their kernels are applied with the spatial axes swapped
+            return run_corrector(stages, grid, self.training, sq_transposed=True)
         # user-defined corrector: module by module in HexagDLy layout, like the reference
         return self.corrector(grid.transpose(2, 3).contiguous()).transpose(2, 3)
 

@@ -18,7 +18,7 @@ import copy
 import numpy as np
 import torch
 
-from .losses import masked_cross_entropy, is_plain_cross_entropy
+from .losses import masked_cross_entropy, is_plain_cross_entropy, MAX_FUSED_CLASSES
 from . import parallel
 
 
@@ -100,10 +100,10 @@ def gridwise_step(model, inputs, labels, criterion, accum_iters=1, train=True, n
     outputs = model(inputs)
     assert outputs.shape[2] == labels.shape[1] and outputs.shape[3] == labels.shape[2], \
         "Output tensor does not match label dimensions!"
-    if is_plain_cross_entropy(criterion) and outputs.is_cuda:
+    if is_plain_cross_entropy(criterion) and outputs.is_cuda and outputs.shape[1] <= MAX_FUSED_CLASSES:
         loss, acc = masked_cross_entropy(outputs, labels, accum_iters, n_fg_override)
         extra = None
-    else:   # user-supplied criterion: the reference's generic path
+    else:   # user-supplied criterion (or more classes than the fused kernel holds in registers): the reference's generic path
         o = outputs.permute((0, 2, 3, 1))
         o = torch.reshape(o, (-1, o.shape[-1]))
         l = torch.reshape(labels, (-1,))
@@ -117,8 +117,88 @@ def gridwise_step(model, inputs, labels, criterion, accum_iters=1, train=True, n
     return loss, acc, extra
 
 
+# ---- CUDA-graph replay of the training step (opt-in: GRIDNEXT_B200_GRAPH=1 or use_cuda_graphs(True)) ----------------------------
+_USE_GRAPHS = [os.environ.get('GRIDNEXT_B200_GRAPH', '0') == '1']
+
+
+def use_cuda_graphs(on=True):
+    """Replay the grid-wise training step (forward, masked CE, backward, all-reduce, optimizer step) as ONE captured CUDA graph
+    per batch shape.  The count-only configuration (BASELINE configs[0]) is ~60 short kernels per step and launch-bound when
+    they are issued one by one from Python; a replay issues them back to back.  Needs ``accum_iters == 1``, a plain
+    ``nn.CrossEntropyLoss`` and an optimizer that can be captured (``torch.optim.Adam/AdamW`` are switched to
+    ``capturable=True`` when their state is still empty); anything else runs eagerly as before."""
+    _USE_GRAPHS[0] = bool(on)
+
+
+def _make_capturable(opt):
+    if opt is None:
+        return True
+    if not isinstance(opt, (torch.optim.Adam, torch.optim.AdamW)):
+        return isinstance(opt, torch.optim.SGD)
+    if all(g.get('capturable', False) for g in opt.param_groups):
+        return True
+    if len(opt.state) == 0:
+        for g in opt.param_groups:
+            g['capturable'] = True
+        return True
+    return False
+
+
+class _GraphedStep:
+    """Static input buffers + one CUDA graph per batch signature.  The first batch of a signature runs eagerly (lazy optimizer
+    state, workspace plans); the second is captured; later ones copy into the static buffers and replay."""
+
+    def __init__(self, fn):
+        self.fn, self.seen, self.graphs = fn, {}, {}
+
+    @staticmethod
+    def _sig(inputs, labels):
+        xs = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        return tuple((tuple(x.shape), x.dtype) for x in xs) + ((tuple(labels.shape), labels.dtype),)
+
+    def __call__(self, inputs, labels):
+        sig = self._sig(inputs, labels)
+        entry = self.graphs.get(sig)
+        if entry is None:
+            if sig not in self.seen:
+                self.seen[sig] = True
+                return self.fn(inputs, labels)
+            xs = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+            static_x = [torch.empty_like(x) for x in xs]
+            static_y = torch.empty_like(labels)
+            for a, b in zip(static_x, xs):
+                a.copy_(b)
+            static_y.copy_(labels)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            arg = static_x if isinstance(inputs, (list, tuple)) else static_x[0]
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                self.fn(arg, static_y)
+            self.graphs[sig] = (g, static_x, static_y)
+            g.replay()
+            return None
+        g, static_x, static_y = entry
+        xs = inputs if isinstance(inputs, (list, tuple)) else [inputs]
+        for a, b in zip(static_x, xs):
+            a.copy_(b, non_blocking=True)
+        static_y.copy_(labels, non_blocking=True)
+        g.replay()
+        return None
+
+    def release(self):
+        self.graphs.clear()
+
+
 def train_gridwise(model, dataloaders, criterion, optimizer, num_epochs=10, outfile=None,
                    f_opt=None, accum_iters=1):
+    """Grid-wise training loop (/root/reference/gridnext/training.py:101-209), same signature and return triple.
+
+    Data parallel (``torch.distributed`` initialised, one process per GPU): every rank iterates ITS shard of the arrays
+    (``parallel.shard_indices`` / a DistributedSampler); gradients are summed in one flat all-reduce per optimizer step.  The
+    ranks must see the same number of batches per phase (checked up front; a mismatch raises instead of hanging in NCCL).
+    ``parallel.configure(loss_norm='global')`` divides every rank's loss sum by the GLOBAL foreground count (= the single-process
+    result on the concatenated batch) instead of averaging per-rank means; ``parallel.configure(sync_bn=True)``
+    makes the corrector's BatchNorm2d layers use statistics over all ranks' cells."""
     since = time.time()
     train_history, val_history = [], []
     best_model_wts = copy.deepcopy(model.state_dict())
@@ -129,65 +209,104 @@ def train_gridwise(model, dataloaders, criterion, optimizer, num_epochs=10, outf
     device = torch.device("cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cpu")
     model.to(device)
     bucket = parallel.GradBucket([p for p in model.parameters() if p.requires_grad]) if dist_on else None
+    global_norm = dist_on and parallel.config().loss_norm == 'global'
+    fused_ce = is_plain_cross_entropy(criterion) and device.type == 'cuda'
 
     def say(*a):
         if rank0:
             print(*a, flush=True)
 
-    for epoch in range(num_epochs):
-        say('Epoch {}/{}'.format(epoch, num_epochs - 1))
-        say('-' * 10)
-        for phase in ['train', 'val']:
-            model.train() if phase == 'train' else model.eval()
-            model.patch_classifier.eval()      # training.py:126 -- f's BN/dropout frozen
+    run = torch.zeros(4, device=device, dtype=torch.float64)   # loss*batch, corrects, foreground, labels out of range
 
-            run = torch.zeros(3, device=device, dtype=torch.float64)   # loss*batch, corrects, foreground
-            n_seen = 0
-            for batch_ind, (inputs, labels) in enumerate(dataloaders[phase]):
-                batch_size = labels.size(0)
-                n_seen += batch_size
-                inputs = _to_device(inputs, device)
-                labels = labels.to(device, non_blocking=True)
-                with torch.set_grad_enabled(phase == 'train'):
-                    loss, acc, extra = gridwise_step(model, inputs, labels, criterion, accum_iters, phase == 'train')
-                    if phase == 'train' and batch_ind % accum_iters == 0:
-                        if bucket is not None:
-                            bucket.allreduce_mean()
-                        optimizer.step()
-                        optimizer.zero_grad()
-                        if f_opt is not None:
-                            f_opt.step()
-                            f_opt.zero_grad()
-                run[0] += loss.detach().double() * batch_size
-                if acc is not None:
-                    run[1] += acc[2]
-                    run[2] += acc[1]
-                else:
-                    run[1] += extra[0]
-                    run[2] += extra[1]
-            n_total = len(dataloaders[phase].dataset)
-            if dist_on:
-                cnt = torch.tensor([float(n_seen)], device=device, dtype=torch.float64)
-                parallel.allreduce_sum_(run)
-                parallel.allreduce_sum_(cnt)
-                n_total = int(cnt.item())
-            r = run.tolist()                       # the one host sync of the phase
-            epoch_loss = r[0] / max(n_total, 1)
-            epoch_acc = r[1] / r[2] if r[2] > 0 else float('nan')
-            say('{} Loss: {:.4f} Acc: {:.4f}'.format(phase, epoch_loss, epoch_acc))
-
-            if phase == 'val' and epoch_loss < best_loss:
-                best_loss = epoch_loss
-                best_model_wts = copy.deepcopy(model.state_dict())
-                if outfile is not None and rank0:
-                    torch.save(model.state_dict(), outfile)
-                    if f_opt is not None:
-                        torch.save({'g_opt': optimizer.state_dict(), 'f_opt': f_opt.state_dict()},
-                                   os.path.splitext(outfile)[0] + ".opt")
+    def one_batch(inputs, labels, phase, step_now):
+        batch_size = labels.size(0)
+        nfg = None
+        if global_norm and fused_ce:
+            nfg = (labels > 0).sum().double().reshape(1)
+            parallel.allreduce_sum_(nfg)
+        with torch.set_grad_enabled(phase == 'train'):
+            loss, acc, extra = gridwise_step(model, inputs, labels, criterion, accum_iters, phase == 'train', nfg)
+            if phase == 'train' and step_now:
+                if bucket is not None:
+                    if global_norm and fused_ce:
+                        bucket.allreduce_sum()          # every rank's loss is already divided by the global count
                     else:
-                        torch.save(optimizer.state_dict(), os.path.splitext(outfile)[0] + ".opt")
-            (val_history if phase == 'val' else train_history).append(epoch_loss)
-        say()
+                        bucket.allreduce_mean()
+                # with a gradient bucket the .grad tensors are views of it: zero them in place so that the next backward
+                # accumulates straight into the bucket (no per-parameter copy before the all-reduce)
+                optimizer.step()
+                optimizer.zero_grad(set_to_none=bucket is None)
+                if f_opt is not None:
+                    f_opt.step()
+                    f_opt.zero_grad(set_to_none=bucket is None)
+        run[0] += loss.detach().double() * batch_size
+        if acc is not None:
+            run[1] += acc[2]
+            run[2] += acc[1]
+            run[3] += acc[3]
+        else:
+            run[1] += extra[0]
+            run[2] += extra[1]
+
+    graphed = None
+    if (_USE_GRAPHS[0] and device.type == 'cuda' and accum_iters == 1 and fused_ce
+            and _make_capturable(optimizer) and _make_capturable(f_opt)):
+        graphed = _GraphedStep(lambda x, y: one_batch(x, y, 'train', True))
+
+    try:
+        for epoch in range(num_epochs):
+            say('Epoch {}/{}'.format(epoch, num_epochs - 1))
+            say('-' * 10)
+            for phase in ['train', 'val']:
+                model.train() if phase == 'train' else model.eval()
+                model.patch_classifier.eval()      # training.py:126 -- f's BN/dropout frozen
+                if dist_on:
+                    parallel.check_equal_across_ranks(len(dataloaders[phase]), "number of %s batches" % phase)
+                run.zero_()
+                n_seen = 0
+                for batch_ind, (inputs, labels) in enumerate(dataloaders[phase]):
+                    n_seen += labels.size(0)
+                    inputs = _to_device(inputs, device)
+                    labels = labels.to(device, non_blocking=True)
+                    if graphed is not None and phase == 'train':
+                        graphed(inputs, labels)
+                    else:
+                        one_batch(inputs, labels, phase, batch_ind % accum_iters == 0)
+                n_total = len(dataloaders[phase].dataset)
+                if dist_on:
+                    cnt = torch.tensor([float(n_seen)], device=device, dtype=torch.float64)
+                    tot = run.clone()
+                    parallel.allreduce_sum_(tot)
+                    parallel.allreduce_sum_(cnt)
+                    n_total = int(cnt.item())
+                    r = tot.tolist()
+                    if global_norm and fused_ce:
+                        # each rank's loss is (its loss sum / global fg count): the batch loss is their sum over ranks
+                        n_total = max(n_total // parallel.world_size(), 1)
+                else:
+                    r = run.tolist()                       # the one host sync of the phase
+                if r[3] > 0:
+                    raise IndexError("Target out of bounds: %d labels exceed the %d classes of the model output" % (int(r[3]), model.n_classes))
+                epoch_loss = r[0] / max(n_total, 1)
+                epoch_acc = r[1] / r[2] if r[2] > 0 else float('nan')
+                say('{} Loss: {:.4f} Acc: {:.4f}'.format(phase, epoch_loss, epoch_acc))
+
+                if phase == 'val' and epoch_loss < best_loss:
+                    best_loss = epoch_loss
+                    best_model_wts = copy.deepcopy(model.state_dict())
+                    if outfile is not None and rank0:
+                        torch.save(model.state_dict(), outfile)
+                        if f_opt is not None:
+                            torch.save({'g_opt': optimizer.state_dict(), 'f_opt': f_opt.state_dict()},
+                                       os.path.splitext(outfile)[0] + ".opt")
+                        else:
+                            torch.save(optimizer.state_dict(), os.path.splitext(outfile)[0] + ".opt")
+                (val_history if phase == 'val' else train_history).append(epoch_loss)
+            say()
+    finally:
+        if graphed is not None:
+            torch.cuda.synchronize()
+            graphed.release()          # graphs (and the NCCL work captured in them) go before the process group does
 
     time_elapsed = time.time() - since
     say('Training complete in {:.0f}m {:.0f}s'.format(time_elapsed // 60, time_elapsed % 60))

@@ -68,9 +68,16 @@ int gn_bn_act_fwd(const float* x, const float* scale, const float* shift, float*
 int gn_bn_act_bwd(const float* dA, const float* h, const float* scale, const float* shift, const float* mean_invstd,
                   double* sums, double count, int training, float* dH, float* dgamma, float* dbeta, int B, int C, long HW,
                   int relu, gn_stream_t stream);
+/* The same in two calls (sum reduction, then apply) so that a data-parallel SyncBN can all-reduce `sums` in between
+ * (the reference is single-device, gridnext/training.py:21,111). */
+int gn_bn_act_bwd_reduce(const float* dA, const float* h, const float* scale, const float* shift, const float* mean_invstd,
+                         double* sums, int B, int C, long HW, int relu, gn_stream_t stream);
+int gn_bn_act_bwd_apply(const float* dA, const float* h, const float* scale, const float* shift, const float* mean_invstd,
+                        const double* sums, double count, int training, float* dH, float* dgamma, float* dbeta, int B, int C,
+                        long HW, int relu, gn_stream_t stream);
 
 /* ---- foreground-masked cross-entropy: replaces gridnext/training.py:152-160 (+ its backward).
- * acc fp64[4]: {sum of spot losses, n_foreground, n_correct, -}; loss_out[0] = mean * loss_scale;
+ * acc fp64[4]: {sum of spot losses, n_foreground, n_correct, n labels > C}; loss_out[0] = mean * loss_scale;
  * dlogits (nullable) = d(loss_out)/d(logits).  n_fg_override (nullable, device fp64[1]) replaces the
  * local foreground count as the normaliser (global count under data parallelism). */
 int gn_masked_ce(const float* logits, const long long* labels, float* dlogits, double* acc, float* loss_out,

@@ -87,3 +87,80 @@ def test_bucket_single_process_is_a_no_op_collective():
     before = b.flat.clone()
     b.allreduce_mean()
     assert torch.equal(before, b.flat) and not parallel.is_distributed()
+
+
+# ---- round 2: rank-count agreement, parameters without gradients, train_gridwise under two ranks ---------------------------
+class _ToyGrid(nn.Module):
+    """A GridNet-shaped toy: patch_classifier attribute, (B, C, H, W) -> (B, C, H, W), one parameter that never gets a gradient."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(5)
+        self.patch_classifier = nn.Identity()
+        self.n_classes = 3
+        self.mix = nn.Conv2d(3, 3, 1)
+        self.unused = nn.Parameter(torch.ones(2))
+
+    def forward(self, x):
+        return self.mix(x)
+
+
+def _toy_data(n):
+    g = torch.Generator(); g.manual_seed(11)
+    return torch.utils.data.TensorDataset(torch.randn(n, 3, 4, 5, generator=g), torch.randint(0, 4, (n, 4, 5), generator=g))
+
+
+def _train_worker(rank, world, port, out, n_arrays):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from gridnext_b200.training import train_gridwise
+        ds = _toy_data(n_arrays)
+        mine = torch.utils.data.Subset(ds, parallel.shard_indices(len(ds)))
+        dls = {'train': torch.utils.data.DataLoader(mine, batch_size=1), 'val': torch.utils.data.DataLoader(mine, batch_size=1)}
+        model = _ToyGrid()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-2, weight_decay=0.1)
+        try:
+            model, vh, th = train_gridwise(model, dls, nn.CrossEntropyLoss(), opt, num_epochs=2)
+            out.put((rank, 'ok', [p.detach().numpy().copy() for p in model.parameters()], vh, th))
+        except RuntimeError as exc:
+            out.put((rank, 'error', str(exc), None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(target, world, *args):
+    port = _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=target, args=(r, world, port, q) + args) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+def test_train_gridwise_two_ranks_same_weights_and_untouched_dead_parameter():
+    """Both ranks end with identical weights (one all-reduce per step), histories agree, and the parameter that receives no
+    gradient on any rank is NOT stepped (Adam with weight decay would move it if the bucket handed it a zero gradient)."""
+    res = _spawn(_train_worker, 2, 4)
+    assert all(r[1] == 'ok' for r in res), res
+    (_, _, p0, vh0, th0), (_, _, p1, vh1, th1) = res
+    import numpy as np
+    for a, b in zip(p0, p1):
+        assert np.array_equal(a, b)
+    assert vh0 == vh1 and th0 == th1 and len(vh0) == 2
+    ref = _ToyGrid()
+    names = [n for n, _ in ref.named_parameters()]
+    got = dict(zip(names, p0))
+    assert np.array_equal(got['unused'], ref.unused.detach().numpy())              # untouched
+    assert not np.array_equal(got['mix.weight'], ref.mix.weight.detach().numpy())   # trained
+
+
+def test_train_gridwise_unequal_batch_counts_fail_loudly():
+    """5 arrays over 2 ranks = 3 vs 2 batches: every rank raises before the first collective instead of hanging."""
+    res = _spawn(_train_worker, 2, 5)
+    assert all(r[1] == 'error' and 'disagree' in r[2] for r in res), res
