@@ -103,9 +103,18 @@ class GradBucket:
             off += p.numel()
         self.live = None          # per parameter: did ANY rank produce a gradient for it (decided at the first all-reduce)
         self._touched = [False] * len(self.params)
-        for i, p in enumerate(self.params):
-            p.register_post_accumulate_grad_hook(lambda _p, i=i: self._touched.__setitem__(i, True))
+        self._hooks = [p.register_post_accumulate_grad_hook(lambda _p, i=i: self._touched.__setitem__(i, True))
+                       for i, p in enumerate(self.params)]
         self.attach()
+
+    def close(self):
+        """Detach from the parameters: remove the hooks and give every parameter a gradient tensor of its own again."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        for p, v in zip(self.params, self.views):
+            if p.grad is not None and p.grad.data_ptr() == v.data_ptr():
+                p.grad = v.clone()
 
     def attach(self):
         """(Re)point every ``p.grad`` at its bucket slice, keeping any gradient already accumulated.  A parameter without a

@@ -307,6 +307,8 @@ def train_gridwise(model, dataloaders, criterion, optimizer, num_epochs=10, outf
         if graphed is not None:
             torch.cuda.synchronize()
             graphed.release()          # graphs (and the NCCL work captured in them) go before the process group does
+        if bucket is not None:
+            bucket.close()
 
     time_elapsed = time.time() - since
     say('Training complete in {:.0f}m {:.0f}s'.format(time_elapsed // 60, time_elapsed % 60))

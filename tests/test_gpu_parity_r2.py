@@ -409,3 +409,29 @@ def test_masked_ce_wide_outputs_and_bad_labels():
     t = Tiny()
     with pytest.raises(IndexError):
         train_gridwise(t, dls, nn.CrossEntropyLoss(), torch.optim.SGD(t.parameters(), lr=0.1), num_epochs=1)
+
+
+def test_fused_adam_equals_foreach_adam_after_three_steps():
+    """bench.py steps with torch.optim.Adam(fused=True, capturable=True) (3 launches instead of ~750): same parameters and
+    optimizer state as the for-each form the reference's notebooks get by default, to 1e-6, on the count GridNet's parameters."""
+    from gridnext_b200.gridnet_models import GridNetHexOddr
+    torch.manual_seed(0)
+    nets = [GridNetHexOddr(tutorial_mlp(40, 7), (40,), (78, 64), 7).cuda() for _ in range(2)]
+    nets[1].load_state_dict(nets[0].state_dict())
+    opts = [torch.optim.Adam(nets[0].parameters(), lr=1e-3, capturable=True, fused=True),
+            torch.optim.Adam(nets[1].parameters(), lr=1e-3, capturable=True, foreach=True)]
+    g = torch.Generator(device='cuda'); g.manual_seed(1)
+    for step in range(3):
+        grads = [torch.randn(p.shape, device='cuda', generator=g) for p in nets[0].parameters()]
+        for net, opt in zip(nets, opts):
+            for p, gr in zip(net.parameters(), grads):
+                p.grad = gr.clone()
+            opt.step()
+    worst = 0.0
+    for (k, a), (_, b) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
+        worst = max(worst, relmax(a, b))
+    for pa, pb in zip(nets[0].parameters(), nets[1].parameters()):
+        sa, sb = opts[0].state[pa], opts[1].state[pb]
+        worst = max(worst, relmax(sa['exp_avg'], sb['exp_avg']), relmax(sa['exp_avg_sq'], sb['exp_avg_sq']))
+    report(test='fused_adam_vs_foreach', worst_rel=worst)
+    assert worst < 1e-6, worst

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""One launch of each DenseNet tensor-core kernel at the block-1 and block-3 shapes of DenseNet-121 @128 px (quarter array:
+1,248 spots), for `ncu --set full` captures (development tool).  Every kernel is launched twice: ncu captures all, the summary
+quotes the second (warm instruction cache / TMA descriptors)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gridnext_b200 import tc
+
+NSP = int(os.environ.get('KB_SPOTS', '1248'))
+dev, bf = 'cuda', torch.bfloat16
+for H, cin, ct in ((32, 160, 256), (8, 640, 1024)):
+    M = NSP * H * H
+    C = (torch.randn(M, ct, device=dev) * 0.5).to(bf)
+    a2 = torch.relu(torch.randn(M, 128, device=dev)).to(bf)
+    dC = (torch.randn(M, ct, device=dev) * 0.1).to(bf)
+    dz = (torch.randn(M, 128, device=dev) * 0.1).to(bf)
+    w1 = (torch.randn(128, cin, device=dev) * 0.05).to(bf)
+    w1t = w1.t().contiguous()
+    sc, sh = torch.rand(cin, device=dev) + 0.5, torch.randn(cin, device=dev) * 0.1
+    s2, t2 = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.1
+    colsum = torch.zeros(2, cin, device=dev)
+    colsum2 = torch.zeros(2, 128, device=dev)
+    w2 = torch.randn(32, 128, 3, 3, device=dev) * 0.03
+    wp, wpt = tc.conv3x3_pack(w2, 0), tc.conv3x3_pack(w2, 1)
+    dw = torch.zeros(128, cin, device=dev)
+    dwp = torch.zeros(9, 128, 32, device=dev)
+    for _ in range(2):
+        tc.gemm_bf16(C[:, :cin], w1, out=a2, scale=s2, shift=t2, relu=True, xf_scale=sc, xf_shift=sh)
+        tc.gemm_bf16(dz, w1t, out=dC[:, :cin], bn=dict(ref=C[:, :cin], ref_is_raw=True, sc=sc, sh=sh, p0=sh, p1=sc, colsum=colsum, rmw=True))
+        tc.gemm_tn_bf16(dz, C[:, :cin], dw, sc, sh)
+        tc.conv3x3_bf16(a2, NSP, H, H, 128, wp, 32, C[:, cin:cin + 32])
+        tc.conv3x3_bf16(dC[:, cin:cin + 32], NSP, H, H, 32, wpt, 128, dz, bn=dict(ref=a2, ref_is_raw=False, sc=s2, sh=None, p0=s2, p1=s2, colsum=colsum2))
+        tc.conv3x3_wgrad_into(a2, dC[:, cin:cin + 32], NSP, H, H, 128, 32, dwp)
+    torch.cuda.synchronize()
+    del C, a2, dC, dz
+print('ok')
