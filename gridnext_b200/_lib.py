@@ -46,6 +46,7 @@ _SIGS = {
     'gn_masked_ce': [vp, vp, vp, vp, vp, vp, cf, ci, ci, cl, vp],
     'gn_spot_table': [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp],
     'gn_patch_gather': [vp, cl, ci, ci, vp, ci, ci, vp, vp, vp, ci, vp],
+    'gn_patch_gather_resize': [vp, cl, ci, ci, vp, ci, ci, ci, vp, vp, ci, ci, vp, vp, vp, ci, vp],
     'gn_normalize_u8': [vp, vp, cl, ci, vp, vp, vp, ci, vp],
     'gn_cast_f32_bf16': [vp, vp, cl, vp],
     'gn_rows_affine_bf16': [vp, cl, vp, vp, ci, vp, cl, cl, ci, ci, vp],

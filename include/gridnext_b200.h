@@ -86,6 +86,13 @@ int gn_masked_ce(const float* logits, const long long* labels, float* dlogits, d
 /* ---- spot-patch gather: replaces gridnext/imgprocess.py:185-238 (grid_from_wsi_visium) */
 int gn_spot_table(const unsigned char* in_tissue, const int* array_row, const int* array_col, const double* pxl_row,
                   const double* pxl_col, int n_spots, int h_st, int w_st, int* cells, int* n_dropped, gn_stream_t stream);
+/* window_size != patch_size (gridnext/imgprocess.py:188-195,221: Image.fromarray(patch).resize((P, P)), Pillow BICUBIC):
+ * the ws x ws window (ws even, edge-clamped) around every spot is resampled to P x P in Pillow's 8-bit fixed-point arithmetic
+ * (22 fractional bits, horizontal then vertical pass, uint8 intermediate) -- bit-exact.  bounds [P][2] = (first tap, count),
+ * kk [P][ksize] int32 coefficients, max_span = the largest tap count: the host builds them like Resample.c precompute_coeffs. */
+int gn_patch_gather_resize(const unsigned char* img, long pitch, int H, int W, const int* cells, int n_cells, int ws, int P,
+                           const int* bounds, const int* kk, int ksize, int max_span, const float* mean, const float* stdv,
+                           void* out, int out_bf16, gn_stream_t stream);
 /* ToTensor + Normalize of a pre-cropped uint8 patch grid (cells, 3, P, P); valid (nullable) marks present cells */
 int gn_normalize_u8(const unsigned char* in, const unsigned char* valid, long n_cells, int P, const float* mean, const float* stdv,
                     void* out, int out_bf16, gn_stream_t stream);

@@ -14,11 +14,80 @@ index helper pseudo_hex_to_oddr (imgprocess.py:26-32 == utils.py:64-70):
   * cells with y_ind >= 78 or x_ind > 64 are skipped (x_ind == 64 raises IndexError upstream)
   * out-of-tissue cells stay exactly 0.0                                (:206)
 
-Only the pure-crop case (2*(w//2) == patch_size) is restated: that is the configuration the
-benchmark uses (P = w = 128) and the only one a GPU kernel can reproduce bit-exactly without
-re-implementing Pillow's fixed-point bicubic resampler.
+When the window side 2*(w//2) differs from patch_size the reference resizes with ``Image.fromarray(patch).resize((P, P))``
+(:221), i.e. Pillow's default BICUBIC.  Pillow (pinned by the installed wheel, 12.2.0; src/libImaging/Resample.c) resamples
+8-bit images in fixed point -- per-axis taps [xmin, xmin+n) around (xx+0.5)*in/out with support 2*max(in/out, 1), bicubic
+(a = -0.5) weights normalised in double and rounded to 22 fractional bits, a horizontal pass into a uint8 intermediate
+(clip8((2^21 + sum) >> 22)) and then a vertical pass -- restated here in numpy (``pillow_resize``) and pinned against the real
+``PIL.Image.resize`` in tests/test_oracle_golden.py and against reference-generated vectors (p2_gather_resize).
 """
 import numpy as np
+
+PRECISION_BITS = 32 - 8 - 2
+
+
+def _bicubic(x):
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pillow_coeffs(in_size, out_size):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the BICUBIC filter over the whole axis.
+    -> bounds (out, 2) int64 [first tap, tap count], integer coefficients (out, ksize)."""
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int64)
+    kk = np.zeros((out_size, ksize), np.float64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        ww = 0.0
+        for x in range(xmax):
+            w = _bicubic((x + xmin - center + 0.5) * ss)
+            kk[xx, x] = w
+            ww += w
+        if ww != 0.0:
+            kk[xx, :xmax] /= ww
+        bounds[xx] = (xmin, xmax)
+    ik = np.trunc(np.where(kk < 0, -0.5 + kk * (1 << PRECISION_BITS), 0.5 + kk * (1 << PRECISION_BITS))).astype(np.int64)
+    return bounds, ik
+
+
+def _clip8(v):
+    return np.clip(v >> PRECISION_BITS, 0, 255).astype(np.uint8)
+
+
+def pillow_resize(img, P):
+    """(h, w, c) uint8 -> (P, P, c) uint8, equal to np.array(Image.fromarray(img).resize((P, P))) (BICUBIC)."""
+    h, w, c = img.shape
+    if (h, w) == (P, P):
+        return img.copy()
+    tmp = img
+    if w != P:
+        bh, kh = pillow_coeffs(w, P)
+        tmp = np.zeros((h, P, c), np.uint8)
+        for xx in range(P):
+            xmin, n = bh[xx]
+            acc = (1 << (PRECISION_BITS - 1)) + (img[:, xmin:xmin + n, :].astype(np.int64) * kh[xx, :n][None, :, None]).sum(1)
+            tmp[:, xx, :] = _clip8(acc)
+    if h == P:
+        return tmp
+    bv, kv = pillow_coeffs(h, P)
+    out = np.zeros((P, P, c), np.uint8)
+    for yy in range(P):
+        ymin, n = bv[yy]
+        acc = (1 << (PRECISION_BITS - 1)) + (tmp[ymin:ymin + n].astype(np.int64) * kv[yy, :n][:, None, None]).sum(0)
+        out[yy] = _clip8(acc)
+    return out
 
 VISIUM_H_ST = 78
 VISIUM_W_ST = 64
@@ -57,13 +126,13 @@ def grid_from_image(img, in_tissue, array_row, array_col, pxl_row, pxl_col,
     else:
         raise ValueError("Window size must be a float or int")
     hw = w // 2
-    if 2 * hw != patch_size:
-        raise NotImplementedError("oracle restates the pure-crop case only")
     out = np.zeros((h_st, w_st, 3, patch_size, patch_size), dtype=np.float32)
     for x_ind, y_ind, x_px, y_px in spot_table(in_tissue, array_row, array_col, pxl_row, pxl_col):
         ys = np.clip(np.arange(y_px - hw, y_px + hw), 0, ydim - 1)   # edge padding == clamp
         xs = np.clip(np.arange(x_px - hw, x_px + hw), 0, xdim - 1)
-        patch = img[ys][:, xs]                                        # (P, P, 3) u8
+        patch = img[ys][:, xs]                                        # (2*hw, 2*hw, 3) u8
+        if 2 * hw != patch_size:
+            patch = pillow_resize(patch, patch_size)
         patch = np.transpose(patch, (2, 0, 1))
         if y_ind >= h_st or x_ind >= w_st:
             continue

@@ -310,8 +310,53 @@ def extras(manifest, mods):
         KEYS.update(old)
 
 
+def extras2(manifest, mods):
+    """Round-2 vectors: grid_from_wsi_visium with window_size != patch_size (Pillow BICUBIC resize inside the reference loop,
+    imgprocess.py:188-195,221), a float window, and a non-Normalize transform."""
+    from oracle import synth
+    gm, dn, tr, ip = mods
+    from PIL import Image
+    from torchvision import transforms
+    tis, rows, cols, pr, pc = synth.synth_positions(pitch_col=5.5, pitch_row=9.6, org_row=3.0, org_col=2.0)
+    Himg, Wimg = 790, 730
+    img = synth.synth_image(Himg, Wimg, seed=7, smooth=True)
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        Image.fromarray(img).save(os.path.join(td, 'img.png'))
+        sp = os.path.join(td, 'outs', 'spatial'); os.makedirs(sp)
+        with open(os.path.join(sp, 'tissue_positions.csv'), 'w') as fh:
+            fh.write('barcode,in_tissue,array_row,array_col,pxl_row_in_fullres,pxl_col_in_fullres\n')
+            for i in range(len(tis)):
+                fh.write('BC%05d-1,%d,%d,%d,%r,%r\n' % (i, tis[i], rows[i], cols[i], float(pr[i]), float(pc[i])))
+        f, d = os.path.join(td, 'img.png'), os.path.join(td, 'outs')
+        out['down_24_to_16'] = ip.grid_from_wsi_visium(f, d, patch_size=16, window_size=24).numpy().astype(np.uint8)
+        out['up_10_to_16'] = ip.grid_from_wsi_visium(f, d, patch_size=16, window_size=10).numpy().astype(np.uint8)
+        out['float_0.03_to_12'] = ip.grid_from_wsi_visium(f, d, patch_size=12, window_size=0.03).numpy().astype(np.uint8)     # int(0.03 * 730) = 21 -> side 20
+        nrm = ip.grid_from_wsi_visium(f, d, patch_size=16, window_size=24,
+                                      preprocess_xform=transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225]))
+        out['down_24_to_16_nrm_sub'] = nrm.numpy()[::11, ::9]
+        gray = ip.grid_from_wsi_visium(f, d, patch_size=16, window_size=16,
+                                       preprocess_xform=transforms.Compose([transforms.Grayscale(num_output_channels=3), transforms.Normalize([0.5] * 3, [0.25] * 3)]))
+        out['crop_16_gray_nrm_sub'] = gray.numpy()[::11, ::9]
+    # keep the fixture small: every 4th grid row / column plus the cells next to all four borders
+    ys = sorted(set(range(0, 78, 4)) | {1, 76, 77})
+    xs = sorted(set(range(0, 64, 4)) | {1, 62, 63})
+    for k in list(out):
+        if not k.endswith('_sub'):
+            out[k] = out[k][np.ix_(ys, xs)]
+    out['cells_y'], out['cells_x'] = np.asarray(ys), np.asarray(xs)
+    np.savez_compressed(os.path.join(OUT, 'p2_gather_resize.npz'), **out)
+    manifest['p2_gather_resize'] = dict(Himg=Himg, Wimg=Wimg, pitch_col=5.5, pitch_row=9.6, org_row=3.0, org_col=2.0, img_seed=7,
+                                        cases=sorted(k for k in out if not k.startswith('cells_')), pillow=Image.__version__ if hasattr(Image, '__version__') else None)
+
+
 if __name__ == '__main__':
-    if '--extras' in sys.argv:
+    if '--extras2' in sys.argv:
+        man = json.load(open(os.path.join(OUT, 'manifest.json')))
+        extras2(man, import_reference())
+        with open(os.path.join(OUT, 'manifest.json'), 'w') as fh:
+            json.dump(man, fh, indent=1, sort_keys=True)
+    elif '--extras' in sys.argv:
         man = json.load(open(os.path.join(OUT, 'manifest.json')))
         torch.set_num_threads(os.cpu_count())
         extras(man, import_reference())

@@ -287,3 +287,37 @@ def test_patch_grid_oracle_matches_reference_dataset(golden):
     grid, annots = D.patch_grid(patches, coords, adict)
     assert np.array_equal(annots, gold['annots_grid'])
     assert grid.shape == gold['patch_grid'].shape and np.array_equal(grid, gold['patch_grid'])
+
+
+# ---- round 2: window_size != patch_size (Pillow BICUBIC resize inside the reference's gather loop) ---------------------------
+def test_pillow_resize_restatement_equals_pil():
+    """oracle.gather_ref.pillow_resize == PIL.Image.resize (default BICUBIC for RGB), bit for bit, up- and down-scaling."""
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    for w, P in [(256, 224), (64, 32), (100, 128), (128, 64), (30, 48), (48, 30), (254, 256), (20, 224), (24, 16), (10, 16)]:
+        img = rng.integers(0, 256, (w, w, 3), dtype=np.uint8)
+        assert np.array_equal(gather_ref.pillow_resize(img, P), np.array(Image.fromarray(img).resize((P, P)))), (w, P)
+
+
+def test_product_resize_table_equals_oracle_table():
+    """gridnext_b200.imgprocess.pillow_bicubic_table (what the CUDA kernel consumes) == the oracle's restatement."""
+    from gridnext_b200.imgprocess import pillow_bicubic_table
+    for w, P in [(256, 224), (24, 16), (10, 16), (20, 12), (512, 224), (300, 299)]:
+        b, k, ksize, span = pillow_bicubic_table(w, P)
+        bo, ko = gather_ref.pillow_coeffs(w, P)
+        assert np.array_equal(b, bo) and np.array_equal(k, ko) and ksize == ko.shape[1] and span == int(bo[:, 1].max())
+
+
+def test_gather_with_resize_matches_reference(golden):
+    """grid_from_wsi_visium with window_size 24 / 10 / 0.03 (float) and patch sizes 16 / 16 / 12: the oracle against vectors
+    produced by the reference function itself (oracle/make_golden.py --extras2)."""
+    m = MAN['p2_gather_resize']
+    gold = golden('p2_gather_resize')
+    tis, rows, cols, pr, pc = synth.synth_positions(pitch_col=m['pitch_col'], pitch_row=m['pitch_row'], org_row=m['org_row'], org_col=m['org_col'])
+    img = synth.synth_image(m['Himg'], m['Wimg'], seed=m['img_seed'], smooth=True)
+    sel = np.ix_(gold['cells_y'], gold['cells_x'])
+    for key, P, w in (('down_24_to_16', 16, 24), ('up_10_to_16', 16, 10), ('float_0.03_to_12', 12, 0.03)):
+        got = gather_ref.grid_from_image(img, tis, rows, cols, pr, pc, patch_size=P, window_size=w)
+        assert np.array_equal(got[sel], gold[key].astype(np.float32)), key
+    nrm = gather_ref.grid_from_image(img, tis, rows, cols, pr, pc, patch_size=16, window_size=24, mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+    assert np.array_equal(nrm[::11, ::9], gold['down_24_to_16_nrm_sub'])
