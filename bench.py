@@ -28,7 +28,6 @@ Legs of the B200 arm:
   --impl reference   times only the CPU arm, K steps after W warm-ups, same metric/config.
 """
 import argparse
-import copy
 import json
 import os
 import subprocess
@@ -447,9 +446,11 @@ def main():
         # GPU and not the Python/ctypes launch overhead of the host loop.
         try:
             torch.cuda.synchronize()
+            torch.cuda.empty_cache()          # the eager warm-up's cached blocks would otherwise sit beside the graph's private pool
+            pool = torch.cuda.graph_pool_handle()     # all graphs of this process replay one at a time: they share one memory pool
             for slot in range(wl.n_slots()):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                with torch.cuda.graph(g, pool=pool, capture_error_mode='thread_local'):
                     wl.step_resident(slot)
                 g.replay()
                 graphs.append(g)
@@ -515,14 +516,18 @@ def main():
         prefetch(cur ^ 1)
         return float(e2e_loss[0].item())          # D2H read of the step's result
 
-    step_e2e(); step_e2e()
+    if not graphed:
+        step_e2e(); step_e2e()
     if graphed:
         try:
+            torch.cuda.synchronize()
+            wl.d_labels.copy_(wl.h_labels)
+            wl.copy_in(0); wl.copy_in(1)      # both halves of the double buffer hold real inputs while the graphs are captured (and replayed once)
             torch.cuda.synchronize()
             for half in ((0, 1) if in_place else (0,)):
                 cur_inputs[0] = wl.e2e_inputs(half)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                with torch.cuda.graph(g, pool=pool, capture_error_mode='thread_local'):
                     e2e_train_part()
                 g.replay()
                 e2e_graphs[half] = g
@@ -556,7 +561,12 @@ def main():
         if cfg == 'c2' and not args.no_eager_baseline:
             try:
                 from tools import eager_baseline
-                m2 = copy.deepcopy(wl.model)
+                from gridnext_b200.densenet import DenseNet
+                from gridnext_b200.gridnet_models import GridNetHexOddr
+                m2 = GridNetHexOddr(DenseNet(num_classes=N_CLS, small_inputs=False, efficient=False, drop_rate=0, **DENSENET_KW), (3, P, P), (H_ST, W_ST), N_CLS)
+                m2.load_state_dict(wl.model.state_dict())
+                m2.to(dev)
+                m2.train(); m2.patch_classifier.eval()
                 eager = eager_baseline.run(m2, wl.patches.view(-1, 3, P, P), wl.labels)
                 eager['what'] = ('reference module graph (DenseNet-121 f eval, torch.cat concat; hex g as dense 3x3 pairs; masked CE) under PyTorch '
                                  'eager on this GPU, f fwd+bwd in 256-spot chunks without recompute, no optimizer step')

@@ -43,6 +43,9 @@ _SIGS = {
     'gn_bn_act_bwd': [vp, vp, vp, vp, vp, vp, cd, ci, vp, vp, vp, ci, ci, cl, ci, vp],
     'gn_bn_act_bwd_reduce': [vp, vp, vp, vp, vp, vp, ci, ci, cl, ci, vp],
     'gn_bn_act_bwd_apply': [vp, vp, vp, vp, vp, vp, cd, ci, vp, vp, vp, ci, ci, cl, ci, vp],
+    'gn_corrector_fused_supported': [ci, vp, vp],
+    'gn_corrector_fused_fwd': [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp],
+    'gn_corrector_fused_bwd': [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp],
     'gn_masked_ce': [vp, vp, vp, vp, vp, vp, cf, ci, ci, cl, vp],
     'gn_spot_table': [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp],
     'gn_patch_gather': [vp, cl, ci, ci, vp, ci, ci, vp, vp, vp, ci, vp],
@@ -127,7 +130,7 @@ def check(rc, what=''):
 
 
 # kernels launched per C-ABI call (for the benchmark's gpu_launches count); default 1
-KERNELS_PER_CALL = {'gn_cell_inverse': 2, 'gn_mm_fg_consistency': 2, 'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0, 'gn_prep_job_bytes': 0,
+KERNELS_PER_CALL = {'gn_corrector_fused_supported': 0, 'gn_cell_inverse': 2, 'gn_mm_fg_consistency': 2, 'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0, 'gn_prep_job_bytes': 0,
                     'gn_device_sm_count': 0, 'gn_hexconv_n_taps': 0}
 LAUNCHES = [0]
 PROFILE = None      # when a dict: name -> [n_calls, [cuda event pairs]]

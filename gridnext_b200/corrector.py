@@ -110,6 +110,8 @@ class _CorrectorFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.saved is None:
+            raise RuntimeError('corrector: backward a second time (saved activations were released; use a fresh forward)')
         meta, saved, sp = ctx.meta, ctx.saved, ctx.stage_params
         B, H, W = ctx.dims
         grad = dout.contiguous().float()
@@ -168,6 +170,111 @@ class _CorrectorFn(torch.autograd.Function):
         return (dx, None) + tuple(flat)
 
 
+# ---- the whole corrector in one launch per direction (csrc/corrector_fused.cu) ---------------------------------------------------
+# 'auto': below the batch size where the tensor-core hexconv takes over, all-hexagonal kernel_size-1 correctors up to 32 channels wide
+# run as ONE persistent kernel forward and ONE backward; '0' disables, '1' forces it for every eligible corrector.
+import os as _os
+import ctypes as _ct
+FUSED_MODE = _os.environ.get('GRIDNEXT_B200_G_FUSED', 'auto')
+_SYNC = {}
+
+
+def _fused_eligible(meta, x):
+    if FUSED_MODE == '0' or len(meta) > 8:
+        return False
+    modes = set()
+    for m in meta:
+        if m['kind'] != 'hex' or m['ksize'] != 1 or m['cin'] > 32 or m['cout'] > 32:
+            return False
+        if m['bn'] is not None:
+            if m['bn']['sync']:
+                return False
+            modes.add(bool(m['bn']['training']))
+    if len(modes) > 1 or meta[0]['bn'] is not None or meta[0]['relu']:
+        return False
+    if FUSED_MODE == '1':
+        return True
+    return x.shape[0] * x.shape[2] * x.shape[3] < hx.TENSOR_CORE_MIN_CELLS
+
+
+def _ptr_array(ptrs):
+    return (_ct.c_void_p * len(ptrs))(*[p.value if isinstance(p, _ct.c_void_p) else p for p in ptrs])
+
+
+class _CorrectorFusedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, meta, *params):
+        _lib.require_cuda(x)
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        dev = x.device
+        L = len(meta)
+        it = iter(params)
+        per_stage, pptr = [], []
+        for st in meta:
+            k0, k1 = next(it).contiguous(), next(it).contiguous()
+            bias = next(it) if st['has_bias'] else None
+            gamma = beta = None
+            rm = rv = None
+            if st['bn'] is not None:
+                gamma, beta = next(it), next(it)
+                rm, rv = st['bn']['running_mean'], st['bn']['running_var']
+            per_stage.append((k0, k1, bias, gamma, beta))
+            pptr += [ptr(k0), ptr(k1), ptr(bias), ptr(gamma), ptr(beta), ptr(rm), ptr(rv)]
+        cin = (_ct.c_int * L)(*[st['cin'] for st in meta])
+        cout = (_ct.c_int * L)(*[st['cout'] for st in meta])
+        pro = (_ct.c_int * L)(*[2 if st['bn'] is not None else (1 if st['relu'] else 0) for st in meta])
+        mom = (_ct.c_float * L)(*[st['bn']['momentum'] if st['bn'] is not None else 0.1 for st in meta])
+        eps = (_ct.c_float * L)(*[st['bn']['eps'] if st['bn'] is not None else 1e-5 for st in meta])
+        bn_training = 1 if any(st['bn'] is not None and st['bn']['training'] for st in meta) else 0
+        acts = [torch.empty((B, st['cout'], H, W), device=dev, dtype=torch.float32) for st in meta]
+        stats = torch.zeros((L, 64), device=dev, dtype=torch.float64)
+        consts = torch.empty((L, 128), device=dev, dtype=torch.float32)
+        sync = _SYNC.get(dev)
+        if sync is None:
+            sync = _SYNC[dev] = torch.zeros(2, device=dev, dtype=torch.int32)
+        call('gn_corrector_fused_fwd', ptr(x), _ptr_array([ptr(a) for a in acts]), _ptr_array(pptr), cin, cout, pro, mom, eps, L, B, H, W, bn_training,
+             ptr(stats), ptr(consts), ptr(sync), stream())
+        ctx.meta, ctx.per_stage, ctx.x, ctx.acts, ctx.consts, ctx.stats = meta, per_stage, x, acts, consts, stats
+        ctx.arrs = (pptr, cin, cout, pro, eps, bn_training, sync)
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, dout):
+        if ctx.acts is None:
+            raise RuntimeError('corrector: backward through the fused node a second time (its saved activations were released)')
+        meta, per_stage, x, acts, consts = ctx.meta, ctx.per_stage, ctx.x, ctx.acts, ctx.consts
+        pptr, cin, cout, pro, eps, bn_training, sync = ctx.arrs
+        L = len(meta)
+        B, _, H, W = x.shape
+        dev = x.device
+        dout = dout.contiguous().float()
+        need_dx = ctx.needs_input_grad[0]
+        gb = [torch.empty((B, st['cin'], H, W), device=dev, dtype=torch.float32) if (j > 0 or need_dx) else None for j, st in enumerate(meta)]
+        # one zero-filled workspace: [sums fp64 L*64][dwp L*7*32*32][dbias_acc L*32]
+        zb = torch.zeros(L * 128 + L * 7168 + L * 32, device=dev, dtype=torch.float32)
+        sums = zb[:L * 128].view(torch.float64)
+        dwp = zb[L * 128:L * 128 + L * 7168]
+        dba = zb[L * 128 + L * 7168:]
+        grads, gptr = [], []
+        for st, (k0, k1, bias, gamma, beta) in zip(meta, per_stage):
+            g = [torch.empty_like(k0), torch.empty_like(k1), torch.empty_like(bias) if bias is not None else None,
+                 torch.empty_like(gamma) if gamma is not None else None, torch.empty_like(beta) if beta is not None else None]
+            grads.append(g)
+            gptr += [ptr(t) for t in g]
+        call('gn_corrector_fused_bwd', ptr(x), _ptr_array([ptr(a) for a in acts]), ptr(dout), _ptr_array([ptr(t) for t in gb]), _ptr_array(pptr),
+             _ptr_array(gptr), cin, cout, pro, eps, L, B, H, W, bn_training, ptr(dwp), ptr(dba), ptr(sums), ptr(ctx.stats), ptr(consts), ptr(sync), stream())
+        flat = []
+        for st, g in zip(meta, grads):
+            flat += [g[0], g[1]]
+            if st['has_bias']:
+                flat.append(g[2])
+            if st['bn'] is not None:
+                flat += [g[3], g[4]]
+        ctx.acts = None
+        return (gb[0] if need_dx else None, None) + tuple(flat)
+
+
 def run_corrector(stages, x, training, sq_transposed=False):
     """x: (B, f_dim, H, W) Visium layout -> (B, n_out, H, W).  ``sq_transposed``: Cartesian nn.Conv2d stages act on the
     TRANSPOSED grid (a hexagonal model hands its corrector the HexagDLy layout, gridnet_models.py:177-185), i.e. with
@@ -199,4 +306,6 @@ def run_corrector(stages, x, training, sq_transposed=False):
         meta.append(m)
     if x.shape[1] != meta[0]['cin']:
         raise ValueError('corrector: expected %d input channels, got %d' % (meta[0]['cin'], x.shape[1]))
+    if _fused_eligible(meta, x):
+        return _CorrectorFusedFn.apply(x, meta, *params)
     return _CorrectorFn.apply(x, meta, *params)

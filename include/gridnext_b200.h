@@ -76,6 +76,25 @@ int gn_bn_act_bwd_apply(const float* dA, const float* h, const float* scale, con
                         const double* sums, double count, int training, float* dH, float* dgamma, float* dbeta, int B, int C,
                         long HW, int relu, gn_stream_t stream);
 
+/* ---- the whole corrector nn.Sequential of gridnet_models.py:128-148 (hexagdly.Conv2d kernel_size 1, <= 32 channels, [BatchNorm2d]
+ * + ReLU in front of any stage) as ONE persistent launch per direction (csrc/corrector_fused.cu): activations stay in L2, BatchNorm
+ * statistics are reduced between phases by grid-wide barriers, weights are read from / gradients written to the parameter layout
+ * kernel0 (Cout, Cin, 3, 1), kernel1 (Cout, Cin, 2, 2).  All pointer arrays are HOST arrays of device pointers:
+ *   act[L]     outputs of every stage, (B, cout[j], H, W) fp32 (act[L-1] is the result; all are kept for the backward)
+ *   params[7L] per stage: kernel0, kernel1, bias (nullable), then the BatchNorm IN FRONT of the stage: gamma, beta, running_mean,
+ *              running_var (null when pro[j] != 2);  pro[j]: 0 none, 1 ReLU, 2 BatchNorm + ReLU applied to the stage's input
+ *   stats [L][64] fp64 zeroed by the caller; consts [L][128] fp32 (written by fwd, read by bwd); sync: 2 x u32, zeroed ONCE.
+ * bwd: gb[L] gradient w.r.t. every stage's (transformed) input, gb[0] = dx (nullable); grads[5L] per stage: d kernel0, d kernel1,
+ * d bias, d gamma, d beta; dwp [L][7][32][32], dbias_acc [L][32], sums [L][64] fp64 zeroed by the caller. */
+int gn_corrector_fused_supported(int L, const int* cin, const int* cout);
+int gn_corrector_fused_fwd(const float* x, float* const* act, const void* const* params, const int* cin, const int* cout, const int* pro,
+                           const float* momentum, const float* eps, int L, int B, int H, int W, int bn_training, double* stats,
+                           float* consts, unsigned* sync, gn_stream_t stream);
+int gn_corrector_fused_bwd(const float* x, float* const* act, const float* dout, float* const* gb, const void* const* params,
+                           void* const* grads, const int* cin, const int* cout, const int* pro, const float* eps, int L, int B, int H,
+                           int W, int bn_training, float* dwp, float* dbias_acc, double* sums, double* stats, float* consts, unsigned* sync,
+                           gn_stream_t stream);
+
 /* ---- foreground-masked cross-entropy: replaces gridnext/training.py:152-160 (+ its backward).
  * acc fp64[4]: {sum of spot losses, n_foreground, n_correct, n labels > C}; loss_out[0] = mean * loss_scale;
  * dlogits (nullable) = d(loss_out)/d(logits).  n_fg_override (nullable, device fp64[1]) replaces the

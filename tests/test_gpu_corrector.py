@@ -144,11 +144,18 @@ def _load_into(module, sd):
     return module
 
 
+@pytest.mark.parametrize('path', ['one_launch', 'layered'])
 @pytest.mark.parametrize('use_bn,training', [(True, True), (True, False), (False, True)])
-@pytest.mark.parametrize('shape', [(2, 7, 78, 64), (3, 14, 9, 7)])
-def test_fused_corrector_matches_oracle(use_bn, training, shape):
+@pytest.mark.parametrize('shape', [(2, 7, 78, 64), (3, 14, 9, 7), (1, 7, 5, 70), (20, 7, 78, 64)])
+def test_fused_corrector_matches_oracle(use_bn, training, shape, path, monkeypatch):
+    """Both executions of the corrector -- the one-launch persistent kernel (csrc/corrector_fused.cu: all stages, BatchNorm
+    reductions and weight gradients in one forward and one backward launch) and the layer-by-layer kernels -- against the fp64
+    oracle: output, input gradient, every parameter gradient, running statistics.  (1, 7, 5, 70): two column tiles per row."""
     import torch.nn as nn
+    from gridnext_b200 import corrector as corr, hexagdly as hx
     from gridnext_b200.gridnet_models import GridNetHexOddr
+    monkeypatch.setattr(corr, 'FUSED_MODE', '1' if path == 'one_launch' else '0')
+    monkeypatch.setattr(hx, 'TENSOR_CORE_MODE', '0')          # layered: the exact-fp32 kernels (the tensor-core ones have their own test)
     B, f_dim, H, W = shape
     n_cls = 5
     net = GridNetHexOddr(nn.Identity(), (f_dim,), (H, W), n_cls, use_bn=use_bn, f_dim=f_dim)
