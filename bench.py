@@ -569,7 +569,7 @@ def main():
                 m2.train(); m2.patch_classifier.eval()
                 eager = eager_baseline.run(m2, wl.patches.view(-1, 3, P, P), wl.labels)
                 eager['what'] = ('reference module graph (DenseNet-121 f eval, torch.cat concat; hex g as dense 3x3 pairs; masked CE) under PyTorch '
-                                 'eager on this GPU, f fwd+bwd in 256-spot chunks without recompute, no optimizer step')
+                                 'eager on this GPU, f fwd+bwd in 192-spot chunks without recompute, no optimizer step')
                 del m2
             except Exception as exc:
                 eager = dict(error=repr(exc))

@@ -98,23 +98,31 @@ __device__ __forceinline__ void cf_exit(unsigned* sync) {
 
 // s_w[t][ci][co] (co contiguous, CF_C wide, zero padded) for the forward (mode 0: ci = layer input channel) or the data
 // gradient (mode 1: ci = layer OUTPUT channel, taps point-reflected).
+// (The 7168 / 256 = 28 elements per thread are fetched seven at a time -- independent loads in flight -- because a phase is only
+// a few microseconds long and a dependent chain of 28 L2 round trips would cost more than its arithmetic.)
 __device__ void cf_stage_weights(float* s_w, const float* __restrict__ k0, const float* __restrict__ k1, int Cin, int Cout, int mode) {
-    for (int e = threadIdx.x; e < CF_T * CF_C * CF_C; e += CF_THREADS) {
-        const int t = e / (CF_C * CF_C), ci = (e / CF_C) % CF_C, co = e % CF_C;
-        int o, c;                      // layer output / input channel of this element
-        if (mode == 0) { c = ci; o = co; } else { o = ci; c = co; }
-        float v = 0.f;
-        if (o < Cout && c < Cin) {
-            if (t < 3) {
-                const int a = mode == 0 ? t : 2 - t;
-                v = __ldg(k0 + ((long)o * Cin + c) * 3 + a);
-            } else {
-                int a = (t - 3) & 1, side = (t - 3) >> 1;
-                if (mode == 1) { a = 1 - a; side = 1 - side; }
-                v = __ldg(k1 + (((long)o * Cin + c) * 2 + a) * 2 + side);
+    for (int e0 = threadIdx.x; e0 < CF_T * CF_C * CF_C; e0 += 7 * CF_THREADS) {
+        float v[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            const int e = e0 + q * CF_THREADS;
+            const int t = e / (CF_C * CF_C), ci = (e / CF_C) % CF_C, co = e % CF_C;
+            int o, c;                      // layer output / input channel of this element
+            if (mode == 0) { c = ci; o = co; } else { o = ci; c = co; }
+            v[q] = 0.f;
+            if (o < Cout && c < Cin) {
+                if (t < 3) {
+                    const int a = mode == 0 ? t : 2 - t;
+                    v[q] = __ldg(k0 + ((long)o * Cin + c) * 3 + a);
+                } else {
+                    int a = (t - 3) & 1, side = (t - 3) >> 1;
+                    if (mode == 1) { a = 1 - a; side = 1 - side; }
+                    v[q] = __ldg(k1 + (((long)o * Cin + c) * 2 + a) * 2 + side);
+                }
             }
         }
-        s_w[e] = v;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) s_w[e0 + q * CF_THREADS] = v[q];
     }
 }
 
@@ -189,22 +197,34 @@ __global__ void __launch_bounds__(CF_THREADS, 1) corrector_fused_fwd_kernel(cons
         }
         const bool want_stats = j + 1 < a.L && a.pro[j + 1] == 2 && a.bn_training;
         if (tid < 2 * CF_C) s_stat[tid] = 0.0;
-        cf_stage_weights(s_w, a.k0[j], a.k1[j], Cin, Cout, 0);
+        if (j == 0) cf_stage_weights(s_w, a.k0[0], a.k1[0], Cin, Cout, 0);      // later stages: staged before the preceding barrier
         __syncthreads();
         const int pro = a.pro[j];
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int xt = u % a.n_xt, y = (u / a.n_xt) % a.H, b = u / (a.n_xt * a.H);
             const int x0 = xt * CF_TW;
             const float* inb = in + (long)b * Cin * HW;
-            for (int e = tid; e < Cin * 3 * CF_SW; e += CF_THREADS) {
-                const int c = e / (3 * CF_SW), r = (e / CF_SW) % 3, xx = e % CF_SW;
-                const int gy = y + r - 1, gx = x0 + xx - 1;
-                float v = 0.f;
-                if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-                    v = __ldcg(inb + (long)c * HW + (long)gy * a.W + gx);
-                    if (pro) v = fmaxf(fmaf(v, bn.sc[c], bn.sh[c]), 0.f);
+            const int n_in = Cin * 3 * CF_SW;
+            for (int e0 = tid; e0 < n_in; e0 += 8 * CF_THREADS) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int e = e0 + q * CF_THREADS;
+                    const int c = e / (3 * CF_SW), r = (e / CF_SW) % 3, xx = e % CF_SW;
+                    const int gy = y + r - 1, gx = x0 + xx - 1;
+                    v[q] = 0.f;
+                    if (e < n_in && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) v[q] = __ldcg(inb + (long)c * HW + (long)gy * a.W + gx);
                 }
-                s_in[e] = v;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int e = e0 + q * CF_THREADS;
+                    if (e < n_in) {
+                        const int c = e / (3 * CF_SW), r = (e / CF_SW) % 3, xx = e % CF_SW;
+                        const int gy = y + r - 1, gx = x0 + xx - 1;
+                        const bool in_grid = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+                        s_in[e] = (pro && in_grid) ? fmaxf(fmaf(v[q], bn.sc[c], bn.sh[c]), 0.f) : v[q];
+                    }
+                }
             }
             __syncthreads();
             float acc[8];
@@ -234,7 +254,12 @@ __global__ void __launch_bounds__(CF_THREADS, 1) corrector_fused_fwd_kernel(cons
             __syncthreads();
             if (tid < 2 * CF_C && (tid & 31) < Cout && s_stat[tid] != 0.0) atomicAdd(a.stats + (j + 1) * 64 + tid, s_stat[tid]);
         }
-        if (j + 1 < a.L) cf_grid_barrier(a.sync, epoch);
+        if (j + 1 < a.L) {
+            // the next stage's weights do not depend on the barrier: fetch them while the slower CTAs finish this phase
+            __syncthreads();
+            cf_stage_weights(s_w, a.k0[j + 1], a.k1[j + 1], a.cin[j + 1], a.cout[j + 1], 0);
+            cf_grid_barrier(a.sync, epoch);
+        }
     }
     cf_exit(a.sync);
 }
@@ -306,7 +331,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) corrector_fused_bwd_kernel(cons
             s_db[tid] = 0.f;
         }
         if (tid < 2 * CF_C) s_sum[tid] = 0.0;
-        cf_stage_weights(s_w, a.k0[j], a.k1[j], Cin, Cout, 1);
+        if (j == a.L - 1) cf_stage_weights(s_w, a.k0[j], a.k1[j], Cin, Cout, 1);      // earlier stages: staged before the preceding barrier
         float wacc[4][8];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -323,28 +348,56 @@ __global__ void __launch_bounds__(CF_THREADS, 1) corrector_fused_bwd_kernel(cons
             // ---- dY rows y-1..y+1 (zero outside the grid), [o][row][x]
             const float* db_ = dsrc + (long)b * Cout * HW;
             const float* hb_ = hout + (long)b * Cout * HW;
-            for (int e = tid; e < Cout * 3 * CF_SW; e += CF_THREADS) {
-                const int o = e / (3 * CF_SW), r = (e / CF_SW) % 3, xx = e % CF_SW;
-                const int gy = y + r - 1, gx = x0 + xx - 1;
-                float v = 0.f;
-                if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-                    const long idx = (long)o * HW + (long)gy * a.W + gx;
-                    v = __ldcg(db_ + idx);
-                    if (pro_out) v = cf_dy(v, __ldcg(hb_ + idx), pro_out, a.bn_training, bn_out, o);
+            const int n_dy = Cout * 3 * CF_SW;
+            for (int e0 = tid; e0 < n_dy; e0 += 4 * CF_THREADS) {
+                float v[4], h[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = e0 + q * CF_THREADS;
+                    const int o = e / (3 * CF_SW), r = (e / CF_SW) % 3, xx = e % CF_SW;
+                    const int gy = y + r - 1, gx = x0 + xx - 1;
+                    v[q] = 0.f; h[q] = 0.f;
+                    if (e < n_dy && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+                        const long idx = (long)o * HW + (long)gy * a.W + gx;
+                        v[q] = __ldcg(db_ + idx);
+                        if (pro_out) h[q] = __ldcg(hb_ + idx);
+                    }
                 }
-                s_dy[e] = v;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = e0 + q * CF_THREADS;
+                    if (e < n_dy) {
+                        const int o = e / (3 * CF_SW), r = (e / CF_SW) % 3, xx = e % CF_SW;
+                        const int gy = y + r - 1, gx = x0 + xx - 1;
+                        const bool in_grid = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+                        s_dy[e] = (pro_out && in_grid) ? cf_dy(v[q], h[q], pro_out, a.bn_training, bn_out, o) : v[q];
+                    }
+                }
             }
             // ---- transformed input rows y-1..y+1, channel-contiguous: chunk (c >> 2) ^ (xx & 7), element c & 3
             const float* xb_ = xin + (long)b * Cin * HW;
-            for (int e = tid; e < Cin * 3 * CF_SW; e += CF_THREADS) {
-                const int c = e / (3 * CF_SW), r = (e / CF_SW) % 3, xx = e % CF_SW;
-                const int gy = y + r - 1, gx = x0 + xx - 1;
-                float v = 0.f;
-                if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-                    v = __ldcg(xb_ + (long)c * HW + (long)gy * a.W + gx);
-                    if (pro_in) v = fmaxf(fmaf(v, bn_in.sc[c], bn_in.sh[c]), 0.f);
+            const int n_x = Cin * 3 * CF_SW;
+            for (int e0 = tid; e0 < n_x; e0 += 8 * CF_THREADS) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int e = e0 + q * CF_THREADS;
+                    const int c = e / (3 * CF_SW), r = (e / CF_SW) % 3, xx = e % CF_SW;
+                    const int gy = y + r - 1, gx = x0 + xx - 1;
+                    v[q] = 0.f;
+                    if (e < n_x && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) v[q] = __ldcg(xb_ + (long)c * HW + (long)gy * a.W + gx);
                 }
-                s_x[(r * CF_SW + xx) * CF_C + ((((c >> 2) ^ (xx & 7)) << 2) | (c & 3))] = v;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int e = e0 + q * CF_THREADS;
+                    if (e < n_x) {
+                        const int c = e / (3 * CF_SW), r = (e / CF_SW) % 3, xx = e % CF_SW;
+                        const int gy = y + r - 1, gx = x0 + xx - 1;
+                        const bool in_grid = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+                        s_x[(r * CF_SW + xx) * CF_C + ((((c >> 2) ^ (xx & 7)) << 2) | (c & 3))] =
+                            (pro_in && in_grid) ? fmaxf(fmaf(v[q], bn_in.sc[c], bn_in.sh[c]), 0.f) : v[q];
+                    }
+                }
             }
             __syncthreads();
             // ---- dY of row y, channel-contiguous (zero padded to 32 channels)
@@ -425,6 +478,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) corrector_fused_bwd_kernel(cons
         }
         if (a.dbias[j] != nullptr && tid < Cout && dbacc != 0.f) atomicAdd(a.dbias_acc + j * CF_C + tid, dbacc);
         if (want_sums && tid < 2 * CF_C && (tid & 31) < Cin && s_sum[tid] != 0.0) atomicAdd(a.sums + j * 64 + tid, s_sum[tid]);
+        if (j > 0) {
+            __syncthreads();
+            cf_stage_weights(s_w, a.k0[j - 1], a.k1[j - 1], a.cin[j - 1], a.cout[j - 1], 1);
+        }
         cf_grid_barrier(a.sync, epoch);
     }
     // ---- last phase: packed weight gradients -> parameter layout; bias gradients; a BatchNorm in front of stage 0 (not a

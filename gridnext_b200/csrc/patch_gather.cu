@@ -142,36 +142,53 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const unsigned char* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA path for cells whose window lies inside the image (all but the few spots within P/2 of a border).  TMA boxes must
-// start on a 16-byte boundary of the innermost dimension (a misaligned start faults -- measured), so the image is viewed as
-// rows of uint32 and the box starts at the 16-byte boundary below the window's first byte; the byte offset d (0..15, the
-// same for every row of a cell) is removed with funnel shifts when a thread unpacks its 4 pixels (12 bytes).  Border / out-of-tissue cells are left to the generic kernel above (`only_rest` = 1).
-#define PG_RPC 32            // patch rows per CTA
+// Persistent TMA-pipelined gather (the default whenever the image can be described by a tensor map: 16-byte row pitch, W % 4 == 0,
+// P % 32 == 0).  Work item = (cell, tile of 32 patch rows); 2 CTAs per SM walk the item list with a ring of PG_STAGES shared-memory
+// tiles: one thread issues the TMA load of item i + PG_STAGES while all 256 threads convert item i, so the loads of several tiles
+// are always in flight and the value table (3 x 256 floats, two IEEE divisions each) is built once per CTA instead of once per
+// tile.  (The first version launched one short-lived CTA per tile: 163 us for 4,992 spots at P = 128 -> bf16, 69 % of the copy
+// bandwidth, with the table construction and the un-overlapped load latency of every CTA on the critical path.)
+// TMA boxes must start on a 16-byte boundary of the innermost dimension (a misaligned start faults -- measured), so the image is
+// viewed as rows of uint32 and the box starts at the 16-byte boundary below the window's first byte; the byte offset d (0..15, the
+// same for every row of a cell) is removed with funnel shifts when a thread unpacks its 4 pixels (12 bytes).
+// Cells whose window hangs over an image border (edge clamp == np.pad(mode='edge')) take clamped per-pixel loads in the same
+// kernel; out-of-tissue cells are zero-filled: one launch writes the whole grid.
+#define PG_RPC 32            // patch rows per tile
+#define PG_STAGES 4
 
 __device__ __forceinline__ bool pg_interior(int cx, int cy, int hw, int P, int H, int W) {
     return cx - hw >= 0 && cx - hw + P <= W && cy - hw >= 0 && cy - hw + P <= H;
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(256) patch_gather_tma_kernel(const __grid_constant__ CUtensorMap tmImg, int H, int W, const int* __restrict__ cells,
-                                                               int P, int row_bytes, const float* __restrict__ mean,
-                                                               const float* __restrict__ stdv, OutT* __restrict__ out) {
+__global__ void __launch_bounds__(256, 2) patch_gather_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const unsigned char* __restrict__ img,
+                                                                  long pitch, int H, int W, const int* __restrict__ cells, int n_cells, int P,
+                                                                  int row_bytes, int stages, const float* __restrict__ mean,
+                                                                  const float* __restrict__ stdv, OutT* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char sm[];
-    __shared__ __align__(8) uint64_t bar;
-    const int cell = blockIdx.x, r0 = blockIdx.y * PG_RPC;
-    const int cx = cells[3 * cell + 0], cy = cells[3 * cell + 1], valid = cells[3 * cell + 2];
-    const int hw = P / 2;
-    if (!valid || !pg_interior(cx, cy, hw, P, H, W)) return;
+    __shared__ __align__(8) uint64_t bar[PG_STAGES];
     const int tid = threadIdx.x;
     float* lut = reinterpret_cast<float*>(sm);                        // [3][256]
-    unsigned char* rows = sm + 3 * 256 * sizeof(float);               // [PG_RPC][row_bytes] (+ 16 bytes of slack)
-    const int b0 = 3 * (cx - hw);                                     // first byte of the window in its image row
-    const int a0 = b0 & ~15, d = b0 - a0;
+    unsigned char* ring = sm + 3 * 256 * sizeof(float);               // [stages][PG_RPC][row_bytes]
+    const int tile_bytes = PG_RPC * row_bytes;
+    const int tiles = P / PG_RPC, groups = P / 4, hw = P / 2;
+    const int n_items = n_cells * tiles;
+
+    auto issue = [&](int item, int s) {                               // thread 0 only
+        const int cell = item / tiles, r0 = (item - cell * tiles) * PG_RPC;
+        const int cx = __ldg(cells + 3 * cell), cy = __ldg(cells + 3 * cell + 1), valid = __ldg(cells + 3 * cell + 2);
+        if (valid && pg_interior(cx, cy, hw, P, H, W)) {
+            const int a0 = (3 * (cx - hw)) & ~15;
+            gnptx::mbar_arrive_expect_tx(&bar[s], (uint32_t)tile_bytes);
+            gnptx::tma_load_2d(&tmImg, &bar[s], ring + (size_t)s * tile_bytes, a0 >> 2, cy - hw + r0);
+        } else {
+            gnptx::mbar_arrive(&bar[s]);                              // nothing to load: complete the phase
+        }
+    };
+
     if (tid == 0) {
-        gnptx::mbar_init(&bar, 1);
+        for (int s = 0; s < stages; ++s) gnptx::mbar_init(&bar[s], 1);
         gnptx::fence_barrier_init();
-        gnptx::mbar_arrive_expect_tx(&bar, (uint32_t)(PG_RPC * row_bytes));
-        gnptx::tma_load_2d(&tmImg, &bar, rows, a0 >> 2, cy - hw + r0);
     }
     // value table: raw u8 -> float, or ((v / 255) - mean) / std in IEEE fp32 like ToTensor + Normalize
     for (int e = tid; e < 3 * 256; e += 256) {
@@ -181,29 +198,70 @@ __global__ void __launch_bounds__(256) patch_gather_tma_kernel(const __grid_cons
         lut[e] = f;
     }
     __syncthreads();
-    gnptx::mbar_wait(&bar, 0);
-    // thread = 4 pixels (12 bytes): four 4-byte shared loads from the word holding the first byte, one funnel shift per word
-    // (the byte phase (d & 3) is uniform), 12 table look-ups, and one 8/16-byte store per channel -- consecutive lanes write
-    // consecutive addresses of the output row.
-    const int groups = P / 4;
-    const int sh = (d & 3) * 8;
-    OutT* ocell = out + (long)cell * 3 * P * P;
-    for (int e = tid; e < PG_RPC * groups; e += 256) {
-        const int r = e / groups, g = e - r * groups;
-        const unsigned* src = reinterpret_cast<const unsigned*>(rows + (size_t)r * row_bytes + ((12 * g + d) & ~3));
-        const unsigned i0 = src[0], i1 = src[1], i2 = src[2], i3 = src[3];
-        const unsigned w[3] = {__funnelshift_r(i0, i1, sh), __funnelshift_r(i1, i2, sh), __funnelshift_r(i2, i3, sh)};
-        float v[3][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int byte = 3 * j + c;
-                v[c][j] = lut[c * 256 + ((w[byte >> 2] >> (8 * (byte & 3))) & 0xff)];
+    if (tid == 0)
+        for (int s = 0; s < stages; ++s) {
+            const int item = blockIdx.x + s * gridDim.x;
+            if (item < n_items) issue(item, s);
+        }
+    int s = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int cell = item / tiles, r0 = (item - cell * tiles) * PG_RPC;
+        const int cx = __ldg(cells + 3 * cell), cy = __ldg(cells + 3 * cell + 1), valid = __ldg(cells + 3 * cell + 2);
+        OutT* ocell = out + (long)cell * 3 * P * P;
+        gnptx::mbar_wait(&bar[s], phase);
+        if (!valid) {
+            for (int e = tid; e < 3 * PG_RPC * groups; e += 256) {
+                const int c = e / (PG_RPC * groups), r = (e / groups) % PG_RPC, g = e % groups;
+                Pack4<OutT>::store(ocell + ((long)c * P + r0 + r) * P + 4 * g, 0.f, 0.f, 0.f, 0.f);
             }
+        } else if (pg_interior(cx, cy, hw, P, H, W)) {
+            // thread = 4 pixels (12 bytes): four 4-byte shared loads from the word holding the first byte, one funnel shift per word
+            // (the byte phase (d & 3) is uniform), 12 table look-ups, and one 8/16-byte store per channel -- consecutive lanes write
+            // consecutive addresses of the output row.
+            const int b0 = 3 * (cx - hw), d = b0 - (b0 & ~15);
+            const int sh = (d & 3) * 8;
+            const unsigned char* rows = ring + (size_t)s * tile_bytes;
+            for (int e = tid; e < PG_RPC * groups; e += 256) {
+                const int r = e / groups, g = e - r * groups;
+                const unsigned* src = reinterpret_cast<const unsigned*>(rows + (size_t)r * row_bytes + ((12 * g + d) & ~3));
+                const unsigned i0 = src[0], i1 = src[1], i2 = src[2], i3 = src[3];
+                const unsigned w[3] = {__funnelshift_r(i0, i1, sh), __funnelshift_r(i1, i2, sh), __funnelshift_r(i2, i3, sh)};
+                float v[3][4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-            Pack4<OutT>::store(ocell + ((long)c * P + r0 + r) * P + 4 * g, v[c][0], v[c][1], v[c][2], v[c][3]);
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int byte = 3 * j + c;
+                        v[c][j] = lut[c * 256 + ((w[byte >> 2] >> (8 * (byte & 3))) & 0xff)];
+                    }
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    Pack4<OutT>::store(ocell + ((long)c * P + r0 + r) * P + 4 * g, v[c][0], v[c][1], v[c][2], v[c][3]);
+            }
+        } else {
+            // window over an image border: clamped coordinates (a few dozen cells per array)
+            for (int e = tid; e < PG_RPC * groups; e += 256) {
+                const int r = e / groups, g = e - r * groups;
+                const int gy = min(max(cy - hw + r0 + r, 0), H - 1);
+                float v[3][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int gx = min(max(cx - hw + 4 * g + j, 0), W - 1);
+                    const unsigned char* px = img + (long)gy * pitch + 3L * gx;
+                    v[0][j] = lut[px[0]]; v[1][j] = lut[256 + px[1]]; v[2][j] = lut[512 + px[2]];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    Pack4<OutT>::store(ocell + ((long)c * P + r0 + r) * P + 4 * g, v[c][0], v[c][1], v[c][2], v[c][3]);
+            }
+        }
+        __syncthreads();                                              // every thread is done with stage s
+        if (tid == 0) {
+            const int nxt = item + stages * gridDim.x;
+            if (nxt < n_items) issue(nxt, s);
+        }
+        if (++s == stages) { s = 0; phase ^= 1; }
     }
 }
 
@@ -248,24 +306,29 @@ GN_API int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, c
         uint32_t box[2] = {(uint32_t)(row_bytes / 4), PG_RPC};
         int rc = gn_tmap_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, img, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
-        const size_t smem_t = 3 * 256 * sizeof(float) + (size_t)PG_RPC * row_bytes + 16;
-        dim3 grid_t(n_cells, P / PG_RPC);
+        int stages = PG_STAGES;
+        while (stages > 2 && 3 * 256 * sizeof(float) + (size_t)stages * PG_RPC * row_bytes + 16 > 100 * 1024) --stages;   // two CTAs per SM
+        const size_t smem_t = 3 * 256 * sizeof(float) + (size_t)stages * PG_RPC * row_bytes + 16;
+        const int n_items = n_cells * (P / PG_RPC);
+        int grid_t = 2 * gn_num_sms();
+        if (grid_t > n_items) grid_t = n_items;
         if (out_bf16) {
             GN_CUDA(cudaFuncSetAttribute(patch_gather_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-            patch_gather_tma_kernel<__nv_bfloat16><<<grid_t, 256, smem_t, stream>>>(tm, H, W, cells, P, row_bytes, mean, stdv, (__nv_bfloat16*)out);
+            patch_gather_tma_kernel<__nv_bfloat16><<<grid_t, 256, smem_t, stream>>>(tm, img, pitch, H, W, cells, n_cells, P, row_bytes, stages, mean, stdv,
+                                                                                    (__nv_bfloat16*)out);
         } else {
             GN_CUDA(cudaFuncSetAttribute(patch_gather_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-            patch_gather_tma_kernel<float><<<grid_t, 256, smem_t, stream>>>(tm, H, W, cells, P, row_bytes, mean, stdv, (float*)out);
+            patch_gather_tma_kernel<float><<<grid_t, 256, smem_t, stream>>>(tm, img, pitch, H, W, cells, n_cells, P, row_bytes, stages, mean, stdv, (float*)out);
         }
         GN_LAUNCH_CHECK();
+        return GN_OK;                                                   // the persistent kernel wrote every cell (interior, border, off-tissue)
     }
     dim3 grid(n_cells, gn_ceil_div(P, rpc));
     if (out_bf16)
         patch_gather_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(img, pitch, img_bytes, H, W, cells, P, rpc, row_buf, mean, stdv,
-                                                                        (__nv_bfloat16*)out, use_tma ? 1 : 0);
+                                                                        (__nv_bfloat16*)out, 0);
     else
-        patch_gather_kernel<float><<<grid, 256, smem, stream>>>(img, pitch, img_bytes, H, W, cells, P, rpc, row_buf, mean, stdv, (float*)out,
-                                                               use_tma ? 1 : 0);
+        patch_gather_kernel<float><<<grid, 256, smem, stream>>>(img, pitch, img_bytes, H, W, cells, P, rpc, row_buf, mean, stdv, (float*)out, 0);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

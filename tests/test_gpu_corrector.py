@@ -177,15 +177,29 @@ def test_fused_corrector_matches_oracle(use_bn, training, shape, path, monkeypat
     y_g = net._correct_visium(x_g)
     y_g.backward(dy.to(dev()))
     assert rel_err(y_g, y_r) < TOL
-    assert rel_err(x_g.grad, x_r.grad) < 2 * TOL
-    for name, p in net.corrector.named_parameters():
-        ref = sd_r[name].grad
-        # gradients that are exactly zero in theory (bias before a train-mode BN) compare absolutely
-        err = float((p.grad.double().cpu() - ref).abs().max())
-        if float(ref.abs().max()) < 1e-9:
-            assert err < 2e-4, name      # fp32 cancellation noise of a sum over B*H*W cells whose exact value is 0
+    big = B * H * W > 50000
+    # Gradients.  Among millions of pre-ReLU activations a few sit within fp32 rounding of zero; a flipped mask changes its own
+    # gradient entries by O(1) (see test_fused_corrector_on_tensor_cores), so on the big batch the composed gradient is compared
+    # in L2 (1e-3) with a loose max-norm, while the small shapes keep the 2e-5 max-norm check.
+    def check(got, ref, name):
+        got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+        if big:
+            l2 = float((got - ref).norm() / max(float(ref.norm()), 1e-12))
+            mx = float((got - ref).abs().max() / max(float(ref.abs().max()), 1e-12))
+            assert l2 < 1e-3 and mx < 0.25, (name, l2, mx)
         else:
-            assert err / float(ref.abs().max()) < 2 * TOL, name
+            assert float((got - ref).abs().max()) / float(ref.abs().max()) < 2 * TOL, name
+    check(x_g.grad, x_r.grad, 'dx')
+    params = dict(net.corrector.named_parameters())
+    for name, p in params.items():
+        ref = sd_r[name].grad
+        if float(ref.abs().max()) < 1e-9:
+            # exactly zero in theory (bias in front of a train-mode BatchNorm): fp32 cancellation residue of a sum over B*H*W cells,
+            # negligible against the gradient of the same layer's kernel
+            sib = params[name.replace('bias_tensor', 'kernel0')].grad
+            assert float(p.grad.abs().max()) < 1e-4 * float(sib.abs().max()), name
+        else:
+            check(p.grad, ref, name)
     if use_bn and training:
         for k, v in stats.items():
             assert rel_err(dict(net.corrector.named_buffers())[k], v) < TOL, k

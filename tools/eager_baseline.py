@@ -5,7 +5,7 @@ This is a BASELINE for bench.py's ``gpu_eager_baseline`` object, not a product p
 own module tree (whose children are the reference's nn.Conv2d / nn.BatchNorm2d / nn.Linear, /root/reference/gridnext/densenet.py:
 93-159) with the reference's eager composition (torch.cat concatenation densenet.py:14,75; eval-mode f, training.py:126), and
 hexagdly.Conv2d as the dense-kernel equivalent (two 3x3 convolutions, one per row parity).  Three channels: fp32 with TF32 off,
-fp32 with TF32 on (PyTorch's cuDNN default), bf16 autocast + channels_last.  f is run chunk by chunk (fwd + bwd per chunk, no
+fp32 with TF32 on (PyTorch's cuDNN default), bf16 autocast + channels_last.  f is run in equal chunks of 192 spots (4,992 = 26 x 192: one set of cuDNN-autotuned shapes; fwd + bwd per chunk, no
 recompute -- the reference itself needs ``atonce_patch_limit`` + checkpointing, i.e. an extra forward, to fit a whole array)."""
 import time
 import torch
@@ -67,7 +67,7 @@ def masked_ce_eager(out, labels):
     return F.cross_entropy(o[l > 0], l[l > 0] - 1)
 
 
-def run(model, patches, labels, chunk=256, channels=('fp32', 'tf32', 'bf16_autocast_channels_last')):
+def run(model, patches, labels, chunk=192, channels=('fp32', 'tf32', 'bf16_autocast_channels_last')):
     """model: GridNetHexOddr with a gridnext_b200 DenseNet f (eval) on the device; patches (N, 3, P, P) bf16|fp32 device tensor,
     labels (1, H, W).  -> {channel: dict(ms_per_array, spots_per_s)}."""
     f, g = model.patch_classifier, model.corrector

@@ -1,0 +1,12 @@
+set -x
+O=gpurun_out/r02d
+mkdir -p $O
+python -m pytest tests/test_gpu_corrector.py tests/test_gpu_parity_r2.py tests/test_gpu_gather.py -q -m gpu > $O/pytest.log 2>&1
+tail -12 $O/pytest.log
+python bench.py --config c1 --steps 20 --warmup 3 --no-cpu-baseline --profile-out $O/c1_kernels.json > $O/bench_c1.json 2> $O/bench_c1.err; tail -c 400 $O/bench_c1.err
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_c2.json 2> $O/bench_c2.err; tail -c 400 $O/bench_c2.err
+python tools/kbench_g.py gather corrector > $O/kbench_g.txt 2>&1
+python tools/ncu_targets.py gather corrector > $O/targets_plain.txt 2>&1 && \
+ncu --set full --clock-control none -k regex:"patch_gather|corrector_fused" -c 12 -o /tmp/g_full python tools/ncu_targets.py gather corrector > $O/ncu.log 2>&1
+ncu -i /tmp/g_full.ncu-rep --page raw --csv > $O/g_full_raw.csv 2>/dev/null
+du -sh gpurun_out; ls -la $O
