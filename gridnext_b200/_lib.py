@@ -25,6 +25,8 @@ _SIGS = {
     'gn_hexconv_fwd': [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
     'gn_hexconv_fwd_tc': [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp],
     'gn_hexconv_tc_supported': [ci, ci, ci, ci, ci],
+    'gn_hexconv_tc2_supported': [ci, ci, ci, ci, ci],
+    'gn_hexconv_fwd_tc2': [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp],
     'gn_hexconv_wgrad_tc': [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp],
     'gn_hexconv_wgrad': [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
     'gn_cell_inverse': [vp, ci, vp, ci, vp],
@@ -84,7 +86,7 @@ _SIGS = {
 
 
 def declared_symbols():
-    return sorted(_SIGS) + ['gn_last_error', 'gn_hexconv_tc_workspace_bytes', 'gn_hexconv_tc_wgrad_workspace_bytes']
+    return sorted(_SIGS) + ['gn_last_error', 'gn_hexconv_tc_workspace_bytes', 'gn_hexconv_tc_wgrad_workspace_bytes', 'gn_hexconv_tc2_workspace_bytes']
 
 
 def load():
@@ -106,6 +108,8 @@ def load():
     for nm in ('gn_hexconv_tc_workspace_bytes', 'gn_hexconv_tc_wgrad_workspace_bytes'):
         getattr(lib, nm).restype = ctypes.c_long
         getattr(lib, nm).argtypes = [ci, ci, ci]
+    lib.gn_hexconv_tc2_workspace_bytes.restype = ctypes.c_long
+    lib.gn_hexconv_tc2_workspace_bytes.argtypes = []
     _lib = lib
     return lib
 
@@ -130,7 +134,7 @@ def check(rc, what=''):
 
 
 # kernels launched per C-ABI call (for the benchmark's gpu_launches count); default 1
-KERNELS_PER_CALL = {'gn_corrector_fused_supported': 0, 'gn_cell_inverse': 2, 'gn_mm_fg_consistency': 2, 'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0, 'gn_prep_job_bytes': 0,
+KERNELS_PER_CALL = {'gn_corrector_fused_supported': 0, 'gn_cell_inverse': 2, 'gn_mm_fg_consistency': 2, 'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_hexconv_tc2_supported': 0, 'gn_hexconv_fwd_tc2': 2, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0, 'gn_prep_job_bytes': 0,
                     'gn_device_sm_count': 0, 'gn_hexconv_n_taps': 0}
 LAUNCHES = [0]
 PROFILE = None      # when a dict: name -> [n_calls, [cuda event pairs]]

@@ -1,0 +1,394 @@
+// Hexagonal convolution (kernel_size 1, <= 32 channels, grid width <= 64) on tcgen05 -- second generation: fp32 NCHW in, fp32 NCHW
+// out, NO intermediate layout in global memory.
+//
+// Replaces hexagdly.Conv2d.forward and its data gradient as used by the g network
+// (/root/reference/gridnext/gridnet_models.py:128-148) at large batches.  hexconv_tc.cu (first generation) first rewrote the input
+// into two bf16 parity planes (read 128 B + write 128 B per cell), then loaded two overlapping plane windows per tile (196 B per
+// cell): 580 B of traffic per cell against the 256 algorithmic bytes -- at most 44 % of the HBM roofline, measured 25-29 %.
+// Here the traffic is the algorithmic one (+ one halo row pair per 26 rows):
+//
+//   * a persistent CTA walks strips of 26 consecutive grid rows of one array; the producer warp TMA-loads the fp32 rows (box =
+//     64 columns x 1 row x 32 channels, out-of-grid rows / columns / channels zero-filled) into a staging ring;
+//   * four converter warps apply the previous layer's BatchNorm+ReLU (gridnet_models.py:134-136), split every value into
+//     bf16 hi + lo (x = hi + lo to 16 mantissa bits; fp32-grade accuracy with x_hi w_hi + x_lo w_hi + x_hi w_lo, north_star
+//     1e-5) and write the cell's 128-byte K-major operand row [32 hi | 32 lo] (SWIZZLE_128B) into a ring of 8 grid-row slots
+//     (+ a mirror of slot 0 behind slot 7, so that any two consecutive rows are contiguous); every row is loaded and converted once;
+//   * a tile is two grid rows (y even, y + 1) x 64 columns = the 128 accumulator rows of one UMMA.  The hexagonal neighbourhood
+//     mixes row shifts (y - 1, y + 1) with parity-dependent column shifts.  Row shifts are operand START ADDRESSES (a whole
+//     8 KB slot); column shifts are NOT applied to the operand: the taps are stacked along UMMA N instead --
+//         same row : N = 96 = taps (x-1, x, x+1) x 32 channels      A = rows (y,   y+1)
+//         row above: N = 64 = taps (a = 0, 1)  x 32 channels        A = rows (y-1, y  )
+//         row below: N = 64                                         A = rows (y+1, y+2)
+//     so accumulator column block j of lane q holds E_j[q] = X[row-shifted q] . W_j, and the output is a neighbour-LANE sum
+//         out[x] = L[x-1] + C[x] + R[x+1],  L = E_l + (even row: E_u0 + E_d0), R = E_r + (odd row: E_u1 + E_d1), C = the rest,
+//     two warp shuffles per channel in the epilogue (lanes are columns; the x = 31|32 warp boundary goes through shared memory).
+//     A UMMA with N = 32 costs the same ~45 cycles as one with N = 96 (A-operand fetch bound), so stacking turns 42 MMAs per
+//     tile into 18 (912 cycles per 128 cells against the 1,400 cycles HBM needs for their 32 KB): the kernel can be HBM-bound;
+//   * eight epilogue warps read TMEM, do the lane sums, add the bias, write NCHW fp32 (one coalesced 128-byte store per channel
+//     and warp) and keep the BatchNorm batch statistics of their 16 channels in registers across all tiles (one reduction at the
+//     end, fp64 atomics per CTA only).
+//
+//   warp 0: TMA producer   warp 1: MMA issuer   warps 2-5: converters   warps 6-13: epilogue (TMEM lane group x channel half)
+#include "gn_common.cuh"
+#include "gn_ptx.cuh"
+#include "gn_tma.cuh"
+
+using namespace gnptx;
+
+#define H2_RB 26                     // grid rows per strip (even)
+#define H2_TILES (H2_RB / 2)         // 13 tiles per strip
+#define H2_CHUNKS (H2_TILES + 2)     // 15 row pairs per strip: pair k = rows y0 - 2 + 2k, y0 - 1 + 2k (first / last: one halo row)
+#define H2_STAGES 4                  // fp32 staging ring (one row pair = 16 KB per stage)
+#define H2_ROW_F32 8192              // one staged grid row: 32 channels x 64 columns fp32
+#define H2_SLOT 8192                 // one operand row slot: 64 cells x 128 B
+#define H2_W_ROWS 448                // packed weight rows: S_hi 96, S_lo 96, U_hi 64, U_lo 64, D_hi 64, D_lo 64
+#define H2_W_BYTES (H2_W_ROWS * 128)
+#define H2_THREADS 448
+
+struct Hex2Params {
+    int B, H, W, Cin, Cout;
+    int strips_per_img, n_strips;
+    const float* bias;
+    const float* in_scale;
+    const float* in_shift;
+    float* y;
+    double* stats;
+};
+
+// wp fp32 [7][cin][cout] (gn_hexconv_pack, mode 0 forward / mode 1 data gradient) -> bf16 B-operand tiles, 128-byte rows:
+//   hi tile row = [w_hi(ci 0..31) | w_hi(ci 0..31)]  (against A = [x_hi | x_lo]),  lo tile row = [w_lo(ci 0..31) | 0] (against x_hi)
+//   rows: S_hi [tap 0..2][co], S_lo, U_hi [tap 3,4][co], U_lo, D_hi [tap 5,6][co], D_lo
+__global__ void hex2_pack_kernel(const float* __restrict__ wp, int cin, int cout, __nv_bfloat16* __restrict__ wt) {
+    const int total = H2_W_ROWS * 64;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int kk = e & 63, row = e >> 6;
+        int grp_row = row, tap0, lo;
+        if (row < 192) { lo = row >= 96; grp_row = row - (lo ? 96 : 0); tap0 = 0; }
+        else if (row < 320) { lo = row >= 256; grp_row = row - (lo ? 256 : 192); tap0 = 3; }
+        else { lo = row >= 384; grp_row = row - (lo ? 384 : 320); tap0 = 5; }
+        const int t = tap0 + (grp_row >> 5), co = grp_row & 31, ci = kk & 31;
+        float w = 0.f;
+        if (ci < cin && co < cout) w = wp[((long)t * cin + ci) * cout + co];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        float v;
+        if (!lo) v = __bfloat162float(hi);
+        else v = kk < 32 ? w - __bfloat162float(hi) : 0.f;
+        wt[e] = __float2bfloat16_rn(v);
+    }
+}
+
+__global__ void __launch_bounds__(H2_THREADS, 1)
+hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Hex2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_w, stg_full[H2_STAGES], stg_free[H2_STAGES], ring_full[4], ring_free[4], tm_full[2], tm_free[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_pro[2][32];
+    __shared__ __align__(16) float s_xchg[2][4][2][2][16];       // [tile parity][lane group][channel half][L of lane 31 | R of lane 0][16]
+    __shared__ double s_stat[2 * 32];
+    __shared__ float s_bias[32];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* s_w = sm;                                           // packed weights, 56 KB
+    uint8_t* s_ring = s_w + H2_W_BYTES;                          // 9 operand row slots (slot 8 mirrors slot 0), 72 KB
+    uint8_t* s_stg = s_ring + 9 * H2_SLOT;                       // staging: [stage][row of the pair][32][64] fp32, 64 KB
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x < 64) s_stat[threadIdx.x] = 0.0;
+    if (threadIdx.x < 32) {
+        s_bias[threadIdx.x] = (p.bias != nullptr && threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
+        s_pro[0][threadIdx.x] = (p.in_scale != nullptr && threadIdx.x < p.Cin) ? p.in_scale[threadIdx.x] : 1.f;
+        s_pro[1][threadIdx.x] = (p.in_shift != nullptr && threadIdx.x < p.Cin) ? p.in_shift[threadIdx.x] : 0.f;
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        mbar_init(&bar_w, 1);
+        for (int s = 0; s < H2_STAGES; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_free[s], 4); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&ring_full[s], 4); mbar_init(&ring_free[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tm_full[s], 1); mbar_init(&tm_free[s], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<512>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const bool has_pro = p.in_scale != nullptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            mbar_arrive_expect_tx(&bar_w, H2_W_BYTES);
+            for (int i = 0; i < H2_W_ROWS / 64; ++i) tma_load_2d(&tmW, &bar_w, s_w + i * 64 * 128, 0, i * 64);      // 7 boxes of 64 rows
+            uint32_t gk = 0;                                            // running row-pair index of this CTA
+            for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
+                const int b = strip / p.strips_per_img, y0 = (strip - b * p.strips_per_img) * H2_RB;
+                for (int k = 0; k < H2_CHUNKS; ++k, ++gk) {
+                    const int st = gk % H2_STAGES;
+                    if (gk >= H2_STAGES) mbar_wait(&stg_free[st], ((gk / H2_STAGES) - 1) & 1);
+                    uint8_t* dst = s_stg + (size_t)st * 2 * H2_ROW_F32;
+                    const int r_lo = y0 - 2 + 2 * k;
+                    const bool first = k == 0, last = k == H2_CHUNKS - 1;
+                    mbar_arrive_expect_tx(&stg_full[st], (first || last) ? H2_ROW_F32 : 2 * H2_ROW_F32);
+                    if (!first) tma_load_4d(&tmX, &stg_full[st], dst, 0, r_lo, 0, b);
+                    if (!last) tma_load_4d(&tmX, &stg_full[st], dst + H2_ROW_F32, 0, r_lo + 1, 0, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            const uint32_t idS = idesc_bf16(128, 96, 0, 0), idU = idesc_bf16(128, 64, 0, 0);
+            const uint64_t tmpl = smem_desc_template(0, 1024, LAYOUT_SW128);
+            const uint32_t w0 = smem_u32(s_w), ring0 = smem_u32(s_ring);
+            const uint64_t dS_hi = smem_desc(tmpl, w0), dS_lo = smem_desc(tmpl, w0 + 96 * 128);
+            const uint64_t dU_hi = smem_desc(tmpl, w0 + 192 * 128), dU_lo = smem_desc(tmpl, w0 + 256 * 128);
+            const uint64_t dD_hi = smem_desc(tmpl, w0 + 320 * 128), dD_lo = smem_desc(tmpl, w0 + 384 * 128);
+            mbar_wait(&bar_w, 0);
+            uint32_t gk = 0, waited = 0, tile_seq = 0;
+            for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
+                for (int t = 0; t < H2_TILES; ++t, ++tile_seq) {
+                    // row pairs gk + t, + t + 1, + t + 2 must be converted
+                    while (waited < gk + t + 3) { mbar_wait(&ring_full[waited & 3], (waited >> 2) & 1); ++waited; }
+                    const int acc = tile_seq & 1;
+                    if (tile_seq >= 2) mbar_wait(&tm_free[acc], ((tile_seq >> 1) - 1) & 1);
+                    tc_fence_after();
+                    // slot of row index i (running over all strips: 2 * (gk + pair) + row): i & 7; a pair starting at slot 7 continues in the mirror slot 8
+                    const uint32_t i_own = 2 * (gk + t + 1);                     // first own row (even slot)
+                    const uint32_t a_own = ring0 + ((i_own & 7) * H2_SLOT);
+                    const uint32_t a_up = ring0 + (((i_own - 1) & 7) * H2_SLOT);
+                    const uint32_t a_dn = ring0 + (((i_own + 1) & 7) * H2_SLOT);
+                    const uint32_t d = tmem_base + (uint32_t)(acc * 256);
+                    const uint64_t dA_own = smem_desc(tmpl, a_own), dA_up = smem_desc(tmpl, a_up), dA_dn = smem_desc(tmpl, a_dn);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(d, dA_own + (uint64_t)(2 * k), dS_hi + (uint64_t)(2 * k), idS, k > 0);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_bf16(d, dA_own + (uint64_t)(2 * k), dS_lo + (uint64_t)(2 * k), idS, 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(d + 96, dA_up + (uint64_t)(2 * k), dU_hi + (uint64_t)(2 * k), idU, k > 0);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_bf16(d + 96, dA_up + (uint64_t)(2 * k), dU_lo + (uint64_t)(2 * k), idU, 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(d + 160, dA_dn + (uint64_t)(2 * k), dD_hi + (uint64_t)(2 * k), idU, k > 0);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_bf16(d + 160, dA_dn + (uint64_t)(2 * k), dD_lo + (uint64_t)(2 * k), idU, 1u);
+                    umma_commit(&tm_full[acc]);
+                    umma_commit(&ring_free[(gk + t) & 3]);                       // row pair gk + t is not read again
+                    if (t == H2_TILES - 1) {
+                        umma_commit(&ring_free[(gk + t + 1) & 3]);
+                        umma_commit(&ring_free[(gk + t + 2) & 3]);
+                    }
+                }
+                gk += H2_CHUNKS;
+            }
+        }
+    } else if (warp < 6) {
+        // ------------------------------------------------------------------------------------------ converters: thread = (row of the pair, column)
+        const int cw = warp - 2;                    // 0..3
+        const int r = cw >> 1;                      // row of the pair
+        const int x = ((cw & 1) << 5) | lane;       // column 0..63
+        uint32_t gk = 0;
+        for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
+            const int b = strip / p.strips_per_img, y0 = (strip - b * p.strips_per_img) * H2_RB;
+            (void)b;
+            for (int k = 0; k < H2_CHUNKS; ++k, ++gk) {
+                const int st = gk % H2_STAGES, rs = gk & 3;
+                mbar_wait(&stg_full[st], (gk / H2_STAGES) & 1);
+                if (gk >= 4) mbar_wait(&ring_free[rs], ((gk >> 2) - 1) & 1);
+                const int gy = y0 - 2 + 2 * k + r;
+                const bool loaded = !((k == 0 && r == 0) || (k == H2_CHUNKS - 1 && r == 1));
+                if (loaded) {
+                    const float* src = reinterpret_cast<const float*>(s_stg + (size_t)st * 2 * H2_ROW_F32 + (size_t)r * H2_ROW_F32) + x;
+                    const bool live = has_pro && gy >= 0 && gy < p.H && x < p.W;     // zero padding stays zero
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float v0 = src[(2 * j) * 64], v1 = src[(2 * j + 1) * 64];
+                        if (live) {
+                            v0 = 2 * j < p.Cin ? fmaxf(fmaf(v0, s_pro[0][2 * j], s_pro[1][2 * j]), 0.f) : 0.f;
+                            v1 = 2 * j + 1 < p.Cin ? fmaxf(fmaf(v1, s_pro[0][2 * j + 1], s_pro[1][2 * j + 1]), 0.f) : 0.f;
+                        }
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                        const float2 hf = __bfloat1622float2(h);
+                        const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+                        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    // operand row of this cell: 8 chunks of 16 B, chunk c stored at (c ^ (x & 7)) (SWIZZLE_128B: slots are 1024-byte aligned)
+                    const uint32_t slot = (2 * gk + r) & 7;
+                    uint8_t* row = s_ring + (size_t)slot * H2_SLOT + (size_t)x * 128;
+                    const uint32_t sw = (uint32_t)(x & 7);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(row + (((4 + c) ^ sw) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                    }
+                    if (slot == 0) {
+                        uint8_t* mrow = row + 8 * H2_SLOT;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            *reinterpret_cast<uint4*>(mrow + ((c ^ sw) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                            *reinterpret_cast<uint4*>(mrow + (((4 + c) ^ sw) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                        }
+                    }
+                }
+                fence_proxy_async_smem();            // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&stg_free[st]);
+                    mbar_arrive(&ring_full[rs]);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------ epilogue: warp = (TMEM lane group g, channel half h)
+        const int ew = warp - 6;                     // 0..7
+        const int g = warp & 3;                      // TMEM lanes 32g .. 32g+31 (a warp may only touch the lane quarter warp % 4)
+        const int h = ew >> 2;                       // channels 16h .. 16h+15
+        const int par = g >> 1;                      // row of the tile = parity of the grid row (tiles start on even rows)
+        const int x = ((g & 1) << 5) | lane;
+        const bool right_half = g & 1;
+        float sg[16], sq[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) sg[e] = sq[e] = 0.f;
+        const long chan = (long)p.H * p.W;
+        uint32_t tile_seq = 0;
+        for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
+            const int b = strip / p.strips_per_img, y0 = (strip - b * p.strips_per_img) * H2_RB;
+            for (int t = 0; t < H2_TILES; ++t, ++tile_seq) {
+                const int acc = tile_seq & 1;
+                const int yy = y0 + 2 * t + par;
+                const bool valid = yy < p.H && x < p.W;
+                mbar_wait(&tm_full[acc], (tile_seq >> 1) & 1);
+                tc_fence_after();
+                const uint32_t ta = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * 256 + 16 * h);
+                float L[16], C[16], R[16];
+                {
+                    uint32_t el[16], ec[16], er[16];
+                    tmem_ld16(ta, el);
+                    tmem_ld16(ta + 32, ec);
+                    tmem_ld16(ta + 64, er);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { L[e] = __uint_as_float(el[e]); C[e] = __uint_as_float(ec[e]); R[e] = __uint_as_float(er[e]); }
+                }
+#pragma unroll
+                for (int q8 = 0; q8 < 2; ++q8) {                                               // 8 channels at a time (register budget: 146 per thread)
+                    uint32_t u0[8], u1[8], d0[8], d1[8];
+                    tmem_ld8(ta + 96 + 8 * q8, u0);
+                    tmem_ld8(ta + 128 + 8 * q8, u1);
+                    tmem_ld8(ta + 160 + 8 * q8, d0);
+                    tmem_ld8(ta + 192 + 8 * q8, d1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float a0 = __uint_as_float(u0[e]) + __uint_as_float(d0[e]);      // tap a = 0 of the rows above / below
+                        const float a1 = __uint_as_float(u1[e]) + __uint_as_float(d1[e]);      // tap a = 1
+                        if (par == 0) { L[8 * q8 + e] += a0; C[8 * q8 + e] += a1; }            // even row: columns x-1, x
+                        else { C[8 * q8 + e] += a0; R[8 * q8 + e] += a1; }                     // odd row:  columns x, x+1
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tm_free[acc]);                // the accumulator is in registers
+                // boundary lanes: column 31 | 32 sits between the two warps of a grid row
+                float* xw = &s_xchg[acc][g][h][0][0];
+                if (lane == 31) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(xw + e) = make_float4(L[e], L[e + 1], L[e + 2], L[e + 3]);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(xw + 16 + e) = make_float4(R[e], R[e + 1], R[e + 2], R[e + 3]);
+                }
+                named_bar_sync(3, 256);
+                const float* nb = right_half ? &s_xchg[acc][g - 1][h][0][0] : &s_xchg[acc][g + 1][h][1][0];
+                float* out = p.y + ((long)b * p.Cout * p.H + yy) * p.W + x;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    float lf = __shfl_up_sync(0xffffffffu, L[e], 1);
+                    float rt = __shfl_down_sync(0xffffffffu, R[e], 1);
+                    if (lane == 0) lf = right_half ? nb[e] : 0.f;          // x = 0: zero padding; x = 32: lane 31 of the left warp
+                    if (lane == 31) rt = right_half ? 0.f : nb[e];         // x = 63: zero padding; x = 31: lane 0 of the right warp
+                    const int co = 16 * h + e;
+                    float val = 0.f;
+                    if (co < p.Cout && valid) {
+                        val = C[e] + lf + rt + s_bias[co];
+                        out[co * chan] = val;
+                    }
+                    sg[e] += val;
+                    sq[e] += val * val;
+                }
+            }
+        }
+        if (p.stats != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float a = gn_warp_sum(sg[e]), q = gn_warp_sum(sq[e]);
+                if (lane == 0 && 16 * h + e < p.Cout) {
+                    atomicAdd(&s_stat[16 * h + e], (double)a);
+                    atomicAdd(&s_stat[32 + 16 * h + e], (double)q);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (p.stats != nullptr && threadIdx.x < p.Cout) {
+        atomicAdd(p.stats + threadIdx.x, s_stat[threadIdx.x]);
+        atomicAdd(p.stats + p.Cout + threadIdx.x, s_stat[32 + threadIdx.x]);
+    }
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------- C-ABI
+GN_API long gn_hexconv_tc2_workspace_bytes(void) { return H2_W_BYTES + 1024; }
+
+GN_API int gn_hexconv_tc2_supported(int cin, int cout, int H, int W, int ksize) {
+    return ksize == 1 && cin >= 1 && cin <= 32 && cout >= 1 && cout <= 32 && H >= 2 && W >= 4 && W <= 64 && W % 4 == 0;
+}
+
+// y = hexconv(x') + bias with x' = in_scale ? relu(x * in_scale + in_shift) : x.  Same contract as gn_hexconv_fwd / gn_hexconv_fwd_tc
+// (wp from gn_hexconv_pack: mode 0 forward, mode 1 data gradient); stats (nullable): fp64 [2 * cout] sum / sum of squares, accumulated.
+// workspace: gn_hexconv_tc2_workspace_bytes() of caller-owned device memory, 1024-byte aligned (packed weights).
+GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
+                              double* stats, int B, int cin, int cout, int H, int W, void* workspace, cudaStream_t stream) {
+    GN_REQUIRE(x && wp && y && workspace && B > 0, GN_EINVAL, "hexconv_fwd_tc2: bad arguments");
+    GN_REQUIRE(gn_hexconv_tc2_supported(cin, cout, H, W, 1), GN_EUNSUPPORTED, "hexconv_fwd_tc2: needs kernel_size 1, <= 32 channels, W <= 64 and W % 4 == 0");
+    GN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), GN_EINVAL, "hexconv_fwd_tc2: in_scale/in_shift must come together");
+    GN_REQUIRE(((uintptr_t)workspace & 1023) == 0 && ((uintptr_t)x & 15) == 0, GN_EALIGN, "hexconv_fwd_tc2: workspace must be 1024-byte aligned, x 16-byte aligned");
+    Hex2Params p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = H; p.W = W; p.Cin = cin; p.Cout = cout;
+    p.strips_per_img = gn_ceil_div(H, H2_RB);
+    p.n_strips = B * p.strips_per_img;
+    p.bias = bias; p.in_scale = in_scale; p.in_shift = in_shift; p.y = y; p.stats = stats;
+    __nv_bfloat16* wt = (__nv_bfloat16*)workspace;
+    hex2_pack_kernel<<<gn_ceil_div(H2_W_ROWS * 64, 256), 256, 0, stream>>>(wp, cin, cout, wt);
+    GN_LAUNCH_CHECK();
+    CUtensorMap tmX, tmW;
+    {
+        uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)cin, (uint64_t)B};
+        uint64_t strides[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)cin * H * W * 4};
+        uint32_t box[4] = {64, 1, 32, 1};
+        int rc = gn_tmap_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {64, (uint64_t)H2_W_ROWS};
+        uint64_t strides[1] = {128};
+        uint32_t box[2] = {64, 64};
+        int rc = gn_tmap_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)H2_W_BYTES + 9 * H2_SLOT + (size_t)H2_STAGES * 2 * H2_ROW_F32 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GN_CUDA(cudaFuncSetAttribute(hexconv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int grid = p.n_strips < gn_num_sms() ? p.n_strips : gn_num_sms();
+    hexconv_tc2_kernel<<<grid, H2_THREADS, smem, stream>>>(tmX, tmW, p);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}

@@ -49,6 +49,9 @@ def pack_weights(ks, ksize, cin, cout, mode, kind='hex'):
 # is launch-latency-bound and the exact-fp32 FMA kernel costs the same.  '1' / '0' force one path (tests, benchmarks).
 TENSOR_CORE_MODE = os.environ.get('GRIDNEXT_B200_HEX_TC', 'auto')
 TENSOR_CORE_MIN_CELLS = 16 * 78 * 64
+# '2': the second-generation kernel (csrc/hexconv_tc2.cu: fp32 NCHW in and out, operands converted in shared memory) wherever it
+# supports the shape (grid width <= 64 and a multiple of 4), else the first generation; '1' forces the first generation.
+TENSOR_CORE_GEN = os.environ.get('GRIDNEXT_B200_HEX_TC_GEN', '2')
 
 
 def _use_tc(B, cin, cout, H, W, ksize):
@@ -66,6 +69,11 @@ def hexconv_fwd(x, wp, bias, cout, ksize, in_scale=None, in_shift=None, stats=No
         call('gn_sqconv_fwd', ptr(x), ptr(wp), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(y), ptr(stats), B, cin, cout, H, W, ksize, stream())
         return y
     if _use_tc(B, cin, cout, H, W, ksize):
+        lib = _lib.load()
+        if TENSOR_CORE_GEN != '1' and lib.gn_hexconv_tc2_supported(cin, cout, H, W, ksize):
+            ws, wptr = _aligned_workspace(lib.gn_hexconv_tc2_workspace_bytes(), x.device)
+            call('gn_hexconv_fwd_tc2', ptr(x), ptr(wp), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(y), ptr(stats), B, cin, cout, H, W, wptr, stream())
+            return y
         ws, wptr = _aligned_workspace(_lib.load().gn_hexconv_tc_workspace_bytes(B, H, W), x.device)
         call('gn_hexconv_fwd_tc', ptr(x), ptr(wp), ptr(bias), ptr(in_scale), ptr(in_shift), ptr(y), ptr(stats), B, cin, cout, H, W, wptr, stream())
         return y

@@ -47,6 +47,14 @@ int gn_hexconv_tc_supported(int cin, int cout, int H, int W, int ksize);
 long gn_hexconv_tc_workspace_bytes(int B, int H, int W);
 int gn_hexconv_fwd_tc(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
                       double* stats, int B, int cin, int cout, int H, int W, void* workspace, gn_stream_t stream);
+/* Second generation of the same operation (csrc/hexconv_tc2.cu): fp32 NCHW in and out with NO intermediate layout in global
+ * memory -- rows are TMA-loaded once, converted to the bf16 hi | lo operand in shared memory (previous BatchNorm+ReLU fused there),
+ * the taps of a grid row are stacked along UMMA N and the column shifts become neighbour-lane sums in the epilogue.  Grid width
+ * <= 64 and a multiple of 4; same contract as gn_hexconv_fwd_tc; workspace = gn_hexconv_tc2_workspace_bytes(), 1024-byte aligned. */
+int gn_hexconv_tc2_supported(int cin, int cout, int H, int W, int ksize);
+long gn_hexconv_tc2_workspace_bytes(void);
+int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
+                       double* stats, int B, int cin, int cout, int H, int W, void* workspace, gn_stream_t stream);
 /* Tensor-core weight gradient (same shapes as gn_hexconv_fwd_tc); dbias is not produced: it is gn_bn_stats' channel sum of dY. */
 long gn_hexconv_tc_wgrad_workspace_bytes(int B, int H, int W);
 int gn_hexconv_wgrad_tc(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, int B, int cin,

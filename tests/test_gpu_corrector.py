@@ -57,12 +57,17 @@ def test_hexconv_fwd_bwd_matches_oracle(k, cfg):
         assert rel_err(a.grad, r.grad) < TOL
 
 
+@pytest.mark.parametrize('gen', ['2', '1'])
 @pytest.mark.parametrize('cfg', [(7, 32, 2, 78, 64), (32, 32, 3, 78, 64), (32, 7, 2, 78, 64), (3, 5, 2, 7, 9), (4, 4, 1, 4, 4), (14, 32, 1, 9, 70),
-                                 (32, 32, 17, 78, 64), (20, 12, 3, 11, 33)])
-def test_hexconv_tensor_core_path_matches_oracle(cfg, monkeypatch):
-    """kernel_size 1, <= 32 channels on tcgen05 (bf16 x 3 split): forward and data gradient still within 1e-5 of the fp64 oracle."""
+                                 (32, 32, 17, 78, 64), (20, 12, 3, 11, 33), (32, 32, 5, 27, 64), (16, 24, 2, 53, 32), (32, 32, 40, 78, 64)])
+def test_hexconv_tensor_core_path_matches_oracle(cfg, gen, monkeypatch):
+    """kernel_size 1, <= 32 channels on tcgen05 (bf16 x 3 split): forward and data gradient still within 1e-5 of the fp64 oracle.
+    gen 2 = csrc/hexconv_tc2.cu (fp32 in / out, operands converted in shared memory; grid width <= 64, a multiple of 4 -- other
+    shapes fall through to gen 1 = csrc/hexconv_tc.cu with its parity-plane rewrite).  (27, 64): a strip boundary at row 26;
+    (53, 32): three strips, half-width rows; B = 40: several strips per CTA (ring / staging phases wrap many times)."""
     from gridnext_b200 import hexagdly as hx
     monkeypatch.setattr(hx, 'TENSOR_CORE_MODE', '1')
+    monkeypatch.setattr(hx, 'TENSOR_CORE_GEN', gen)
     cin, cout, B, H, W = cfg
     ks, b, x, dy = rand_hex(cin, cout, 1, B, H, W, seed=77 + cin + H)
     ks_r = [t.clone().double().requires_grad_(True) for t in ks]
