@@ -139,6 +139,7 @@ __device__ __forceinline__ void cf_conv_unit(const float* __restrict__ s_in, con
     for (int t = 0; t < CF_T; ++t) {
         const float* src = s_in + rws[t] * CF_SW + x + 1 + dxs[t];
         const float* w = s_w + t * CF_C * CF_C + 8 * og;
+#pragma unroll 4
         for (int c = 0; c < Cin; ++c) {
             const float v = src[c * 3 * CF_SW];
             const float4 w0 = *reinterpret_cast<const float4*>(w + c * CF_C);

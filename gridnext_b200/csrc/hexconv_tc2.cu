@@ -32,6 +32,7 @@
 #include "gn_common.cuh"
 #include "gn_ptx.cuh"
 #include "gn_tma.cuh"
+#include <stdlib.h>
 
 using namespace gnptx;
 
@@ -48,6 +49,7 @@ using namespace gnptx;
 struct Hex2Params {
     int B, H, W, Cin, Cout;
     int strips_per_img, n_strips;
+    int dbg;                 // development switches (GRIDNEXT_B200_H2_DBG): 1 no output stores, 2 no MMAs, 4 no conversion, 8 no TMEM reads
     const float* bias;
     const float* in_scale;
     const float* in_shift;
@@ -78,7 +80,8 @@ __global__ void hex2_pack_kernel(const float* __restrict__ wp, int cin, int cout
 }
 
 __global__ void __launch_bounds__(H2_THREADS, 1)
-hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Hex2Params p) {
+hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmW,
+                   const Hex2Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_w, stg_full[H2_STAGES], stg_free[H2_STAGES], ring_full[4], ring_free[4], tm_full[2], tm_free[2];
     __shared__ uint32_t tmem_slot;
@@ -101,6 +104,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmX2);
         tma_prefetch_desc(&tmW);
         mbar_init(&bar_w, 1);
         for (int s = 0; s < H2_STAGES; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_free[s], 4); }
@@ -129,9 +133,12 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     uint8_t* dst = s_stg + (size_t)st * 2 * H2_ROW_F32;
                     const int r_lo = y0 - 2 + 2 * k;
                     const bool first = k == 0, last = k == H2_CHUNKS - 1;
+                    // staged layout [channel][row of the pair][x]: a regular pair is ONE box (64 x 2 rows x 32 channels: 512 contiguous bytes per
+                    // channel); the halo pairs at the strip ends load their single row into the same layout with the one-row map
                     mbar_arrive_expect_tx(&stg_full[st], (first || last) ? H2_ROW_F32 : 2 * H2_ROW_F32);
-                    if (!first) tma_load_4d(&tmX, &stg_full[st], dst, 0, r_lo, 0, b);
-                    if (!last) tma_load_4d(&tmX, &stg_full[st], dst + H2_ROW_F32, 0, r_lo + 1, 0, b);
+                    if (first) tma_load_4d(&tmX, &stg_full[st], dst + H2_ROW_F32, 0, r_lo + 1, 0, b);
+                    else if (last) tma_load_4d(&tmX, &stg_full[st], dst, 0, r_lo, 0, b);
+                    else tma_load_4d(&tmX2, &stg_full[st], dst, 0, r_lo, 0, b);
                 }
             }
         }
@@ -160,6 +167,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     const uint32_t a_dn = ring0 + (((i_own + 1) & 7) * H2_SLOT);
                     const uint32_t d = tmem_base + (uint32_t)(acc * 256);
                     const uint64_t dA_own = smem_desc(tmpl, a_own), dA_up = smem_desc(tmpl, a_up), dA_dn = smem_desc(tmpl, a_dn);
+                    if (!(p.dbg & 2)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_bf16(d, dA_own + (uint64_t)(2 * k), dS_hi + (uint64_t)(2 * k), idS, k > 0);
 #pragma unroll
@@ -172,6 +180,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     for (int k = 0; k < 4; ++k) umma_bf16(d + 160, dA_dn + (uint64_t)(2 * k), dD_hi + (uint64_t)(2 * k), idU, k > 0);
 #pragma unroll
                     for (int k = 0; k < 2; ++k) umma_bf16(d + 160, dA_dn + (uint64_t)(2 * k), dD_lo + (uint64_t)(2 * k), idU, 1u);
+                    }
                     umma_commit(&tm_full[acc]);
                     umma_commit(&ring_free[(gk + t) & 3]);                       // row pair gk + t is not read again
                     if (t == H2_TILES - 1) {
@@ -197,13 +206,16 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 if (gk >= 4) mbar_wait(&ring_free[rs], ((gk >> 2) - 1) & 1);
                 const int gy = y0 - 2 + 2 * k + r;
                 const bool loaded = !((k == 0 && r == 0) || (k == H2_CHUNKS - 1 && r == 1));
-                if (loaded) {
-                    const float* src = reinterpret_cast<const float*>(s_stg + (size_t)st * 2 * H2_ROW_F32 + (size_t)r * H2_ROW_F32) + x;
+                if (loaded && !(p.dbg & 4)) {
+                    // regular pair: [c][r][x] (128 floats per channel); halo pair: its one row as [c][x] in the half of the stage it was loaded to
+                    const bool halo = k == 0 || k == H2_CHUNKS - 1;
+                    const int cs = halo ? 64 : 128;
+                    const float* src = reinterpret_cast<const float*>(s_stg + (size_t)st * 2 * H2_ROW_F32) + (halo ? r * (H2_ROW_F32 / 4) : r * 64) + x;
                     const bool live = has_pro && gy >= 0 && gy < p.H && x < p.W;     // zero padding stays zero
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        float v0 = src[(2 * j) * 64], v1 = src[(2 * j + 1) * 64];
+                        float v0 = src[(2 * j) * cs], v1 = src[(2 * j + 1) * cs];
                         if (live) {
                             v0 = 2 * j < p.Cin ? fmaxf(fmaf(v0, s_pro[0][2 * j], s_pro[1][2 * j]), 0.f) : 0.f;
                             v1 = 2 * j + 1 < p.Cin ? fmaxf(fmaf(v1, s_pro[0][2 * j + 1], s_pro[1][2 * j + 1]), 0.f) : 0.f;
@@ -263,7 +275,9 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 tc_fence_after();
                 const uint32_t ta = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * 256 + 16 * h);
                 float L[16], C[16], R[16];
-                {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) L[e] = C[e] = R[e] = 0.f;
+                if (!(p.dbg & 8)) {
                     uint32_t el[16], ec[16], er[16];
                     tmem_ld16(ta, el);
                     tmem_ld16(ta + 32, ec);
@@ -273,7 +287,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     for (int e = 0; e < 16; ++e) { L[e] = __uint_as_float(el[e]); C[e] = __uint_as_float(ec[e]); R[e] = __uint_as_float(er[e]); }
                 }
 #pragma unroll
-                for (int q8 = 0; q8 < 2; ++q8) {                                               // 8 channels at a time (register budget: 146 per thread)
+                for (int q8 = 0; q8 < ((p.dbg & 8) ? 0 : 2); ++q8) {                           // 8 channels at a time (register budget: 146 per thread)
                     uint32_t u0[8], u1[8], d0[8], d1[8];
                     tmem_ld8(ta + 96 + 8 * q8, u0);
                     tmem_ld8(ta + 128 + 8 * q8, u1);
@@ -314,7 +328,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     float val = 0.f;
                     if (co < p.Cout && valid) {
                         val = C[e] + lf + rt + s_bias[co];
-                        out[co * chan] = val;
+                        if (!(p.dbg & 1)) out[co * chan] = val;
                     }
                     sg[e] += val;
                     sq[e] += val * val;
@@ -363,15 +377,22 @@ GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias
     p.strips_per_img = gn_ceil_div(H, H2_RB);
     p.n_strips = B * p.strips_per_img;
     p.bias = bias; p.in_scale = in_scale; p.in_shift = in_shift; p.y = y; p.stats = stats;
+    {
+        const char* e = getenv("GRIDNEXT_B200_H2_DBG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     __nv_bfloat16* wt = (__nv_bfloat16*)workspace;
     hex2_pack_kernel<<<gn_ceil_div(H2_W_ROWS * 64, 256), 256, 0, stream>>>(wp, cin, cout, wt);
     GN_LAUNCH_CHECK();
-    CUtensorMap tmX, tmW;
+    CUtensorMap tmX, tmX2, tmW;
     {
         uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)cin, (uint64_t)B};
         uint64_t strides[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)cin * H * W * 4};
         uint32_t box[4] = {64, 1, 32, 1};
         int rc = gn_tmap_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+        box[1] = 2;
+        rc = gn_tmap_encode(&tmX2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     }
     {
@@ -388,7 +409,7 @@ GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias
         attr_set = true;
     }
     const int grid = p.n_strips < gn_num_sms() ? p.n_strips : gn_num_sms();
-    hexconv_tc2_kernel<<<grid, H2_THREADS, smem, stream>>>(tmX, tmW, p);
+    hexconv_tc2_kernel<<<grid, H2_THREADS, smem, stream>>>(tmX, tmX2, tmW, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -260,27 +260,64 @@ class _Geometry:
         self.c_final = c
 
 
-def _check_supported(net):
+def _outside_kernel_envelope(net):
+    """None when the tcgen05 kernels cover this configuration, else the reason (string).  The envelope is what the GridNet hot
+    path uses (every notebook: growth_rate 32, bn_size 4, 64 stem channels, small_inputs=False, drop_rate 0): TMA needs 16-byte
+    aligned channel slices (multiples of 8 bf16), UMMA needs N a multiple of 16."""
     if net.small_inputs:
-        raise NotImplementedError('DenseNet (B200): small_inputs=True (3x3 stem) is not on the GridNet hot path')
+        return 'small_inputs=True (3x3 stem without norm0 / pool0)'
     f = net.features
     if f.conv0.out_channels % 8 or f.conv0.out_channels > 128:
-        raise NotImplementedError('DenseNet (B200): num_init_features must be a multiple of 8, at most 128')
+        return 'num_init_features must be a multiple of 8, at most 128'
     for name, m in f.named_children():
         if name.startswith('denseblock'):
             for l in m.children():
                 g, b = l.conv2.out_channels, l.conv1.out_channels
                 if g % 8 or g > 48 or b % 16 or b > 128:
-                    raise NotImplementedError('DenseNet (B200): growth_rate must be a multiple of 8 (<= 48) and bn_size*growth_rate a multiple of 16 (<= 128)')
+                    return 'growth_rate must be a multiple of 8 (<= 48) and bn_size*growth_rate a multiple of 16 (<= 128)'
                 if l.drop_rate > 0 and l.training:
-                    raise NotImplementedError('DenseNet (B200): dropout in training mode is not implemented')
+                    return 'dropout in training mode'
         if name.startswith('transition') and m.conv.out_channels % 8:
-            raise NotImplementedError('DenseNet (B200): transition widths must be multiples of 8')
+            return 'transition widths must be multiples of 8'
+    return None
+
+
+def _check_supported(net):
     modes = set(bool(b.training) for b in _bn_list(net))
     if len(modes) != 1:
         raise NotImplementedError('DenseNet (B200): BatchNorm layers must be all in train mode or all in eval mode')
     if any(not b.track_running_stats for b in _bn_list(net)):
         raise NotImplementedError('DenseNet (B200): BatchNorm without running statistics is not supported')
+
+
+_WARNED = set()
+
+
+def _reference_graph_forward(net, x):
+    """The reference's module graph (densenet.py:21-44,57-75,152-159) evaluated with PyTorch's own CUDA operators: used ONLY for
+    configurations outside the kernels' envelope (the constructor's defaults -- growth_rate 12, small_inputs=True -- and train-mode
+    dropout), none of which the GridNet notebooks use.  Loud by design: a one-time warning names the reason."""
+    import torch.nn.functional as F
+    f = net.features
+    h = f.conv0(x.float())
+    if hasattr(f, 'norm0'):
+        h = f.pool0(f.relu0(f.norm0(h)))
+    for name, m in f.named_children():
+        if name.startswith('denseblock'):
+            feats = [h]
+            for layer in m.children():
+                t = torch.cat(feats, 1)
+                t = layer.conv1(F.relu(layer.norm1(t)))
+                t = layer.conv2(F.relu(layer.norm2(t)))
+                if layer.drop_rate > 0:
+                    t = F.dropout(t, p=layer.drop_rate, training=layer.training)
+                feats.append(t)
+            h = torch.cat(feats, 1)
+        elif name.startswith('transition'):
+            h = m.pool(m.conv(F.relu(m.norm(h))))
+    h = F.relu(f.norm_final(h))
+    h = F.adaptive_avg_pool2d(h, (1, 1)).view(h.size(0), -1)
+    return net.classifier(h) if net.classify else h
 
 
 def _forward_chunk(net, geo, cst, plan, x, save):
@@ -798,4 +835,13 @@ class DenseNet(nn.Module):
                 param.data.fill_(0)
 
     def forward(self, x):
+        why = _outside_kernel_envelope(self)
+        if why is not None:
+            _lib.require_cuda(x)
+            if why not in _WARNED:
+                import warnings
+                _WARNED.add(why)
+                warnings.warn('gridnext_b200 DenseNet: %s is outside the tcgen05 kernels\' envelope; this configuration runs the reference '
+                              'module graph with PyTorch\'s CUDA operators (correct, not the optimised path)' % why, stacklevel=2)
+            return _reference_graph_forward(self, x)
         return _DenseNetFn.apply(x, self, *self.parameters())

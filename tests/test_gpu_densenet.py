@@ -201,3 +201,31 @@ def test_densenet_rejects_unsupported_modes():
         net(torch.zeros(2, 3, 32, 32, device='cuda'))
     with pytest.raises(RuntimeError):
         net.eval()(torch.zeros(1, 3, 32, 32))
+
+
+def test_default_constructor_runs_forward_and_backward():
+    """The reference's DEFAULT DenseNet() (densenet.py:93-95: growth_rate 12, block_config (16, 16, 16), 24 stem channels,
+    small_inputs=True) lies outside the tcgen05 kernels' channel envelope (12 is not a multiple of 8): it runs the reference module
+    graph with PyTorch's CUDA operators, announced by a warning, and matches the fp32 oracle; train-mode dropout takes the same path."""
+    import warnings
+    from gridnext_b200.densenet import DenseNet
+    torch.manual_seed(0)
+    net = DenseNet(num_classes=10).cuda().eval()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    g = torch.Generator(); g.manual_seed(4)
+    x = torch.randn(3, 3, 32, 32, generator=g)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        out = net(x.cuda())
+    assert list(out.shape) == [3, 10]
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    with torch.no_grad():
+        ref = R.densenet_forward(sd, x)
+    assert relmax(out.detach(), ref) < 2e-2                    # cuDNN's default TF32 convolutions vs the fp32 oracle
+    out.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    drop = DenseNet(growth_rate=8, block_config=(2, 2), num_init_features=16, bn_size=2, num_classes=7, small_inputs=False, drop_rate=0.2).cuda().train()
+    y = drop(torch.randn(4, 3, 32, 32, device='cuda'))
+    assert list(y.shape) == [4, 7] and torch.isfinite(y).all()
+    with pytest.raises(RuntimeError):
+        DenseNet(num_classes=10)(torch.zeros(1, 3, 32, 32))     # CPU tensors are still refused: there is no CPU path
