@@ -11,8 +11,8 @@
 //     64 columns x 1 row x 32 channels, out-of-grid rows / columns / channels zero-filled) into a staging ring;
 //   * four converter warps apply the previous layer's BatchNorm+ReLU (gridnet_models.py:134-136), split every value into
 //     bf16 hi + lo (x = hi + lo to 16 mantissa bits; fp32-grade accuracy with x_hi w_hi + x_lo w_hi + x_hi w_lo, north_star
-//     1e-5) and write the cell's 128-byte K-major operand row [32 hi | 32 lo] (SWIZZLE_128B) into a ring of 8 grid-row slots
-//     (+ a mirror of slot 0 behind slot 7, so that any two consecutive rows are contiguous); every row is loaded and converted once;
+//     1e-5) and write the cell's 128-byte K-major operand row [32 hi | 32 lo] (SWIZZLE_128B) into a ring of 12 grid-row slots
+//     (+ a mirror of slot 0 behind slot 11, so that any two consecutive rows are contiguous); every row is loaded and converted once;
 //   * a tile is two grid rows (y even, y + 1) x 64 columns = the 128 accumulator rows of one UMMA.  The hexagonal neighbourhood
 //     mixes row shifts (y - 1, y + 1) with parity-dependent column shifts.  Row shifts are operand START ADDRESSES (a whole
 //     8 KB slot); column shifts are NOT applied to the operand: the taps are stacked along UMMA N instead --
@@ -39,7 +39,9 @@ using namespace gnptx;
 #define H2_RB 26                     // grid rows per strip (even)
 #define H2_TILES (H2_RB / 2)         // 13 tiles per strip
 #define H2_CHUNKS (H2_TILES + 2)     // 15 row pairs per strip: pair k = rows y0 - 2 + 2k, y0 - 1 + 2k (first / last: one halo row)
-#define H2_STAGES 4                  // fp32 staging ring (one row pair = 16 KB per stage)
+#define H2_STAGES 3                  // fp32 staging ring (one row pair = 16 KB per stage)
+#define H2_RP 6                      // operand ring depth in row pairs: a tile reads 3, so the converters may run 3 pairs ahead of the MMAs
+                                     // (with 4 the converter <-> MMA barrier hand-offs were on the critical path: 2.4 us per tile with all work switched off)
 #define H2_ROW_F32 8192              // one staged grid row: 32 channels x 64 columns fp32
 #define H2_SLOT 8192                 // one operand row slot: 64 cells x 128 B
 #define H2_W_ROWS 448                // packed weight rows: S_hi 96, S_lo 96, U_hi 64, U_lo 64, D_hi 64, D_lo 64
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
 hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmW,
                    const Hex2Params p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_w, stg_full[H2_STAGES], stg_free[H2_STAGES], ring_full[4], ring_free[4], tm_full[2], tm_free[2];
+    __shared__ __align__(8) uint64_t bar_w, stg_full[H2_STAGES], stg_free[H2_STAGES], ring_full[H2_RP], ring_free[H2_RP], tm_full[2], tm_free[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_pro[2][32];
     __shared__ __align__(16) float s_xchg[2][4][2][2][16];       // [tile parity][lane group][channel half][L of lane 31 | R of lane 0][16]
@@ -92,8 +94,8 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* s_w = sm;                                           // packed weights, 56 KB
-    uint8_t* s_ring = s_w + H2_W_BYTES;                          // 9 operand row slots (slot 8 mirrors slot 0), 72 KB
-    uint8_t* s_stg = s_ring + 9 * H2_SLOT;                       // staging: [stage][row of the pair][32][64] fp32, 64 KB
+    uint8_t* s_ring = s_w + H2_W_BYTES;                          // 2 * H2_RP operand row slots + a mirror of slot 0 behind the last one, 104 KB
+    uint8_t* s_stg = s_ring + (2 * H2_RP + 1) * H2_SLOT;         // staging: [stage][32 channels][row of the pair][64] fp32, 48 KB
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x < 64) s_stat[threadIdx.x] = 0.0;
@@ -108,7 +110,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tma_prefetch_desc(&tmW);
         mbar_init(&bar_w, 1);
         for (int s = 0; s < H2_STAGES; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_free[s], 4); }
-        for (int s = 0; s < 4; ++s) { mbar_init(&ring_full[s], 4); mbar_init(&ring_free[s], 1); }
+        for (int s = 0; s < H2_RP; ++s) { mbar_init(&ring_full[s], 4); mbar_init(&ring_free[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tm_full[s], 1); mbar_init(&tm_free[s], 8); }
         fence_barrier_init();
     }
@@ -136,9 +138,15 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     // staged layout [channel][row of the pair][x]: a regular pair is ONE box (64 x 2 rows x 32 channels: 512 contiguous bytes per
                     // channel); the halo pairs at the strip ends load their single row into the same layout with the one-row map
                     mbar_arrive_expect_tx(&stg_full[st], (first || last) ? H2_ROW_F32 : 2 * H2_ROW_F32);
-                    if (first) tma_load_4d(&tmX, &stg_full[st], dst + H2_ROW_F32, 0, r_lo + 1, 0, b);
-                    else if (last) tma_load_4d(&tmX, &stg_full[st], dst, 0, r_lo, 0, b);
-                    else tma_load_4d(&tmX2, &stg_full[st], dst, 0, r_lo, 0, b);
+                    // A TMA operation walks the rows of its box (here 256-byte rows 20 KB apart) nearly one at a time: with one 64-row box
+                    // per pair the loads alone took 0.19 ms for 256 arrays (1.7 TB/s; measured with every other role switched off).  Eight
+                    // boxes of 4 channels per pair keep 32 operations in flight per SM instead of 4.
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (first) tma_load_4d(&tmX, &stg_full[st], dst + H2_ROW_F32 + i * 1024, 0, r_lo + 1, 4 * i, b);
+                        else if (last) tma_load_4d(&tmX, &stg_full[st], dst + i * 1024, 0, r_lo, 4 * i, b);
+                        else tma_load_4d(&tmX2, &stg_full[st], dst + i * 2048, 0, r_lo, 4 * i, b);
+                    }
                 }
             }
         }
@@ -156,15 +164,16 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
                 for (int t = 0; t < H2_TILES; ++t, ++tile_seq) {
                     // row pairs gk + t, + t + 1, + t + 2 must be converted
-                    while (waited < gk + t + 3) { mbar_wait(&ring_full[waited & 3], (waited >> 2) & 1); ++waited; }
+                    while (waited < gk + t + 3) { mbar_wait(&ring_full[waited % H2_RP], (waited / H2_RP) & 1); ++waited; }
                     const int acc = tile_seq & 1;
                     if (tile_seq >= 2) mbar_wait(&tm_free[acc], ((tile_seq >> 1) - 1) & 1);
                     tc_fence_after();
-                    // slot of row index i (running over all strips: 2 * (gk + pair) + row): i & 7; a pair starting at slot 7 continues in the mirror slot 8
+                    // slot of row index i (running over all strips: 2 * (gk + pair) + row): i mod 12; a pair starting at the last slot continues
+                    // in the mirror slot behind it
                     const uint32_t i_own = 2 * (gk + t + 1);                     // first own row (even slot)
-                    const uint32_t a_own = ring0 + ((i_own & 7) * H2_SLOT);
-                    const uint32_t a_up = ring0 + (((i_own - 1) & 7) * H2_SLOT);
-                    const uint32_t a_dn = ring0 + (((i_own + 1) & 7) * H2_SLOT);
+                    const uint32_t a_own = ring0 + ((i_own % (2 * H2_RP)) * H2_SLOT);
+                    const uint32_t a_up = ring0 + (((i_own - 1) % (2 * H2_RP)) * H2_SLOT);
+                    const uint32_t a_dn = ring0 + (((i_own + 1) % (2 * H2_RP)) * H2_SLOT);
                     const uint32_t d = tmem_base + (uint32_t)(acc * 256);
                     const uint64_t dA_own = smem_desc(tmpl, a_own), dA_up = smem_desc(tmpl, a_up), dA_dn = smem_desc(tmpl, a_dn);
                     if (!(p.dbg & 2)) {
@@ -182,10 +191,10 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     for (int k = 0; k < 2; ++k) umma_bf16(d + 160, dA_dn + (uint64_t)(2 * k), dD_lo + (uint64_t)(2 * k), idU, 1u);
                     }
                     umma_commit(&tm_full[acc]);
-                    umma_commit(&ring_free[(gk + t) & 3]);                       // row pair gk + t is not read again
+                    umma_commit(&ring_free[(gk + t) % H2_RP]);                   // row pair gk + t is not read again
                     if (t == H2_TILES - 1) {
-                        umma_commit(&ring_free[(gk + t + 1) & 3]);
-                        umma_commit(&ring_free[(gk + t + 2) & 3]);
+                        umma_commit(&ring_free[(gk + t + 1) % H2_RP]);
+                        umma_commit(&ring_free[(gk + t + 2) % H2_RP]);
                     }
                 }
                 gk += H2_CHUNKS;
@@ -201,9 +210,9 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const int b = strip / p.strips_per_img, y0 = (strip - b * p.strips_per_img) * H2_RB;
             (void)b;
             for (int k = 0; k < H2_CHUNKS; ++k, ++gk) {
-                const int st = gk % H2_STAGES, rs = gk & 3;
+                const int st = gk % H2_STAGES, rs = gk % H2_RP;
                 mbar_wait(&stg_full[st], (gk / H2_STAGES) & 1);
-                if (gk >= 4) mbar_wait(&ring_free[rs], ((gk >> 2) - 1) & 1);
+                if (gk >= H2_RP) mbar_wait(&ring_free[rs], ((gk / H2_RP) - 1) & 1);
                 const int gy = y0 - 2 + 2 * k + r;
                 const bool loaded = !((k == 0 && r == 0) || (k == H2_CHUNKS - 1 && r == 1));
                 if (loaded && !(p.dbg & 4)) {
@@ -227,7 +236,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                         lo[j] = *reinterpret_cast<const uint32_t*>(&l);
                     }
                     // operand row of this cell: 8 chunks of 16 B, chunk c stored at (c ^ (x & 7)) (SWIZZLE_128B: slots are 1024-byte aligned)
-                    const uint32_t slot = (2 * gk + r) & 7;
+                    const uint32_t slot = (2 * gk + r) % (2 * H2_RP);
                     uint8_t* row = s_ring + (size_t)slot * H2_SLOT + (size_t)x * 128;
                     const uint32_t sw = (uint32_t)(x & 7);
 #pragma unroll
@@ -236,7 +245,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                         *reinterpret_cast<uint4*>(row + (((4 + c) ^ sw) << 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
                     }
                     if (slot == 0) {
-                        uint8_t* mrow = row + 8 * H2_SLOT;
+                        uint8_t* mrow = row + 2 * H2_RP * H2_SLOT;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             *reinterpret_cast<uint4*>(mrow + ((c ^ sw) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
@@ -388,7 +397,7 @@ GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias
     {
         uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)cin, (uint64_t)B};
         uint64_t strides[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)cin * H * W * 4};
-        uint32_t box[4] = {64, 1, 32, 1};
+        uint32_t box[4] = {64, 1, 4, 1};
         int rc = gn_tmap_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
         box[1] = 2;
@@ -402,7 +411,7 @@ GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias
         int rc = gn_tmap_encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
-    const size_t smem = (size_t)H2_W_BYTES + 9 * H2_SLOT + (size_t)H2_STAGES * 2 * H2_ROW_F32 + 1024;
+    const size_t smem = (size_t)H2_W_BYTES + (2 * H2_RP + 1) * H2_SLOT + (size_t)H2_STAGES * 2 * H2_ROW_F32 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         GN_CUDA(cudaFuncSetAttribute(hexconv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -154,28 +154,22 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const unsigned char* 
 // Cells whose window hangs over an image border (edge clamp == np.pad(mode='edge')) take clamped per-pixel loads in the same
 // kernel; out-of-tissue cells are zero-filled: one launch writes the whole grid.
 #define PG_RPC 32            // patch rows per tile
-#define PG_STAGES 6
-#define PG_THREADS 512
-#define PG_LUT_BYTES (3 * 256 * 32 * 4)
+#define PG_STAGES 4
 
 __device__ __forceinline__ bool pg_interior(int cx, int cy, int hw, int P, int H, int W) {
     return cx - hw >= 0 && cx - hw + P <= W && cy - hw >= 0 && cy - hw + P <= H;
 }
 
-// The value table (u8 -> float, or ToTensor + Normalize) is replicated per LANE: entry e of lane l lives at word e * 32 + l, i.e. in
-// bank l, so the twelve data-dependent look-ups a thread makes per 4 pixels never conflict (96 KB of the 227 KB; one CTA of 16 warps
-// per SM).  With one shared copy 62 % of all shared-memory wavefronts were bank-conflict replays and the kernel was bound by them
-// (ncu: l1tex 75 %, DRAM 61 %: profiles/r02_gather_before.txt).
 template <typename OutT>
-__global__ void __launch_bounds__(PG_THREADS, 1) patch_gather_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const unsigned char* __restrict__ img,
-                                                                         long pitch, int H, int W, const int* __restrict__ cells, int n_cells, int P,
-                                                                         int row_bytes, int stages, const float* __restrict__ mean,
-                                                                         const float* __restrict__ stdv, OutT* __restrict__ out) {
+__global__ void __launch_bounds__(256, 2) patch_gather_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const unsigned char* __restrict__ img,
+                                                                  long pitch, int H, int W, const int* __restrict__ cells, int n_cells, int P,
+                                                                  int row_bytes, int stages, const float* __restrict__ mean,
+                                                                  const float* __restrict__ stdv, OutT* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char sm[];
     __shared__ __align__(8) uint64_t bar[PG_STAGES];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* lut = reinterpret_cast<float*>(sm) + lane;                 // [3 * 256][32 lanes]: this lane's column
-    unsigned char* ring = sm + PG_LUT_BYTES;                          // [stages][PG_RPC][row_bytes]
+    const int tid = threadIdx.x;
+    float* lut = reinterpret_cast<float*>(sm);                        // [3][256]
+    unsigned char* ring = sm + 3 * 256 * sizeof(float);               // [stages][PG_RPC][row_bytes]
     const int tile_bytes = PG_RPC * row_bytes;
     const int tiles = P / PG_RPC, groups = P / 4, hw = P / 2;
     const int n_items = n_cells * tiles;
@@ -196,21 +190,19 @@ __global__ void __launch_bounds__(PG_THREADS, 1) patch_gather_tma_kernel(const _
         for (int s = 0; s < stages; ++s) gnptx::mbar_init(&bar[s], 1);
         gnptx::fence_barrier_init();
     }
+    // value table: raw u8 -> float, or ((v / 255) - mean) / std in IEEE fp32 like ToTensor + Normalize
+    for (int e = tid; e < 3 * 256; e += 256) {
+        const int c = e >> 8, v = e & 255;
+        float f = (float)v;
+        if (mean != nullptr) f = __fdiv_rn(__fsub_rn(__fdiv_rn(f, 255.0f), mean[c]), stdv[c]);
+        lut[e] = f;
+    }
     __syncthreads();
     if (tid == 0)
         for (int s = 0; s < stages; ++s) {
             const int item = blockIdx.x + s * gridDim.x;
             if (item < n_items) issue(item, s);
         }
-    // value table: raw u8 -> float, or ((v / 255) - mean) / std in IEEE fp32 like ToTensor + Normalize; every lane of a warp computes
-    // the same entry and stores it to its own bank (the first loads are in flight meanwhile)
-    for (int e = warp; e < 3 * 256; e += PG_THREADS / 32) {
-        const int c = e >> 8, v = e & 255;
-        float f = (float)v;
-        if (mean != nullptr) f = __fdiv_rn(__fsub_rn(__fdiv_rn(f, 255.0f), mean[c]), stdv[c]);
-        lut[e * 32] = f;
-    }
-    __syncthreads();
     int s = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -219,7 +211,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) patch_gather_tma_kernel(const _
         OutT* ocell = out + (long)cell * 3 * P * P;
         gnptx::mbar_wait(&bar[s], phase);
         if (!valid) {
-            for (int e = tid; e < 3 * PG_RPC * groups; e += PG_THREADS) {
+            for (int e = tid; e < 3 * PG_RPC * groups; e += 256) {
                 const int c = e / (PG_RPC * groups), r = (e / groups) % PG_RPC, g = e % groups;
                 Pack4<OutT>::store(ocell + ((long)c * P + r0 + r) * P + 4 * g, 0.f, 0.f, 0.f, 0.f);
             }
@@ -230,26 +222,31 @@ __global__ void __launch_bounds__(PG_THREADS, 1) patch_gather_tma_kernel(const _
             const int b0 = 3 * (cx - hw), d = b0 - (b0 & ~15);
             const int sh = (d & 3) * 8;
             const unsigned char* rows = ring + (size_t)s * tile_bytes;
-            for (int e = tid; e < PG_RPC * groups; e += PG_THREADS) {
-                const int r = e / groups, g = e - r * groups;
-                const unsigned* src = reinterpret_cast<const unsigned*>(rows + (size_t)r * row_bytes + ((12 * g + d) & ~3));
-                const unsigned i0 = src[0], i1 = src[1], i2 = src[2], i3 = src[3];
-                const unsigned w[3] = {__funnelshift_r(i0, i1, sh), __funnelshift_r(i1, i2, sh), __funnelshift_r(i2, i3, sh)};
-                float v[3][4];
+            // warp = patch rows (r = warp, warp + 8, ...), lane = 4-pixel groups: no integer division in the inner loop (the kernel is
+            // bound by instruction issue, ~145 instructions per 4 pixels in the first version: ncu, profiles/r02d_ncu_full_gather_corrector.txt)
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int r = warp; r < PG_RPC; r += 8) {
+                const unsigned char* rowp = rows + (size_t)r * row_bytes;
+                OutT* orow = ocell + (long)(r0 + r) * P;
+                for (int g = lane; g < groups; g += 32) {
+                    const unsigned* src = reinterpret_cast<const unsigned*>(rowp + ((12 * g + d) & ~3));
+                    const unsigned i0 = src[0], i1 = src[1], i2 = src[2], i3 = src[3];
+                    const unsigned w[3] = {__funnelshift_r(i0, i1, sh), __funnelshift_r(i1, i2, sh), __funnelshift_r(i2, i3, sh)};
+                    float v[3][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const int byte = 3 * j + c;
-                        v[c][j] = lut[(c * 256 + ((w[byte >> 2] >> (8 * (byte & 3))) & 0xff)) * 32];
-                    }
+                        for (int c = 0; c < 3; ++c) {
+                            const int byte = 3 * j + c;
+                            v[c][j] = lut[c * 256 + ((w[byte >> 2] >> (8 * (byte & 3))) & 0xff)];
+                        }
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    Pack4<OutT>::store(ocell + ((long)c * P + r0 + r) * P + 4 * g, v[c][0], v[c][1], v[c][2], v[c][3]);
+                    for (int c = 0; c < 3; ++c) Pack4<OutT>::store(orow + (long)c * P * P + 4 * g, v[c][0], v[c][1], v[c][2], v[c][3]);
+                }
             }
         } else {
             // window over an image border: clamped coordinates (a few dozen cells per array)
-            for (int e = tid; e < PG_RPC * groups; e += PG_THREADS) {
+            for (int e = tid; e < PG_RPC * groups; e += 256) {
                 const int r = e / groups, g = e - r * groups;
                 const int gy = min(max(cy - hw + r0 + r, 0), H - 1);
                 float v[3][4];
@@ -257,7 +254,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) patch_gather_tma_kernel(const _
                 for (int j = 0; j < 4; ++j) {
                     const int gx = min(max(cx - hw + 4 * g + j, 0), W - 1);
                     const unsigned char* px = img + (long)gy * pitch + 3L * gx;
-                    v[0][j] = lut[px[0] * 32]; v[1][j] = lut[(256 + px[1]) * 32]; v[2][j] = lut[(512 + px[2]) * 32];
+                    v[0][j] = lut[px[0]]; v[1][j] = lut[256 + px[1]]; v[2][j] = lut[512 + px[2]];
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
@@ -315,18 +312,18 @@ GN_API int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, c
         int rc = gn_tmap_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, img, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
         int stages = PG_STAGES;
-        while (stages > 2 && PG_LUT_BYTES + (size_t)stages * PG_RPC * row_bytes + 16 > 220 * 1024) --stages;
-        const size_t smem_t = PG_LUT_BYTES + (size_t)stages * PG_RPC * row_bytes + 16;
+        while (stages > 2 && 3 * 256 * sizeof(float) + (size_t)stages * PG_RPC * row_bytes + 16 > 100 * 1024) --stages;   // two CTAs per SM
+        const size_t smem_t = 3 * 256 * sizeof(float) + (size_t)stages * PG_RPC * row_bytes + 16;
         const int n_items = n_cells * (P / PG_RPC);
-        int grid_t = gn_num_sms();
+        int grid_t = 2 * gn_num_sms();
         if (grid_t > n_items) grid_t = n_items;
         if (out_bf16) {
             GN_CUDA(cudaFuncSetAttribute(patch_gather_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-            patch_gather_tma_kernel<__nv_bfloat16><<<grid_t, PG_THREADS, smem_t, stream>>>(tm, img, pitch, H, W, cells, n_cells, P, row_bytes, stages, mean, stdv,
+            patch_gather_tma_kernel<__nv_bfloat16><<<grid_t, 256, smem_t, stream>>>(tm, img, pitch, H, W, cells, n_cells, P, row_bytes, stages, mean, stdv,
                                                                                     (__nv_bfloat16*)out);
         } else {
             GN_CUDA(cudaFuncSetAttribute(patch_gather_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-            patch_gather_tma_kernel<float><<<grid_t, PG_THREADS, smem_t, stream>>>(tm, img, pitch, H, W, cells, n_cells, P, row_bytes, stages, mean, stdv, (float*)out);
+            patch_gather_tma_kernel<float><<<grid_t, 256, smem_t, stream>>>(tm, img, pitch, H, W, cells, n_cells, P, row_bytes, stages, mean, stdv, (float*)out);
         }
         GN_LAUNCH_CHECK();
         return GN_OK;                                                   // the persistent kernel wrote every cell (interior, border, off-tissue)

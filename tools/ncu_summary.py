@@ -56,5 +56,22 @@ def raw(path):
                 print('  %-86s %s %s' % (k, d[k], units[hdr.index(k)]))
 
 
+def rawcsv(path):
+    """Same summary from a `ncu -i rep --page raw --csv` export made on the GPU box (the .ncu-rep itself is too big to bring back)."""
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    extra = ['l1tex__throughput.avg.pct_of_peak_sustained_active', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+             'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+             'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
+             'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio']
+    print('# ncu --set full --clock-control none: selected raw metrics per captured launch (%s)' % path)
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        print('--- %s  grid %s block %s' % (d.get('Kernel Name', '?')[:110], d.get('Grid Size'), d.get('Block Size')))
+        for k in RAW_KEYS + extra:
+            if k in d:
+                print('  %-86s %s %s' % (k, d[k], units[hdr.index(k)]))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'raw': raw}[sys.argv[1]](sys.argv[2])
+    {'launches': launches, 'raw': raw, 'rawcsv': rawcsv}[sys.argv[1]](sys.argv[2])
