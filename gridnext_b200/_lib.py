@@ -26,6 +26,7 @@ _SIGS = {
     'gn_hexconv_fwd_tc': [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp],
     'gn_hexconv_tc_supported': [ci, ci, ci, ci, ci],
     'gn_hexconv_tc2_supported': [ci, ci, ci, ci, ci],
+    'gn_hexconv_tc2_set_trace': [vp],
     'gn_hexconv_fwd_tc2': [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp],
     'gn_hexconv_wgrad_tc': [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp],
     'gn_hexconv_wgrad': [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
@@ -134,7 +135,7 @@ def check(rc, what=''):
 
 
 # kernels launched per C-ABI call (for the benchmark's gpu_launches count); default 1
-KERNELS_PER_CALL = {'gn_corrector_fused_supported': 0, 'gn_cell_inverse': 2, 'gn_mm_fg_consistency': 2, 'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_hexconv_tc2_supported': 0, 'gn_hexconv_fwd_tc2': 2, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0, 'gn_prep_job_bytes': 0,
+KERNELS_PER_CALL = {'gn_corrector_fused_supported': 0, 'gn_cell_inverse': 2, 'gn_mm_fg_consistency': 2, 'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_hexconv_tc2_supported': 0, 'gn_hexconv_tc2_set_trace': 0, 'gn_hexconv_fwd_tc2': 2, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0, 'gn_prep_job_bytes': 0,
                     'gn_device_sm_count': 0, 'gn_hexconv_n_taps': 0}
 LAUNCHES = [0]
 PROFILE = None      # when a dict: name -> [n_calls, [cuda event pairs]]

@@ -36,6 +36,11 @@
 
 using namespace gnptx;
 
+#define H2_TRACE(ev, idx)                                                                 \
+    do {                                                                                  \
+        if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 64) p.trace[(ev) * 64 + (idx)] = clock64(); \
+    } while (0)
+
 #define H2_RB 26                     // grid rows per strip (even)
 #define H2_TILES (H2_RB / 2)         // 13 tiles per strip
 #define H2_CHUNKS (H2_TILES + 2)     // 15 row pairs per strip: pair k = rows y0 - 2 + 2k, y0 - 1 + 2k (first / last: one halo row)
@@ -51,6 +56,7 @@ using namespace gnptx;
 struct Hex2Params {
     int B, H, W, Cin, Cout;
     int strips_per_img, n_strips;
+    long long* trace;        // development: per-role clock64 timestamps of CTA 0 ([13 events][64]), see tools/hextc_trace.py
     int dbg;                 // development switches (GRIDNEXT_B200_H2_DBG): 1 no output stores, 2 no MMAs, 4 no conversion, 8 no TMEM reads
     const float* bias;
     const float* in_scale;
@@ -90,7 +96,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     __shared__ float s_pro[2][32];
     __shared__ __align__(16) float s_xchg[2][4][2][2][16];       // [tile parity][lane group][channel half][L of lane 31 | R of lane 0][16]
     __shared__ double s_stat[2 * 32];
-    __shared__ float s_bias[32];
+    __shared__ __align__(16) float s_bias[32];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* s_w = sm;                                           // packed weights, 56 KB
@@ -168,6 +174,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     const int acc = tile_seq & 1;
                     if (tile_seq >= 2) mbar_wait(&tm_free[acc], ((tile_seq >> 1) - 1) & 1);
                     tc_fence_after();
+                    H2_TRACE(4, tile_seq);
                     // slot of row index i (running over all strips: 2 * (gk + pair) + row): i mod 12; a pair starting at the last slot continues
                     // in the mirror slot behind it
                     const uint32_t i_own = 2 * (gk + t + 1);                     // first own row (even slot)
@@ -196,6 +203,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                         umma_commit(&ring_free[(gk + t + 1) % H2_RP]);
                         umma_commit(&ring_free[(gk + t + 2) % H2_RP]);
                     }
+                    H2_TRACE(5, tile_seq);
                 }
                 gk += H2_CHUNKS;
             }
@@ -211,8 +219,10 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             (void)b;
             for (int k = 0; k < H2_CHUNKS; ++k, ++gk) {
                 const int st = gk % H2_STAGES, rs = gk % H2_RP;
-                mbar_wait(&stg_full[st], (gk / H2_STAGES) & 1);
-                if (gk >= H2_RP) mbar_wait(&ring_free[rs], ((gk / H2_RP) - 1) & 1);
+                mbar_wait_backoff(&stg_full[st], (gk / H2_STAGES) & 1);
+                if (threadIdx.x == 64) H2_TRACE(1, gk);
+                if (gk >= H2_RP) mbar_wait_backoff(&ring_free[rs], ((gk / H2_RP) - 1) & 1);
+                if (threadIdx.x == 64) H2_TRACE(2, gk);
                 const int gy = y0 - 2 + 2 * k + r;
                 const bool loaded = !((k == 0 && r == 0) || (k == H2_CHUNKS - 1 && r == 1));
                 if (loaded && !(p.dbg & 4)) {
@@ -259,6 +269,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     mbar_arrive(&stg_free[st]);
                     mbar_arrive(&ring_full[rs]);
                 }
+                if (threadIdx.x == 64) H2_TRACE(3, gk);
             }
         }
     } else {
@@ -280,8 +291,10 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 const int acc = tile_seq & 1;
                 const int yy = y0 + 2 * t + par;
                 const bool valid = yy < p.H && x < p.W;
-                mbar_wait(&tm_full[acc], (tile_seq >> 1) & 1);
+                mbar_wait_backoff(&tm_full[acc], (tile_seq >> 1) & 1);
                 tc_fence_after();
+                if (threadIdx.x == 192) H2_TRACE(6, tile_seq);
+                if (threadIdx.x == 416) H2_TRACE(11, tile_seq);
                 const uint32_t ta = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * 256 + 16 * h);
                 float L[16], C[16], R[16];
 #pragma unroll
@@ -314,6 +327,13 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tm_free[acc]);                // the accumulator is in registers
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[16 * h + 4 * q]);
+                    C[4 * q] += b4.x; C[4 * q + 1] += b4.y; C[4 * q + 2] += b4.z; C[4 * q + 3] += b4.w;
+                }
+                if (threadIdx.x == 192) H2_TRACE(7, tile_seq);
+                if (threadIdx.x == 416) H2_TRACE(12, tile_seq);
                 // boundary lanes: column 31 | 32 sits between the two warps of a grid row
                 float* xw = &s_xchg[acc][g][h][0][0];
                 if (lane == 31) {
@@ -324,24 +344,47 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
                     for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(xw + 16 + e) = make_float4(R[e], R[e + 1], R[e + 2], R[e + 3]);
                 }
+                if (threadIdx.x == 192) H2_TRACE(9, tile_seq);
                 named_bar_sync(3, 256);
-                const float* nb = right_half ? &s_xchg[acc][g - 1][h][0][0] : &s_xchg[acc][g + 1][h][1][0];
-                float* out = p.y + ((long)b * p.Cout * p.H + yy) * p.W + x;
+                if (threadIdx.x == 192) H2_TRACE(10, tile_seq);
+                // every lane reads the neighbour warp's boundary values (a broadcast load) and selects: lane-conditional loads compiled into one
+                // divergent branch per channel and made this tail 5,000 cycles long (the whole kernel ran at 6,300 cycles per tile; clock64 trace)
+                const float4* nb4 = reinterpret_cast<const float4*>(right_half ? &s_xchg[acc][g - 1][h][0][0] : &s_xchg[acc][g + 1][h][1][0]);
+                float nbv[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t4 = nb4[q];
+                    nbv[4 * q] = t4.x; nbv[4 * q + 1] = t4.y; nbv[4 * q + 2] = t4.z; nbv[4 * q + 3] = t4.w;
+                }
+                float* outp = p.y + ((long)b * p.Cout * p.H + yy) * p.W + x + (long)(16 * h) * chan;      // advanced by one channel plane per element
+                const int n_ch = min(16, p.Cout - 16 * h);                                                // channels of this half that exist
+                const bool store = valid && !(p.dbg & 1);
+                // all 32 shuffles first, back to back (independent), then the arithmetic: issued element by element the in-order warp waited out
+                // a shuffle + a shared-memory latency per channel (2,650 cycles for this loop; clock64 trace)
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    float lf = __shfl_up_sync(0xffffffffu, L[e], 1);
-                    float rt = __shfl_down_sync(0xffffffffu, R[e], 1);
-                    if (lane == 0) lf = right_half ? nb[e] : 0.f;          // x = 0: zero padding; x = 32: lane 31 of the left warp
-                    if (lane == 31) rt = right_half ? 0.f : nb[e];         // x = 63: zero padding; x = 31: lane 0 of the right warp
-                    const int co = 16 * h + e;
-                    float val = 0.f;
-                    if (co < p.Cout && valid) {
-                        val = C[e] + lf + rt + s_bias[co];
-                        if (!(p.dbg & 1)) out[co * chan] = val;
-                    }
-                    sg[e] += val;
-                    sq[e] += val * val;
+                    L[e] = __shfl_up_sync(0xffffffffu, L[e], 1);
+                    R[e] = __shfl_down_sync(0xffffffffu, R[e], 1);
                 }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    // x = 0 / x = 63: zero padding; x = 32 takes L of the left warp's lane 31, x = 31 takes R of the right warp's lane 0
+                    const float lf = lane == 0 ? (right_half ? nbv[e] : 0.f) : L[e];
+                    const float rt = lane == 31 ? (right_half ? 0.f : nbv[e]) : R[e];
+                    const bool ok = valid && e < n_ch;
+                    const float val = ok ? C[e] + lf + rt : 0.f;                                           // the bias is already in C
+                    if (store && e < n_ch) *outp = val;
+                    outp += chan;
+                    C[e] = val;
+                }
+                if (p.stats != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        sg[e] += C[e];
+                        sq[e] = fmaf(C[e], C[e], sq[e]);
+                    }
+                }
+                if (threadIdx.x == 192) H2_TRACE(8, tile_seq);
             }
         }
         if (p.stats != nullptr) {
@@ -365,6 +408,13 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------- C-ABI
+static long long* g_h2_trace = nullptr;
+// development: device buffer of 9 x 64 int64 that CTA 0 of the next launches fills with clock64() timestamps per pipeline event
+GN_API int gn_hexconv_tc2_set_trace(long long* dev_buf) {
+    g_h2_trace = dev_buf;
+    return GN_OK;
+}
+
 GN_API long gn_hexconv_tc2_workspace_bytes(void) { return H2_W_BYTES + 1024; }
 
 GN_API int gn_hexconv_tc2_supported(int cin, int cout, int H, int W, int ksize) {
@@ -390,6 +440,7 @@ GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias
         const char* e = getenv("GRIDNEXT_B200_H2_DBG");
         p.dbg = e ? atoi(e) : 0;
     }
+    p.trace = g_h2_trace;
     __nv_bfloat16* wt = (__nv_bfloat16*)workspace;
     hex2_pack_kernel<<<gn_ceil_div(H2_W_ROWS * 64, 256), 256, 0, stream>>>(wp, cin, cout, wt);
     GN_LAUNCH_CHECK();

@@ -53,6 +53,7 @@ int gn_hexconv_fwd_tc(const float* x, const float* wp, const float* bias, const 
  * <= 64 and a multiple of 4; same contract as gn_hexconv_fwd_tc; workspace = gn_hexconv_tc2_workspace_bytes(), 1024-byte aligned. */
 int gn_hexconv_tc2_supported(int cin, int cout, int H, int W, int ksize);
 long gn_hexconv_tc2_workspace_bytes(void);
+int gn_hexconv_tc2_set_trace(long long* dev_buf);   /* development: 9 x 64 clock64() timestamps of CTA 0's pipeline events, or NULL */
 int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias, const float* in_scale, const float* in_shift, float* y,
                        double* stats, int B, int cin, int cout, int H, int W, void* workspace, gn_stream_t stream);
 /* Tensor-core weight gradient (same shapes as gn_hexconv_fwd_tc); dbias is not produced: it is gn_bn_stats' channel sum of dY. */
