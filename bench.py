@@ -556,6 +556,33 @@ def main():
         sweep = c4_sweep(dev)
         json.dump(sweep, open(args.profile_out, 'w'), indent=1)
 
+    infer = None
+    if rank == 0 and world == 1 and cfg in ('c1', 'c2'):
+        # the evaluation loop of utils.all_fgd_predictions (reference utils.py:20-57) on the same resident inputs: gather (c2) -> f -> g ->
+        # fused foreground softmax / argmax, no gradients; eager launches, one host read per array (the loop's own contract)
+        from gridnext_b200.utils import fg_predictions
+        wl.model.eval()
+        try:
+            def infer_step():
+                with torch.no_grad():
+                    if cfg == 'c2':
+                        wl.ip.gather_patches(wl.img, wl.cells, P, MEAN, STD, torch.bfloat16, out=wl.patches[0])
+                    out = wl.model(wl.model_inputs(0))
+                    return fg_predictions(out, wl.labels)
+            for _ in range(3):
+                infer_step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                infer_step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_inf = e0.elapsed_time(e1) / args.steps
+            infer = dict(value=SPOTS * wl.arrays / (ms_inf * 1e-3), unit='spots/s', ms_per_step=ms_inf,
+                         what='all_fgd_predictions step: f + g forward + foreground softmax/argmax, no grad, eager launches')
+        finally:
+            wl.model.train(); wl.model.patch_classifier.eval()
     if rank == 0:
         eager = None
         if cfg == 'c2' and not args.no_eager_baseline:
@@ -593,6 +620,8 @@ def main():
                     roofline=roof, cpu_baseline=cpu)
         if eager is not None:
             line['gpu_eager_baseline'] = eager
+        if infer is not None:
+            line['inference'] = infer
         print(json.dumps(line), flush=True)
     shutdown(world, graphs + [g for g in e2e_graphs if g is not None])
 
@@ -692,7 +721,8 @@ def roofline_from_profile(prof, wl, step_ms, args):
 
 
 def c4_sweep(dev):
-    """BASELINE configs[3]: single hexagdly.Conv2d(C, C, k) forward and forward+backward over C x k x B, graph-replayed."""
+    """BASELINE configs[3]: single hexagdly.Conv2d(C, C, k) forward and forward+backward over C x k x B, graph-replayed.
+    Algorithmic bytes: forward 4 (Cin + Cout) per cell; backward 4 (Cout + 2 Cin) (dX) + 4 (Cin + Cout) (dW) per cell."""
     from gridnext_b200 import hexagdly as hx
     pk = peaks()
     rows = []
@@ -702,19 +732,21 @@ def c4_sweep(dev):
             for B in (1, 4, 16, 64, 256):
                 conv = hx.Conv2d(C, C, k).to(dev)
                 ks = hx._kernels(conv)
-                x = torch.randn(B, C, H_ST, W_ST, device=dev)
+                x = torch.randn(B, C, H_ST, W_ST, device=dev, requires_grad=True)
                 dy = torch.randn(B, C, H_ST, W_ST, device=dev)
-                wp = hx.pack_weights(ks, k, C, C, 0)
-                wpt = hx.pack_weights(ks, k, C, C, 1)
                 cells = B * SPOTS
 
                 def fwd():
-                    hx.hexconv_fwd(x, wp, conv.bias_tensor, C, k)
+                    with torch.no_grad():
+                        hx.hexconv_visium(x, ks, conv.bias_tensor)
 
-                def bwd():
-                    hx.hexconv_fwd(dy, wpt, None, C, k)
-                    hx.hexconv_wgrad(x, dy, k)
-                for name, fn, by, fl in (('fwd', fwd, 8.0 * C * cells, 2.0 * T * C * C * cells), ('bwd', bwd, 16.0 * C * cells, 4.0 * T * C * C * cells)):
+                def bwd():          # forward + backward through the public functional (dx, dW, db), as autograd runs it
+                    y = hx.hexconv_visium(x, ks, conv.bias_tensor)
+                    y.backward(dy)
+                    x.grad = None
+                    for t in conv.parameters():
+                        t.grad = None
+                for name, fn, by, fl in (('fwd', fwd, 8.0 * C * cells, 2.0 * T * C * C * cells), ('fwd_bwd', bwd, 28.0 * C * cells, 6.0 * T * C * C * cells)):
                     fn(); torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):

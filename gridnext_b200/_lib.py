@@ -49,6 +49,7 @@ _SIGS = {
     'gn_corrector_fused_supported': [ci, vp, vp],
     'gn_corrector_fused_fwd': [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp],
     'gn_corrector_fused_bwd': [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp],
+    'gn_fg_predictions': [vp, vp, vp, vp, vp, vp, ci, ci, cl, vp],
     'gn_masked_ce': [vp, vp, vp, vp, vp, vp, cf, ci, ci, cl, vp],
     'gn_spot_table': [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp],
     'gn_patch_gather': [vp, cl, ci, ci, vp, ci, ci, vp, vp, vp, ci, vp],

@@ -211,6 +211,46 @@ __global__ void ce_finalize_kernel(const double* __restrict__ acc, const double*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Evaluation loop (utils.all_fgd_predictions, /root/reference/gridnext/utils.py:44-52): foreground mask, labels - 1, soft-max and
+// arg-max over the classes, written compacted in grid order.  offsets[cell] = number of foreground cells before `cell`.
+__global__ void __launch_bounds__(256) fg_predictions_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                             const int* __restrict__ offsets, long long* __restrict__ true_out,
+                                                             long long* __restrict__ pred_out, float* __restrict__ smax_out, int C, long HW,
+                                                             long n) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        const long long lab = labels[e];
+        if (lab <= 0) continue;
+        const long b = e / HW, p = e % HW;
+        const float* lp = logits + b * C * HW + p;
+        float m = -INFINITY;
+        int am = 0;
+        for (int c = 0; c < C; ++c) {
+            const float v = __ldg(lp + (long)c * HW);
+            if (v > m) { m = v; am = c; }                  // first maximum, like torch.argmax
+        }
+        float se = 0.f;
+        for (int c = 0; c < C; ++c) se += expf(__ldg(lp + (long)c * HW) - m);
+        const float inv = 1.f / se;
+        const long o = offsets[e];
+        true_out[o] = lab - 1;
+        pred_out[o] = am;
+        float* sp = smax_out + o * C;
+        for (int c = 0; c < C; ++c) sp[c] = expf(__ldg(lp + (long)c * HW) - m) * inv;
+    }
+}
+
+GN_API int gn_fg_predictions(const float* logits, const long long* labels, const int* offsets, long long* true_out, long long* pred_out,
+                             float* smax_out, int B, int C, long HW, cudaStream_t stream) {
+    GN_REQUIRE(logits && labels && offsets && true_out && pred_out && smax_out && B > 0 && C > 0 && HW > 0, GN_EINVAL, "fg_predictions: bad arguments");
+    const long n = (long)B * HW;
+    long blocks = (n + 255) / 256;
+    if (blocks > 8L * gn_num_sms()) blocks = 8L * gn_num_sms();
+    fg_predictions_kernel<<<(unsigned)blocks, 256, 0, stream>>>(logits, labels, offsets, true_out, pred_out, smax_out, C, HW, n);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C-ABI
 GN_API int gn_bn_finalize(const double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
                           float momentum, float eps, double count, float* scale, float* shift, float* mean_invstd, int C,

@@ -152,8 +152,18 @@ class _HexConvFn(torch.autograd.Function):
 
 
 def hexconv_visium(x, ks, bias=None):
-    """Functional hexagonal convolution on (B, C, H, W) with the hex parity taken on the row index."""
-    return _HexConvFn.apply(x, bias, len(ks) - 1, *ks)
+    """Functional hexagonal convolution on (B, C, H, W) with the hex parity taken on the row index.
+    kernel_size 1, <= 32 channels, below the tensor-core batch threshold: the persistent one-launch kernels of the corrector
+    (csrc/corrector_fused.cu) with a single stage -- all SMs busy at any batch size, no pack / unpack launches."""
+    ksize = len(ks) - 1
+    if ksize == 1 and x.is_cuda:
+        from . import corrector as _corr
+        cout, cin = int(ks[0].shape[0]), int(ks[0].shape[1])
+        meta = [dict(kind='hex', ksize=1, cin=cin, cout=cout, nk=2, has_bias=bias is not None, bn=None, relu=False)]
+        if x.dim() == 4 and x.shape[1] == cin and _corr._fused_eligible(meta, x):
+            params = list(ks) + ([bias] if bias is not None else [])
+            return _corr._CorrectorFusedFn.apply(x, meta, *params)
+    return _HexConvFn.apply(x, bias, ksize, *ks)
 
 
 class Conv2d(nn.Module):

@@ -111,6 +111,12 @@ int gn_corrector_fused_bwd(const float* x, float* const* act, const float* dout,
 int gn_masked_ce(const float* logits, const long long* labels, float* dlogits, double* acc, float* loss_out,
                  const double* n_fg_override, float loss_scale, int B, int C, long HW, gn_stream_t stream);
 
+/* ---- evaluation loop: replaces the mask / labels - 1 / softmax / argmax of gridnext/utils.py:44-52 (all_fgd_predictions).
+ * offsets[cell] = number of foreground cells (label > 0) before `cell` in (b, y, x) order; outputs are compacted in that order:
+ * true_out[n_fg] = label - 1, pred_out[n_fg] = argmax over classes, smax_out[n_fg][C] = softmax. */
+int gn_fg_predictions(const float* logits, const long long* labels, const int* offsets, long long* true_out, long long* pred_out,
+                      float* smax_out, int B, int C, long HW, gn_stream_t stream);
+
 /* ---- spot-patch gather: replaces gridnext/imgprocess.py:185-238 (grid_from_wsi_visium) */
 int gn_spot_table(const unsigned char* in_tissue, const int* array_row, const int* array_col, const double* pxl_row,
                   const double* pxl_col, int n_spots, int h_st, int w_st, int* cells, int* n_dropped, gn_stream_t stream);
