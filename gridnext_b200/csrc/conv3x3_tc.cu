@@ -35,6 +35,9 @@ struct Conv3Params {
     int epi_mode;         // 0 plain store, 1 BnBwdEpi (reference tile fetched by TMA)
     int img;              // > 0: small feature maps -- R = img * (H+2): a tile is img whole padded images, loaded with one TMA box per image
     int stack;            // 1: the three kx taps of a kernel row are stacked along UMMA N (3 MMAs chains of N = 3*CO instead of 9 of N = CO)
+    int eager_drain;      // 1: a staging slot is released as soon as ITS store has read it (not one sub-tile later): the slot ring, not any pipe, paces the data gradient
+    __nv_bfloat16* out;   // stacked forward: the epilogue stores straight from registers (32 B = one sector per thread and 16-channel half)
+    long ldo;
     BnBwdEpi bn;
 };
 
@@ -192,7 +195,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
             mbar_init(&bar_tfull[s], 1);
-            mbar_init(&bar_tempty[s], EPI_WARPS);
+            mbar_init(&bar_tempty[s], (EPI_MODE == 0 && EPI_WARPS == 16) ? 8 : EPI_WARPS);
         }
         for (int s = 0; s < C3_MAX_ESTAGES; ++s) {
             mbar_init(&bar_efull[s], 1);
@@ -309,8 +312,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
         }
     } else if (warp == 3) {
-        // ---- epilogue drain
-        if (elect_one()) {
+        // ---- epilogue drain (the two-group stacked forward stores from registers: nothing to drain)
+        if (!(EPI_MODE == 0 && EPI_WARPS == 16) && elect_one()) {
             int es = 0, prev_es = -1;
             uint32_t eph = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -327,17 +330,97 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                         c3_row_next(H2, n, yp);
                     }
                     tma_store_commit();
-                    if (prev_es >= 0) {
-                        tma_store_wait_read<1>();
-                        mbar_arrive(&bar_eempty[prev_es]);
+                    if (p.eager_drain) {
+                        tma_store_wait_read<0>();
+                        mbar_arrive(&bar_eempty[es]);
+                    } else {
+                        if (prev_es >= 0) {
+                            tma_store_wait_read<1>();
+                            mbar_arrive(&bar_eempty[prev_es]);
+                        }
+                        prev_es = es;
                     }
-                    prev_es = es;
                     if (++es == p.e_stages) { es = 0; eph ^= 1; }
                 }
             }
             tma_store_wait_all<0>();
         }
         __syncwarp();
+    } else if (EPI_MODE == 0 && EPI_WARPS == 16) {
+        // ---- stacked forward, two epilogue groups of 8 warps: group gi owns TMEM accumulator buffer gi, i.e. every other tile of this
+        // CTA, so two tiles are in the epilogue at once (one group of 8 in-order warps needed ~2,200 cycles per tile for ~200 dependent
+        // instructions and set the pace of the whole kernel).  Results leave as 32-byte register stores: no staging slot, no drain hop.
+        // warp (g, h) of a group: accumulator rows 32g..32g+31, channels 16h..16h+15
+        const int gi = (warp - 4) >> 3;
+        const int g = warp & 3;
+        const int h = ((warp - 4) >> 2) & 1;
+        const int trow = g * 32 + lane;
+        const int r_loc = trow / W2, xp = trow % W2;
+        uint32_t acc_phase = 0;
+        int it = 0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(gi * 256);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            if ((it & 1) != gi) continue;
+            int n, yp;
+            c3_row_coords(tile * R + r_loc, total_rows, H2, p.Nimg, n, yp);
+            const bool valid = r_loc < R && n >= 0 && n < p.Nimg && yp >= 1 && yp <= p.H && xp >= 1 && xp <= p.W;
+            mbar_wait(&bar_tfull[gi], acc_phase);
+            acc_phase ^= 1;
+            tc_fence_after();
+            uint32_t r0[16], r1[16], r2[16];
+            tmem_ld16(taddr + 16 * h, r0);
+            tmem_ld16(taddr + p.CO + 16 * h, r1);
+            tmem_ld16(taddr + 2 * p.CO + 16 * h, r2);
+            tmem_ld_wait();
+            tc_fence_before();
+            float4* xw = reinterpret_cast<float4*>(&s_xchg[gi][g][0][16 * h]);
+            if (lane == 31) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    xw[q] = make_float4(__uint_as_float(r0[4 * q]), __uint_as_float(r0[4 * q + 1]), __uint_as_float(r0[4 * q + 2]),
+                                        __uint_as_float(r0[4 * q + 3]));
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    xw[8 + q] = make_float4(__uint_as_float(r2[4 * q]), __uint_as_float(r2[4 * q + 1]), __uint_as_float(r2[4 * q + 2]),
+                                            __uint_as_float(r2[4 * q + 3]));
+            }
+            named_bar_sync(2 + gi, 8 * 32);           // the accumulator is in registers: the MMA warp may refill the buffer
+            if (lane == 0) mbar_arrive(&bar_tempty[gi]);
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[e]), 1);
+                const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[e]), 1);
+                v[e] = __uint_as_float(r1[e]) + (lane > 0 ? up : 0.f) + (lane < 31 ? dn : 0.f);
+            }
+            if (lane == 0 && g > 0) {
+                const float4* xr = reinterpret_cast<const float4*>(&s_xchg[gi][g - 1][0][16 * h]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t = xr[q];
+                    v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                }
+            }
+            if (lane == 31 && g < 3) {
+                const float4* xr = reinterpret_cast<const float4*>(&s_xchg[gi][g + 1][1][16 * h]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t = xr[q];
+                    v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                }
+            }
+            if (valid) {
+                __nv_bfloat16* o = p.out + (((long)n * p.H + (yp - 1)) * p.W + (xp - 1)) * p.ldo + 16 * h;
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (16 * h + 8 * q < p.CO)
+                        *reinterpret_cast<uint4*>(o + 8 * q) = make_uint4(c3_pack_bf16x2(v[8 * q], v[8 * q + 1]), c3_pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                                          c3_pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), c3_pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+            }
+            named_bar_sync(2 + gi, 8 * 32);           // the exchange rows are read: the group's next tile may overwrite them
+        }
     } else if (EPI_WARPS == 16) {
         // ---- epilogue, register-accumulating form (see the kernel comment): warp (g, cb), sub-tile j = cb / 2, half h = cb % 2
         const int g = warp & 3;
@@ -632,6 +715,8 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
     p.nsub = (CO + 63) / 64;
     p.epi_mode = bn_ref != nullptr ? 1 : 0;
     p.stack = (p.epi_mode == 0 && CO <= 32 && (3 * CO) % 16 == 0 && W % 2 == 0) ? 1 : 0;
+    p.out = (__nv_bfloat16*)out; p.ldo = ldo;
+    p.eager_drain = gn_env_flag("GN_C3_LAZY_DRAIN") ? 0 : 1;
     GN_REQUIRE(((uintptr_t)out & 15) == 0 && ldo % 8 == 0, GN_EALIGN, "conv3x3: output view must be 16-byte aligned with a pitch that is a multiple of 8");
     if (p.epi_mode == 1) {
         GN_REQUIRE(bn_sc && bn_p0 && bn_p1 && (!bn_ref_is_raw || bn_sh), GN_EINVAL, "conv3x3: incomplete BN-backward epilogue arguments");
@@ -691,12 +776,16 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
         if (p.epi_mode) {
             GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        } else GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else {
+            GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GN_CUDA(cudaFuncSetAttribute(conv3x3_kernel<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         max_set[p.epi_mode] = (int)smem;
     }
     const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
     if (p.epi_mode && p.nsub <= 2 && p.e_stages >= 2) conv3x3_kernel<1, 16><<<grid, 640, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
     else if (p.epi_mode) conv3x3_kernel<1, 8><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
+    else if (p.stack && !gn_env_flag("GN_C3_FWD_ONE_GROUP")) conv3x3_kernel<0, 16><<<grid, 640, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
     else conv3x3_kernel<0, 8><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
@@ -719,6 +808,14 @@ struct Conv3WgParams {
     int img;                        // > 0: small images -- a tile is img WHOLE padded images (img * (H+2) * (W+2) <= 128 positions), one TMA box per
                                     // image and operand: no halo rows from neighbouring images and 3 * img TMA instructions per tile instead of ~47
     int k16;                        // reduction steps of 16 positions per tile
+    // chunk mode (CO <= 32): a tile is ONE contiguous run of padded positions fetched with three TMA boxes (two channel groups of X, one dY):
+    //   rt > 0: rt interior rows of one image (X box = rt + 2 rows: the halo rows come with it, 1 + 2/rt re-read instead of 1.86x)
+    //   rt = 0: ni whole padded images (box spans the image dimension)
+    // the position count is the REDUCTION length, so it is not tied to 128: ~300 positions per tile, three kx taps stacked along N
+    int chunk, rt, ni, tiles_per_img;
+    int x_front;                    // slack positions in front of the X box (rt = 0: tap row ky = 0 reaches W + 2 positions back)
+    int xa_rows;                    // 128-byte rows per channel group of one X stage
+    int y_bytes;                    // bytes of one dY stage (1024 B of zeros in front: position -1)
     float* dwp;                     // [9][CI][CO] fp32
 };
 
@@ -731,11 +828,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W2 = p.W + 2, H2 = p.H + 2, HALO = p.W + 3;
-    const int a_group_bytes = p.a_rows * 128;
+    const int a_group_bytes = (p.chunk ? p.xa_rows : p.a_rows) * 128;
     const int a_bytes = 2 * a_group_bytes;
     const int b_row_bytes = p.stack ? 64 : 128;      // stacked: dY as [position][32 channels] SWIZZLE_64B, so that a 32-channel group is one MN atom
     const int b_ext = p.stack ? 1 : 0;               // ... and positions P0-1 .. P0+128 are needed
-    const int b_bytes = p.b_rows * b_row_bytes;
+    const int b_bytes = p.chunk ? p.y_bytes : p.b_rows * b_row_bytes;
     const int stage_bytes = a_bytes + b_bytes;
 
     if (warp == 0 && lane == 0) {
@@ -748,7 +845,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_init(&bar_done, 1);
         fence_barrier_init();
     }
-    if (p.img > 0) {
+    if (p.img > 0 || p.chunk) {
         // positions between the images' data and the next multiple of 16, and the slack rows the shifted taps reach, are never
         // written by TMA: they must hold zeros (dY) / finite values (X) for the whole kernel
         uint4* z = reinterpret_cast<uint4*>(sm);
@@ -772,6 +869,18 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 mbar_wait(&bar_empty[stage], phase ^ 1);
                 uint8_t* sa = sm + (size_t)stage * stage_bytes;
+                if (p.chunk) {
+                    const int nimg = p.rt > 0 ? 1 : p.ni;
+                    const int xr = p.rt > 0 ? p.rt + 2 : H2, yr = p.rt > 0 ? p.rt : H2;
+                    int n, y0;
+                    if (p.rt > 0) { n = tile / p.tiles_per_img; y0 = (tile - n * p.tiles_per_img) * p.rt; } else { n = tile * p.ni; y0 = -1; }
+                    mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(nimg * W2 * (2 * xr * 128 + yr * 64)));
+                    for (int g = 0; g < 2; ++g)
+                        tma_load_4d(&tmX, &bar_full[stage], sa + (size_t)g * a_group_bytes + (size_t)p.x_front * 128, g * 64, -1, p.rt > 0 ? y0 - 1 : -1, n);
+                    tma_load_4d(&tmDY, &bar_full[stage], sa + a_bytes + 1024, 0, -1, y0, n);
+                    if (p.stages == 2) { stage ^= 1; if (stage == 0) phase ^= 1; } else { phase ^= 1; }
+                    continue;
+                }
                 if (p.img > 0) {
                     mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(3 * p.img * img_pos * 128));
                     for (int i = 0; i < p.img; ++i) {
@@ -825,7 +934,22 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 const int R0 = lo >= 0 ? lo / W2 : -((-lo + W2 - 1) / W2);
                 const int a_row0 = p.img > 0 ? img_front : (int)(P0 - R0 * W2);
                 const uint32_t a_base = smem_u32(sm + (size_t)stage * stage_bytes);
-                if (p.img > 0) {
+                if (p.chunk) {
+                    // same stacked contraction as below over the tile's k16 * 16 positions; position -1 is the 64 zero bytes in front of the dY box
+                    const uint32_t b_base = a_base + a_bytes + 1024 - 64;
+                    const int q0 = p.x_front + (p.rt > 0 ? W2 : 0);          // buffer row of the tile's first position
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t a_addr = a_base + (q0 + (ky - 1) * W2) * 128;
+                        const uint32_t d = tmem_base + (uint32_t)(ky * 96);
+                        uint64_t da = smem_desc(tmplA, a_addr), db = smem_desc(tmplBs, b_base);
+                        uint32_t acc = first_tile ? 0u : 1u;
+                        for (int k = 0; k < p.k16; ++k) {
+                            umma_bf16(d, da, db, idesc_s, acc);
+                            da += 128; db += 64; acc = 1u;                  // 2048 B / 1024 B per step in descriptor units of 16 B
+                        }
+                    }
+                } else if (p.img > 0) {
                     const uint32_t b_base = a_base + a_bytes;
                     for (int t = 0; t < 9; ++t) {
                         const uint32_t a_addr = a_base + (a_row0 + (t / 3 - 1) * W2 + (t % 3 - 1)) * 128;
@@ -921,29 +1045,76 @@ GN_API int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long l
     GN_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= CI && ldy >= CO, GN_EALIGN, "conv3x3_wgrad: bad pitches");
     GN_REQUIRE(W + 2 <= 256, GN_EUNSUPPORTED, "conv3x3_wgrad: width %d too large", W);
     Conv3WgParams p;
+    memset(&p, 0, sizeof(p));
     p.Nimg = Nimg; p.H = H; p.W = W; p.CI = CI; p.CO = CO; p.NP = ((CO + 15) / 16) * 16;
-    const int W2 = W + 2, HALO = W + 3;
-    p.a_rows = ((127 + 2 * HALO) / W2 + 2) * W2;
-    p.img = (H + 2) * (W + 2) <= 128 ? 128 / ((H + 2) * (W + 2)) : 0;
-    p.k16 = p.img > 0 ? (p.img * (H + 2) * (W + 2) + 15) / 16 : 8;
-    p.stack = (p.img == 0 && CO <= 32 && W % 2 == 0 && W >= 24) ? 1 : 0;   // measured: pays for the 32-pixel rows of block 1 only     // 64-byte dY rows: TMA destinations stay 128-byte aligned only for even W + 2
-    p.b_rows = ((127 + 2 * p.stack) / W2 + 2) * W2;
-    p.n_tiles = (int)(((long)(H + 2) * W2 * Nimg + 127) / 128);
-    if (p.img > 0) {
-        p.a_rows = ((W2 + 1) + 128 + (W2 + 1) + 7) / 8 * 8;
-        p.b_rows = 128;
-        p.n_tiles = (Nimg + p.img - 1) / p.img;
-    }
+    const int W2 = W + 2, H2 = H + 2, HALO = W + 3;
     p.dwp = dwp;
-    const size_t stage_b = (size_t)(2 * p.a_rows) * 128 + (size_t)p.b_rows * (p.stack ? 64 : 128);
-    p.stages = (2 * stage_b + 1024 <= 227 * 1024 - 256) ? 2 : 1;
-    const size_t smem = p.stages * stage_b + 1024;
+    size_t smem = 0;
+    static int chunk_npos = -1;         // target positions per tile (GN_WG_NPOS = 0 switches the chunk mode off: development A/B)
+    if (chunk_npos < 0) {
+        const char* e = getenv("GN_WG_NPOS");
+        chunk_npos = e ? atoi(e) : 304;
+    }
+    if (CO <= 32 && chunk_npos > 0 && W2 <= 256 && W2 <= chunk_npos) {
+        const int img_pos = H2 * W2;
+        int npos;
+        if (2 * img_pos <= chunk_npos) {                       // several whole padded images per tile
+            p.ni = chunk_npos / img_pos;
+            if (p.ni > Nimg) p.ni = Nimg;
+            if (p.ni > 256) p.ni = 256;
+            p.rt = 0;
+            npos = p.ni * img_pos;
+            p.x_front = ((W2 + 7) / 8) * 8;
+            p.n_tiles = (Nimg + p.ni - 1) / p.ni;
+            p.tiles_per_img = 0;
+        } else {                                               // rt interior rows of one image, split evenly
+            int rmax = chunk_npos / W2;
+            if (rmax > H) rmax = H;
+            if (rmax > 254) rmax = 254;
+            p.tiles_per_img = (H + rmax - 1) / rmax;
+            p.rt = (H + p.tiles_per_img - 1) / p.tiles_per_img;
+            p.ni = 1;
+            npos = p.rt * W2;
+            p.x_front = 0;
+            p.n_tiles = Nimg * p.tiles_per_img;
+        }
+        p.k16 = (npos + 15) / 16;
+        p.xa_rows = ((p.x_front + (p.rt > 0 ? W2 : 0) + W2 + 16 * p.k16 + 7) / 8) * 8;
+        const int x_box_rows = p.rt > 0 ? (p.rt + 2) * W2 : npos;
+        if (p.xa_rows < ((p.x_front + x_box_rows + 7) / 8) * 8) p.xa_rows = ((p.x_front + x_box_rows + 7) / 8) * 8;
+        p.y_bytes = 1024 + (((16 * p.k16 + 2) * 64 + 1023) / 1024) * 1024;
+        const size_t stage_b = (size_t)2 * p.xa_rows * 128 + (size_t)p.y_bytes;
+        if (stage_b + 1024 <= 227 * 1024 - 256) {
+            p.chunk = 1;
+            p.stack = 1;
+            p.stages = (2 * stage_b + 1024 <= 227 * 1024 - 256) ? 2 : 1;
+            smem = p.stages * stage_b + 1024;
+        }
+    }
+    if (!p.chunk) {
+        p.rt = p.ni = p.tiles_per_img = p.x_front = p.xa_rows = p.y_bytes = 0;
+        p.a_rows = ((127 + 2 * HALO) / W2 + 2) * W2;
+        p.img = (H + 2) * (W + 2) <= 128 ? 128 / ((H + 2) * (W + 2)) : 0;
+        p.k16 = p.img > 0 ? (p.img * (H + 2) * (W + 2) + 15) / 16 : 8;
+        p.stack = (p.img == 0 && CO <= 32 && W % 2 == 0 && W >= 24) ? 1 : 0;   // 64-byte dY rows: TMA destinations stay 128-byte aligned only for even W + 2
+        p.b_rows = ((127 + 2 * p.stack) / W2 + 2) * W2;
+        p.n_tiles = (int)(((long)(H + 2) * W2 * Nimg + 127) / 128);
+        if (p.img > 0) {
+            p.a_rows = ((W2 + 1) + 128 + (W2 + 1) + 7) / 8 * 8;
+            p.b_rows = 128;
+            p.n_tiles = (Nimg + p.img - 1) / p.img;
+        }
+        const size_t stage_b = (size_t)(2 * p.a_rows) * 128 + (size_t)p.b_rows * (p.stack ? 64 : 128);
+        p.stages = (2 * stage_b + 1024 <= 227 * 1024 - 256) ? 2 : 1;
+        smem = p.stages * stage_b + 1024;
+    }
     GN_REQUIRE(smem <= 227 * 1024 - 256, GN_EUNSUPPORTED, "conv3x3_wgrad: tile does not fit shared memory (%zu B)", smem);
     CUtensorMap tmX, tmDY;
     {
         uint64_t dims[4] = {(uint64_t)CI, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t strides[3] = {(uint64_t)ldx * 2, (uint64_t)W * ldx * 2, (uint64_t)H * W * ldx * 2};
         uint32_t box[4] = {64, (uint32_t)W2, p.img > 0 ? (uint32_t)(H + 2) : 1u, 1};
+        if (p.chunk) { box[2] = p.rt > 0 ? (uint32_t)(p.rt + 2) : (uint32_t)H2; box[3] = (uint32_t)p.ni; }
         int rc = gn_tmap_encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
@@ -951,6 +1122,7 @@ GN_API int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long l
         uint64_t dims[4] = {(uint64_t)CO, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t strides[3] = {(uint64_t)ldy * 2, (uint64_t)W * ldy * 2, (uint64_t)H * W * ldy * 2};
         uint32_t box[4] = {p.stack ? 32u : 64u, (uint32_t)W2, p.img > 0 ? (uint32_t)(H + 2) : 1u, 1};
+        if (p.chunk) { box[2] = p.rt > 0 ? (uint32_t)p.rt : (uint32_t)H2; box[3] = (uint32_t)p.ni; }
         int rc = gn_tmap_encode(&tmDY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dy, dims, strides, box,
                                 p.stack ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;

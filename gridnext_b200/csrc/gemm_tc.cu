@@ -56,6 +56,7 @@ struct GemmParams {
     int relu;
     const float* xf_scale;     // per K index (XFORM kernels)
     const float* xf_shift;
+    int eager_drain;           // release a staging slot as soon as its own store has read it
     int epi_mode;              // 0: affine/ReLU store, 1: BN+ReLU backward (BnBwdEpi), bf16 output
     BnBwdEpi bn;
     int stages;                // main-loop ring depth
@@ -301,11 +302,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (EPI == EPI_BNBWD && p.bn.rmw) tma_reduce_add_2d(&tmOut, s_slots + (size_t)es * p.slot_bytes, nb * BN + j * 64, mb * GEMM_BM);
                     else tma_store_2d(&tmOut, s_slots + (size_t)es * p.slot_bytes, nb * BN + j * 64, mb * GEMM_BM);
                     tma_store_commit();
-                    if (prev_es >= 0) {
-                        tma_store_wait_read<1>();          // the previous sub-tile's store has drained its slot
-                        mbar_arrive(&bar_eempty[prev_es]);
+                    if (p.eager_drain) {
+                        tma_store_wait_read<0>();
+                        mbar_arrive(&bar_eempty[es]);
+                    } else {
+                        if (prev_es >= 0) {
+                            tma_store_wait_read<1>();          // the previous sub-tile's store has drained its slot
+                            mbar_arrive(&bar_eempty[prev_es]);
+                        }
+                        prev_es = es;
                     }
-                    prev_es = es;
                     if (++es == p.e_stages) { es = 0; eph ^= 1; }
                 }
             }
@@ -606,6 +612,7 @@ GN_API int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M,
     p.num_k_blocks = gn_ceil_div(K, GEMM_BK);
     p.out = out; p.ldc = ldc; p.out_fp32 = out_fp32; p.accumulate = accumulate;
     p.scale = scale; p.shift = shift; p.relu = relu; p.xf_scale = xf_scale; p.xf_shift = xf_shift;
+    p.eager_drain = gn_env_flag("GN_GEMM_LAZY_DRAIN") ? 0 : 1;
     p.epi_mode = bn_ref != nullptr ? 1 : 0;
     if (p.epi_mode == 1) {
         GN_REQUIRE(!out_fp32 && !accumulate && !scale && !shift && !relu, GN_EINVAL, "gemm_bf16: BN-backward epilogue needs a plain bf16 output");

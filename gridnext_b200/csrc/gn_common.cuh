@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #define GN_API extern "C" __attribute__((visibility("default")))
 
@@ -35,6 +36,12 @@ void gn_set_error(const char* fmt, ...);
 static inline int gn_ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 int gn_num_sms();
+
+// development A/B switches: an environment variable set to a non-zero integer
+static inline int gn_env_flag(const char* name) {
+    const char* e = getenv(name);
+    return e && atoi(e) != 0;
+}
 
 __device__ __forceinline__ float gn_warp_sum(float v) {
 #pragma unroll
