@@ -73,33 +73,81 @@ __device__ __forceinline__ void colsum_block_end(float* s_sum, int C, float* col
 }
 
 // ------------------------------------------------------------------------------------------------ stem (pool0; conv0 lives in stem_conv.cu)
-// 3x3 / stride 2 / pad 1 max pool, NHWC; idx = ky*3+kx of the first maximum (PyTorch tie rule)
+// 3x3 / stride 2 / pad 1 max pool, NHWC; idx = ky*3+kx of the first maximum (PyTorch tie rule).
+// The kernel was bound by instruction issue (ncu: 835 M warp instructions, 650 per 8-channel item, ALU pipe 65 %, DRAM 36 %): a
+// compare + two selects + conversions per (tap, channel).  Now every (tap, channel) is ONE signed-integer max on a 32-bit key:
+//   key = order(bf16 bits) << 16 | (15 - tap)        order(b) = b ^ (b < 0 ? 0x7fff : 0): bf16 bit patterns in signed-integer order
+// so the maximum carries its own arg-max, and among equal values the lowest tap wins (the tie rule) -- 4 instructions per pair.
+__device__ __forceinline__ int mp_key(uint32_t w_shifted_or_masked_with_low) {
+    const int k = (int)w_shifted_or_masked_with_low;
+    return k ^ ((k >> 31) & 0x7fff0000);
+}
 __global__ void __launch_bounds__(256) maxpool3s2_fwd_kernel(const __nv_bfloat16* __restrict__ in, long ldi, int N, int Hi, int Wi, int C,
                                                               __nv_bfloat16* __restrict__ out, long ldo, unsigned char* __restrict__ idx) {
     const int Ho = Hi / 2, Wo = Wi / 2, G = C / 8;
     const int total = N * Ho * Wo * G;                     // < 2^31 (checked by the launcher): 32-bit index arithmetic
+    const uint32_t ld16 = (uint32_t)(ldi >> 3);            // pixel pitch in 16-byte units (checked: ldi % 8 == 0, whole tensor < 2^35 bytes)
+    const uint4* in16 = reinterpret_cast<const uint4*>(in);
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int op = e / G, cg = e - op * G;
         const int q = op / Wo, ox = op - q * Wo;
         const int n = q / Ho, oy = q - n * Ho;
-        V8 best; unsigned char bi[8];
+        int best[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { best.v[j] = -INFINITY; bi[j] = 0; }
+        for (int j = 0; j < 8; ++j) best[j] = (int)0x80000000;
+        // Only the first row / column of windows reaches outside the image (Hi, Wi even).  Such a tap is redirected to the in-image tap
+        // of the same window that reads the same pixel row / column (ky 0 -> 1, kx 0 -> 1) WITH that tap's index: a duplicate key
+        // changes nothing, and the loop stays free of divergent branches.
+        const int ky_min = oy == 0 ? 1 : 0, kx_min = ox == 0 ? 1 : 0;
+        const uint32_t pix0 = (uint32_t)((n * Hi + 2 * oy - 1) * Wi + 2 * ox - 1);      // pixel of tap (0, 0); may wrap, only used with in-image offsets
+        // all nine loads first (one round trip to memory per item instead of nine dependent ones), then one sign test for the item
+        uint4 t[9];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            const int iy = 2 * oy - 1 + ky;
-            if (iy < 0 || iy >= Hi) continue;
+            const int eky = ky == 0 ? ky_min : ky;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const int ix = 2 * ox - 1 + kx;
-                if (ix < 0 || ix >= Wi) continue;
-                const V8 v = ld_bf16x8(in + (((long)n * Hi + iy) * Wi + ix) * ldi + cg * 8);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (v.v[j] > best.v[j]) { best.v[j] = v.v[j]; bi[j] = (unsigned char)(ky * 3 + kx); }
+                const int ekx = kx == 0 ? kx_min : kx;
+                t[ky * 3 + kx] = __ldg(in16 + (size_t)(pix0 + (uint32_t)(eky * Wi + ekx)) * ld16 + cg);
             }
         }
-        st_bf16x8(out + (long)op * ldo + cg * 8, best);
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) any |= t[k].x | t[k].y | t[k].z | t[k].w;
+        const bool nonneg = (any & 0x80008000u) == 0u;    // always, behind a ReLU: bf16 bit patterns already are in integer order
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int eky = ky == 0 ? ky_min : ky;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ekx = kx == 0 ? kx_min : kx;
+                const uint32_t w[4] = {t[ky * 3 + kx].x, t[ky * 3 + kx].y, t[ky * 3 + kx].z, t[ky * 3 + kx].w};
+                const uint32_t low = (uint32_t)(15 - (eky * 3 + ekx));
+                if (nonneg) {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        best[2 * h] = max(best[2 * h], (int)__byte_perm(w[h], low, 0x1054));          // (lower bf16 << 16) | low
+                        best[2 * h + 1] = max(best[2 * h + 1], (int)__byte_perm(w[h], low, 0x3254));  // (upper bf16 << 16) | low
+                    }
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        best[2 * h] = max(best[2 * h], mp_key(__byte_perm(w[h], low, 0x1054)));
+                        best[2 * h + 1] = max(best[2 * h + 1], mp_key(__byte_perm(w[h], low, 0x3254)));
+                    }
+                }
+            }
+        }
+        uint32_t vb[8], bi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            vb[j] = (uint32_t)mp_key((uint32_t)best[j]);          // the transform is its own inverse on the upper half
+            bi[j] = 15u - ((uint32_t)best[j] & 15u);
+        }
+        uint4 o;
+        o.x = __byte_perm(vb[0], vb[1], 0x7632); o.y = __byte_perm(vb[2], vb[3], 0x7632);
+        o.z = __byte_perm(vb[4], vb[5], 0x7632); o.w = __byte_perm(vb[6], vb[7], 0x7632);
+        *reinterpret_cast<uint4*>(out + (long)op * ldo + cg * 8) = o;
         uint2 pk;
         pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
         pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
@@ -124,48 +172,50 @@ __device__ __forceinline__ void colsum_thread_flush(float* s_sum, int C, int cg,
 
 // Work unit = the 2x2 input quad {2a, 2a+1} x {2b, 2b+1}: it touches exactly the four windows (a, b), (a, b+1), (a+1, b),
 // (a+1, b+1), so every pooled gradient / arg-max byte is loaded once per quad instead of once per input pixel.
-__global__ void __launch_bounds__(256) maxpool3s2_bnrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, long ldp,
-                                                                    const unsigned char* __restrict__ idx,
-                                                                    const __nv_bfloat16* __restrict__ act, long lda, int N, int Hi, int Wi,
-                                                                    int C, const float* __restrict__ sc, const float* __restrict__ p0,
-                                                                    const float* __restrict__ p1, __nv_bfloat16* __restrict__ dz, long ldz,
-                                                                    float* __restrict__ colsum, int ldsum, int G, int ppb) {
+// A thread owns FOUR channels (8-byte vectors): with eight the kernel needed 125 registers, ran at 24 % occupancy and was bound by
+// load latency (ncu: issue-active 46 %, DRAM 53 %); with four it fits 64 registers and twice as many quads are in flight per SM.
+__global__ void __launch_bounds__(256, 4) maxpool3s2_bnrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dpool, long ldp,
+                                                                       const unsigned char* __restrict__ idx,
+                                                                       const __nv_bfloat16* __restrict__ act, long lda, int N, int Hi, int Wi,
+                                                                       int C, const float* __restrict__ sc, const float* __restrict__ p0,
+                                                                       const float* __restrict__ p1, __nv_bfloat16* __restrict__ dz, long ldz,
+                                                                       float* __restrict__ colsum, int ldsum, int G4, int ppb) {
     extern __shared__ float s_sum[];
     colsum_block_begin(s_sum, C);
     const int Ho = Hi / 2, Wo = Wi / 2;
-    const int cg = threadIdx.x % G, pl = threadIdx.x / G;
-    const V8 s = ld_f32x8(sc + cg * 8);
-    float sg[8], sx[8];
+    const int cg = threadIdx.x % G4, pl = threadIdx.x / G4;      // cg: group of 4 channels
+    const float4 s = *reinterpret_cast<const float4*>(sc + cg * 4);
+    const float sv[4] = {s.x, s.y, s.z, s.w};
+    float sg[4], sx[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sx[j] = 0.f; }
+    for (int j = 0; j < 4; ++j) { sg[j] = 0.f; sx[j] = 0.f; }
     const int nquads = N * Ho * Wo;
     for (int qd = blockIdx.x * ppb + pl; qd < nquads; qd += gridDim.x * ppb) {
         const int b = qd % Wo, t = qd / Wo, a = t % Ho, n = t / Ho;
         // the four windows; w = wy*2 + wx with (wy, wx) = window offset from (a, b)
-        V8 d[4];
-        uint2 pk[4];
+        uint2 d[4];          // 4 bf16 gradients per window
+        uint32_t pk[4];      // 4 arg-max bytes per window
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const int oy = a + (w >> 1), ox = b + (w & 1);
             if (oy < Ho && ox < Wo) {
                 const long op = ((long)n * Ho + oy) * Wo + ox;
-                pk[w] = *reinterpret_cast<const uint2*>(idx + op * C + cg * 8);
-                d[w] = ld_bf16x8(dpool + op * ldp + cg * 8);
+                pk[w] = *reinterpret_cast<const uint32_t*>(idx + op * C + cg * 4);
+                d[w] = *reinterpret_cast<const uint2*>(dpool + op * ldp + cg * 4);
             } else {
-                pk[w] = make_uint2(0xffffffffu, 0xffffffffu);          // tap 255 never matches
-#pragma unroll
-                for (int j = 0; j < 8; ++j) d[w].v[j] = 0.f;
+                pk[w] = 0xffffffffu;                                   // tap 255 never matches
+                d[w] = make_uint2(0u, 0u);
             }
         }
+        const long ip00 = ((long)n * Hi + 2 * a) * Wi + 2 * b;
+        uint2 av4[4];
+#pragma unroll
+        for (int pi = 0; pi < 4; ++pi) av4[pi] = *reinterpret_cast<const uint2*>(act + (ip00 + (pi >> 1) * Wi + (pi & 1)) * lda + cg * 4);
 #pragma unroll
         for (int py = 0; py < 2; ++py)
 #pragma unroll
             for (int px = 0; px < 2; ++px) {
-                const int iy = 2 * a + py, ix = 2 * b + px;
-                const long ip = ((long)n * Hi + iy) * Wi + ix;
-                V8 g;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
                 // pixel (2a+py, 2b+px) lies in window (a+wy, b+wx) at tap ky = py + 1 - 2 wy, kx = px + 1 - 2 wx (wy <= py, wx <= px)
 #pragma unroll
                 for (int wy = 0; wy <= py; ++wy)
@@ -173,25 +223,32 @@ __global__ void __launch_bounds__(256) maxpool3s2_bnrelu_bwd_kernel(const __nv_b
                     for (int wx = 0; wx <= px; ++wx) {
                         const int w = wy * 2 + wx;
                         const unsigned k = (unsigned)((py + 1 - 2 * wy) * 3 + (px + 1 - 2 * wx));
+                        const float dv[4] = {__uint_as_float(d[w].x << 16), __uint_as_float(d[w].x & 0xffff0000u), __uint_as_float(d[w].y << 16),
+                                             __uint_as_float(d[w].y & 0xffff0000u)};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const unsigned bsel = ((j < 4 ? pk[w].x : pk[w].y) >> (8 * (j & 3))) & 0xff;
-                            if (bsel == k) g.v[j] += d[w].v[j];
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            if (((pk[w] >> (8 * j)) & 0xffu) == k) g[j] += dv[j];
                     }
-                const V8 av = ld_bf16x8(act + ip * lda + cg * 8);
-                V8 o;
+                const uint2 aw = av4[py * 2 + px];
+                const float av[4] = {__uint_as_float(aw.x << 16), __uint_as_float(aw.x & 0xffff0000u), __uint_as_float(aw.y << 16),
+                                     __uint_as_float(aw.y & 0xffff0000u)};
+                float o[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float gg = av.v[j] > 0.f ? g.v[j] : 0.f;
+                for (int j = 0; j < 4; ++j) {
+                    const float gg = av[j] > 0.f ? g[j] : 0.f;
                     sg[j] += gg;
-                    sx[j] += gg * av.v[j];
-                    o.v[j] = gg * s.v[j];
+                    sx[j] = fmaf(gg, av[j], sx[j]);
+                    o[j] = gg * sv[j];
                 }
-                st_bf16x8(dz + ip * ldz + cg * 8, o);
+                *reinterpret_cast<uint2*>(dz + (ip00 + py * Wi + px) * ldz + cg * 4) = make_uint2(gn_pack_bf16x2(o[0], o[1]), gn_pack_bf16x2(o[2], o[3]));
             }
     }
-    colsum_thread_flush(s_sum, C, cg, sg, sx, p0, p1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = cg * 4 + j;
+        atomicAdd(&s_sum[c], sg[j]);
+        atomicAdd(&s_sum[C + c], __ldg(p1 + c) * (sx[j] - __ldg(p0 + c) * sg[j]));
+    }
     colsum_block_end(s_sum, C, colsum, ldsum);
 }
 
@@ -228,7 +285,7 @@ __global__ void __launch_bounds__(256) bnrelu_avgpool2_fwd_kernel(const __nv_bfl
 // pool_div = 4 with (H, W) -> (H/2, W/2) for the transitions; for the head pass Hp = Wp = 1 semantics via `gap` = 1:
 //   gap: dP is fp32 [N, C] (gradient of the pooled features), divisor H*W.
 template <bool GAP>
-__global__ void __launch_bounds__(256) pool_bnrelu_bwd_kernel(const void* __restrict__ dpool, long ldp, const __nv_bfloat16* __restrict__ raw,
+__global__ void __launch_bounds__(256, 4) pool_bnrelu_bwd_kernel(const void* __restrict__ dpool, long ldp, const __nv_bfloat16* __restrict__ raw,
                                                                long ldr, int N, int H, int W, int C, const float* __restrict__ sc,
                                                                const float* __restrict__ sh, const float* __restrict__ p0,
                                                                const float* __restrict__ p1, __nv_bfloat16* __restrict__ dC, long ldc,
@@ -391,7 +448,8 @@ GN_API int gn_maxpool3s2_fwd(const void* in, long ldi, int N, int Hi, int Wi, in
     GN_REQUIRE(in && out && idx && N > 0 && Hi % 2 == 0 && Wi % 2 == 0 && C % 8 == 0 && ldi % 8 == 0 && ldo % 8 == 0, GN_EINVAL,
                "maxpool3s2_fwd: bad arguments");
     const long total = (long)N * (Hi / 2) * (Wi / 2) * (C / 8);
-    GN_REQUIRE(total < (1L << 31), GN_EUNSUPPORTED, "maxpool3s2_fwd: too many elements for 32-bit indexing");
+    GN_REQUIRE(total < (1L << 31) && (long)N * Hi * Wi < (1L << 31), GN_EUNSUPPORTED, "maxpool3s2_fwd: too many elements for 32-bit indexing");
+    GN_REQUIRE(((uintptr_t)in & 15) == 0, GN_EALIGN, "maxpool3s2_fwd: input must be 16-byte aligned");
     maxpool3s2_fwd_kernel<<<grid_for(total, 16), 256, 0, stream>>>((const __nv_bfloat16*)in, ldi, N, Hi, Wi, C, (__nv_bfloat16*)out, ldo, idx);
     GN_LAUNCH_CHECK();
     return GN_OK;
@@ -402,8 +460,9 @@ GN_API int gn_maxpool3s2_bnrelu_bwd(const void* dpool, long ldp, const unsigned 
                                     cudaStream_t stream) {
     GN_REQUIRE(dpool && idx && act && sc && p0 && p1 && dz && colsum && N > 0 && C % 8 == 0 && C <= 2048, GN_EINVAL,
                "maxpool3s2_bnrelu_bwd: bad arguments");
-    const int G = C / 8;
-    GN_REQUIRE(G <= 256 && (long)N * Hi * Wi < (1L << 31), GN_EUNSUPPORTED, "maxpool3s2_bnrelu_bwd: at most 2048 channels and 2^31 pixels");
+    const int G = C / 4;           // threads own four channels
+    GN_REQUIRE(G <= 256 && (long)N * Hi * Wi < (1L << 31), GN_EUNSUPPORTED, "maxpool3s2_bnrelu_bwd: at most 1024 channels and 2^31 pixels");
+    GN_REQUIRE(ldp % 4 == 0 && lda % 4 == 0 && ldz % 4 == 0, GN_EALIGN, "maxpool3s2_bnrelu_bwd: pitches must be multiples of 4 elements");
     const int ppb = 256 / G;
     GN_REQUIRE(Hi % 2 == 0 && Wi % 2 == 0, GN_EINVAL, "maxpool3s2_bnrelu_bwd: odd spatial size");
     unsigned grid = (unsigned)gn_ceil_div((long)N * (Hi / 2) * (Wi / 2), ppb);

@@ -57,6 +57,11 @@ struct GemmParams {
     const float* xf_scale;     // per K index (XFORM kernels)
     const float* xf_shift;
     int eager_drain;           // release a staging slot as soon as its own store has read it
+    int res_b;                 // 1: all k-blocks of B (one n-block) stay resident in shared memory for the life of the CTA.  Re-streaming the
+                               // weights with every M tile doubled the L2 -> SM traffic of the forward conv1 (K = c_in against N = 128), and
+                               // L2 -> SM bandwidth is no higher than HBM bandwidth: 4.7 TB/s algorithmic at 6.0 TB/s into the SMs
+    int stage_bytes;           // ring slot: A (+ B unless resident)
+    int epi_ld, xf_ld;         // pitches of the per-column / per-k constant tables in shared memory: N and K rounded up to 64
     int epi_mode;              // 0: affine/ReLU store, 1: BN+ReLU backward (BnBwdEpi), bf16 output
     BnBwdEpi bn;
     int stages;                // main-loop ring depth
@@ -154,37 +159,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[GEMM_MAX_STAGES], bar_xf[GEMM_MAX_STAGES], bar_empty[GEMM_MAX_STAGES], bar_tfull[2], bar_tempty[2];
     __shared__ __align__(8) uint64_t bar_efull[GEMM_MAX_ESTAGES], bar_eready[GEMM_MAX_ESTAGES], bar_eempty[GEMM_MAX_ESTAGES];
+    __shared__ __align__(8) uint64_t bar_bres;
     __shared__ uint32_t tmem_slot;
 
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     const int STAGES = p.stages;
-    uint8_t* s_slots = sm + (size_t)STAGES * Cfg::STAGE_BYTES;                                   // e_stages x slot_bytes
-    float* s_epi = reinterpret_cast<float*>(s_slots + (EPI == EPI_DIRECT ? 0 : (size_t)p.e_stages * p.slot_bytes));   // [4][GEMM_EPI_MAX_N]
-    float* s_cs = s_epi + 2 * GEMM_EPI_MAX_N;                                                     // [2][GEMM_EPI_MAX_N] column sums (EPI_BNBWD; reuses the p0/p1 rows)
-    float* s_xf = s_epi + (EPI == EPI_DIRECT ? 0 : 4 * GEMM_EPI_MAX_N);                           // [2][GEMM_MAX_XF_K]
+    const int stage_bytes = p.stage_bytes;
+    uint8_t* s_bres = sm + (size_t)STAGES * stage_bytes;                                         // resident B: num_k_blocks x B_BYTES
+    uint8_t* s_slots = s_bres + (p.res_b ? (size_t)p.num_k_blocks * Cfg::B_BYTES : 0);           // e_stages x slot_bytes
+    const int epi_ld = p.epi_ld, xf_ld = p.xf_ld;                                                 // row pitches of the constant tables (floats)
+    float* s_epi = reinterpret_cast<float*>(s_slots + (EPI == EPI_DIRECT ? 0 : (size_t)p.e_stages * p.slot_bytes));   // [4][epi_ld]
+    float* s_cs = s_epi + 2 * epi_ld;                                                     // [2][epi_ld] column sums (EPI_BNBWD; reuses the p0/p1 rows)
+    float* s_xf = s_epi + (EPI == EPI_DIRECT ? 0 : 4 * epi_ld);                           // [2][xf_ld]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (XFORM) {
         const int kpad = p.num_k_blocks * GEMM_BK;
         for (int i = threadIdx.x; i < kpad; i += blockDim.x) {
             s_xf[i] = i < p.K ? p.xf_scale[i] : 0.f;
-            s_xf[GEMM_MAX_XF_K + i] = i < p.K ? p.xf_shift[i] : 0.f;
+            s_xf[xf_ld + i] = i < p.K ? p.xf_shift[i] : 0.f;
         }
     }
     if (EPI != EPI_DIRECT) {
         // per-column epilogue constants, zero beyond N (those accumulator columns are zero as well)
-        const int npad = min(GEMM_EPI_MAX_N, ((p.N + 63) / 64) * 64);
+        const int npad = epi_ld;
         for (int i = threadIdx.x; i < npad; i += blockDim.x) {
             const bool in = i < p.N;
             if (EPI == EPI_STORE) {
                 s_epi[i] = in ? (p.scale ? p.scale[i] : 1.f) : 0.f;
-                s_epi[GEMM_EPI_MAX_N + i] = in ? (p.shift ? p.shift[i] : 0.f) : 0.f;
+                s_epi[epi_ld + i] = in ? (p.shift ? p.shift[i] : 0.f) : 0.f;
             } else {
                 s_epi[i] = in ? p.bn.sc[i] : 0.f;
-                s_epi[GEMM_EPI_MAX_N + i] = (in && p.bn.sh) ? p.bn.sh[i] : 0.f;
-                s_epi[2 * GEMM_EPI_MAX_N + i] = 0.f;          // s_cs: sum g
-                s_epi[3 * GEMM_EPI_MAX_N + i] = 0.f;          // s_cs: sum g * ref
+                s_epi[epi_ld + i] = (in && p.bn.sh) ? p.bn.sh[i] : 0.f;
+                s_epi[2 * epi_ld + i] = 0.f;          // s_cs: sum g
+                s_epi[3 * epi_ld + i] = 0.f;          // s_cs: sum g * ref
             }
         }
     }
@@ -203,6 +212,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&bar_eready[s], GEMM_EPI_WARPS);
             mbar_init(&bar_eempty[s], 1);
         }
+        mbar_init(&bar_bres, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_tfull[a], 1);
             mbar_init(&bar_tempty[a], GEMM_EPI_WARPS);
@@ -222,15 +232,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            if (p.res_b) {
+                mbar_arrive_expect_tx(&bar_bres, (uint32_t)(nkb * Cfg::B_BYTES));
+                for (int kb = 0; kb < nkb; ++kb) tma_load_2d(&tmB, &bar_bres, s_bres + (size_t)kb * Cfg::B_BYTES, kb * GEMM_BK, 0);
+            }
             for (int it = 0;; ++it) {
                 int nb, mb;
                 if (!gemm_next_tile<EPI>(it, p, nb, mb)) break;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&bar_empty[stage], phase ^ 1);
-                    uint8_t* sa = sm + (size_t)stage * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = sm + (size_t)stage * stage_bytes;
+                    mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)stage_bytes);
                     tma_load_2d(&tmA, &bar_full[stage], sa, kb * GEMM_BK, mb * GEMM_BM);
-                    tma_load_2d(&tmB, &bar_full[stage], sa + GEMM_A_BYTES, kb * GEMM_BK, nb * BN);
+                    if (!p.res_b) tma_load_2d(&tmB, &bar_full[stage], sa + GEMM_A_BYTES, kb * GEMM_BK, nb * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -244,6 +258,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            if (p.res_b) mbar_wait(&bar_bres, 0);
             for (int it = 0;; ++it) {
                 int nb_, mb_;
                 if (!gemm_next_tile<EPI>(it, p, nb_, mb_)) break;
@@ -253,8 +268,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(XFORM ? &bar_xf[stage] : &bar_full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sm + (size_t)stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + GEMM_A_BYTES;
+                    const uint32_t a_addr = smem_u32(sm + (size_t)stage * stage_bytes);
+                    const uint32_t b_addr = p.res_b ? smem_u32(s_bres + (size_t)kb * Cfg::B_BYTES) : a_addr + GEMM_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k)
                         umma_bf16(d, smem_desc(tmpl, a_addr + k * 32), smem_desc(tmpl, b_addr + k * 32), idesc, (uint32_t)((kb | k) != 0));
@@ -419,8 +434,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int q = 0; q < 4; ++q) {
                             const uint32_t off = (((uint32_t)(h * 4 + q)) ^ sw) << 4;
                             const float4 c0a = *reinterpret_cast<const float4*>(cst + 8 * q), c0b = *reinterpret_cast<const float4*>(cst + 8 * q + 4);
-                            const float4 c1a = *reinterpret_cast<const float4*>(cst + GEMM_EPI_MAX_N + 8 * q),
-                                         c1b = *reinterpret_cast<const float4*>(cst + GEMM_EPI_MAX_N + 8 * q + 4);
+                            const float4 c1a = *reinterpret_cast<const float4*>(cst + epi_ld + 8 * q),
+                                         c1b = *reinterpret_cast<const float4*>(cst + epi_ld + 8 * q + 4);
                             const float k0[8] = {c0a.x, c0a.y, c0a.z, c0a.w, c0b.x, c0b.y, c0b.z, c0b.w};     // scale
                             const float k1[8] = {c1a.x, c1a.y, c1a.z, c1a.w, c1b.x, c1b.y, c1b.z, c1b.w};     // shift
                             uint32_t res[4];
@@ -459,7 +474,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (EPI == EPI_BNBWD && want_sums) {
                             const float sg = gn_warp_colsum32(v, lane), sx = gn_warp_colsum32(gx, lane);
                             atomicAdd(&s_cs[col0 + lane], sg);
-                            atomicAdd(&s_cs[GEMM_EPI_MAX_N + col0 + lane], sx);
+                            atomicAdd(&s_cs[epi_ld + col0 + lane], sx);
                         }
                     }
                     fence_proxy_async_smem();
@@ -478,7 +493,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (EPI == EPI_BNBWD && want_sums) {
             named_bar_sync(1, GEMM_EPI_THREADS);            // every epilogue warp has added its last partial sums
             for (int col = threadIdx.x - 4 * 32; col < p.N; col += GEMM_EPI_THREADS) {
-                const float sg = s_cs[col], sx = s_cs[GEMM_EPI_MAX_N + col];
+                const float sg = s_cs[col], sx = s_cs[epi_ld + col];
                 atomicAdd(p.bn.colsum + col, sg);
                 atomicAdd(p.bn.colsum + p.bn.ldsum + col, __ldg(p.bn.p1 + col) * (sx - __ldg(p.bn.p0 + col) * sg));
             }
@@ -506,15 +521,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int k0 = kb * GEMM_BK + ((pc ^ (par * 4 + (lane >> 3))) << 3);   // logical K index of the chunk's first element
                     const float4 s0 = *reinterpret_cast<const float4*>(s_xf + k0);
                     const float4 s1 = *reinterpret_cast<const float4*>(s_xf + k0 + 4);
-                    const float4 t0 = *reinterpret_cast<const float4*>(s_xf + GEMM_MAX_XF_K + k0);
-                    const float4 t1 = *reinterpret_cast<const float4*>(s_xf + GEMM_MAX_XF_K + k0 + 4);
+                    const float4 t0 = *reinterpret_cast<const float4*>(s_xf + xf_ld + k0);
+                    const float4 t1 = *reinterpret_cast<const float4*>(s_xf + xf_ld + k0 + 4);
                     cs[par][0] = s0.x; cs[par][1] = s0.y; cs[par][2] = s0.z; cs[par][3] = s0.w;
                     cs[par][4] = s1.x; cs[par][5] = s1.y; cs[par][6] = s1.z; cs[par][7] = s1.w;
                     ct[par][0] = t0.x; ct[par][1] = t0.y; ct[par][2] = t0.z; ct[par][3] = t0.w;
                     ct[par][4] = t1.x; ct[par][5] = t1.y; ct[par][6] = t1.z; ct[par][7] = t1.w;
                 }
                 mbar_wait(&bar_full[stage], phase);
-                uint8_t* sa = sm + (size_t)stage * Cfg::STAGE_BYTES + (w * 32 + (lane >> 3)) * 128 + pc * 16;
+                uint8_t* sa = sm + (size_t)stage * stage_bytes + (w * 32 + (lane >> 3)) * 128 + pc * 16;
                 uint4 v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(sa + i * 512);
@@ -549,21 +564,32 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
     const int budget = 227 * 1024 - 1024 - 512;        // dynamic shared memory minus alignment slack and static barriers
-    int fixed = XFORM ? 2 * GEMM_MAX_XF_K * 4 : 0;
+    p.xf_ld = p.num_k_blocks * GEMM_BK;
+    p.epi_ld = p.num_n_blocks * BN < GEMM_EPI_MAX_N ? p.num_n_blocks * BN : GEMM_EPI_MAX_N;      // every column a tile can touch
+    int fixed = XFORM ? 2 * p.xf_ld * 4 : 0;
     if (EPI != EPI_DIRECT) {
         p.slot_bytes = GEMM_SUB_BYTES;       // read-modify-write goes through the TMA reduction: no old-output tile in shared memory
         p.e_stages = EPI == EPI_BNBWD ? 6 : 4;
-        fixed += 4 * GEMM_EPI_MAX_N * 4 + p.e_stages * p.slot_bytes;
+        { const char* e = getenv("GN_GEMM_ESTAGES"); if (e && atoi(e) >= 2 && atoi(e) <= GEMM_MAX_ESTAGES) p.e_stages = atoi(e); }
+        fixed += 4 * p.epi_ld * 4 + p.e_stages * p.slot_bytes;
     } else {
         p.slot_bytes = 0;
         p.e_stages = 1;
     }
-    int stages = (budget - fixed) / Cfg::STAGE_BYTES;
+    p.res_b = 0;
+    p.stage_bytes = Cfg::STAGE_BYTES;
+    const int res_bytes = p.num_k_blocks * Cfg::B_BYTES;
+    if (p.num_n_blocks == 1 && p.num_m_blocks > 2 * gn_num_sms() && budget - fixed - res_bytes >= 4 * GEMM_A_BYTES && !gn_env_flag("GN_GEMM_NO_RESB")) {
+        p.res_b = 1;
+        p.stage_bytes = GEMM_A_BYTES;
+        fixed += res_bytes;
+    }
+    int stages = (budget - fixed) / p.stage_bytes;
     if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
-    if (stages > 2 * p.num_k_blocks && stages > 2) stages = 2 * p.num_k_blocks > 2 ? 2 * p.num_k_blocks : 2;
+    if (!p.res_b && stages > 2 * p.num_k_blocks && stages > 2) stages = 2 * p.num_k_blocks > 2 ? 2 * p.num_k_blocks : 2;
     GN_REQUIRE(stages >= 2, GN_EUNSUPPORTED, "gemm_bf16: shared memory budget exhausted (BN %d)", BN);
     p.stages = stages;
-    const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + fixed + 1024;
+    const size_t smem = (size_t)stages * p.stage_bytes + fixed + 1024;
     static size_t attr_set = 0;
     if (smem > attr_set) {
         GN_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, XFORM, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -625,6 +651,7 @@ GN_API int gn_gemm_bf16(const void* a, long lda, const void* b, long ldb, int M,
     int epi = EPI_DIRECT;
     if (!out_fp32 && N <= GEMM_EPI_MAX_N && tma_ok(out, ldc) && (p.epi_mode == 0 || tma_ok(bn_ref, bn_ldref)))
         epi = p.epi_mode == 1 ? EPI_BNBWD : EPI_STORE;
+    if (epi == EPI_STORE && gn_env_flag("GN_GEMM_FORCE_DIRECT")) epi = EPI_DIRECT;
     CUtensorMap tmA, tmB, tmOut, tmRef;
     memset(&tmOut, 0, sizeof(tmOut));
     memset(&tmRef, 0, sizeof(tmRef));

@@ -229,3 +229,47 @@ def test_default_constructor_runs_forward_and_backward():
     assert list(y.shape) == [4, 7] and torch.isfinite(y).all()
     with pytest.raises(RuntimeError):
         DenseNet(num_classes=10)(torch.zeros(1, 3, 32, 32))     # CPU tensors are still refused: there is no CPU path
+
+
+@pytest.mark.parametrize('signed', [False, True])
+@pytest.mark.parametrize('N,H,C,ldo', [(3, 16, 64, 256), (2, 8, 16, 16), (1, 64, 64, 96)])
+def test_stem_maxpool_forward_backward_match_torch(N, H, C, ldo, signed):
+    """pool0 (densenet.py:111, MaxPool2d(3, 2, 1)): values bit-equal, arg-max taps equal to torch's first-maximum rule (ties included:
+    the input is quantised to a few levels), and the fused pool / ReLU / BatchNorm-scale backward against autograd."""
+    import torch.nn.functional as F
+    from gridnext_b200._lib import call, ptr, stream
+    g = torch.Generator(); g.manual_seed(11)
+    x = (torch.randn((N, C, H, H), generator=g) * 2).round() / 2            # many exact ties
+    if not signed:
+        x = torch.relu(x)
+    x = (x + 0.0).to(torch.bfloat16)                                        # no -0.0: torch's max treats it as a tie with +0.0
+    ref, ridx = F.max_pool2d(x.float(), 3, 2, 1, return_indices=True)
+    Ho = H // 2
+    oy = torch.arange(Ho).view(1, 1, Ho, 1); ox = torch.arange(Ho).view(1, 1, 1, Ho)
+    ky = ridx // H - (2 * oy - 1); kx = ridx % H - (2 * ox - 1)
+    rtap = (ky * 3 + kx).permute(0, 2, 3, 1).reshape(-1, C)
+    xin = x.permute(0, 2, 3, 1).reshape(-1, C).contiguous().cuda()
+    out = torch.zeros((N * Ho * Ho, ldo), dtype=torch.bfloat16, device='cuda')
+    idx = torch.empty((N * Ho * Ho, C), dtype=torch.uint8, device='cuda')
+    call('gn_maxpool3s2_fwd', ptr(xin), C, N, H, H, C, ptr(out), ldo, ptr(idx), stream())
+    assert torch.equal(out[:, :C].float().cpu(), ref.permute(0, 2, 3, 1).reshape(-1, C))
+    assert torch.equal(idx.cpu().long(), rtap)
+    if signed:
+        return
+    # backward: dz = scatter(dpool) * [act > 0] * sc, column sums sum g and p1 * (sum g*act - p0 * sum g)
+    dp = (torch.randn((N * Ho * Ho, C), generator=g) * 0.1).to(torch.bfloat16)
+    sc, p0, p1 = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    xr = x.float().requires_grad_(True)
+    F.max_pool2d(xr, 3, 2, 1).backward(dp.float().reshape(N, Ho, Ho, C).permute(0, 3, 1, 2))
+    gm = (xr.grad * (x.float() > 0)).permute(0, 2, 3, 1).reshape(-1, C)
+    dpb = torch.zeros((N * Ho * Ho, ldo), dtype=torch.bfloat16, device='cuda'); dpb[:, :C] = dp.cuda()
+    dz = torch.empty((N * H * H, C), dtype=torch.bfloat16, device='cuda')
+    colsum = torch.zeros((2, C), dtype=torch.float32, device='cuda')
+    scd, p0d, p1d = sc.cuda(), p0.cuda(), p1.cuda()
+    call('gn_maxpool3s2_bnrelu_bwd', ptr(dpb), ldo, ptr(idx), ptr(xin), C, N, H, H, C, ptr(scd), ptr(p0d), ptr(p1d), ptr(dz), C, ptr(colsum), C,
+         stream())
+    act = xin.float().cpu()
+    assert float((dz.float().cpu() - gm * sc).abs().max()) <= 1e-2 * float((gm * sc).abs().max())
+    assert float((colsum[0].cpu() - gm.sum(0)).abs().max()) <= 1e-4 * max(1.0, float(gm.sum(0).abs().max()))
+    ref_x = p1 * ((gm * act).sum(0) - p0 * gm.sum(0))
+    assert float((colsum[1].cpu() - ref_x).abs().max()) <= 1e-4 * max(1.0, float(ref_x.abs().max()))
