@@ -31,6 +31,9 @@ using namespace gnptx;
 struct StemParams {
     int N, P, Ho, CO, NP;
     int RT;                // output rows per tile
+    int G, S;              // forward: G row-tiles share one pipeline stage (one strip box, one accumulator hand-off: the ~1 us of barrier traffic per
+                           // stage dwarfed the 14 MMAs of a 64-position tile), S of them share one staging slot / TMA store
+    int supers_per_img, n_super;
     int vs;                // virtual positions per output row = P + 8
     int tiles_per_img, n_tiles;
     int rows_in;           // image rows per strip = 2*RT + 5
@@ -139,7 +142,7 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
         fence_barrier_init();
     }
-    if (warp == 3) tmem_alloc<256>(&tmem_slot);
+    if (warp == 3) tmem_alloc<512>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -151,8 +154,8 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             for (int ky = 0; ky < 7; ++ky) tma_load_2d(&tmW, &bar_w, s_w + ky * p.NP * 64, 0, ky * p.CO);
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int n = tile / p.tiles_per_img, oy0 = (tile - n * p.tiles_per_img) * p.RT;
+            for (int tile = blockIdx.x; tile < p.n_super; tile += gridDim.x) {
+                const int n = tile / p.supers_per_img, oy0 = (tile - n * p.supers_per_img) * p.G * p.RT;
                 mbar_wait(&bar_empty[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(p.rows_in * p.pitchB));
                 tma_load_3d(&tmX, &bar_full[stage], s_x + (size_t)stage * p.strip_alloc, -4, 2 * oy0 - 3, n);
@@ -169,17 +172,19 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             mbar_wait(&bar_w, 0);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < p.n_super; tile += gridDim.x) {
                 mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
                 mbar_wait(&bar_full[stage], phase);
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(acc * 128);
-                const uint64_t descA = smem_desc(tmplA, smem_u32(s_x + (size_t)stage * p.strip_alloc));
+                for (int g = 0; g < p.G; ++g) {
+                    const uint32_t d = tmem_base + (uint32_t)(acc * 256 + g * p.NP);
+                    const uint64_t descA = smem_desc(tmplA, smem_u32(s_x + (size_t)stage * p.strip_alloc) + (uint32_t)(g * 2 * p.RT * p.pitchB));
 #pragma unroll
-                for (int ky = 0; ky < 7; ++ky)
+                    for (int ky = 0; ky < 7; ++ky)
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        umma_bf16(d, descA + (uint64_t)(ky * pitch16 + ks * 2), descW + (uint64_t)(ky * wk16 + ks * 2), idesc, (uint32_t)((ky | ks) != 0));
+                        for (int ks = 0; ks < 2; ++ks)
+                            umma_bf16(d, descA + (uint64_t)(ky * pitch16 + ks * 2), descW + (uint64_t)(ky * wk16 + ks * 2), idesc, (uint32_t)((ky | ks) != 0));
+                }
                 umma_commit(&bar_empty[stage]);
                 umma_commit(&bar_tfull[acc]);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -191,8 +196,8 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (elect_one()) {
             int es = 0;
             uint32_t eph = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
-                for (int j = 0; j < p.nsub; ++j) {
+            for (int tile = blockIdx.x; tile < p.n_super; tile += gridDim.x)
+                for (int j = 0; j < (p.G / p.S) * p.nsub; ++j) {
                     mbar_wait(&bar_eempty[es], eph ^ 1);
                     mbar_arrive(&bar_efull[es]);
                     if (++es == p.e_stages) { es = 0; eph ^= 1; }
@@ -202,22 +207,21 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (elect_one()) {
             int es = 0, prev_es = -1;
             uint32_t eph = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int n = tile / p.tiles_per_img, oy0 = (tile - n * p.tiles_per_img) * p.RT;
+            for (int tile = blockIdx.x; tile < p.n_super; tile += gridDim.x) {
+                const int n = tile / p.supers_per_img, oy0 = (tile - n * p.supers_per_img) * p.G * p.RT;
                 const int row0 = (n * p.Ho + oy0) * p.Ho;
-                for (int j = 0; j < p.nsub; ++j) {
-                    mbar_wait(&bar_eready[es], eph);
-                    const uint8_t* slot = s_slots + (size_t)es * STEM_SUB_BYTES;
-                    for (int rt = 0; rt < p.RT; ++rt) tma_store_2d(&tmOut, slot + (size_t)rt * p.Ho * 128, j * 64, row0 + rt * p.Ho);
-                    tma_store_commit();
-                    if (prev_es >= 0) {
-                        tma_store_wait_read<1>();
-                        mbar_arrive(&bar_eempty[prev_es]);
+                for (int sp = 0; sp < p.G / p.S; ++sp)
+                    for (int j = 0; j < p.nsub; ++j) {
+                        mbar_wait(&bar_eready[es], eph);
+                        // the S * RT output rows of a slot are consecutive rows of the [N*Ho*Ho, CO] output: one box
+                        tma_store_2d(&tmOut, s_slots + (size_t)es * STEM_SUB_BYTES, j * 64, row0 + sp * p.S * p.RT * p.Ho);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();
+                        mbar_arrive(&bar_eempty[es]);
+                        if (++es == p.e_stages) { es = 0; eph ^= 1; }
                     }
-                    prev_es = es;
-                    if (++es == p.e_stages) { es = 0; eph ^= 1; }
-                }
             }
+            (void)prev_es;
             tma_store_wait_all<0>();
         }
         __syncwarp();
@@ -230,41 +234,44 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t sw = (uint32_t)(mrow & 7);
         int acc = 0, es = 0;
         uint32_t acc_phase = 0, eph = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < p.n_super; tile += gridDim.x) {
             mbar_wait(&bar_tfull[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * 128);
-            for (int j = 0; j < p.nsub; ++j) {
-                mbar_wait(&bar_efull[es], eph);
-                const int c0 = j * 64 + h * 32;
-                __syncwarp();
-                if (c0 < p.NP) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c0, r);
-                    tmem_ld_wait();
-                    if (valid) {
-                        uint8_t* rowp = s_slots + (size_t)es * STEM_SUB_BYTES + mrow * 128;
-                        const float* cst = s_epi + c0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(acc * 256);
+            for (int sp = 0; sp < p.G / p.S; ++sp)
+                for (int j = 0; j < p.nsub; ++j) {
+                    mbar_wait(&bar_efull[es], eph);
+                    const int c0 = j * 64 + h * 32;
+                    __syncwarp();
+                    if (c0 < p.NP) {
+                        for (int si = 0; si < p.S; ++si) {
+                            uint32_t r[32];
+                            tmem_ld32(taddr + (uint32_t)((sp * p.S + si) * p.NP + c0), r);
+                            tmem_ld_wait();
+                            if (valid) {
+                                uint8_t* rowp = s_slots + (size_t)es * STEM_SUB_BYTES + (si * p.RT * p.Ho + mrow) * 128;      // S > 1: RT * Ho is a multiple of 8
+                                const float* cst = s_epi + c0;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float o[8];
+                                for (int q = 0; q < 4; ++q) {
+                                    float o[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float x = fmaf(__uint_as_float(r[8 * q + e]), cst[8 * q + e], cst[STEM_MAX_CO + 8 * q + e]);
-                                o[e] = p.relu ? fmaxf(x, 0.f) : x;
+                                    for (int e = 0; e < 8; ++e) {
+                                        const float x = fmaf(__uint_as_float(r[8 * q + e]), cst[8 * q + e], cst[STEM_MAX_CO + 8 * q + e]);
+                                        o[e] = p.relu ? fmaxf(x, 0.f) : x;
+                                    }
+                                    uint4 t;
+                                    t.x = gn_pack_bf16x2(o[0], o[1]); t.y = gn_pack_bf16x2(o[2], o[3]);
+                                    t.z = gn_pack_bf16x2(o[4], o[5]); t.w = gn_pack_bf16x2(o[6], o[7]);
+                                    *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(h * 4 + q)) ^ sw) << 4)) = t;
+                                }
                             }
-                            uint4 t;
-                            t.x = gn_pack_bf16x2(o[0], o[1]); t.y = gn_pack_bf16x2(o[2], o[3]);
-                            t.z = gn_pack_bf16x2(o[4], o[5]); t.w = gn_pack_bf16x2(o[6], o[7]);
-                            *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(h * 4 + q)) ^ sw) << 4)) = t;
                         }
                     }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_eready[es]);
+                    if (++es == p.e_stages) { es = 0; eph ^= 1; }
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_eready[es]);
-                if (++es == p.e_stages) { es = 0; eph ^= 1; }
-            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[acc]);
@@ -274,7 +281,7 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 3) tmem_dealloc<256>(tmem_base);
+    if (warp == 3) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
@@ -288,7 +295,7 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = 2 * 128 * 128;                                   // dZ0 tile: 2 channel groups x 128 positions x 128 B
-    const int stage_bytes = p.strip_alloc + a_bytes;
+    const int stage_bytes = p.strip_alloc + p.G * a_bytes;               // G row-tiles per stage: one strip, G dZ0 tiles
     const int ngroups = (p.CO + 63) >> 6;
 
     // zero everything once: the dropped positions of the dZ0 tile and the slack behind each strip must read as 0 forever
@@ -306,22 +313,24 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    const bool has_work = (int)blockIdx.x < p.n_tiles;
+    const bool has_work = (int)blockIdx.x < p.n_super;
 
     if (warp == 0) {
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int n = tile / p.tiles_per_img, oy0 = (tile - n * p.tiles_per_img) * p.RT;
+            for (int tile = blockIdx.x; tile < p.n_super; tile += gridDim.x) {
+                const int n = tile / p.supers_per_img, oy0 = (tile - n * p.supers_per_img) * p.G * p.RT;
                 const int row0 = (n * p.Ho + oy0) * p.Ho;
                 mbar_wait(&bar_empty[stage], phase ^ 1);
                 uint8_t* st = sm + (size_t)stage * stage_bytes;
-                mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(p.rows_in * p.pitchB + p.RT * ngroups * p.Ho * 128));
+                mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(p.rows_in * p.pitchB + p.G * p.RT * ngroups * p.Ho * 128));
                 tma_load_3d(&tmX, &bar_full[stage], st, -4, 2 * oy0 - 3, n);
-                for (int rt = 0; rt < p.RT; ++rt)
-                    for (int gi = 0; gi < ngroups; ++gi)
-                        tma_load_2d(&tmDz, &bar_full[stage], st + p.strip_alloc + gi * 16384 + (size_t)rt * p.vs * 128, gi * 64, row0 + rt * p.Ho);
+                for (int g = 0; g < p.G; ++g)
+                    for (int rt = 0; rt < p.RT; ++rt)
+                        for (int gi = 0; gi < ngroups; ++gi)
+                            tma_load_2d(&tmDz, &bar_full[stage], st + p.strip_alloc + g * a_bytes + gi * 16384 + (size_t)rt * p.vs * 128, gi * 64,
+                                        row0 + (g * p.RT + rt) * p.Ho);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -334,19 +343,21 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             uint32_t started = 0;                                                      // bit ky: accumulator ky holds data
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < p.n_super; tile += gridDim.x) {
                 mbar_wait(&bar_full[stage], phase);
                 tc_fence_after();
                 const uint32_t st = smem_u32(sm + (size_t)stage * stage_bytes);
-                const uint64_t descB = smem_desc(tmplB, st), descA = smem_desc(tmplA, st + p.strip_alloc);
+                for (int g = 0; g < p.G; ++g) {
+                    const uint64_t descB = smem_desc(tmplB, st + (uint32_t)(g * 2 * p.RT * p.pitchB)), descA = smem_desc(tmplA, st + p.strip_alloc + g * a_bytes);
 #pragma unroll
-                for (int ky = 0; ky < 7; ++ky) {
+                    for (int ky = 0; ky < 7; ++ky) {
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        if (p.kstep_mask & (1u << s)) {
-                            umma_bf16(tmem_base + (uint32_t)(ky * STEM_KQ), descA + (uint64_t)(s * 128), descB + (uint64_t)(ky * pitch16 + s * 16), idesc,
-                                      (started >> ky) & 1u);
-                            started |= 1u << ky;
+                        for (int s = 0; s < 8; ++s) {
+                            if (p.kstep_mask & (1u << s)) {
+                                umma_bf16(tmem_base + (uint32_t)(ky * STEM_KQ), descA + (uint64_t)(s * 128), descB + (uint64_t)(ky * pitch16 + s * 16), idesc,
+                                          (started >> ky) & 1u);
+                                started |= 1u << ky;
+                            }
                         }
                     }
                 }
@@ -419,6 +430,19 @@ GN_API int gn_stem_conv_fwd(const void* xq, int N, int P, const void* wq, int CO
     if (rc) return rc;
     GN_REQUIRE(ldo >= CO && ldo % 8 == 0 && ((uintptr_t)out & 15) == 0, GN_EALIGN, "stem_conv_fwd: output pitch must be a multiple of 8 and 16-byte aligned");
     p.scale = scale; p.shift = shift; p.relu = relu;
+    // row-tiles per pipeline stage: two accumulator buffers of G * NP columns in 512 TMEM columns (the second buffer starts at column 256)
+    p.G = 1;
+    if (!gn_env_flag("GN_STEM_G1"))
+        for (int g = 4; g > 1; g >>= 1)
+            if (p.tiles_per_img % g == 0 && g * p.NP <= 256) { p.G = g; break; }
+    p.S = 1;
+    if ((p.RT * p.Ho) % 8 == 0)
+        for (int sv = p.G; sv > 1; sv >>= 1)
+            if (p.G % sv == 0 && sv * p.RT * p.Ho <= 128) { p.S = sv; break; }
+    p.supers_per_img = p.tiles_per_img / p.G;
+    p.n_super = N * p.supers_per_img;
+    p.rows_in = 2 * p.G * p.RT + 5;
+    p.strip_alloc = ((p.rows_in * p.pitchB + STEM_SLACK + 1023) / 1024) * 1024;
     const int w_bytes = ((7 * p.NP * 64 + 1023) / 1024) * 1024;
     const int budget = 227 * 1024 - 1024 - 512;
     p.e_stages = 3;
@@ -431,14 +455,14 @@ GN_API int gn_stem_conv_fwd(const void* xq, int N, int P, const void* wq, int CO
     if (rc) return rc;
     rc = gn_tmap_bf16_2d(&tmW, wq, (uint64_t)7 * CO, STEM_KQ, STEM_KQ, STEM_KQ, (uint32_t)p.NP, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
-    rc = gn_tmap_bf16_2d(&tmOut, out, (uint64_t)N * p.Ho * p.Ho, (uint64_t)CO, (uint64_t)ldo, 64, (uint32_t)p.Ho);
+    rc = gn_tmap_bf16_2d(&tmOut, out, (uint64_t)N * p.Ho * p.Ho, (uint64_t)CO, (uint64_t)ldo, 64, (uint32_t)(p.S * p.RT * p.Ho));
     if (rc) return rc;
     static size_t attr_set = 0;
     if (smem > attr_set) {
         GN_CUDA(cudaFuncSetAttribute(stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
+    const int grid = p.n_super < gn_num_sms() ? p.n_super : gn_num_sms();
     stem_fwd_kernel<<<grid, 384, smem, stream>>>(tmX, tmW, tmOut, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
@@ -452,7 +476,17 @@ GN_API int gn_stem_conv_wgrad(const void* xq, int N, int P, const void* dz, long
     if (rc) return rc;
     GN_REQUIRE(ldz >= CO && ldz % 8 == 0 && ((uintptr_t)dz & 15) == 0, GN_EALIGN, "stem_conv_wgrad: gradient pitch must be a multiple of 8 and 16-byte aligned");
     p.dwq = dwq;
-    const int stage_bytes = p.strip_alloc + 2 * 128 * 128;
+    p.G = 1;
+    if (!gn_env_flag("GN_STEM_G1"))
+        for (int g = 4; g > 1; g >>= 1)       // largest group that still leaves two pipeline stages
+            if (p.tiles_per_img % g == 0 &&
+                2 * ((((2 * g * p.RT + 5) * p.pitchB + STEM_SLACK + 1023) / 1024) * 1024 + g * 2 * 128 * 128) <= 227 * 1024 - 1024 - 512) { p.G = g; break; }
+    p.S = 1;
+    p.supers_per_img = p.tiles_per_img / p.G;
+    p.n_super = N * p.supers_per_img;
+    p.rows_in = 2 * p.G * p.RT + 5;
+    p.strip_alloc = ((p.rows_in * p.pitchB + STEM_SLACK + 1023) / 1024) * 1024;
+    const int stage_bytes = p.strip_alloc + p.G * 2 * 128 * 128;
     const int budget = 227 * 1024 - 1024 - 512;
     p.stages = budget / stage_bytes;
     if (p.stages > 4) p.stages = 4;
@@ -468,7 +502,7 @@ GN_API int gn_stem_conv_wgrad(const void* xq, int N, int P, const void* dz, long
         GN_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
+    const int grid = p.n_super < gn_num_sms() ? p.n_super : gn_num_sms();
     stem_wgrad_kernel<<<grid, 192, smem, stream>>>(tmX, tmDz, p);
     GN_LAUNCH_CHECK();
     return GN_OK;

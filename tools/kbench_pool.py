@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Pooling / element-wise kernels of the DenseNet path at the DenseNet-121 @128 px / 4,992-spot shapes (development tool).
 
-    python tools/kbench_pool.py [names...]      names: maxpool_fwd maxpool_bwd avgpool_fwd pool_bwd
+    python tools/kbench_pool.py [names...]      names: maxpool_fwd maxpool_bwd avgpool_fwd pool_bwd stem_fwd stem_wgrad
 One JSON line per case: CUDA-event time (median), algorithmic GB/s and its fraction of the measured copy bandwidth.
 """
 import json, sys, os
@@ -49,6 +49,24 @@ def main(names):
                                 ptr(dz0), c0, ptr(colsum), 4096, stream()),
                    3.0 * M1 * c0 + 4.0 * M0 * c0, 'maxpool_bwd')
         del act0, C, idx0
+        torch.cuda.empty_cache()
+    if sel('stem_fwd') or sel('stem_wgrad'):
+        from gridnext_b200 import tc
+        P, CO = 128, 64
+        x = torch.randn(n, 3, P, P, device=dev).to(bf)
+        xq = tc.stem_pack_input(x)
+        w = torch.randn(CO, 3, 7, 7, device=dev) * 0.1
+        wq = tc.stem_pack_weight(w)
+        sc, sh = torch.rand(CO, device=dev) + 0.5, torch.randn(CO, device=dev) * 0.1
+        M0 = n * (P // 2) ** 2
+        out = torch.empty(M0, CO, device=dev, dtype=bf)
+        if sel('stem_fwd'):
+            timeit(lambda: tc.stem_conv_fwd(xq, wq, scale=sc, shift=sh, relu=True, out=out), 8.0 * n * P * P + 2.0 * M0 * CO, 'stem_fwd')
+        if sel('stem_wgrad'):
+            dz = (torch.randn(M0, CO, device=dev) * 0.1).to(bf)
+            dwq = torch.zeros(CO, 224, device=dev)
+            timeit(lambda: tc.stem_conv_wgrad_into(xq, dz, CO, dwq), 8.0 * n * P * P + 2.0 * M0 * CO, 'stem_wgrad')
+        del x, xq, out
         torch.cuda.empty_cache()
     for H, ct in ((32, 256), (16, 512), (8, 1024)):
         M = n * H * H
