@@ -160,7 +160,11 @@ __device__ __forceinline__ bool pg_interior(int cx, int cy, int hw, int P, int H
     return cx - hw >= 0 && cx - hw + P <= W && cy - hw >= 0 && cy - hw + P <= H;
 }
 
-template <typename OutT>
+// REP: copies of the value table, copy (lane % REP) is the one a lane reads.  The table look-ups are data dependent, so with one copy the
+// 32 lanes of a look-up hit random banks: ncu counted 62 % of all shared-memory wavefronts as conflict replays and the shared-memory pipe,
+// not HBM, set the pace (12 look-ups x ~3.5 wavefronts per 4 pixels).  Entry (c, v) of copy k sits at word (c*256 + v) * REP + k, i.e. in bank
+// (v * REP + k) % 32: with REP = 16 only the two lanes that share a copy can collide (and only when v differs by a multiple of 2).
+template <typename OutT, int REP>
 __global__ void __launch_bounds__(256, 2) patch_gather_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const unsigned char* __restrict__ img,
                                                                   long pitch, int H, int W, const int* __restrict__ cells, int n_cells, int P,
                                                                   int row_bytes, int stages, const float* __restrict__ mean,
@@ -168,8 +172,9 @@ __global__ void __launch_bounds__(256, 2) patch_gather_tma_kernel(const __grid_c
     extern __shared__ __align__(128) unsigned char sm[];
     __shared__ __align__(8) uint64_t bar[PG_STAGES];
     const int tid = threadIdx.x;
-    float* lut = reinterpret_cast<float*>(sm);                        // [3][256]
-    unsigned char* ring = sm + 3 * 256 * sizeof(float);               // [stages][PG_RPC][row_bytes]
+    float* lut = reinterpret_cast<float*>(sm);                        // [3][256][REP]
+    unsigned char* ring = sm + 3 * 256 * REP * sizeof(float);         // [stages][PG_RPC][row_bytes]
+    const float* lutp = lut + (tid & (REP - 1));                      // this lane's copy
     const int tile_bytes = PG_RPC * row_bytes;
     const int tiles = P / PG_RPC, groups = P / 4, hw = P / 2;
     const int n_items = n_cells * tiles;
@@ -195,7 +200,8 @@ __global__ void __launch_bounds__(256, 2) patch_gather_tma_kernel(const __grid_c
         const int c = e >> 8, v = e & 255;
         float f = (float)v;
         if (mean != nullptr) f = __fdiv_rn(__fsub_rn(__fdiv_rn(f, 255.0f), mean[c]), stdv[c]);
-        lut[e] = f;
+#pragma unroll
+        for (int k = 0; k < REP; ++k) lut[e * REP + k] = f;
     }
     __syncthreads();
     if (tid == 0)
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(256, 2) patch_gather_tma_kernel(const __grid_c
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             const int byte = 3 * j + c;
-                            v[c][j] = lut[c * 256 + ((w[byte >> 2] >> (8 * (byte & 3))) & 0xff)];
+                            v[c][j] = lutp[(c * 256 + (int)__byte_perm(w[byte >> 2], 0, 0x4440 | (byte & 3))) * REP];
                         }
 #pragma unroll
                     for (int c = 0; c < 3; ++c) Pack4<OutT>::store(orow + (long)c * P * P + 4 * g, v[c][0], v[c][1], v[c][2], v[c][3]);
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(256, 2) patch_gather_tma_kernel(const __grid_c
                 for (int j = 0; j < 4; ++j) {
                     const int gx = min(max(cx - hw + 4 * g + j, 0), W - 1);
                     const unsigned char* px = img + (long)gy * pitch + 3L * gx;
-                    v[0][j] = lut[px[0]]; v[1][j] = lut[256 + px[1]]; v[2][j] = lut[512 + px[2]];
+                    v[0][j] = lutp[px[0] * REP]; v[1][j] = lutp[(256 + px[1]) * REP]; v[2][j] = lutp[(512 + px[2]) * REP];
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
@@ -311,20 +317,25 @@ GN_API int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, c
         uint32_t box[2] = {(uint32_t)(row_bytes / 4), PG_RPC};
         int rc = gn_tmap_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, img, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
+        // 16 table copies when three or more ring stages still fit beside them (two CTAs per SM), else 8
+        const size_t ring1 = (size_t)PG_RPC * row_bytes;
+        const int rep = (3 * 256 * 16 * sizeof(float) + 3 * ring1 + 16 <= 100 * 1024) ? 16 : 8;
+        const size_t lut_bytes = 3 * 256 * (size_t)rep * sizeof(float);
         int stages = PG_STAGES;
-        while (stages > 2 && 3 * 256 * sizeof(float) + (size_t)stages * PG_RPC * row_bytes + 16 > 100 * 1024) --stages;   // two CTAs per SM
-        const size_t smem_t = 3 * 256 * sizeof(float) + (size_t)stages * PG_RPC * row_bytes + 16;
+        while (stages > 2 && lut_bytes + (size_t)stages * ring1 + 16 > 100 * 1024) --stages;   // two CTAs per SM
+        const size_t smem_t = lut_bytes + (size_t)stages * ring1 + 16;
         const int n_items = n_cells * (P / PG_RPC);
         int grid_t = 2 * gn_num_sms();
         if (grid_t > n_items) grid_t = n_items;
-        if (out_bf16) {
-            GN_CUDA(cudaFuncSetAttribute(patch_gather_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-            patch_gather_tma_kernel<__nv_bfloat16><<<grid_t, 256, smem_t, stream>>>(tm, img, pitch, H, W, cells, n_cells, P, row_bytes, stages, mean, stdv,
-                                                                                    (__nv_bfloat16*)out);
-        } else {
-            GN_CUDA(cudaFuncSetAttribute(patch_gather_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-            patch_gather_tma_kernel<float><<<grid_t, 256, smem_t, stream>>>(tm, img, pitch, H, W, cells, n_cells, P, row_bytes, stages, mean, stdv, (float*)out);
-        }
+#define PG_LAUNCH(T, R)                                                                                                                        \
+    do {                                                                                                                                       \
+        GN_CUDA(cudaFuncSetAttribute(patch_gather_tma_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));                \
+        patch_gather_tma_kernel<T, R><<<grid_t, 256, smem_t, stream>>>(tm, img, pitch, H, W, cells, n_cells, P, row_bytes, stages, mean, stdv, \
+                                                                       (T*)out);                                                               \
+    } while (0)
+        if (out_bf16) { if (rep == 16) PG_LAUNCH(__nv_bfloat16, 16); else PG_LAUNCH(__nv_bfloat16, 8); }
+        else { if (rep == 16) PG_LAUNCH(float, 16); else PG_LAUNCH(float, 8); }
+#undef PG_LAUNCH
         GN_LAUNCH_CHECK();
         return GN_OK;                                                   // the persistent kernel wrote every cell (interior, border, off-tissue)
     }
