@@ -660,6 +660,9 @@ def roofline_from_profile(prof, wl, step_ms, args):
         add('gn_gemm_bf16', 2.0 * M_ * N_ * K_, 2.0 * M_ * (K_ + N_ * (3 if g[16] else 1)))       # BN-backward epilogue: read ref, read+write out
     for a, b, g in prof.get('gn_gemm_tn_bf16', []):
         add('gn_gemm_tn_bf16', 2.0 * g[4] * g[5] * g[6], 2.0 * g[6] * (g[4] + g[5]))
+    for a, b, g in prof.get('gn_conv1x1_bwd_bf16', []):          # data gradient + weight gradient of the bottleneck conv: one pass over dz, C, dC
+        M_, N_ = g[4], g[5]
+        add('gn_conv1x1_bwd_bf16', 4.0 * M_ * N_ * 128, 2.0 * M_ * (128 + N_ * (3 if g[16] else 2)))
     for a, b, g in prof.get('gn_conv3x3_bf16', []):
         px = g[2] * g[3] * g[4]
         add('gn_conv3x3_bf16', 2.0 * 9 * px * g[5] * g[8], 2.0 * px * (g[5] + g[8] * (2 if g[11] else 1)))
@@ -687,7 +690,7 @@ def roofline_from_profile(prof, wl, step_ms, args):
     dom = max(table, key=lambda k: table[k]['ms'])
     pk = peaks()
     traffic = committed_traffic().get(wl.cfg, {}).get(dom)
-    tensor_bound = dom in ('gn_gemm_bf16', 'gn_gemm_tn_bf16', 'gn_conv3x3_bf16', 'gn_conv3x3_wgrad_bf16', 'gn_stem_conv_fwd', 'gn_stem_conv_wgrad')
+    tensor_bound = dom in ('gn_gemm_bf16', 'gn_gemm_tn_bf16', 'gn_conv1x1_bwd_bf16', 'gn_conv3x3_bf16', 'gn_conv3x3_wgrad_bf16', 'gn_stem_conv_fwd', 'gn_stem_conv_wgrad')
     roof = dict(kernel=dom, launches=table[dom]['calls'], share_of_step=table[dom]['share'], peak_source=pk['src'],
                 traffic=None if traffic is None else traffic.get('dram_bytes_per_launch'))
     if dom in flops and tensor_bound:
@@ -715,7 +718,7 @@ def roofline_from_profile(prof, wl, step_ms, args):
         def ints(g):
             return [a if isinstance(a, int) else (None if a is None else 'p') for a in g]
         calls = {k: [dict(ms=a.elapsed_time(b), args=ints(g)) for a, b, g in v] for k, v in prof.items()
-                 if k in ('gn_gemm_bf16', 'gn_gemm_tn_bf16', 'gn_conv3x3_bf16', 'gn_conv3x3_wgrad_bf16')}
+                 if k in ('gn_gemm_bf16', 'gn_gemm_tn_bf16', 'gn_conv1x1_bwd_bf16', 'gn_conv3x3_bf16', 'gn_conv3x3_wgrad_bf16')}
         json.dump(dict(step_ms=step_ms, instrumented_total_ms=total, kernels=table, calls=calls), open(args.profile_out, 'w'), indent=1, sort_keys=True)
     return roof
 

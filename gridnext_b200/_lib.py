@@ -63,6 +63,7 @@ _SIGS = {
     'gn_bn_train_fix_coeffs': [vp, vp, vp, vp, vp, cl, ci, vp, vp, ci, vp],
     'gn_bn_train_fix_bf16': [vp, cl, vp, cl, cl, ci, vp, vp, vp],
     'gn_gemm_tn_bf16': [vp, cl, vp, cl, ci, ci, ci, vp, cl, vp, vp, vp],
+    'gn_conv1x1_bwd_bf16': [vp, cl, vp, cl, ci, ci, vp, cl, vp, cl, vp, vp, vp, vp, vp, ci, ci, vp, cl, vp],
     'gn_prep_job_bytes': [],
     'gn_prepare_weights': [vp, ci, cl, vp, vp],
     'gn_unpack_gradients': [vp, ci, cl, vp, vp],

@@ -400,6 +400,16 @@ class _Grads:
         plan.gflat.zero_()
 
 
+def _conv1_backward(dz, w1t, dx, dw, bn):
+    """Backward of a dense layer's norm1 -> relu1 -> conv1 (densenet.py:12-18,26-27): data gradient with the BatchNorm/ReLU backward
+    epilogue and the weight gradient.  One kernel when the views allow it (bottleneck width 128), else the two GEMMs."""
+    if tc.conv1x1_bwd_fusable(dz, w1t, dx, bn['ref']):
+        tc.conv1x1_bwd_bf16(dz, w1t, dx, bn, dw)
+    else:
+        tc.gemm_tn_bf16(dz, bn['ref'], dw, bn['sc'], bn['sh'])
+        tc.gemm_bf16(dz, w1t, out=dx, bn=bn)
+
+
 def _backward_chunk(net, geo, cst, plan, saved, dout, grads):
     n, dev, bf = saved['n'], dout.device, torch.bfloat16
     f = net.features
@@ -444,9 +454,8 @@ def _backward_chunk(net, geo, cst, plan, saved, dout, grads):
             tc.conv3x3_wgrad_into(a2, dY, n, H, H, bott, g, plan.g(('dwp2', id(layer)), (9, bott, g)))
             tc.conv3x3_bf16(dY, n, H, H, g, plan.w('wp2t', id(layer)), bott, dz,
                             bn=dict(ref=a2, ref_is_raw=False, sc=k2['sc'], sh=None, p0=k2['beta'], p1=k2['inv_gamma'], colsum=colsum_of(k2)))
-            tc.gemm_tn_bf16(dz, C[:, :cin], plan.g(('dw1', id(layer)), (bott, cin)), k1['sc'], k1['sh'])
-            tc.gemm_bf16(dz, plan.w('w1t', id(layer))[:, :bott], out=dC[:, :cin],
-                         bn=dict(ref=C[:, :cin], ref_is_raw=True, sc=k1['sc'], sh=k1['sh'], p0=k1['mean'], p1=k1['invstd'],
+            _conv1_backward(dz, plan.w('w1t', id(layer))[:, :bott], dC[:, :cin], plan.g(('dw1', id(layer)), (bott, cin)),
+                            dict(ref=C[:, :cin], ref_is_raw=True, sc=k1['sc'], sh=k1['sh'], p0=k1['mean'], p1=k1['invstd'],
                                  colsum=colsum_of(k1), rmw=True))
         if bi > 0:
             prev, prec = geo.blocks[bi - 1], saved['blocks'][bi - 1]
@@ -668,9 +677,8 @@ def _backward_train(net, geo, cst, plan, saved, dout, grads):
                             bn=dict(ref=z, ref_is_raw=True, sc=k2['sc'], sh=k2['sh'], p0=k2['mean'], p1=k2['invstd'], colsum=colsum_of(k2)))
             _fix_coeffs(colsum_of(k2), k2, M, False, Fz, bott)
             _fix(dz, z, bott, Fz[0], Fz[1])
-            tc.gemm_tn_bf16(dz, C[:, :cin], plan.g(('dw1', id(layer)), (bott, cin)), k1['sc'], k1['sh'])
-            tc.gemm_bf16(dz, plan.w('w1t', id(layer))[:, :bott], out=dC[:, :cin],
-                         bn=dict(ref=C[:, :cin], ref_is_raw=True, sc=k1['sc'], sh=k1['sh'], p0=k1['mean'], p1=k1['invstd'],
+            _conv1_backward(dz, plan.w('w1t', id(layer))[:, :bott], dC[:, :cin], plan.g(('dw1', id(layer)), (bott, cin)),
+                            dict(ref=C[:, :cin], ref_is_raw=True, sc=k1['sc'], sh=k1['sh'], p0=k1['mean'], p1=k1['invstd'],
                                  colsum=colsum_of(k1), rmw=True))
             _fix_coeffs(colsum_of(k1), k1, M, True, F, cin)
         c_in = blk['c_in']

@@ -1,4 +1,5 @@
 """Python faces of the tensor-core (tcgen05) entry points.  Thin: argument checks + the ctypes call."""
+import os
 import torch
 from . import _lib
 from ._lib import ptr, stream, call
@@ -42,6 +43,35 @@ def gemm_bf16(a, b, out=None, out_dtype=torch.bfloat16, accumulate=False, scale=
          1 if accumulate else 0, ptr(scale), ptr(shift), 1 if relu else 0, ptr(xf_scale), ptr(xf_shift),
          *_bn_args(bn), 1 if (bn is not None and bn.get('rmw')) else 0, stream())
     return out
+
+
+def conv1x1_bwd_fusable(dz, wt, dx, ref):
+    """True when gn_conv1x1_bwd_bf16 can take these views (bottleneck width 128, TMA-addressable operands)."""
+    if os.environ.get('GRIDNEXT_B200_FUSED_BWD1X1', '1') == '0':
+        return False
+    if dz.shape[1] != 128 or wt.shape[1] != 128:
+        return False
+    for t in (dz, wt, dx, ref):
+        if t.dtype != torch.bfloat16 or t.stride(1) != 1 or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0:
+            return False
+    return True
+
+
+def conv1x1_bwd_bf16(dz, wt, dx, bn, dw):
+    """dx (+)= BN/ReLU-backward(dz @ wt.T) and dw += dz.T @ relu(bn(ref)) in one pass over dz and ref (see gn_conv1x1_bwd_bf16)."""
+    _lib.require_cuda(dz, wt, dx, dw)
+    M, K, lddz = _rows_pitch(dz)
+    N, Kb, ldw = _rows_pitch(wt)
+    Mo, No, lddx = _rows_pitch(dx)
+    if K != 128 or Kb != 128 or (Mo, No) != (M, N) or tuple(dw.shape) != (128, N) or dw.dtype != torch.float32:
+        raise ValueError('conv1x1_bwd_bf16: shape mismatch')
+    if not bn['ref_is_raw']:
+        raise ValueError('conv1x1_bwd_bf16: the reference must be the raw (pre-BatchNorm) tensor')
+    _, _, ldref = _rows_pitch(bn['ref'])
+    cs = bn.get('colsum')
+    call('gn_conv1x1_bwd_bf16', ptr(dz), lddz, ptr(wt), ldw, M, N, ptr(dx), lddx, ptr(bn['ref']), ldref, ptr(bn['sc']), ptr(bn['sh']),
+         ptr(bn['p0']), ptr(bn['p1']), ptr(cs), cs.stride(0) if cs is not None else 0, 1 if bn.get('rmw') else 0, ptr(dw), dw.stride(0), stream())
+    return dx
 
 
 def gemm_tn_bf16(a, b, out, xf_scale=None, xf_shift=None):

@@ -158,6 +158,16 @@ int gn_rows_affine_bf16(const float* in, long ldi, const float* scale, const flo
 int gn_gemm_tn_bf16(const void* a, long lda, const void* b, long ldb, int Mo, int No, int Kp, float* out, long ldo,
                     const float* xf_scale, const float* xf_shift, gn_stream_t stream);
 
+/* Backward of the bottleneck 1x1 convolution of a dense layer in ONE kernel (gridnext/densenet.py:12-18,26-27: conv1(relu(norm1(cat)));
+ * what autograd computes for those lines): dx[M, N] (+)= (dz[M,128] @ wt[N,128]^T) * [ref*sc + sh > 0] * sc  with the BatchNorm
+ * column sums of gn_gemm_bf16's bn_* epilogue (ref = raw concat columns, p0 = mean, p1 = invstd), AND
+ * dw[128, N] (fp32, pitch lddw) += dz^T @ relu(ref*sc + sh), the result of gn_gemm_tn_bf16 on the same operands, from the tiles
+ * the data gradient already holds on chip (no second pass over dz and ref).  Bottleneck width is 128; all bf16 views must be
+ * 16-byte aligned with pitches that are multiples of 8 elements. */
+int gn_conv1x1_bwd_bf16(const void* dz, long lddz, const void* wt, long ldw, int M, int N, void* dx, long lddx, const void* ref, long ldref,
+                        const float* sc, const float* sh, const float* p0, const float* p1, float* colsum, int ldsum, int rmw, float* dw,
+                        long lddw, gn_stream_t stream);
+
 /* ---- 3x3 / pad 1 convolution, NHWC bf16, tcgen05 implicit GEMM: replaces F.conv2d of densenet.py:30-31 (conv2 of
  * each dense layer) and its data gradient.  gn_conv3x3_pack: fp32 (CO, CI, 3, 3) weights -> bf16 [9*CO, ldw]
  * (mode 0, forward) or flipped/transposed [9*CI, ldw] (mode 1, data gradient; then call gn_conv3x3_bf16 with the

@@ -98,3 +98,51 @@ def test_gemm_bn_relu_backward_epilogue(M, N, K):
     assert rel(dc[:, :N].float().cpu(), ref_dc) < 1.5e-2
     assert torch.equal(dc[:, N:].cpu(), dc0[:, N:])
     assert rel(colsum[0].cpu(), ref_g) < 2e-3 and rel(colsum[1].cpu(), ref_gx) < 2e-3
+
+
+@pytest.mark.parametrize('M,N,rmw', [(1000, 224, True), (4100, 992, True), (300, 64, True), (128, 96, False), (40000, 128, True),
+                                     (20000, 160, True), (9000, 320, True), (77, 480, True), (66000, 256, True)])
+def test_conv1x1_backward_fused_dgrad_bn_wgrad(M, N, rmw):
+    """gn_conv1x1_bwd_bf16: the data gradient with the BatchNorm/ReLU backward epilogue AND the weight gradient of a dense layer's
+    bottleneck 1x1 convolution (densenet.py:12-18,26-27) in one kernel, against fp32 torch on the same bf16 inputs and against
+    the two separate kernels it replaces."""
+    from gridnext_b200.tc import conv1x1_bwd_bf16, conv1x1_bwd_fusable, gemm_bf16, gemm_tn_bf16
+    K = 128
+    dz, wt = rnd((M, K), 31, 0.5), rnd((N, K), 32, 0.1)
+    craw = rnd((M, N + 32), 33)
+    g = torch.Generator(); g.manual_seed(34)
+    mean, invstd = torch.randn(N, generator=g) * 0.2, torch.rand(N, generator=g) + 0.5
+    gamma, beta = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.3
+    sc = gamma * invstd
+    sh = beta - mean * sc
+    dc0 = rnd((M, N + 32), 35)
+    acc = dz.float() @ wt.float().t()
+    a = craw[:, :N].float() * sc + sh
+    gg = acc * (a > 0)
+    ref_dc = (dc0[:, :N].float() if rmw else 0) + gg * sc
+    ref_g = gg.sum(0)
+    ref_gx = (gg * (craw[:, :N].float() - mean) * invstd).sum(0)
+    ref_dw = (dz.double().t() @ torch.relu(a).to(torch.bfloat16).double()).float() + 1.0
+    dzc, wtc, crawc = dz.cuda(), wt.cuda(), craw.cuda()
+    consts = dict(sc=sc.cuda(), sh=sh.cuda(), p0=mean.cuda(), p1=invstd.cuda())
+
+    dc = dc0.clone().cuda()
+    colsum = torch.zeros((2, N), dtype=torch.float32, device='cuda')
+    dw = torch.ones((K, N), dtype=torch.float32, device='cuda')
+    assert conv1x1_bwd_fusable(dzc, wtc, dc[:, :N], crawc[:, :N])
+    conv1x1_bwd_bf16(dzc, wtc, dc[:, :N], dict(ref=crawc[:, :N], ref_is_raw=True, colsum=colsum, rmw=rmw, **consts), dw)
+    torch.cuda.synchronize()
+    assert rel(dc[:, :N].float().cpu(), ref_dc) < 1.5e-2
+    assert torch.equal(dc[:, N:].cpu(), dc0[:, N:])
+    assert rel(colsum[0].cpu(), ref_g) < 2e-3 and rel(colsum[1].cpu(), ref_gx) < 2e-3
+    assert rel(dw.cpu(), ref_dw) < 3e-3
+
+    # the two kernels it replaces, on the same inputs
+    dc2 = dc0.clone().cuda()
+    colsum2 = torch.zeros((2, N), dtype=torch.float32, device='cuda')
+    dw2 = torch.ones((K, N), dtype=torch.float32, device='cuda')
+    gemm_tn_bf16(dzc, crawc[:, :N], dw2, consts['sc'], consts['sh'])
+    gemm_bf16(dzc, wtc, out=dc2[:, :N], bn=dict(ref=crawc[:, :N], ref_is_raw=True, colsum=colsum2, rmw=rmw, **consts))
+    assert rel(dc[:, :N].float().cpu(), dc2[:, :N].float().cpu()) < 1e-2          # bf16 re-rounding of the += in L2
+    assert rel(dw.cpu(), dw2.cpu()) < 1e-4
+    assert rel(colsum.cpu(), colsum2.cpu()) < 1e-4

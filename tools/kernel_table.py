@@ -16,6 +16,8 @@ for name in c:
             by = 2 * a[4] * (a[6] + a[5] * (3 if a[16] else 1))
         elif name == 'gn_gemm_tn_bf16':
             key = (a[4], a[5], a[6]); fl = 2 * a[4] * a[5] * a[6]; by = 2 * a[6] * (a[4] + a[5])
+        elif name == 'gn_conv1x1_bwd_bf16':
+            key = (a[4], a[5], 128, 'dgrad+bn+wgrad'); fl = 4 * a[4] * a[5] * 128; by = 2 * a[4] * (128 + a[5] * (3 if a[16] else 2))
         elif name == 'gn_conv3x3_bf16':
             key = (a[2], a[3], a[5], a[8], 'bn' if a[11] else ''); fl = 2 * 9 * a[2] * a[3] * a[4] * a[5] * a[8]
             by = 2 * a[2] * a[3] * a[4] * (a[5] + a[8] * (2 if a[11] else 1))
