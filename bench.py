@@ -71,7 +71,7 @@ def peaks():
 
 def committed_traffic():
     """DRAM bytes per launch of the step's kernels from the committed ncu capture of this same command (profiles/)."""
-    path = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    path = os.path.join(ROOT, 'profiles', 'r02s_traffic.json')
     try:
         return json.load(open(path))
     except Exception:
