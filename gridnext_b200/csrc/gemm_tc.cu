@@ -147,11 +147,11 @@ __device__ __forceinline__ bool gemm_next_tile(int it, const GemmParams& p, int&
 // Operand-transform warps: 4, or 8 in two groups that take alternate k-blocks (EPI_STORE: the forward conv1).  One warp per
 // scheduler cannot hide the LDS -> FMA -> STS latency of a 16 KB tile inside the ~760 cycles HBM needs to deliver it; with two
 // groups every group has two k-block periods per tile.
-template <bool XFORM, int EPI>
-struct GemmThreads { static constexpr int XF_WARPS = XFORM ? (EPI == EPI_STORE ? 8 : 4) : 0; static constexpr int N = (12 + XF_WARPS) * 32; };
+template <bool XFORM, int EPI, int XFW = 8>
+struct GemmThreads { static constexpr int XF_WARPS = XFORM ? (EPI == EPI_STORE ? XFW : 4) : 0; static constexpr int N = (12 + XF_WARPS) * 32; };
 
-template <int BN, bool XFORM, int EPI>
-__global__ void __launch_bounds__(GemmThreads<XFORM, EPI>::N, 1)
+template <int BN, bool XFORM, int EPI, int XFW = 8>
+__global__ void __launch_bounds__(GemmThreads<XFORM, EPI, XFW>::N, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                  const __grid_constant__ CUtensorMap tmRef, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
@@ -442,10 +442,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (EPI == EPI_STORE) {
 #pragma unroll
                                 for (int e2 = 0; e2 < 4; ++e2) {
-                                    float x0 = fmaf(__uint_as_float(r[8 * q + 2 * e2]), k0[2 * e2], k1[2 * e2]);
-                                    float x1 = fmaf(__uint_as_float(r[8 * q + 2 * e2 + 1]), k0[2 * e2 + 1], k1[2 * e2 + 1]);
-                                    if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-                                    res[e2] = pack_bf16x2(x0, x1);
+                                    const uint64_t x = ffma2(f32x2(__uint_as_float(r[8 * q + 2 * e2]), __uint_as_float(r[8 * q + 2 * e2 + 1])),
+                                                             f32x2(k0[2 * e2], k0[2 * e2 + 1]), f32x2(k1[2 * e2], k1[2 * e2 + 1]));
+                                    res[e2] = p.relu ? f32x2_to_bf16x2_relu(x) : f32x2_to_bf16x2(x);
                                 }
                             } else {
                                 const bool is_raw = p.bn.ref_is_raw != 0;
@@ -502,20 +501,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================== operand transform: A <- relu(A * scale[k] + shift[k]) in place =====================
         const int w = (warp - 12) & 3;
         const int grp = (warp - 12) >> 2;                           // which of the alternating k-block groups this warp belongs to
-        constexpr int NGRP = GemmThreads<XFORM, EPI>::XF_WARPS / 4;
+        constexpr int NGRP = GemmThreads<XFORM, EPI, XFW>::XF_WARPS / 4;
         int stage = 0, cnt = 0;
         uint32_t phase = 0;
         for (int it = 0;; ++it) {
             int nb_, mb_;
             if (!gemm_next_tile<EPI>(it, p, nb_, mb_)) break;
-            for (int kb = 0; kb < nkb; ++kb, ++cnt) {
-                if (NGRP == 2 && (cnt & 1) != grp) {
+            for (int kb = 0; kb < nkb; ++kb, cnt = (cnt + 1 == NGRP ? 0 : cnt + 1)) {
+                if (NGRP > 1 && cnt != grp) {
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     continue;
                 }
                 // row & 7 of the rows this lane touches is ((i & 1) * 4 + (lane >> 3)): two sets of 8 constants per k-block
                 const int pc = lane & 7;                            // physical 16-byte chunk in the 128-byte row
-                float cs[2][8], ct[2][8];
+                uint64_t cs[2][4], ct[2][4];                        // packed fp32 pairs: one FFMA2 + one F2FP.RELU per bf16 pair
 #pragma unroll
                 for (int par = 0; par < 2; ++par) {
                     const int k0 = kb * GEMM_BK + ((pc ^ (par * 4 + (lane >> 3))) << 3);   // logical K index of the chunk's first element
@@ -523,10 +522,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const float4 s1 = *reinterpret_cast<const float4*>(s_xf + k0 + 4);
                     const float4 t0 = *reinterpret_cast<const float4*>(s_xf + xf_ld + k0);
                     const float4 t1 = *reinterpret_cast<const float4*>(s_xf + xf_ld + k0 + 4);
-                    cs[par][0] = s0.x; cs[par][1] = s0.y; cs[par][2] = s0.z; cs[par][3] = s0.w;
-                    cs[par][4] = s1.x; cs[par][5] = s1.y; cs[par][6] = s1.z; cs[par][7] = s1.w;
-                    ct[par][0] = t0.x; ct[par][1] = t0.y; ct[par][2] = t0.z; ct[par][3] = t0.w;
-                    ct[par][4] = t1.x; ct[par][5] = t1.y; ct[par][6] = t1.z; ct[par][7] = t1.w;
+                    cs[par][0] = f32x2(s0.x, s0.y); cs[par][1] = f32x2(s0.z, s0.w); cs[par][2] = f32x2(s1.x, s1.y); cs[par][3] = f32x2(s1.z, s1.w);
+                    ct[par][0] = f32x2(t0.x, t0.y); ct[par][1] = f32x2(t0.z, t0.w); ct[par][2] = f32x2(t1.x, t1.y); ct[par][3] = f32x2(t1.z, t1.w);
                 }
                 mbar_wait(&bar_full[stage], phase);
                 uint8_t* sa = sm + (size_t)stage * stage_bytes + (w * 32 + (lane >> 3)) * 128 + pc * 16;
@@ -536,15 +533,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int par = i & 1;
-                    float2 f;
-                    f = unpack_bf16x2(v[i].x);
-                    v[i].x = pack_bf16x2(fmaxf(fmaf(f.x, cs[par][0], ct[par][0]), 0.f), fmaxf(fmaf(f.y, cs[par][1], ct[par][1]), 0.f));
-                    f = unpack_bf16x2(v[i].y);
-                    v[i].y = pack_bf16x2(fmaxf(fmaf(f.x, cs[par][2], ct[par][2]), 0.f), fmaxf(fmaf(f.y, cs[par][3], ct[par][3]), 0.f));
-                    f = unpack_bf16x2(v[i].z);
-                    v[i].z = pack_bf16x2(fmaxf(fmaf(f.x, cs[par][4], ct[par][4]), 0.f), fmaxf(fmaf(f.y, cs[par][5], ct[par][5]), 0.f));
-                    f = unpack_bf16x2(v[i].w);
-                    v[i].w = pack_bf16x2(fmaxf(fmaf(f.x, cs[par][6], ct[par][6]), 0.f), fmaxf(fmaf(f.y, cs[par][7], ct[par][7]), 0.f));
+                    v[i].x = f32x2_to_bf16x2_relu(ffma2(bf16x2_to_f32x2(v[i].x), cs[par][0], ct[par][0]));
+                    v[i].y = f32x2_to_bf16x2_relu(ffma2(bf16x2_to_f32x2(v[i].y), cs[par][1], ct[par][1]));
+                    v[i].z = f32x2_to_bf16x2_relu(ffma2(bf16x2_to_f32x2(v[i].z), cs[par][2], ct[par][2]));
+                    v[i].w = f32x2_to_bf16x2_relu(ffma2(bf16x2_to_f32x2(v[i].w), cs[par][3], ct[par][3]));
                     *reinterpret_cast<uint4*>(sa + i * 512) = v[i];
                 }
                 fence_proxy_async_smem();
@@ -559,7 +551,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 3) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int BN, bool XFORM, int EPI>
+template <int BN, bool XFORM, int EPI, int XFW = 8>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRef, GemmParams& p,
                        cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
@@ -592,14 +584,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     const size_t smem = (size_t)stages * p.stage_bytes + fixed + 1024;
     static size_t attr_set = 0;
     if (smem > attr_set) {
-        GN_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, XFORM, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GN_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, XFORM, EPI, XFW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int grid = tiles < gn_num_sms() ? tiles : gn_num_sms();
     if (EPI != EPI_DIRECT && p.num_n_blocks > 1 && grid > 1)
         while (grid % 2 == 0 && p.num_n_blocks % 2 == 0 || grid % 3 == 0 && p.num_n_blocks % 3 == 0) --grid;      // coprime with the n-block count
-    gemm_bf16_kernel<BN, XFORM, EPI><<<grid, GemmThreads<XFORM, EPI>::N, smem, stream>>>(tmA, tmB, tmOut, tmRef, p);
+    gemm_bf16_kernel<BN, XFORM, EPI, XFW><<<grid, GemmThreads<XFORM, EPI, XFW>::N, smem, stream>>>(tmA, tmB, tmOut, tmRef, p);
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -608,9 +600,10 @@ template <int BN>
 static int dispatch_gemm(bool xform, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRef,
                          GemmParams& p, cudaStream_t stream) {
     if (epi == EPI_BNBWD) return launch_gemm<BN, false, EPI_BNBWD>(tmA, tmB, tmOut, tmRef, p, stream);
-    if (epi == EPI_STORE)
-        return xform ? launch_gemm<BN, true, EPI_STORE>(tmA, tmB, tmOut, tmRef, p, stream)
-                     : launch_gemm<BN, false, EPI_STORE>(tmA, tmB, tmOut, tmRef, p, stream);
+    if (epi == EPI_STORE) {
+        if (!xform) return launch_gemm<BN, false, EPI_STORE>(tmA, tmB, tmOut, tmRef, p, stream);
+        return launch_gemm<BN, true, EPI_STORE, 8>(tmA, tmB, tmOut, tmRef, p, stream);
+    }
     return xform ? launch_gemm<BN, true, EPI_DIRECT>(tmA, tmB, tmOut, tmRef, p, stream)
                  : launch_gemm<BN, false, EPI_DIRECT>(tmA, tmB, tmOut, tmRef, p, stream);
 }

@@ -187,6 +187,50 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32 pairs (sm_100: FFMA2 / FMUL2 issue two fp32 operations per instruction) and bf16 packing with a fused ReLU ----------
+// The element-wise roles of the tensor-core kernels (BatchNorm+ReLU operand transform, epilogues) are bound by instruction issue:
+// per bf16 pair the affine + ReLU + re-pack was 2 FFMA + 2 FMNMX + 1 F2FP; it is now 1 FFMA2 + 1 F2FP.RELU, bit-identical results.
+__device__ __forceinline__ uint64_t f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+    return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    lo = __uint_as_float(a);
+    hi = __uint_as_float(b);
+}
+// a bf16 pair (low half = first element) -> packed fp32 pair
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t w) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(w << 16), "r"(w & 0xffff0000u));
+    return r;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// packed fp32 pair -> bf16 pair (round to nearest even), optionally max(., 0) in the same instruction
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(uint64_t v) {
+    uint32_t a, b, r;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "r"(b), "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2_relu(uint64_t v) {
+    uint32_t a, b, r;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "r"(b), "r"(a));
+    return r;
+}
+
 // ---- descriptors --------------------------------------------------------------------------------
 enum : uint64_t { LAYOUT_NONE = 0, LAYOUT_SW128 = 2, LAYOUT_SW64 = 4, LAYOUT_SW32 = 6 };
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel micro-benchmarks at the DenseNet-121 @128 px / 4,992-spot shapes (development tool, not the bench contract).
 
-    python tools/kbench.py [names...]       names: gemm_xf gemm_bn gemm_tn conv_fwd conv_dgrad conv_wgrad stem
+    python tools/kbench.py [names...]       names: gemm_xf gemm_noxf bwd1x1 gemm_bn gemm_tn conv_fwd conv_dgrad conv_wgrad stem
 Prints one JSON line per case: CUDA-event time (median of reps), algorithmic TFLOP/s and GB/s.
 """
 import json, sys, os
@@ -51,6 +51,13 @@ def main(names):
             if sel('gemm_xf'):
                 timeit(lambda: tc.gemm_bf16(C[:, :cin], w1, out=a2, scale=s2, shift=t2, relu=True, xf_scale=sc, xf_shift=sh),
                        2.0 * M * 128 * cin, 2.0 * M * (cin + 128), 'gemm_xf', block=bi + 1, cin=cin)
+            if sel('gemm_noxf'):     # speed probe: the same GEMM without the BN+ReLU operand transform in shared memory
+                timeit(lambda: tc.gemm_bf16(C[:, :cin], w1, out=a2, scale=s2, shift=t2, relu=True),
+                       2.0 * M * 128 * cin, 2.0 * M * (cin + 128), 'gemm_noxf', block=bi + 1, cin=cin)
+            if sel('bwd1x1'):
+                dw = torch.zeros(128, cin, device=dev)
+                timeit(lambda: tc.conv1x1_bwd_bf16(dz, w1t, dC[:, :cin], dict(ref=C[:, :cin], ref_is_raw=True, sc=sc, sh=sh, p0=sh, p1=sc, colsum=colsum, rmw=True), dw),
+                       4.0 * M * 128 * cin, 2.0 * M * (128 + 3 * cin), 'bwd1x1', block=bi + 1, cin=cin)
             if sel('gemm_bn'):
                 timeit(lambda: tc.gemm_bf16(dz, w1t, out=dC[:, :cin], bn=dict(ref=C[:, :cin], ref_is_raw=True, sc=sc, sh=sh, p0=sh, p1=sc, colsum=colsum, rmw=True)),
                        2.0 * M * 128 * cin, 2.0 * M * (128 + 3 * cin), 'gemm_bn', block=bi + 1, cin=cin)
