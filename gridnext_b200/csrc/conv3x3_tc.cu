@@ -174,6 +174,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
     float* s_cs = s_epi + 4 * C3_MAX_CO;                                                        // [2][C3_MAX_CO] column sums of this CTA
     if (EPI_MODE == 1) {
+        // the BN-backward epilogue multiplies by what the slot holds even for rows outside the image (their gradient is zero): no NaN bit patterns
+        for (int i = threadIdx.x; i < p.e_stages * (slot_bytes / 16); i += blockDim.x) reinterpret_cast<uint4*>(s_slots)[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
         for (int i = threadIdx.x; i < C3_MAX_CO; i += blockDim.x) {
             s_cs[i] = 0.f;
             s_cs[C3_MAX_CO + i] = 0.f;
@@ -431,9 +434,10 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const int r_loc = trow / W2, xp = trow % W2;
         const bool active = j < p.nsub;
         const bool is_raw = p.bn.ref_is_raw != 0;
-        float sg[32], sx[32];
+        // column sums as packed fp32 pairs: FADD2 / FFMA2 / FMUL2 do two columns per instruction (this epilogue is bound by instruction issue)
+        uint64_t sg2[16], sx2[16];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) sg[e] = sx[e] = 0.f;
+        for (int e = 0; e < 16; ++e) sg2[e] = sx2[e] = 0ull;
         int acc = 0;
         uint32_t acc_phase = 0;
         int es = j % p.e_stages;
@@ -460,24 +464,25 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                     uint32_t res[2];
 #pragma unroll
                     for (int e2 = 0; e2 < 2; ++e2) {
-                        const float2 rf = c3_unpack_bf16x2(rw[e2]);
-                        const float2 sc2 = *reinterpret_cast<const float2*>(cst + 4 * ch + 2 * e2);
-                        float2 sh2 = make_float2(0.f, 0.f);
-                        if (is_raw) sh2 = *reinterpret_cast<const float2*>(cst + C3_MAX_CO + 4 * ch + 2 * e2);
-                        float o2[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int e = 4 * ch + 2 * e2 + u;
-                            const float ref = u ? rf.y : rf.x;
-                            const float sc = u ? sc2.y : sc2.x;
-                            const float a = is_raw ? fmaf(ref, sc, u ? sh2.y : sh2.x) : ref;
-                            const bool on = valid && a > 0.f;               // dropped rows hold stale shared memory: select, never multiply
-                            const float gg = on ? __uint_as_float(r[2 * e2 + u]) : 0.f;
-                            sg[e] += gg;
-                            sx[e] += on ? gg * ref : 0.f;                   // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
-                            o2[u] = gg * sc;
+                        // rows outside the image keep whatever the slot held (finite: the slots are cleared once at kernel start and only
+                        // ever hold TMA-loaded activations or results), their gradient is forced to zero by `valid`
+                        const uint64_t ref2 = bf16x2_to_f32x2(rw[e2]);
+                        const float2 sc2f = *reinterpret_cast<const float2*>(cst + 4 * ch + 2 * e2);
+                        const uint64_t sc2 = f32x2(sc2f.x, sc2f.y);
+                        float a_lo, a_hi;
+                        if (is_raw) {
+                            const float2 sh2f = *reinterpret_cast<const float2*>(cst + C3_MAX_CO + 4 * ch + 2 * e2);
+                            f32x2_unpack(ffma2(ref2, sc2, f32x2(sh2f.x, sh2f.y)), a_lo, a_hi);
+                        } else {
+                            f32x2_unpack(ref2, a_lo, a_hi);
                         }
-                        res[e2] = c3_pack_bf16x2(o2[0], o2[1]);
+                        const float g_lo = (valid && a_lo > 0.f) ? __uint_as_float(r[2 * e2]) : 0.f;
+                        const float g_hi = (valid && a_hi > 0.f) ? __uint_as_float(r[2 * e2 + 1]) : 0.f;
+                        const uint64_t g2 = f32x2(g_lo, g_hi);
+                        const int e = 2 * ch + e2;
+                        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sg2[e]) : "l"(g2));
+                        sx2[e] = ffma2(g2, ref2, sx2[e]);                      // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
+                        res[e2] = f32x2_to_bf16x2(fmul2(g2, sc2));
                     }
                     *reinterpret_cast<uint2*>(rowp + off) = make_uint2(res[0], res[1]);
                 }
@@ -494,6 +499,12 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             if (acc == 0) acc_phase ^= 1;
         }
         if (active && p.bn.colsum != nullptr) {
+            float sg[32], sx[32];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                f32x2_unpack(sg2[e], sg[2 * e], sg[2 * e + 1]);
+                f32x2_unpack(sx2[e], sx[2 * e], sx[2 * e + 1]);
+            }
             const float tg = gn_warp_colsum32(sg, lane), tx = gn_warp_colsum32(sx, lane);
             const int col = cb * 32 + lane;
             if (col < p.CO) {

@@ -281,22 +281,20 @@ gemm_bwd1x1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     uint32_t res[4], xf[4];
 #pragma unroll
                     for (int e2 = 0; e2 < 4; ++e2) {
-                        const float2 rf = bw_unpack(rw[e2]);
-                        float o2[2], a2[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int e = 8 * q + 2 * e2 + u;
-                            const float ref = u ? rf.y : rf.x;
-                            const float sc = k0[2 * e2 + u];
-                            const float a = fmaf(ref, sc, k1[2 * e2 + u]);
-                            const float gg = a > 0.f ? __uint_as_float(r[e]) : 0.f;
-                            gx[e] = gg * ref;                 // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
-                            v[e] = gg;
-                            o2[u] = gg * sc;
-                            a2[u] = fmaxf(a, 0.f);
-                        }
-                        res[e2] = bw_pack(o2[0], o2[1]);
-                        xf[e2] = bw_pack(a2[0], a2[1]);
+                        // packed fp32 pairs: a = ref*sc + sh (FFMA2), relu(a) -> bf16 in the pack instruction, g*ref and g*sc as FMUL2
+                        const uint64_t ref2 = bf16x2_to_f32x2(rw[e2]);
+                        const uint64_t sc2 = f32x2(k0[2 * e2], k0[2 * e2 + 1]);
+                        const uint64_t a2 = ffma2(ref2, sc2, f32x2(k1[2 * e2], k1[2 * e2 + 1]));
+                        float a_lo, a_hi;
+                        f32x2_unpack(a2, a_lo, a_hi);
+                        const float g_lo = a_lo > 0.f ? __uint_as_float(r[8 * q + 2 * e2]) : 0.f;
+                        const float g_hi = a_hi > 0.f ? __uint_as_float(r[8 * q + 2 * e2 + 1]) : 0.f;
+                        const uint64_t g2 = f32x2(g_lo, g_hi);
+                        v[8 * q + 2 * e2] = g_lo;
+                        v[8 * q + 2 * e2 + 1] = g_hi;
+                        f32x2_unpack(fmul2(g2, ref2), gx[8 * q + 2 * e2], gx[8 * q + 2 * e2 + 1]);   // sum g*xhat = p1 * (sum g*ref - p0 * sum g), applied at the flush
+                        res[e2] = f32x2_to_bf16x2(fmul2(g2, sc2));
+                        xf[e2] = f32x2_to_bf16x2_relu(a2);
                     }
                     *reinterpret_cast<uint4*>(row_p + off) = make_uint4(res[0], res[1], res[2], res[3]);
                     *reinterpret_cast<uint4*>(row_x + off) = make_uint4(xf[0], xf[1], xf[2], xf[3]);
