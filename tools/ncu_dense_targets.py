@@ -29,6 +29,7 @@ for H, cin, ct in ((32, 160, 256), (8, 640, 1024)):
         tc.gemm_bf16(C[:, :cin], w1, out=a2, scale=s2, shift=t2, relu=True, xf_scale=sc, xf_shift=sh)
         tc.gemm_bf16(dz, w1t, out=dC[:, :cin], bn=dict(ref=C[:, :cin], ref_is_raw=True, sc=sc, sh=sh, p0=sh, p1=sc, colsum=colsum, rmw=True))
         tc.gemm_tn_bf16(dz, C[:, :cin], dw, sc, sh)
+        tc.conv1x1_bwd_bf16(dz, w1t, dC[:, :cin], dict(ref=C[:, :cin], ref_is_raw=True, sc=sc, sh=sh, p0=sh, p1=sc, colsum=colsum, rmw=True), dw)
         tc.conv3x3_bf16(a2, NSP, H, H, 128, wp, 32, C[:, cin:cin + 32])
         tc.conv3x3_bf16(dC[:, cin:cin + 32], NSP, H, H, 32, wpt, 128, dz, bn=dict(ref=a2, ref_is_raw=False, sc=s2, sh=None, p0=s2, p1=s2, colsum=colsum2))
         tc.conv3x3_wgrad_into(a2, dC[:, cin:cin + 32], NSP, H, H, 128, 32, dwp)
