@@ -23,6 +23,7 @@ dx -= c0 + c1*x applied once per channel after all of its consumers have accumul
 import math
 from collections import OrderedDict
 
+import os
 import torch
 import torch.nn as nn
 
@@ -400,6 +401,18 @@ class _Grads:
         plan.gflat.zero_()
 
 
+def _saved_bytes_per_spot(geo, c0):
+    """Bytes of activations _forward_chunk keeps per spot for the backward (bf16 unless noted): packed patch, conv0 output,
+    max-pool arg-max bytes, every block's concat buffer, one bottleneck tensor per dense layer, the transition inputs."""
+    n = geo.P * geo.P * 8 + geo.H0 * geo.H0 * c0 * 2 + geo.H1 * geo.H1 * c0
+    for blk in geo.blocks:
+        hw = blk['H'] * blk['H']
+        n += hw * blk['c_tot'] * 2 + len(blk['layers']) * hw * blk['bott'] * 2
+        if blk['trans'] is not None:
+            n += (hw // 4) * blk['c_tot'] * 2
+    return n
+
+
 def _conv1_backward(dz, w1t, dx, dw, bn):
     """Backward of a dense layer's norm1 -> relu1 -> conv1 (densenet.py:12-18,26-27): data gradient with the BatchNorm/ReLU backward
     epilogue and the weight gradient.  One kernel when the views allow it (bottleneck width 128), else the two GEMMs."""
@@ -741,9 +754,34 @@ class _DenseNetFn(torch.autograd.Function):
             out, saved = _forward_chunk(net, geo, cst, plan, x, need_grad)
             ctx.saved, ctx.x = saved, None
         else:
-            outs = [_forward_chunk(net, geo, cst, plan, x[i:i + MAX_SPOTS_RESIDENT], False)[0] for i in range(0, N, MAX_SPOTS_RESIDENT)]
+            # Chunk-wise forward.  A chunk's activations are KEPT for the backward while device memory allows (180 GB hold four Visium
+            # arrays of DenseNet-121 @128 px: train_gridwise at batch 4 then runs without any recomputation); the other chunks are
+            # re-run in the backward.  Decided per chunk from the allocator's figures; not under CUDA-graph capture (the graph's pool
+            # would pin the memory for good).
+            outs, kept = [], {}
+            may_keep = need_grad and not torch.cuda.is_current_stream_capturing() and os.environ.get('GRIDNEXT_B200_KEEP_CHUNKS', '1') != '0'
+            per_spot = _saved_bytes_per_spot(geo, net.features.conv0.out_channels)
+            for i in range(0, N, MAX_SPOTS_RESIDENT):
+                xi = x[i:i + MAX_SPOTS_RESIDENT]
+                keep = False
+                if may_keep:
+                    free, _ = torch.cuda.mem_get_info(x.device)
+                    avail = free + torch.cuda.memory_reserved(x.device) - torch.cuda.memory_allocated(x.device)
+                    # what stays + the transients of one chunk's backward (~0.3x of its saved bytes) + slack for fragmentation
+                    keep = avail - per_spot * xi.shape[0] > 0.4 * per_spot * MAX_SPOTS_RESIDENT + (8 << 30)
+                if keep:
+                    try:
+                        o, kept[i] = _forward_chunk(net, geo, cst, plan, xi, True)
+                    except torch.cuda.OutOfMemoryError:
+                        may_keep = False
+                        kept.pop(i, None)
+                        torch.cuda.empty_cache()
+                        o = _forward_chunk(net, geo, cst, plan, xi, False)[0]
+                else:
+                    o = _forward_chunk(net, geo, cst, plan, xi, False)[0]
+                outs.append(o)
             out = torch.cat(outs, 0)
-            ctx.saved, ctx.x = None, (x if need_grad else None)
+            ctx.saved, ctx.kept, ctx.x = None, kept, (x if need_grad else None)
         return out
 
     @staticmethod
@@ -758,12 +796,14 @@ class _DenseNetFn(torch.autograd.Function):
             _backward_chunk(net, geo, cst, plan, ctx.saved, dout, grads)
             ctx.saved = None
         else:
-            x = ctx.x
+            x, kept = ctx.x, ctx.kept
             for i in range(0, x.shape[0], MAX_SPOTS_RESIDENT):
-                _, saved = _forward_chunk(net, geo, cst, plan, x[i:i + MAX_SPOTS_RESIDENT], True)
+                saved = kept.pop(i, None)
+                if saved is None:
+                    _, saved = _forward_chunk(net, geo, cst, plan, x[i:i + MAX_SPOTS_RESIDENT], True)
                 _backward_chunk(net, geo, cst, plan, saved, dout[i:i + MAX_SPOTS_RESIDENT].contiguous(), grads)
                 del saved
-            ctx.x = None
+            ctx.x = ctx.kept = None
         # map accumulated gradients onto the parameter list: views of two fresh flat buffers
         gret, gunp = plan.finish()
         bn_grads = grads.bn_colsum

@@ -91,14 +91,24 @@ def test_chunked_recompute_equals_resident_path(monkeypatch):
         return out.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()}
     out_res, g_res = run()
     monkeypatch.setattr(dn, 'MAX_SPOTS_RESIDENT', 16)          # 16 + 16 + 8 spots
-    out_chk, g_chk = run()
-    assert torch.equal(out_res, out_chk)
-    worst = max((relmax(g_chk[k], g_res[k]), k) for k in g_res)
-    report(test='chunked_recompute_small', worst_grad_relmax=worst[0], tensor=worst[1])
-    assert worst[0] < 2e-3, worst
+    from gridnext_b200 import _lib
+    for keep, n_stem in (('0', 6), ('1', 3)):                  # backward re-runs every chunk | the chunks' activations are kept (memory allows)
+        monkeypatch.setenv('GRIDNEXT_B200_KEEP_CHUNKS', keep)
+        _lib.PROFILE = {}
+        try:
+            out_chk, g_chk = run()
+            torch.cuda.synchronize()
+            assert len(_lib.PROFILE.get('gn_stem_conv_fwd', [])) == n_stem, {k: len(v) for k, v in _lib.PROFILE.items()}
+        finally:
+            _lib.PROFILE = None
+        assert torch.equal(out_res, out_chk)
+        worst = max((relmax(g_chk[k], g_res[k]), k) for k in g_res)
+        report(test='chunked_%s_small' % ('kept' if keep == '1' else 'recompute'), worst_grad_relmax=worst[0], tensor=worst[1])
+        assert worst[0] < 2e-3, worst
 
 
-def test_c3_multimodal_densenet121_two_arrays_chunked():
+@pytest.mark.parametrize('keep', ['0', '1'])
+def test_c3_multimodal_densenet121_two_arrays_chunked(monkeypatch, keep):
     """BASELINE configs[2] at 2 arrays (9,984 spots > MAX_SPOTS_RESIDENT): GridNetHexMM with DenseNet-121 @128 and the
     tutorial MLP over 5,000 genes (reference gridnet_models.py:193-235, training.py:119-171).
       (1) image-f logits of 64 sub-sampled spots vs the fp32 oracle (bf16 tolerance 2e-2);
@@ -108,6 +118,7 @@ def test_c3_multimodal_densenet121_two_arrays_chunked():
     from gridnext_b200 import densenet as dn, _lib
     from gridnext_b200.gridnet_models import GridNetHexMM
     from gridnext_b200.losses import masked_cross_entropy
+    monkeypatch.setenv('GRIDNEXT_B200_KEEP_CHUNKS', keep)      # '0': the backward re-runs both chunks; '1': their activations are kept (memory allows)
     G, n_cls, B, P, H, W = 5000, 7, 2, 128, 78, 64
     fi = dn.DenseNet(num_classes=n_cls, small_inputs=False, **DN121)
     fc = tutorial_mlp(G, n_cls)
@@ -138,9 +149,9 @@ def test_c3_multimodal_densenet121_two_arrays_chunked():
         calls = {k: len(v) for k, v in _lib.PROFILE.items()}
     finally:
         _lib.PROFILE = None
-    # the count f ran on the tensor-core train-BN path, the image f on the tcgen05 kernels, chunked (2 forward + 2 recompute passes)
+    # the count f ran on the tensor-core train-BN path, the image f on the tcgen05 kernels, chunked (2 forward + 2 recompute passes | 2 kept)
     assert calls.get('gn_colstats_bf16', 0) >= 2 and calls.get('gn_gemm_tn_bf16', 0) > 0, calls
-    assert calls.get('gn_stem_conv_fwd', 0) == 4, calls
+    assert calls.get('gn_stem_conv_fwd', 0) == (4 if keep == '0' else 2), calls
     assert list(pp.shape) == [B, 2 * n_cls, H, W] and list(out.shape) == [B, n_cls, H, W]
 
     # (1) image-f logits on a sub-sample vs the fp32 oracle
