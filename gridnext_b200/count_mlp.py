@@ -233,6 +233,8 @@ class _CountMLPFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         comp, xb, acts, raws, tks = ctx.comp, ctx.xb, ctx.acts, ctx.raws, ctx.tks
+        if acts is None:
+            raise RuntimeError('count MLP (B200): backward a second time (saved activations were released; use a fresh forward)')
         stages = comp.stages
         B, G, HW = ctx.dims
         N = B * HW

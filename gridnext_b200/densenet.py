@@ -787,6 +787,8 @@ class _DenseNetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         net, geo, cst, plan = ctx.net, ctx.geo, ctx.cst, ctx.plan
+        if ctx.saved is None and getattr(ctx, 'x', None) is None:
+            raise RuntimeError('DenseNet (B200): backward a second time (saved activations were released; use a fresh forward)')
         dout = dout.contiguous().float()
         grads = _Grads(net, cst, plan)
         if ctx.train_bn:
