@@ -150,7 +150,13 @@ __device__ __forceinline__ bool gemm_next_tile(int it, const GemmParams& p, int&
 template <bool XFORM, int EPI, int XFW = 8>
 struct GemmThreads { static constexpr int XF_WARPS = XFORM ? (EPI == EPI_STORE ? XFW : 4) : 0; static constexpr int N = (12 + XF_WARPS) * 32; };
 
-template <int BN, bool XFORM, int EPI, int XFW = 8>
+// XT (operand transform into TENSOR MEMORY): the transform warps read the raw A tile from shared memory once
+// (thread = tile row), apply BatchNorm+ReLU in registers and write the bf16 operand with tcgen05.st into a ring of four 32-column TMEM
+// stages; the MMA takes A from there.  Against the in-place transform this drops the transform's store and the tensor core's A fetch from
+// the shared-memory port (per 64-channel k-block 704 -> 512 wavefronts), which -- not HBM, not issue slots -- bounded the forward conv1.
+#define GEMM_XT_STAGES 4
+#define GEMM_XT_COL0 256
+template <int BN, bool XFORM, int EPI, int XFW = 8, bool XT = false>
 __global__ void __launch_bounds__(GemmThreads<XFORM, EPI, XFW>::N, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                  const __grid_constant__ CUtensorMap tmRef, const GemmParams p) {
@@ -159,7 +165,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[GEMM_MAX_STAGES], bar_xf[GEMM_MAX_STAGES], bar_empty[GEMM_MAX_STAGES], bar_tfull[2], bar_tempty[2];
     __shared__ __align__(8) uint64_t bar_efull[GEMM_MAX_ESTAGES], bar_eready[GEMM_MAX_ESTAGES], bar_eempty[GEMM_MAX_ESTAGES];
-    __shared__ __align__(8) uint64_t bar_bres;
+    __shared__ __align__(8) uint64_t bar_bres, bar_tfree[GEMM_XT_STAGES];
     __shared__ uint32_t tmem_slot;
 
     const uint32_t raw = smem_u32(smem_raw);
@@ -177,8 +183,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (XFORM) {
         const int kpad = p.num_k_blocks * GEMM_BK;
         for (int i = threadIdx.x; i < kpad; i += blockDim.x) {
-            s_xf[i] = i < p.K ? p.xf_scale[i] : 0.f;
-            s_xf[xf_ld + i] = i < p.K ? p.xf_shift[i] : 0.f;
+            const float sc = i < p.K ? p.xf_scale[i] : 0.f, sh = i < p.K ? p.xf_shift[i] : 0.f;
+            if (XT) {                                   // {scale k, scale k+1, shift k, shift k+1}: one 16-byte broadcast load per channel pair
+                s_xf[(i >> 1) * 4 + (i & 1)] = sc;
+                s_xf[(i >> 1) * 4 + 2 + (i & 1)] = sh;
+            } else {
+                s_xf[i] = sc;
+                s_xf[xf_ld + i] = sh;
+            }
         }
     }
     if (EPI != EPI_DIRECT) {
@@ -205,8 +217,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int s = 0; s < GEMM_MAX_STAGES; ++s) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_xf[s], 4);
-            mbar_init(&bar_empty[s], 1);
+            mbar_init(&bar_empty[s], XT ? (p.res_b ? 4 : 5) : 1);   // XT: the four transform warps release the stage (+ the MMA when it holds streamed weights)
         }
+        for (int s = 0; s < GEMM_XT_STAGES; ++s) mbar_init(&bar_tfree[s], 1);
         for (int s = 0; s < GEMM_MAX_ESTAGES; ++s) {
             mbar_init(&bar_efull[s], 1);
             mbar_init(&bar_eready[s], GEMM_EPI_WARPS);
@@ -219,7 +232,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         fence_barrier_init();
     }
-    if (warp == 3) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
+    if (warp == 3) tmem_alloc<(XT ? 512 : Cfg::TMEM_COLS)>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -258,6 +271,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            uint32_t kc = 0;                                   // XT: running k-block count of this CTA -> TMEM operand stage
             if (p.res_b) mbar_wait(&bar_bres, 0);
             for (int it = 0;; ++it) {
                 int nb_, mb_;
@@ -266,6 +280,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < nkb; ++kb) {
+                    if (XT) {
+                        const int ts = (int)(kc & (GEMM_XT_STAGES - 1));
+                        mbar_wait(&bar_xf[ts], (kc / GEMM_XT_STAGES) & 1);
+                        if (!p.res_b) mbar_wait(&bar_full[stage], phase);      // the B half of the stage (already complete: the transform waited for it)
+                        tc_fence_after();
+                        const uint32_t a_t = tmem_base + (uint32_t)(GEMM_XT_COL0 + ts * 32);
+                        const uint32_t b_x = p.res_b ? smem_u32(s_bres + (size_t)kb * Cfg::B_BYTES)
+                                                     : smem_u32(sm + (size_t)stage * stage_bytes) + GEMM_A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k)
+                            umma_bf16_ts(d, a_t + (uint32_t)(k * 8), smem_desc(tmpl, b_x + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                        umma_commit(&bar_tfree[ts]);
+                        if (!p.res_b) umma_commit(&bar_empty[stage]);          // streamed weights: the stage is free once these MMAs have read B
+                        ++kc;
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_wait(XFORM ? &bar_xf[stage] : &bar_full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sm + (size_t)stage * stage_bytes);
@@ -504,11 +535,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         constexpr int NGRP = GemmThreads<XFORM, EPI, XFW>::XF_WARPS / 4;
         int stage = 0, cnt = 0;
         uint32_t phase = 0;
+        uint32_t kc = 0;
         for (int it = 0;; ++it) {
             int nb_, mb_;
             if (!gemm_next_tile<EPI>(it, p, nb_, mb_)) break;
-            for (int kb = 0; kb < nkb; ++kb, cnt = (cnt + 1 == NGRP ? 0 : cnt + 1)) {
+            for (int kb = 0; kb < nkb; ++kb, cnt = (cnt + 1 == NGRP ? 0 : cnt + 1), ++kc) {
                 if (NGRP > 1 && cnt != grp) {
+                    // the other group's k-block: still wait for its data.  A parity wait tells phases apart only modulo 2, so a group must
+                    // never reach use u of a stage before use u-1 (the other group's, when the ring depth is odd) has landed -- with an odd
+                    // ring the XT variant failed intermittently (launch failure after a stage was read and released one phase early)
+                    mbar_wait(&bar_full[stage], phase);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    continue;
+                }
+                if (XT) {
+                    // thread = tile row (TMEM lane 32w + lane): 8 swizzled 16-byte chunks of the raw row -> BatchNorm + ReLU -> 32 bf16 pairs -> TMEM
+                    const int ts = (int)(kc & (GEMM_XT_STAGES - 1));
+                    const int row = w * 32 + lane;
+                    const uint32_t swz = (uint32_t)(row & 7);
+                    mbar_wait(&bar_full[stage], phase);
+                    const uint8_t* rowp = sm + (size_t)stage * stage_bytes + row * 128;
+                    uint4 v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const uint4*>(rowp + (((uint32_t)c ^ swz) << 4));
+                    uint32_t r[32];
+                    const float4* cst4 = reinterpret_cast<const float4*>(s_xf) + kb * (GEMM_BK / 2);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t wv[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 k4 = cst4[c * 4 + q];
+                            r[c * 4 + q] = f32x2_to_bf16x2_relu(ffma2(bf16x2_to_f32x2(wv[q]), f32x2(k4.x, k4.y), f32x2(k4.z, k4.w)));
+                        }
+                    }
+                    mbar_wait(&bar_tfree[ts], ((kc / GEMM_XT_STAGES) & 1) ^ 1);      // the MMAs that read this TMEM stage last time are done
+                    tc_fence_after();
+                    tmem_st32(tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(GEMM_XT_COL0 + ts * 32), r);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&bar_xf[ts]);
+                        mbar_arrive(&bar_empty[stage]);                              // the raw tile is in registers / TMEM: the TMA may refill the stage
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     continue;
                 }
@@ -548,7 +618,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 3) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (warp == 3) tmem_dealloc<(XT ? 512 : Cfg::TMEM_COLS)>(tmem_base);
+}
+
+template <int BN, bool XFORM, int EPI, int XFW, bool XT>
+static int launch_gemm_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRef, const GemmParams& p,
+                              int grid, size_t smem, cudaStream_t stream) {
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        GN_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, XFORM, EPI, XFW, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
+    }
+    gemm_bf16_kernel<BN, XFORM, EPI, XFW, XT><<<grid, GemmThreads<XFORM, EPI, XFW>::N, smem, stream>>>(tmA, tmB, tmOut, tmRef, p);
+    GN_LAUNCH_CHECK();
+    return GN_OK;
 }
 
 template <int BN, bool XFORM, int EPI, int XFW = 8>
@@ -582,18 +665,16 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     GN_REQUIRE(stages >= 2, GN_EUNSUPPORTED, "gemm_bf16: shared memory budget exhausted (BN %d)", BN);
     p.stages = stages;
     const size_t smem = (size_t)stages * p.stage_bytes + fixed + 1024;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        GN_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, XFORM, EPI, XFW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     int grid = tiles < gn_num_sms() ? tiles : gn_num_sms();
     if (EPI != EPI_DIRECT && p.num_n_blocks > 1 && grid > 1)
         while (grid % 2 == 0 && p.num_n_blocks % 2 == 0 || grid % 3 == 0 && p.num_n_blocks % 3 == 0) --grid;      // coprime with the n-block count
-    gemm_bf16_kernel<BN, XFORM, EPI, XFW><<<grid, GemmThreads<XFORM, EPI, XFW>::N, smem, stream>>>(tmA, tmB, tmOut, tmRef, p);
-    GN_LAUNCH_CHECK();
-    return GN_OK;
+    if constexpr (XFORM && EPI == EPI_STORE && BN == 128) {
+        // the forward conv1 of a dense layer (N = 128 output channels, resident weights): BatchNorm+ReLU operand transform into tensor memory
+        static const bool xt_on = !gn_env_flag("GN_GEMM_NO_XT");
+        if (xt_on) return launch_gemm_kernel<BN, XFORM, EPI, XFW, true>(tmA, tmB, tmOut, tmRef, p, grid, smem, stream);
+    }
+    return launch_gemm_kernel<BN, XFORM, EPI, XFW, false>(tmA, tmB, tmOut, tmRef, p, grid, smem, stream);
 }
 
 template <int BN>

@@ -146,3 +146,24 @@ def test_conv1x1_backward_fused_dgrad_bn_wgrad(M, N, rmw):
     assert rel(dc[:, :N].float().cpu(), dc2[:, :N].float().cpu()) < 1e-2          # bf16 re-rounding of the += in L2
     assert rel(dw.cpu(), dw2.cpu()) < 1e-4
     assert rel(colsum.cpu(), colsum2.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize('M,N,K', [(40037, 128, 64), (50000, 128, 224), (45000, 96, 480), (38912, 128, 96), (64000, 128, 1000), (300, 128, 64),
+                                   (5000, 100, 160), (129, 128, 992), (200000, 128, 352)])
+def test_gemm_forward_conv1_operand_transform_in_tensor_memory(M, N, K):
+    """The forward conv1 shape of a dense layer (bf16 output through the TMA epilogue, 64 < N <= 128; weights resident in shared memory
+    when they fit and there are enough row tiles, streamed otherwise): BatchNorm+ReLU on the A operand is applied on the way into TENSOR MEMORY (tcgen05.st) and the MMA reads A from there
+    (gemm_tc.cu, XT).  Checked with the BN2+ReLU epilogue of densenet.py:12-18 against fp32 torch on the same bf16 inputs."""
+    from gridnext_b200.tc import gemm_bf16
+    ld = (K + 7) // 8 * 8 + 32                                    # the operand is a column slice of a wider concat buffer
+    a, b = rnd((M, ld), 41), rnd((N, K), 42, 0.1)
+    g = torch.Generator(); g.manual_seed(43)
+    xs, xt = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g) * 0.5
+    s2, t2 = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.2
+    act = torch.relu(a[:, :K].float() * xs + xt).to(torch.bfloat16).float()
+    ref = torch.relu((act @ b.float().t()) * s2 + t2)
+    out = torch.full((M, N + 8), 7.0, dtype=torch.bfloat16, device='cuda')
+    gemm_bf16(a.cuda()[:, :K], b.cuda(), out=out[:, :N], scale=s2.cuda(), shift=t2.cuda(), relu=True, xf_scale=xs.cuda(), xf_shift=xt.cuda())
+    torch.cuda.synchronize()
+    assert rel(out[:, :N].float().cpu(), ref) < 1e-2              # bf16 output rounding
+    assert bool((out[:, N:] == 7.0).all())                       # nothing written beside the view
