@@ -616,7 +616,8 @@ def main():
                                 optimizer=('none' if wl.opt is None else 'torch.optim.Adam(fused=%s, capturable=True)' % (not args.foreach_adam))),
                     clocks=clocks, gpu_launches=launches_per_step * args.steps,
                     e2e=dict(value=spots / (ms_e2e / args.steps * 1e-3), unit='spots/s', h2d_bytes_per_step=wl.h2d_bytes, d2h_bytes_per_step=4,
-                             ms_per_step=ms_e2e / args.steps, host_input=host_what),
+                             ms_per_step=ms_e2e / args.steps, host_input=host_what,
+                             last_loss=float(e2e_loss[0].item())),
                     roofline=roof, cpu_baseline=cpu)
         if eager is not None:
             line['gpu_eager_baseline'] = eager

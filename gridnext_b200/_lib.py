@@ -29,6 +29,7 @@ _SIGS = {
     'gn_hexconv_tc2_set_trace': [vp],
     'gn_hexconv_fwd_tc2': [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp],
     'gn_hexconv_wgrad_tc': [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp],
+    'gn_hexconv_wgrad_tc2': [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp],
     'gn_hexconv_wgrad': [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp],
     'gn_cell_inverse': [vp, ci, vp, ci, vp],
     'gn_grid_gather_rows': [vp, cl, vp, vp, cl, cl, cl, vp],

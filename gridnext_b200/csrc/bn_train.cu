@@ -44,6 +44,7 @@ constexpr int CS_ROWS_PER_LANE = 32;      // rows one thread accumulates in fp32
 // grid (row chunks, column tiles of TG groups); thread = (row lane, 8-channel group)
 __global__ void __launch_bounds__(CS_THREADS) colstats_kernel(const __nv_bfloat16* __restrict__ x, long ld, long M, int C8, int TG,
                                                               double* __restrict__ sum, double* __restrict__ sumsq) {
+    gn_pdl_sync();
     __shared__ float s_part[2][CS_THREADS][9];      // [sum | sumsq][thread][8 (+1 pad)]
     const int tg = threadIdx.x % TG, rl = threadIdx.x / TG, RL = CS_THREADS / TG;
     const int grp = blockIdx.y * TG + tg;
@@ -79,6 +80,7 @@ __global__ void bn_train_coeffs_kernel(const double* __restrict__ sum, const dou
                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                                        float* __restrict__ rmean, float* __restrict__ rvar, float* __restrict__ sc, float* __restrict__ sh,
                                        float* __restrict__ mean, float* __restrict__ invstd, int C) {
+    gn_pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double m = sum[c] * inv_m;
@@ -96,6 +98,7 @@ __global__ void bn_train_coeffs_kernel(const double* __restrict__ sum, const dou
 
 __global__ void __launch_bounds__(256) affine_relu_kernel(const __nv_bfloat16* __restrict__ x, long ldx, __nv_bfloat16* __restrict__ y, long ldy,
                                                           long M, int C8, const float* __restrict__ sc, const float* __restrict__ sh, int relu) {
+    gn_pdl_sync();
     const long total = M * C8;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long r = i / C8;
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(256) affine_relu_kernel(const __nv_bfloat16* _
 __global__ void bn_train_fix_coeffs_kernel(const float* __restrict__ dbeta, const float* __restrict__ dgamma, const float* __restrict__ sc,
                                            const float* __restrict__ invstd, const float* __restrict__ mean, float inv_m, int accumulate,
                                            float* __restrict__ c0, float* __restrict__ c1, int C) {
+    gn_pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float k1 = sc[c] * invstd[c] * dgamma[c] * inv_m;
@@ -127,6 +131,7 @@ __global__ void bn_train_fix_coeffs_kernel(const float* __restrict__ dbeta, cons
 
 __global__ void __launch_bounds__(256) bn_train_fix_kernel(__nv_bfloat16* __restrict__ dx, long lddx, const __nv_bfloat16* __restrict__ x, long ldx,
                                                            long M, int C8, const float* __restrict__ c0, const float* __restrict__ c1) {
+    gn_pdl_sync();
     const long total = M * C8;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long r = i / C8;
@@ -162,7 +167,7 @@ GN_API int gn_colstats_bf16(const void* x, long ld, long M, int C, double* sum, 
     while (TG < C8 && TG < 32) TG *= 2;              // 8-channel groups per CTA (power of two <= 32)
     const int RL = CS_THREADS / TG;
     dim3 grid(gn_ceil_div(M, (long)RL * CS_ROWS_PER_LANE), gn_ceil_div(C8, TG));
-    colstats_kernel<<<grid, CS_THREADS, 0, stream>>>((const __nv_bfloat16*)x, ld, M, C8, TG, sum, sumsq);
+    GN_CUDA(gn_launch(colstats_kernel, dim3(grid), dim3(CS_THREADS), 0, stream, (const __nv_bfloat16*)x, ld, M, C8, TG, sum, sumsq));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -174,8 +179,8 @@ GN_API int gn_bn_train_coeffs(const double* sum, const double* sumsq, long M, co
                               cudaStream_t stream) {
     GN_REQUIRE(sum && sumsq && sc && sh && mean && invstd && M > 0 && C > 0, GN_EINVAL, "bn_train_coeffs: bad arguments");
     const double unbias = M > 1 ? (double)M / (double)(M - 1) : 1.0;
-    bn_train_coeffs_kernel<<<gn_ceil_div(C, 128), 128, 0, stream>>>(sum, sumsq, 1.0 / (double)M, unbias, gamma, beta, eps, momentum, running_mean,
-                                                                    running_var, sc, sh, mean, invstd, C);
+    GN_CUDA(gn_launch(bn_train_coeffs_kernel, dim3(gn_ceil_div(C, 128)), dim3(128), 0, stream, sum, sumsq, 1.0 / (double)M, unbias, gamma, beta, eps, momentum, running_mean,
+                                                                    running_var, sc, sh, mean, invstd, C));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -186,7 +191,7 @@ GN_API int gn_affine_relu_bf16(const void* x, long ldx, void* y, long ldy, long 
     GN_REQUIRE(x && y && sc && sh && M > 0 && C > 0 && ldx >= C && ldy >= C, GN_EINVAL, "affine_relu_bf16: bad arguments");
     GN_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)sc | (uintptr_t)sh) & 15) == 0, GN_EALIGN,
                "affine_relu_bf16: C and pitches must be multiples of 8, pointers 16-byte aligned");
-    affine_relu_kernel<<<stream_blocks(M * (C / 8)), 256, 0, stream>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, M, C / 8, sc, sh, relu);
+    GN_CUDA(gn_launch(affine_relu_kernel, dim3(stream_blocks(M * (C / 8))), dim3(256), 0, stream, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, M, C / 8, sc, sh, relu));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -195,7 +200,7 @@ GN_API int gn_affine_relu_bf16(const void* x, long ldx, void* y, long ldy, long 
 GN_API int gn_bn_train_fix_coeffs(const float* dbeta, const float* dgamma, const float* sc, const float* invstd, const float* mean, long M,
                                   int accumulate, float* c0, float* c1, int C, cudaStream_t stream) {
     GN_REQUIRE(dbeta && dgamma && sc && invstd && mean && c0 && c1 && M > 0 && C > 0, GN_EINVAL, "bn_train_fix_coeffs: bad arguments");
-    bn_train_fix_coeffs_kernel<<<gn_ceil_div(C, 128), 128, 0, stream>>>(dbeta, dgamma, sc, invstd, mean, 1.f / (float)M, accumulate, c0, c1, C);
+    GN_CUDA(gn_launch(bn_train_fix_coeffs_kernel, dim3(gn_ceil_div(C, 128)), dim3(128), 0, stream, dbeta, dgamma, sc, invstd, mean, 1.f / (float)M, accumulate, c0, c1, C));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -205,7 +210,7 @@ GN_API int gn_bn_train_fix_bf16(void* dx, long lddx, const void* x, long ldx, lo
     GN_REQUIRE(dx && x && c0 && c1 && M > 0 && C > 0 && lddx >= C && ldx >= C, GN_EINVAL, "bn_train_fix_bf16: bad arguments");
     GN_REQUIRE(C % 8 == 0 && lddx % 8 == 0 && ldx % 8 == 0 && (((uintptr_t)dx | (uintptr_t)x | (uintptr_t)c0 | (uintptr_t)c1) & 15) == 0, GN_EALIGN,
                "bn_train_fix_bf16: C and pitches must be multiples of 8, pointers 16-byte aligned");
-    bn_train_fix_kernel<<<stream_blocks(M * (C / 8)), 256, 0, stream>>>((__nv_bfloat16*)dx, lddx, (const __nv_bfloat16*)x, ldx, M, C / 8, c0, c1);
+    GN_CUDA(gn_launch(bn_train_fix_kernel, dim3(stream_blocks(M * (C / 8))), dim3(256), 0, stream, (__nv_bfloat16*)dx, lddx, (const __nv_bfloat16*)x, ldx, M, C / 8, c0, c1));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -173,20 +173,6 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     float* s_epi = reinterpret_cast<float*>(s_slots + (size_t)p.e_stages * slot_bytes);         // [4][C3_MAX_CO]
 
     float* s_cs = s_epi + 4 * C3_MAX_CO;                                                        // [2][C3_MAX_CO] column sums of this CTA
-    if (EPI_MODE == 1) {
-        // the BN-backward epilogue multiplies by what the slot holds even for rows outside the image (their gradient is zero): no NaN bit patterns
-        for (int i = threadIdx.x; i < p.e_stages * (slot_bytes / 16); i += blockDim.x) reinterpret_cast<uint4*>(s_slots)[i] = make_uint4(0, 0, 0, 0);
-        fence_proxy_async_smem();
-        for (int i = threadIdx.x; i < C3_MAX_CO; i += blockDim.x) {
-            s_cs[i] = 0.f;
-            s_cs[C3_MAX_CO + i] = 0.f;
-            const bool in = i < p.CO;
-            s_epi[i] = in ? p.bn.sc[i] : 0.f;
-            s_epi[C3_MAX_CO + i] = (in && p.bn.sh) ? p.bn.sh[i] : 0.f;
-            s_epi[2 * C3_MAX_CO + i] = in ? p.bn.p0[i] : 0.f;
-            s_epi[3 * C3_MAX_CO + i] = in ? p.bn.p1[i] : 0.f;
-        }
-    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmXb);
@@ -208,9 +194,25 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 3) tmem_alloc<512>(&tmem_slot);
+    gn_pdl_wait();
+    if (EPI_MODE == 1) {
+        // the BN-backward epilogue multiplies by what the slot holds even for rows outside the image (their gradient is zero): no NaN bit patterns
+        for (int i = threadIdx.x; i < p.e_stages * (slot_bytes / 16); i += blockDim.x) reinterpret_cast<uint4*>(s_slots)[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+        for (int i = threadIdx.x; i < C3_MAX_CO; i += blockDim.x) {
+            s_cs[i] = 0.f;
+            s_cs[C3_MAX_CO + i] = 0.f;
+            const bool in = i < p.CO;
+            s_epi[i] = in ? p.bn.sc[i] : 0.f;
+            s_epi[C3_MAX_CO + i] = (in && p.bn.sh) ? p.bn.sh[i] : 0.f;
+            s_epi[2 * C3_MAX_CO + i] = in ? p.bn.p0[i] : 0.f;
+            s_epi[3 * C3_MAX_CO + i] = in ? p.bn.p1[i] : 0.f;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gn_pdl_trigger();
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
@@ -794,10 +796,10 @@ GN_API int gn_conv3x3_bf16(const void* x, long ldx, int Nimg, int H, int W, int 
         max_set[p.epi_mode] = (int)smem;
     }
     const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
-    if (p.epi_mode && p.nsub <= 2 && p.e_stages >= 2) conv3x3_kernel<1, 16><<<grid, 640, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
-    else if (p.epi_mode) conv3x3_kernel<1, 8><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
-    else if (p.stack && !gn_env_flag("GN_C3_FWD_ONE_GROUP")) conv3x3_kernel<0, 16><<<grid, 640, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
-    else conv3x3_kernel<0, 8><<<grid, 384, smem, stream>>>(tmX, tmXb, tmW, tmOut, tmRef, p);
+    if (p.epi_mode && p.nsub <= 2 && p.e_stages >= 2) GN_CUDA(gn_launch(conv3x3_kernel<1, 16>, dim3(grid), dim3(640), smem, stream, tmX, tmXb, tmW, tmOut, tmRef, p));
+    else if (p.epi_mode) GN_CUDA(gn_launch(conv3x3_kernel<1, 8>, dim3(grid), dim3(384), smem, stream, tmX, tmXb, tmW, tmOut, tmRef, p));
+    else if (p.stack && !gn_env_flag("GN_C3_FWD_ONE_GROUP")) GN_CUDA(gn_launch(conv3x3_kernel<0, 16>, dim3(grid), dim3(640), smem, stream, tmX, tmXb, tmW, tmOut, tmRef, p));
+    else GN_CUDA(gn_launch(conv3x3_kernel<0, 8>, dim3(grid), dim3(384), smem, stream, tmX, tmXb, tmW, tmOut, tmRef, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -865,9 +867,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         fence_proxy_async_smem();
     }
     if (warp == 1) tmem_alloc<512>(&tmem_slot);
+    gn_pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gn_pdl_trigger();
     const uint32_t tmem_base = tmem_slot;
     const bool has_work = (int)blockIdx.x < p.n_tiles;
     const int img_pos = H2 * W2;                 // positions of one padded image
@@ -1144,7 +1148,7 @@ GN_API int gn_conv3x3_wgrad_bf16(const void* x, long ldx, const void* dy, long l
         max_set = (int)smem;
     }
     const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
-    conv3x3_wgrad_kernel<<<grid, 192, smem, stream>>>(tmX, tmDY, p);
+    GN_CUDA(gn_launch(conv3x3_wgrad_kernel, dim3(grid), dim3(192), smem, stream, tmX, tmDY, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -17,6 +17,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
                                    double count, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_invstd, int C, int update_running) {
+    gn_pdl_sync();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double mean = stats[c] / count;
@@ -39,6 +40,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
 __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ running_mean, const float* __restrict__ running_var, float eps,
                                       float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_invstd, int C) {
+    gn_pdl_sync();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float invstd = 1.f / sqrtf(running_var[c] + eps);
@@ -54,6 +56,7 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 
 // per-channel sum / sumsq of an NCHW tensor (used when the producer is not one of our hexconvs)
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int B, int C, long HW) {
+    gn_pdl_sync();
     const int c = blockIdx.x;
     double s = 0.0, q = 0.0;
     const long per = (long)B * HW;
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, float* __restrict__ y, int C, long HW,
                                                          long total, int relu) {
+    gn_pdl_sync();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         int c = (int)((e / HW) % C);
         float v = fmaf(__ldg(x + e), __ldg(scale + c), __ldg(shift + c));
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const float* __r
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 const float* __restrict__ mean_invstd, double* __restrict__ sums,
                                                                 int B, int C, long HW, int relu) {
+    gn_pdl_sync();
     const int c = blockIdx.x;
     const float sc = scale[c], sh_ = shift[c], mean = mean_invstd[c], invstd = mean_invstd[C + c];
     double s = 0.0, q = 0.0;
@@ -126,6 +131,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const float* __re
                                                                double count, int training, float* __restrict__ dH,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                int B, int C, long HW, int relu) {
+    gn_pdl_sync();
     const int c = blockIdx.x;
     const float sc = scale[c], sh_ = shift[c], mean = mean_invstd[c], invstd = mean_invstd[C + c];
     const float mg = training ? (float)(sums[c] / count) : 0.f;
@@ -150,6 +156,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const float* __re
 // masked cross-entropy over (B, C, H, W) logits and (B, H, W) int64 labels (0 = background)
 // acc[0] = sum of per-spot losses, acc[1] = n_foreground, acc[2] = n_correct, acc[3] = labels > C (out of range)   (fp64)
 __global__ void __launch_bounds__(256) ce_count_kernel(const long long* __restrict__ labels, long n, double* __restrict__ acc) {
+    gn_pdl_sync();
     int cnt = 0;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) cnt += labels[e] > 0;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
@@ -160,6 +167,7 @@ __global__ void __launch_bounds__(256) ce_count_kernel(const long long* __restri
 __global__ void __launch_bounds__(256) ce_main_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                                                       float* __restrict__ dlogits, double* __restrict__ acc,
                                                       const double* __restrict__ n_fg_ptr, float grad_scale, int C, long HW, long n) {
+    gn_pdl_sync();
     const double nfg = n_fg_ptr[0];
     const float gs = nfg > 0 ? (float)(grad_scale / nfg) : 0.f;
     double loss = 0.0;
@@ -206,6 +214,7 @@ __global__ void __launch_bounds__(256) ce_main_kernel(const float* __restrict__ 
 
 __global__ void ce_finalize_kernel(const double* __restrict__ acc, const double* __restrict__ n_fg_ptr, float loss_scale,
                                    float* __restrict__ loss_out) {
+    gn_pdl_sync();
     const double nfg = n_fg_ptr[0];
     loss_out[0] = nfg > 0 ? (float)(acc[0] / nfg) * loss_scale : NAN;   // CrossEntropyLoss over an empty set is NaN
 }
@@ -217,6 +226,7 @@ __global__ void __launch_bounds__(256) fg_predictions_kernel(const float* __rest
                                                              const int* __restrict__ offsets, long long* __restrict__ true_out,
                                                              long long* __restrict__ pred_out, float* __restrict__ smax_out, int C, long HW,
                                                              long n) {
+    gn_pdl_sync();
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
         const long long lab = labels[e];
         if (lab <= 0) continue;
@@ -245,7 +255,7 @@ GN_API int gn_fg_predictions(const float* logits, const long long* labels, const
     const long n = (long)B * HW;
     long blocks = (n + 255) / 256;
     if (blocks > 8L * gn_num_sms()) blocks = 8L * gn_num_sms();
-    fg_predictions_kernel<<<(unsigned)blocks, 256, 0, stream>>>(logits, labels, offsets, true_out, pred_out, smax_out, C, HW, n);
+    GN_CUDA(gn_launch(fg_predictions_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, logits, labels, offsets, true_out, pred_out, smax_out, C, HW, n));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -257,8 +267,8 @@ GN_API int gn_bn_finalize(const double* stats, const float* gamma, const float* 
                           int update_running, cudaStream_t stream) {
     GN_REQUIRE(stats && scale && shift && mean_invstd && C > 0 && count > 0, GN_EINVAL, "bn_finalize: bad arguments");
     GN_REQUIRE(!update_running || (running_mean && running_var), GN_EINVAL, "bn_finalize: running stats missing");
-    bn_finalize_kernel<<<gn_ceil_div(C, 128), 128, 0, stream>>>(stats, gamma, beta, running_mean, running_var, momentum, eps, count,
-                                                                 scale, shift, mean_invstd, C, update_running);
+    GN_CUDA(gn_launch(bn_finalize_kernel, dim3(gn_ceil_div(C, 128)), dim3(128), 0, stream, stats, gamma, beta, running_mean, running_var, momentum, eps, count,
+                                                                 scale, shift, mean_invstd, C, update_running));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -266,7 +276,7 @@ GN_API int gn_bn_finalize(const double* stats, const float* gamma, const float* 
 GN_API int gn_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
                              float* scale, float* shift, float* mean_invstd, int C, cudaStream_t stream) {
     GN_REQUIRE(running_mean && running_var && scale && shift && C > 0, GN_EINVAL, "bn_eval_affine: bad arguments");
-    bn_eval_affine_kernel<<<gn_ceil_div(C, 128), 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, scale, shift, mean_invstd, C);
+    GN_CUDA(gn_launch(bn_eval_affine_kernel, dim3(gn_ceil_div(C, 128)), dim3(128), 0, stream, gamma, beta, running_mean, running_var, eps, scale, shift, mean_invstd, C));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -281,7 +291,7 @@ static inline int chunks_for(long per, int C) {
 GN_API int gn_bn_stats(const float* x, double* stats, int B, int C, long HW, cudaStream_t stream) {
     GN_REQUIRE(x && stats && B > 0 && C > 0 && HW > 0, GN_EINVAL, "bn_stats: bad arguments");
     dim3 grid(C, chunks_for((long)B * HW, C));
-    bn_stats_kernel<<<grid, 256, 0, stream>>>(x, stats, B, C, HW);
+    GN_CUDA(gn_launch(bn_stats_kernel, dim3(grid), dim3(256), 0, stream, x, stats, B, C, HW));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -292,7 +302,7 @@ GN_API int gn_bn_act_fwd(const float* x, const float* scale, const float* shift,
     long total = (long)B * C * HW;
     long blocks = (total + 255) / 256;
     if (blocks > 8L * gn_num_sms()) blocks = 8L * gn_num_sms();
-    bn_act_fwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, scale, shift, y, C, HW, total, relu);
+    GN_CUDA(gn_launch(bn_act_fwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, scale, shift, y, C, HW, total, relu));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -303,10 +313,10 @@ GN_API int gn_bn_act_bwd(const float* dA, const float* h, const float* scale, co
     GN_REQUIRE(dA && h && scale && shift && mean_invstd && sums && dH && B > 0 && C > 0 && HW > 0, GN_EINVAL, "bn_act_bwd: bad arguments");
     GN_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), stream));
     dim3 grid(C, chunks_for((long)B * HW, C));
-    bn_act_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(dA, h, scale, shift, mean_invstd, sums, B, C, HW, relu);
+    GN_CUDA(gn_launch(bn_act_bwd_reduce_kernel, dim3(grid), dim3(256), 0, stream, dA, h, scale, shift, mean_invstd, sums, B, C, HW, relu));
     GN_LAUNCH_CHECK();
-    bn_act_bwd_apply_kernel<<<grid, 256, 0, stream>>>(dA, h, scale, shift, mean_invstd, sums, count, training, dH, dgamma, dbeta, B, C,
-                                                      HW, relu);
+    GN_CUDA(gn_launch(bn_act_bwd_apply_kernel, dim3(grid), dim3(256), 0, stream, dA, h, scale, shift, mean_invstd, sums, count, training, dH, dgamma, dbeta, B, C,
+                                                      HW, relu));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -317,7 +327,7 @@ GN_API int gn_bn_act_bwd_reduce(const float* dA, const float* h, const float* sc
     GN_REQUIRE(dA && h && scale && shift && mean_invstd && sums && B > 0 && C > 0 && HW > 0, GN_EINVAL, "bn_act_bwd_reduce: bad arguments");
     GN_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), stream));
     dim3 grid(C, chunks_for((long)B * HW, C));
-    bn_act_bwd_reduce_kernel<<<grid, 256, 0, stream>>>(dA, h, scale, shift, mean_invstd, sums, B, C, HW, relu);
+    GN_CUDA(gn_launch(bn_act_bwd_reduce_kernel, dim3(grid), dim3(256), 0, stream, dA, h, scale, shift, mean_invstd, sums, B, C, HW, relu));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -327,8 +337,8 @@ GN_API int gn_bn_act_bwd_apply(const float* dA, const float* h, const float* sca
                                long HW, int relu, cudaStream_t stream) {
     GN_REQUIRE(dA && h && scale && shift && mean_invstd && sums && dH && B > 0 && C > 0 && HW > 0, GN_EINVAL, "bn_act_bwd_apply: bad arguments");
     dim3 grid(C, chunks_for((long)B * HW, C));
-    bn_act_bwd_apply_kernel<<<grid, 256, 0, stream>>>(dA, h, scale, shift, mean_invstd, sums, count, training, dH, dgamma, dbeta, B, C,
-                                                      HW, relu);
+    GN_CUDA(gn_launch(bn_act_bwd_apply_kernel, dim3(grid), dim3(256), 0, stream, dA, h, scale, shift, mean_invstd, sums, count, training, dH, dgamma, dbeta, B, C,
+                                                      HW, relu));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -341,12 +351,12 @@ GN_API int gn_masked_ce(const float* logits, const long long* labels, float* dlo
     GN_CUDA(cudaMemsetAsync(acc, 0, 4 * sizeof(double), stream));
     long blocks = (n + 255) / 256;
     if (blocks > 4L * gn_num_sms()) blocks = 4L * gn_num_sms();
-    ce_count_kernel<<<(unsigned)blocks, 256, 0, stream>>>(labels, n, acc);
+    GN_CUDA(gn_launch(ce_count_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, labels, n, acc));
     GN_LAUNCH_CHECK();
     const double* nfg = n_fg_override ? n_fg_override : acc + 1;
-    ce_main_kernel<<<(unsigned)blocks, 256, 0, stream>>>(logits, labels, dlogits, acc, nfg, loss_scale, C, HW, n);
+    GN_CUDA(gn_launch(ce_main_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, logits, labels, dlogits, acc, nfg, loss_scale, C, HW, n));
     GN_LAUNCH_CHECK();
-    ce_finalize_kernel<<<1, 1, 0, stream>>>(acc, nfg, loss_scale, loss_out);
+    GN_CUDA(gn_launch(ce_finalize_kernel, dim3(1), dim3(1), 0, stream, acc, nfg, loss_scale, loss_out));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

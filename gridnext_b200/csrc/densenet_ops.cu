@@ -84,6 +84,7 @@ __device__ __forceinline__ int mp_key(uint32_t w_shifted_or_masked_with_low) {
 }
 __global__ void __launch_bounds__(256) maxpool3s2_fwd_kernel(const __nv_bfloat16* __restrict__ in, long ldi, int N, int Hi, int Wi, int C,
                                                               __nv_bfloat16* __restrict__ out, long ldo, unsigned char* __restrict__ idx) {
+    gn_pdl_sync();
     const int Ho = Hi / 2, Wo = Wi / 2, G = C / 8;
     const int total = N * Ho * Wo * G;                     // < 2^31 (checked by the launcher): 32-bit index arithmetic
     const uint32_t ld16 = (uint32_t)(ldi >> 3);            // pixel pitch in 16-byte units (checked: ldi % 8 == 0, whole tensor < 2^35 bytes)
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(256, 4) maxpool3s2_bnrelu_bwd_kernel(const __n
                                                                        int C, const float* __restrict__ sc, const float* __restrict__ p0,
                                                                        const float* __restrict__ p1, __nv_bfloat16* __restrict__ dz, long ldz,
                                                                        float* __restrict__ colsum, int ldsum, int G4, int ppb) {
+    gn_pdl_sync();
     extern __shared__ float s_sum[];
     colsum_block_begin(s_sum, C);
     const int Ho = Hi / 2, Wo = Wi / 2;
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(256, 4) maxpool3s2_bnrelu_bwd_kernel(const __n
 __global__ void __launch_bounds__(256) bnrelu_avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ in, long ldi, int N, int H, int W, int C,
                                                                    const float* __restrict__ sc, const float* __restrict__ sh,
                                                                    __nv_bfloat16* __restrict__ out, long ldo) {
+    gn_pdl_sync();
     const int Ho = H / 2, Wo = W / 2, G = C / 8;
     const int total = N * Ho * Wo * G;                     // < 2^31 (checked by the launcher)
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(256, 4) pool_bnrelu_bwd_kernel(const void* __r
                                                                const float* __restrict__ sh, const float* __restrict__ p0,
                                                                const float* __restrict__ p1, __nv_bfloat16* __restrict__ dC, long ldc,
                                                                float* __restrict__ colsum, int ldsum, int G, int ppb) {
+    gn_pdl_sync();
     extern __shared__ float s_sum[];
     colsum_block_begin(s_sum, C);
     const int cg = threadIdx.x % G, pl = threadIdx.x / G;
@@ -338,6 +342,7 @@ __global__ void __launch_bounds__(256, 4) pool_bnrelu_bwd_kernel(const void* __r
 __global__ void __launch_bounds__(256) bnrelu_gap_fwd_kernel(const __nv_bfloat16* __restrict__ in, long ldi, int N, int HW, int C,
                                                               const float* __restrict__ sc, const float* __restrict__ sh,
                                                               float* __restrict__ feat, long ldf) {
+    gn_pdl_sync();
     const int G = C / 8;
     const long total = (long)N * G;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -361,6 +366,7 @@ __global__ void __launch_bounds__(256) bnrelu_gap_fwd_kernel(const __nv_bfloat16
 // logits[n, j] = sum_c feat[n, c] * w[j, c] + b[j]        one warp per spot, J <= 64
 __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __restrict__ feat, long ldf, const float* __restrict__ w,
                                                                const float* __restrict__ b, int N, int C, int J, float* __restrict__ out) {
+    gn_pdl_sync();
     const int lane = threadIdx.x & 31;
     for (long n = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5); n < N; n += (long)gridDim.x * (blockDim.x >> 5)) {
         for (int j = 0; j < J; ++j) {
@@ -374,6 +380,7 @@ __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __re
 // dfeat[n, c] = sum_j dlog[n, j] * w[j, c]
 __global__ void __launch_bounds__(256) linear_small_bwd_data_kernel(const float* __restrict__ dlog, const float* __restrict__ w, int N, int C,
                                                                     int J, float* __restrict__ dfeat, long ldf) {
+    gn_pdl_sync();
     const long total = (long)N * C;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const int c = (int)(e % C);
@@ -386,6 +393,7 @@ __global__ void __launch_bounds__(256) linear_small_bwd_data_kernel(const float*
 // dw[j, c] += sum_n dlog[n, j] * feat[n, c];  db[j] += sum_n dlog[n, j]     (grid.y splits the spots)
 __global__ void __launch_bounds__(256) linear_small_bwd_weight_kernel(const float* __restrict__ dlog, const float* __restrict__ feat, long ldf,
                                                                       int N, int C, int J, float* __restrict__ dw, float* __restrict__ db) {
+    gn_pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const long per = (N + gridDim.y - 1) / gridDim.y;
     const long n0 = blockIdx.y * per, n1 = min((long)N, n0 + per);
@@ -416,6 +424,7 @@ __global__ void __launch_bounds__(256) linear_small_bwd_weight_kernel(const floa
 __global__ void bn_eval_consts_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                                       const float* __restrict__ var, float eps, int C, float* __restrict__ scale, float* __restrict__ shift,
                                       float* __restrict__ invstd, float* __restrict__ inv_gamma) {
+    gn_pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float is = 1.f / sqrtf(var[c] + eps);
@@ -450,7 +459,7 @@ GN_API int gn_maxpool3s2_fwd(const void* in, long ldi, int N, int Hi, int Wi, in
     const long total = (long)N * (Hi / 2) * (Wi / 2) * (C / 8);
     GN_REQUIRE(total < (1L << 31) && (long)N * Hi * Wi < (1L << 31), GN_EUNSUPPORTED, "maxpool3s2_fwd: too many elements for 32-bit indexing");
     GN_REQUIRE(((uintptr_t)in & 15) == 0, GN_EALIGN, "maxpool3s2_fwd: input must be 16-byte aligned");
-    maxpool3s2_fwd_kernel<<<grid_for(total, 16), 256, 0, stream>>>((const __nv_bfloat16*)in, ldi, N, Hi, Wi, C, (__nv_bfloat16*)out, ldo, idx);
+    GN_CUDA(gn_launch(maxpool3s2_fwd_kernel, dim3(grid_for(total, 16)), dim3(256), 0, stream, (const __nv_bfloat16*)in, ldi, N, Hi, Wi, C, (__nv_bfloat16*)out, ldo, idx));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -467,8 +476,8 @@ GN_API int gn_maxpool3s2_bnrelu_bwd(const void* dpool, long ldp, const unsigned 
     GN_REQUIRE(Hi % 2 == 0 && Wi % 2 == 0, GN_EINVAL, "maxpool3s2_bnrelu_bwd: odd spatial size");
     unsigned grid = (unsigned)gn_ceil_div((long)N * (Hi / 2) * (Wi / 2), ppb);
     if (grid > (unsigned)gn_num_sms() * 8) grid = gn_num_sms() * 8;
-    maxpool3s2_bnrelu_bwd_kernel<<<grid, G * ppb, 2 * C * sizeof(float), stream>>>(
-        (const __nv_bfloat16*)dpool, ldp, idx, (const __nv_bfloat16*)act, lda, N, Hi, Wi, C, sc, p0, p1, (__nv_bfloat16*)dz, ldz, colsum, ldsum, G, ppb);
+    GN_CUDA(gn_launch(maxpool3s2_bnrelu_bwd_kernel, dim3(grid), dim3(G * ppb), 2 * C * sizeof(float), stream, 
+        (const __nv_bfloat16*)dpool, ldp, idx, (const __nv_bfloat16*)act, lda, N, Hi, Wi, C, sc, p0, p1, (__nv_bfloat16*)dz, ldz, colsum, ldsum, G, ppb));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -479,7 +488,7 @@ GN_API int gn_bnrelu_avgpool2_fwd(const void* in, long ldi, int N, int H, int W,
                "bnrelu_avgpool2_fwd: bad arguments");
     const long total = (long)N * (H / 2) * (W / 2) * (C / 8);
     GN_REQUIRE(total < (1L << 31), GN_EUNSUPPORTED, "bnrelu_avgpool2_fwd: too many elements for 32-bit indexing");
-    bnrelu_avgpool2_fwd_kernel<<<grid_for(total, 16), 256, 0, stream>>>((const __nv_bfloat16*)in, ldi, N, H, W, C, sc, sh, (__nv_bfloat16*)out, ldo);
+    GN_CUDA(gn_launch(bnrelu_avgpool2_fwd_kernel, dim3(grid_for(total, 16)), dim3(256), 0, stream, (const __nv_bfloat16*)in, ldi, N, H, W, C, sc, sh, (__nv_bfloat16*)out, ldo));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -498,11 +507,11 @@ GN_API int gn_pool_bnrelu_bwd(const void* dpool, long ldp, int gap, const void* 
     if (grid > (unsigned)gn_num_sms() * 8) grid = gn_num_sms() * 8;
     const size_t smem = 2 * C * sizeof(float);
     if (gap)
-        pool_bnrelu_bwd_kernel<true><<<grid, G * ppb, smem, stream>>>(dpool, ldp, (const __nv_bfloat16*)raw, ldr, N, H, W, C, sc, sh, p0, p1,
-                                                                     (__nv_bfloat16*)dC, ldc, colsum, ldsum, G, ppb);
+        GN_CUDA(gn_launch(pool_bnrelu_bwd_kernel<true>, dim3(grid), dim3(G * ppb), smem, stream, dpool, ldp, (const __nv_bfloat16*)raw, ldr, N, H, W, C, sc, sh, p0, p1,
+                                                                     (__nv_bfloat16*)dC, ldc, colsum, ldsum, G, ppb));
     else
-        pool_bnrelu_bwd_kernel<false><<<grid, G * ppb, smem, stream>>>(dpool, ldp, (const __nv_bfloat16*)raw, ldr, N, H, W, C, sc, sh, p0, p1,
-                                                                      (__nv_bfloat16*)dC, ldc, colsum, ldsum, G, ppb);
+        GN_CUDA(gn_launch(pool_bnrelu_bwd_kernel<false>, dim3(grid), dim3(G * ppb), smem, stream, dpool, ldp, (const __nv_bfloat16*)raw, ldr, N, H, W, C, sc, sh, p0, p1,
+                                                                      (__nv_bfloat16*)dC, ldc, colsum, ldsum, G, ppb));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -510,14 +519,14 @@ GN_API int gn_pool_bnrelu_bwd(const void* dpool, long ldp, int gap, const void* 
 GN_API int gn_bnrelu_gap_fwd(const void* in, long ldi, int N, int HW, int C, const float* sc, const float* sh, float* feat, long ldf,
                              cudaStream_t stream) {
     GN_REQUIRE(in && sc && sh && feat && N > 0 && HW > 0 && C % 8 == 0 && ldi % 8 == 0, GN_EINVAL, "bnrelu_gap_fwd: bad arguments");
-    bnrelu_gap_fwd_kernel<<<grid_for((long)N * (C / 8), 16), 256, 0, stream>>>((const __nv_bfloat16*)in, ldi, N, HW, C, sc, sh, feat, ldf);
+    GN_CUDA(gn_launch(bnrelu_gap_fwd_kernel, dim3(grid_for((long)N * (C / 8), 16)), dim3(256), 0, stream, (const __nv_bfloat16*)in, ldi, N, HW, C, sc, sh, feat, ldf));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
 
 GN_API int gn_linear_small_fwd(const float* feat, long ldf, const float* w, const float* b, int N, int C, int J, float* out, cudaStream_t stream) {
     GN_REQUIRE(feat && w && out && N > 0 && C > 0 && J > 0, GN_EINVAL, "linear_small_fwd: bad arguments");
-    linear_small_fwd_kernel<<<grid_for((long)N * 32, 16), 256, 0, stream>>>(feat, ldf, w, b, N, C, J, out);
+    GN_CUDA(gn_launch(linear_small_fwd_kernel, dim3(grid_for((long)N * 32, 16)), dim3(256), 0, stream, feat, ldf, w, b, N, C, J, out));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -526,7 +535,7 @@ GN_API int gn_linear_small_bwd(const float* dlog, const float* feat, long ldf, c
                                float* dw, float* db, cudaStream_t stream) {
     GN_REQUIRE(dlog && feat && w && N > 0 && C > 0 && J > 0 && J <= 256, GN_EINVAL, "linear_small_bwd: bad arguments");
     if (dfeat) {
-        linear_small_bwd_data_kernel<<<grid_for((long)N * C, 16), 256, 0, stream>>>(dlog, w, N, C, J, dfeat, lddf);
+        GN_CUDA(gn_launch(linear_small_bwd_data_kernel, dim3(grid_for((long)N * C, 16)), dim3(256), 0, stream, dlog, w, N, C, J, dfeat, lddf));
         GN_LAUNCH_CHECK();
     }
     if (dw) {
@@ -534,7 +543,7 @@ GN_API int gn_linear_small_bwd(const float* dlog, const float* feat, long ldf, c
         if (ys < 1) ys = 1;
         if (ys > N) ys = N;
         dim3 grid(gn_ceil_div(C, 256), ys);
-        linear_small_bwd_weight_kernel<<<grid, 256, 0, stream>>>(dlog, feat, ldf, N, C, J, dw, db);
+        GN_CUDA(gn_launch(linear_small_bwd_weight_kernel, dim3(grid), dim3(256), 0, stream, dlog, feat, ldf, N, C, J, dw, db));
         GN_LAUNCH_CHECK();
     }
     return GN_OK;
@@ -543,7 +552,7 @@ GN_API int gn_linear_small_bwd(const float* dlog, const float* feat, long ldf, c
 GN_API int gn_bn_eval_consts(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int C, float* scale,
                              float* shift, float* invstd, float* inv_gamma, cudaStream_t stream) {
     GN_REQUIRE(gamma && beta && mean && var && scale && shift && invstd && inv_gamma && C > 0, GN_EINVAL, "bn_eval_consts: bad arguments");
-    bn_eval_consts_kernel<<<gn_ceil_div(C, 256), 256, 0, stream>>>(gamma, beta, mean, var, eps, C, scale, shift, invstd, inv_gamma);
+    GN_CUDA(gn_launch(bn_eval_consts_kernel, dim3(gn_ceil_div(C, 256)), dim3(256), 0, stream, gamma, beta, mean, var, eps, C, scale, shift, invstd, inv_gamma));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -95,13 +95,6 @@ gemm_bwd1x1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint8_t* s_slots = s_b + 2 * (size_t)b_kb_bytes;                // [BW_ESTAGES][16 KB]
     uint8_t* s_xf = s_slots + (size_t)BW_ESTAGES * BW_SUB_BYTES;    // [BW_XSTAGES][16 KB]
 
-    for (int i = threadIdx.x; i < BW_BN; i += blockDim.x) {
-        const bool in = i < ncols;
-        s_epi[0][i] = in ? p.bn.sc[col_base + i] : 0.f;
-        s_epi[1][i] = in ? p.bn.sh[col_base + i] : 0.f;
-        s_epi[2][i] = 0.f;
-        s_epi[3][i] = 0.f;
-    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -116,9 +109,18 @@ gemm_bwd1x1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         fence_barrier_init();
     }
     if (warp == 3) tmem_alloc<512>(&tmem_slot);
+    gn_pdl_wait();
+    for (int i = threadIdx.x; i < BW_BN; i += blockDim.x) {
+        const bool in = i < ncols;
+        s_epi[0][i] = in ? p.bn.sc[col_base + i] : 0.f;
+        s_epi[1][i] = in ? p.bn.sh[col_base + i] : 0.f;
+        s_epi[2][i] = 0.f;
+        s_epi[3][i] = 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gn_pdl_trigger();
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
@@ -417,7 +419,7 @@ GN_API int gn_conv1x1_bwd_bf16(const void* dz, long lddz, const void* wt, long l
                                      2 * BW_A_BYTES + 2 * 256 * 128 + (BW_ESTAGES + BW_XSTAGES) * BW_SUB_BYTES + 1024));   // = 3 tiles + the 128-row block
         attr_set = true;
     }
-    gemm_bwd1x1_kernel<<<grid, 384, smem, stream>>>(tmA, tmB, tmOut, tmRef, p);
+    GN_CUDA(gn_launch(gemm_bwd1x1_kernel, dim3(grid), dim3(384), smem, stream, tmA, tmB, tmOut, tmRef, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

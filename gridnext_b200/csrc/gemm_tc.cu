@@ -180,6 +180,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float* s_xf = s_epi + (EPI == EPI_DIRECT ? 0 : 4 * epi_ld);                           // [2][xf_ld]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (EPI != EPI_DIRECT) tma_prefetch_desc(&tmOut);
+        if (EPI == EPI_BNBWD) tma_prefetch_desc(&tmRef);
+        for (int s = 0; s < GEMM_MAX_STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_xf[s], 4);
+            mbar_init(&bar_empty[s], XT ? (p.res_b ? 4 : 5) : 1);   // XT: the four transform warps release the stage (+ the MMA when it holds streamed weights)
+        }
+        for (int s = 0; s < GEMM_XT_STAGES; ++s) mbar_init(&bar_tfree[s], 1);
+        for (int s = 0; s < GEMM_MAX_ESTAGES; ++s) {
+            mbar_init(&bar_efull[s], 1);
+            mbar_init(&bar_eready[s], GEMM_EPI_WARPS);
+            mbar_init(&bar_eempty[s], 1);
+        }
+        mbar_init(&bar_bres, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_tfull[a], 1);
+            mbar_init(&bar_tempty[a], GEMM_EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 3) tmem_alloc<(XT ? 512 : Cfg::TMEM_COLS)>(&tmem_slot);
+    gn_pdl_wait();      // everything above overlaps the tail of the preceding kernel; the constant tables below are global reads
     if (XFORM) {
         const int kpad = p.num_k_blocks * GEMM_BK;
         for (int i = threadIdx.x; i < kpad; i += blockDim.x) {
@@ -209,33 +234,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     }
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        if (EPI != EPI_DIRECT) tma_prefetch_desc(&tmOut);
-        if (EPI == EPI_BNBWD) tma_prefetch_desc(&tmRef);
-        for (int s = 0; s < GEMM_MAX_STAGES; ++s) {
-            mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_xf[s], 4);
-            mbar_init(&bar_empty[s], XT ? (p.res_b ? 4 : 5) : 1);   // XT: the four transform warps release the stage (+ the MMA when it holds streamed weights)
-        }
-        for (int s = 0; s < GEMM_XT_STAGES; ++s) mbar_init(&bar_tfree[s], 1);
-        for (int s = 0; s < GEMM_MAX_ESTAGES; ++s) {
-            mbar_init(&bar_efull[s], 1);
-            mbar_init(&bar_eready[s], GEMM_EPI_WARPS);
-            mbar_init(&bar_eempty[s], 1);
-        }
-        mbar_init(&bar_bres, 1);
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&bar_tfull[a], 1);
-            mbar_init(&bar_tempty[a], GEMM_EPI_WARPS);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 3) tmem_alloc<(XT ? 512 : Cfg::TMEM_COLS)>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gn_pdl_trigger();
     const uint32_t tmem_base = tmem_slot;
     const int n_tiles = p.num_m_blocks * p.num_n_blocks;
     const int nkb = p.num_k_blocks;
@@ -629,7 +631,7 @@ static int launch_gemm_kernel(const CUtensorMap& tmA, const CUtensorMap& tmB, co
         GN_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, XFORM, EPI, XFW, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = smem;
     }
-    gemm_bf16_kernel<BN, XFORM, EPI, XFW, XT><<<grid, GemmThreads<XFORM, EPI, XFW>::N, smem, stream>>>(tmA, tmB, tmOut, tmRef, p);
+    GN_CUDA(gn_launch(gemm_bf16_kernel<BN, XFORM, EPI, XFW, XT>, dim3(grid), dim3(GemmThreads<XFORM, EPI, XFW>::N), smem, stream, tmA, tmB, tmOut, tmRef, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -57,9 +57,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(&tmem_slot);
+    gn_pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gn_pdl_trigger();
     const uint32_t tmem_base = tmem_slot;
     const int n_units = p.mo_blocks * p.no_blocks * p.ksplit;
     const int kb_per = (p.kb_total + p.ksplit - 1) / p.ksplit;
@@ -262,9 +264,9 @@ GN_API int gn_gemm_tn_bf16(const void* a, long lda, const void* b, long ldb, int
     const int units = tiles * ksplit;
     const int grid = units < gn_num_sms() ? units : gn_num_sms();
     if (xform)
-        gemm_tn_kernel<true><<<grid, 320, smem, stream>>>(tmA, tmB, p);
+        GN_CUDA(gn_launch(gemm_tn_kernel<true>, dim3(grid), dim3(320), smem, stream, tmA, tmB, p));
     else
-        gemm_tn_kernel<false><<<grid, 192, smem, stream>>>(tmA, tmB, p);
+        GN_CUDA(gn_launch(gemm_tn_kernel<false>, dim3(grid), dim3(192), smem, stream, tmA, tmB, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

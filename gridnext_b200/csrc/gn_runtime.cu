@@ -29,6 +29,12 @@ int gn_num_sms() {
 
 GN_API int gn_device_sm_count(void) { return gn_num_sms(); }
 
+int gn_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) on = gn_env_flag("GN_NO_PDL") ? 0 : 1;
+    return on;
+}
+
 // ------------------------------------------------------------------------------------------------
 #include "gn_tma.cuh"
 typedef CUresult (*gn_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

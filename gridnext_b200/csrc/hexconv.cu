@@ -89,6 +89,7 @@ struct HexKernelPtrsMut {
 // mode 0: Wp[t][ci][co] = K_i[co][ci][a][side]                      (conv cin=Cin,  cout=Cout)
 // mode 1: Wp[t][o ][c ] = K_i[o ][c ][na-1-a][ns-1-side]            (conv cin=Cout, cout=Cin)
 __global__ void hex_pack_kernel(HexKernelPtrs kp, HexTaps taps, int Cin, int Cout, int mode, float* __restrict__ wp) {
+    gn_pdl_sync();
     long total = (long)taps.n * Cin * Cout;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         int t = (int)(e / ((long)Cin * Cout));
@@ -109,6 +110,7 @@ __global__ void hex_pack_kernel(HexKernelPtrs kp, HexTaps taps, int Cin, int Cou
 
 // dK_i[co][ci][a][side] = dWp[t][ci][co]
 __global__ void hex_unpack_grad_kernel(const float* __restrict__ dwp, HexTaps taps, int Cin, int Cout, HexKernelPtrsMut kp) {
+    gn_pdl_sync();
     long total = (long)taps.n * Cin * Cout;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         int t = (int)(e / ((long)Cin * Cout));
@@ -133,6 +135,7 @@ hexconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp, co
                    const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                    float* __restrict__ y, double* __restrict__ stats,
                    int Cin, int Cout, int H, int W, HexTaps taps) {
+    gn_pdl_sync();
     extern __shared__ __align__(16) float smem[];
     const int k = taps.k;
     const int SR = HEX_TR + 2 * k;          // staged rows
@@ -251,6 +254,7 @@ __global__ void __launch_bounds__(HEX_THREADS)
 hexconv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                      const float* __restrict__ dy, float* __restrict__ dwp, float* __restrict__ dbias,
                      int B, int Cin, int Cout, int H, int W, HexTaps taps) {
+    gn_pdl_sync();
     extern __shared__ __align__(16) float smem[];
     const int k = taps.k;
     const int SR = HEX_TR + 2 * k;
@@ -368,7 +372,7 @@ GN_API int gn_hexconv_pack(const float* k0, const float* k1, const float* k2, co
     HexKernelPtrs kp = {{k0, k1, k2, k3}};
     HexTaps taps = make_taps(ksize);
     long total = (long)taps.n * cin * cout;
-    hex_pack_kernel<<<gn_ceil_div(total, 256) > 1024 ? 1024 : gn_ceil_div(total, 256), 256, 0, stream>>>(kp, taps, cin, cout, mode, wp);
+    GN_CUDA(gn_launch(hex_pack_kernel, dim3(gn_ceil_div(total, 256) > 1024 ? 1024 : gn_ceil_div(total, 256)), dim3(256), 0, stream, kp, taps, cin, cout, mode, wp));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -380,7 +384,7 @@ GN_API int gn_hexconv_unpack_grad(const float* dwp, float* dk0, float* dk1, floa
     HexKernelPtrsMut kp = {{dk0, dk1, dk2, dk3}};
     HexTaps taps = make_taps(ksize);
     long total = (long)taps.n * cin * cout;
-    hex_unpack_grad_kernel<<<gn_ceil_div(total, 256) > 1024 ? 1024 : gn_ceil_div(total, 256), 256, 0, stream>>>(dwp, taps, cin, cout, kp);
+    GN_CUDA(gn_launch(hex_unpack_grad_kernel, dim3(gn_ceil_div(total, 256) > 1024 ? 1024 : gn_ceil_div(total, 256)), dim3(256), 0, stream, dwp, taps, cin, cout, kp));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -397,7 +401,7 @@ static int launch_fwd(const float* x, const float* wp, const float* bias, const 
     }
     const int n_xt = gn_ceil_div(W, HEX_TW), n_ct = gn_ceil_div(cout, CO);
     dim3 grid(n_xt * n_ct, gn_ceil_div(H, HEX_TR), B);
-    hexconv_fwd_kernel<CO><<<grid, HEX_THREADS, smem, stream>>>(x, wp, bias, in_scale, in_shift, y, stats, cin, cout, H, W, taps);
+    GN_CUDA(gn_launch(hexconv_fwd_kernel<CO>, grid, dim3(HEX_THREADS), smem, stream, x, wp, bias, in_scale, in_shift, y, stats, cin, cout, H, W, taps));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -435,7 +439,7 @@ static int conv_wgrad_impl(const float* x, const float* in_scale, const float* i
     if (gx > n_tiles) gx = n_tiles;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, gy, gz);
-    hexconv_wgrad_kernel<<<grid, HEX_THREADS, smem, stream>>>(x, in_scale, in_shift, dy, dwp, dbias, B, cin, cout, H, W, taps);
+    GN_CUDA(gn_launch(hexconv_wgrad_kernel, grid, dim3(HEX_THREADS), smem, stream, x, in_scale, in_shift, dy, dwp, dbias, B, cin, cout, H, W, taps));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -456,7 +460,7 @@ GN_API int gn_sqconv_pack(const float* w, int K, int cin, int cout, int mode, fl
     HexKernelPtrs kp = {{w, nullptr, nullptr, nullptr}};
     HexTaps taps = make_square_taps(K);
     long total = (long)taps.n * cin * cout;
-    hex_pack_kernel<<<gn_ceil_div(total, 256) > 1024 ? 1024 : gn_ceil_div(total, 256), 256, 0, stream>>>(kp, taps, cin, cout, mode, wp);
+    GN_CUDA(gn_launch(hex_pack_kernel, dim3(gn_ceil_div(total, 256) > 1024 ? 1024 : gn_ceil_div(total, 256)), dim3(256), 0, stream, kp, taps, cin, cout, mode, wp));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -467,7 +471,7 @@ GN_API int gn_sqconv_unpack_grad(const float* dwp, float* dw, int K, int cin, in
     HexKernelPtrsMut kp = {{dw, nullptr, nullptr, nullptr}};
     HexTaps taps = make_square_taps(K);
     long total = (long)taps.n * cin * cout;
-    hex_unpack_grad_kernel<<<gn_ceil_div(total, 256) > 1024 ? 1024 : gn_ceil_div(total, 256), 256, 0, stream>>>(dwp, taps, cin, cout, kp);
+    GN_CUDA(gn_launch(hex_unpack_grad_kernel, dim3(gn_ceil_div(total, 256) > 1024 ? 1024 : gn_ceil_div(total, 256)), dim3(256), 0, stream, dwp, taps, cin, cout, kp));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

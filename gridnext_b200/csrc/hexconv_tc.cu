@@ -46,6 +46,7 @@ struct HexTcParams {
 __global__ void __launch_bounds__(128) hex_to_planes_kernel(const float* __restrict__ x, const float* __restrict__ in_scale,
                                                             const float* __restrict__ in_shift, int Cin, int H, int W, int Q, int WP,
                                                             __nv_bfloat16* __restrict__ planes) {
+    gn_pdl_sync();
     const int yy = blockIdx.x, b = blockIdx.y;                               // yy in [0, 2Q): rows >= H are written as zeros
     const int par = yy & 1, q = yy >> 1;
     uint4* dst_row = reinterpret_cast<uint4*>(planes + (((long)b * 2 + par) * Q + q) * WP * 64);
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(128) hex_to_planes_kernel(const float* __restr
 
 // wp fp32 [7][cin][cout] -> wtc bf16 [7][2][32 (cout)][64]: tile 0 = [w_hi | w_hi], tile 1 = [w_lo | 0]
 __global__ void hex_pack_tc_kernel(const float* __restrict__ wp, int cin, int cout, __nv_bfloat16* __restrict__ wtc) {
+    gn_pdl_sync();
     const int total = HTC_TAPS * 2 * HTC_C * 64;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int kk = e & 63, co = (e >> 6) & 31, j = (e >> 11) & 1, t = e >> 12;
@@ -124,9 +126,11 @@ hexconv_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<128>(&tmem_slot);
+    gn_pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gn_pdl_trigger();
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
@@ -283,10 +287,10 @@ GN_API int gn_hexconv_fwd_tc(const float* x, const float* wp, const float* bias,
     }
     __nv_bfloat16* planes = (__nv_bfloat16*)workspace;
     __nv_bfloat16* wtc = (__nv_bfloat16*)((uint8_t*)workspace + ((htc_planes_bytes(B, H, W) + 1023) / 1024) * 1024);
-    hex_pack_tc_kernel<<<gn_ceil_div(HTC_TAPS * 2 * HTC_C * 64, 256), 256, 0, stream>>>(wp, cin, cout, wtc);
+    GN_CUDA(gn_launch(hex_pack_tc_kernel, dim3(gn_ceil_div(HTC_TAPS * 2 * HTC_C * 64, 256)), dim3(256), 0, stream, wp, cin, cout, wtc));
     GN_LAUNCH_CHECK();
     dim3 cgrid(2 * p.Q, B);
-    hex_to_planes_kernel<<<cgrid, p.WP <= 96 ? 96 : 128, 0, stream>>>(x, in_scale, in_shift, cin, H, W, p.Q, p.WP, planes);
+    GN_CUDA(gn_launch(hex_to_planes_kernel, cgrid, dim3(p.WP <= 96 ? 96 : 128), 0, stream, x, in_scale, in_shift, cin, H, W, p.Q, p.WP, planes));
     GN_LAUNCH_CHECK();
 
     CUtensorMap tmP, tmW;
@@ -308,7 +312,7 @@ GN_API int gn_hexconv_fwd_tc(const float* x, const float* wp, const float* bias,
         attr_set = smem;
     }
     const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
-    hexconv_tc_kernel<<<grid, 320, smem, stream>>>(tmP, tmW, p);
+    GN_CUDA(gn_launch(hexconv_tc_kernel, dim3(grid), dim3(320), smem, stream, tmP, tmW, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -345,9 +349,11 @@ hexconv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(&tmem_slot);
+    gn_pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gn_pdl_trigger();
     const uint32_t tmem_base = tmem_slot;
     const bool has_work = (int)blockIdx.x < p.n_tiles;
 
@@ -455,9 +461,9 @@ GN_API int gn_hexconv_wgrad_tc(const float* x, const float* in_scale, const floa
     __nv_bfloat16* px = (__nv_bfloat16*)workspace;
     __nv_bfloat16* pdy = (__nv_bfloat16*)((uint8_t*)workspace + pb);
     dim3 cgrid(2 * p.Q, B);
-    hex_to_planes_kernel<<<cgrid, p.WP <= 96 ? 96 : 128, 0, stream>>>(x, in_scale, in_shift, cin, H, W, p.Q, p.WP, px);
+    GN_CUDA(gn_launch(hex_to_planes_kernel, cgrid, dim3(p.WP <= 96 ? 96 : 128), 0, stream, x, in_scale, in_shift, cin, H, W, p.Q, p.WP, px));
     GN_LAUNCH_CHECK();
-    hex_to_planes_kernel<<<cgrid, p.WP <= 96 ? 96 : 128, 0, stream>>>(dy, nullptr, nullptr, cout, H, W, p.Q, p.WP, pdy);
+    GN_CUDA(gn_launch(hex_to_planes_kernel, cgrid, dim3(p.WP <= 96 ? 96 : 128), 0, stream, dy, nullptr, nullptr, cout, H, W, p.Q, p.WP, pdy));
     GN_LAUNCH_CHECK();
     CUtensorMap tmX, tmDY;
     {
@@ -478,7 +484,7 @@ GN_API int gn_hexconv_wgrad_tc(const float* x, const float* in_scale, const floa
         attr_set = smem;
     }
     const int grid = p.n_tiles < gn_num_sms() ? p.n_tiles : gn_num_sms();
-    hexconv_tc_wgrad_kernel<<<grid, 192, smem, stream>>>(tmX, tmDY, p);
+    GN_CUDA(gn_launch(hexconv_tc_wgrad_kernel, dim3(grid), dim3(192), smem, stream, tmX, tmDY, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

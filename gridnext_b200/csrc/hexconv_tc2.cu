@@ -69,6 +69,7 @@ struct Hex2Params {
 //   hi tile row = [w_hi(ci 0..31) | w_hi(ci 0..31)]  (against A = [x_hi | x_lo]),  lo tile row = [w_lo(ci 0..31) | 0] (against x_hi)
 //   rows: S_hi [tap 0..2][co], S_lo, U_hi [tap 3,4][co], U_lo, D_hi [tap 5,6][co], D_lo
 __global__ void hex2_pack_kernel(const float* __restrict__ wp, int cin, int cout, __nv_bfloat16* __restrict__ wt) {
+    gn_pdl_sync();
     const int total = H2_W_ROWS * 64;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int kk = e & 63, row = e >> 6;
@@ -105,11 +106,6 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x < 64) s_stat[threadIdx.x] = 0.0;
-    if (threadIdx.x < 32) {
-        s_bias[threadIdx.x] = (p.bias != nullptr && threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
-        s_pro[0][threadIdx.x] = (p.in_scale != nullptr && threadIdx.x < p.Cin) ? p.in_scale[threadIdx.x] : 1.f;
-        s_pro[1][threadIdx.x] = (p.in_shift != nullptr && threadIdx.x < p.Cin) ? p.in_shift[threadIdx.x] : 0.f;
-    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmX2);
@@ -121,9 +117,16 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(&tmem_slot);
+    gn_pdl_wait();
+    if (threadIdx.x < 32) {
+        s_bias[threadIdx.x] = (p.bias != nullptr && threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
+        s_pro[0][threadIdx.x] = (p.in_scale != nullptr && threadIdx.x < p.Cin) ? p.in_scale[threadIdx.x] : 1.f;
+        s_pro[1][threadIdx.x] = (p.in_shift != nullptr && threadIdx.x < p.Cin) ? p.in_shift[threadIdx.x] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gn_pdl_trigger();
     const uint32_t tmem_base = tmem_slot;
     const bool has_pro = p.in_scale != nullptr;
 
@@ -442,7 +445,7 @@ GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias
     }
     p.trace = g_h2_trace;
     __nv_bfloat16* wt = (__nv_bfloat16*)workspace;
-    hex2_pack_kernel<<<gn_ceil_div(H2_W_ROWS * 64, 256), 256, 0, stream>>>(wp, cin, cout, wt);
+    GN_CUDA(gn_launch(hex2_pack_kernel, dim3(gn_ceil_div(H2_W_ROWS * 64, 256)), dim3(256), 0, stream, wp, cin, cout, wt));
     GN_LAUNCH_CHECK();
     CUtensorMap tmX, tmX2, tmW;
     {
@@ -469,7 +472,7 @@ GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias
         attr_set = true;
     }
     const int grid = p.n_strips < gn_num_sms() ? p.n_strips : gn_num_sms();
-    hexconv_tc2_kernel<<<grid, H2_THREADS, smem, stream>>>(tmX, tmX2, tmW, p);
+    GN_CUDA(gn_launch(hexconv_tc2_kernel, dim3(grid), dim3(H2_THREADS), smem, stream, tmX, tmX2, tmW, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -9,6 +9,7 @@
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long n4, const float* in_tail,
                                                             __nv_bfloat16* out_tail, int tail) {
+    gn_pdl_sync();
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         const float4 v = in[i];
         uint2 o;
@@ -26,7 +27,7 @@ GN_API int gn_cast_f32_bf16(const float* in, void* out, long n, cudaStream_t str
     const int tail = (int)(n - 4 * n4);
     int blocks = gn_ceil_div(n4 > 0 ? n4 : 1, 256);
     if (blocks > gn_num_sms() * 16) blocks = gn_num_sms() * 16;
-    cast_f32_bf16_kernel<<<blocks, 256, 0, stream>>>((const float4*)in, (uint2*)out, n4, in + 4 * n4, (__nv_bfloat16*)out + 4 * n4, tail);
+    GN_CUDA(gn_launch(cast_f32_bf16_kernel, dim3(blocks), dim3(256), 0, stream, (const float4*)in, (uint2*)out, n4, in + 4 * n4, (__nv_bfloat16*)out + 4 * n4, tail));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -34,6 +35,7 @@ GN_API int gn_cast_f32_bf16(const float* in, void* out, long n, cudaStream_t str
 __global__ void __launch_bounds__(256) rows_affine_bf16_kernel(const float* __restrict__ in, long ldi, const float* __restrict__ scale,
                                                                const float* __restrict__ shift, int relu, __nv_bfloat16* __restrict__ out, long ldo,
                                                                long N, int C, int Cpad) {
+    gn_pdl_sync();
     const long total = N * Cpad;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const long r = e / Cpad;
@@ -54,7 +56,7 @@ GN_API int gn_rows_affine_bf16(const float* in, long ldi, const float* scale, co
     GN_REQUIRE(in && out && N > 0 && C > 0 && Cpad >= C && ldo >= Cpad && ldi >= C, GN_EINVAL, "rows_affine_bf16: bad arguments");
     int blocks = gn_ceil_div(N * Cpad, 256);
     if (blocks > gn_num_sms() * 16) blocks = gn_num_sms() * 16;
-    rows_affine_bf16_kernel<<<blocks, 256, 0, stream>>>(in, ldi, scale, shift, relu, (__nv_bfloat16*)out, ldo, N, C, Cpad);
+    GN_CUDA(gn_launch(rows_affine_bf16_kernel, dim3(blocks), dim3(256), 0, stream, in, ldi, scale, shift, relu, (__nv_bfloat16*)out, ldo, N, C, Cpad));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

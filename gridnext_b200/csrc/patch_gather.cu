@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(256, 2) patch_gather_tma_kernel(const __grid_c
         for (int s = 0; s < stages; ++s) gnptx::mbar_init(&bar[s], 1);
         gnptx::fence_barrier_init();
     }
+    gn_pdl_sync();
     // value table: raw u8 -> float, or ((v / 255) - mean) / std in IEEE fp32 like ToTensor + Normalize
     for (int e = tid; e < 3 * 256; e += 256) {
         const int c = e >> 8, v = e & 255;
@@ -330,8 +331,8 @@ GN_API int gn_patch_gather(const unsigned char* img, long pitch, int H, int W, c
 #define PG_LAUNCH(T, R)                                                                                                                        \
     do {                                                                                                                                       \
         GN_CUDA(cudaFuncSetAttribute(patch_gather_tma_kernel<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));                \
-        patch_gather_tma_kernel<T, R><<<grid_t, 256, smem_t, stream>>>(tm, img, pitch, H, W, cells, n_cells, P, row_bytes, stages, mean, stdv, \
-                                                                       (T*)out);                                                               \
+        GN_CUDA(gn_launch(patch_gather_tma_kernel<T, R>, dim3(grid_t), dim3(256), smem_t, stream, tm, img, pitch, H, W, cells, n_cells, P,     \
+                          row_bytes, stages, mean, stdv, (T*)out));                                                                            \
     } while (0)
         if (out_bf16) { if (rep == 16) PG_LAUNCH(__nv_bfloat16, 16); else PG_LAUNCH(__nv_bfloat16, 8); }
         else { if (rep == 16) PG_LAUNCH(float, 16); else PG_LAUNCH(float, 8); }

@@ -50,6 +50,7 @@ struct StemParams {
 // ------------------------------------------------------------------------------------------------ packing
 template <typename InT>
 __global__ void __launch_bounds__(256) stem_pack_input_kernel(const InT* __restrict__ x, int P, uint2* __restrict__ xq) {
+    gn_pdl_sync();
     const int plane = P * P;
     const long n = blockIdx.y;
     const InT* src = x + n * 3 * plane;
@@ -86,8 +87,8 @@ GN_API int gn_stem_pack_input(const void* x, int x_is_bf16, int N, int P, void* 
     GN_REQUIRE(x && xq && N > 0 && P > 0, GN_EINVAL, "stem_pack_input: bad arguments");
     GN_REQUIRE(N <= 65535, GN_EUNSUPPORTED, "stem_pack_input: at most 65535 patches per call");
     dim3 grid((unsigned)gn_ceil_div((long)P * P, 1024), (unsigned)N);
-    if (x_is_bf16) stem_pack_input_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, P, (uint2*)xq);
-    else stem_pack_input_kernel<<<grid, 256, 0, stream>>>((const float*)x, P, (uint2*)xq);
+    if (x_is_bf16) GN_CUDA(gn_launch(stem_pack_input_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, (const __nv_bfloat16*)x, P, (uint2*)xq));
+    else GN_CUDA(gn_launch(stem_pack_input_kernel<float>, grid, dim3(256), 0, stream, (const float*)x, P, (uint2*)xq));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -123,11 +124,6 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     uint8_t* s_slots = s_x + (size_t)p.stages * p.strip_alloc;
     float* s_epi = reinterpret_cast<float*>(s_slots + (size_t)p.e_stages * STEM_SUB_BYTES);      // [2][STEM_MAX_CO]
 
-    for (int i = threadIdx.x; i < STEM_MAX_CO; i += blockDim.x) {
-        const bool in = i < p.CO;
-        s_epi[i] = in ? (p.scale ? p.scale[i] : 1.f) : 0.f;
-        s_epi[STEM_MAX_CO + i] = (in && p.shift) ? p.shift[i] : 0.f;
-    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
@@ -143,9 +139,16 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         fence_barrier_init();
     }
     if (warp == 3) tmem_alloc<512>(&tmem_slot);
+    gn_pdl_wait();
+    for (int i = threadIdx.x; i < STEM_MAX_CO; i += blockDim.x) {
+        const bool in = i < p.CO;
+        s_epi[i] = in ? (p.scale ? p.scale[i] : 1.f) : 0.f;
+        s_epi[STEM_MAX_CO + i] = (in && p.shift) ? p.shift[i] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gn_pdl_trigger();
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
@@ -309,9 +312,11 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<256>(&tmem_slot);
+    gn_pdl_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gn_pdl_trigger();
     const uint32_t tmem_base = tmem_slot;
     const bool has_work = (int)blockIdx.x < p.n_super;
 
@@ -463,7 +468,7 @@ GN_API int gn_stem_conv_fwd(const void* xq, int N, int P, const void* wq, int CO
         attr_set = smem;
     }
     const int grid = p.n_super < gn_num_sms() ? p.n_super : gn_num_sms();
-    stem_fwd_kernel<<<grid, 384, smem, stream>>>(tmX, tmW, tmOut, p);
+    GN_CUDA(gn_launch(stem_fwd_kernel, dim3(grid), dim3(384), smem, stream, tmX, tmW, tmOut, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -503,7 +508,7 @@ GN_API int gn_stem_conv_wgrad(const void* xq, int N, int P, const void* dz, long
         attr_set = smem;
     }
     const int grid = p.n_super < gn_num_sms() ? p.n_super : gn_num_sms();
-    stem_wgrad_kernel<<<grid, 192, smem, stream>>>(tmX, tmDz, p);
+    GN_CUDA(gn_launch(stem_wgrad_kernel, dim3(grid), dim3(192), smem, stream, tmX, tmDz, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -29,6 +29,7 @@ __device__ __forceinline__ int prep_find(const GnPrepJob* jobs, int n, long item
 
 template <typename OutT>
 __global__ void __launch_bounds__(256) prep_kernel(const GnPrepJob* __restrict__ jobs, int n_jobs, long total, OutT* __restrict__ dst) {
+    gn_pdl_sync();
     for (long item = blockIdx.x * (long)blockDim.x + threadIdx.x; item < total; item += (long)gridDim.x * blockDim.x) {
         const GnPrepJob j = jobs[prep_find(jobs, n_jobs, item)];
         const int e = (int)(item - j.start);
@@ -81,8 +82,8 @@ static int prep_launch(const void* jobs, int n_jobs, long total, void* dst, int 
     GN_REQUIRE(jobs && dst && n_jobs > 0 && total > 0, GN_EINVAL, "prepare_weights: bad arguments");
     int blocks = gn_ceil_div(total, 256);
     if (blocks > gn_num_sms() * 16) blocks = gn_num_sms() * 16;
-    if (dst_bf16) prep_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const GnPrepJob*)jobs, n_jobs, total, (__nv_bfloat16*)dst);
-    else prep_kernel<float><<<blocks, 256, 0, stream>>>((const GnPrepJob*)jobs, n_jobs, total, (float*)dst);
+    if (dst_bf16) GN_CUDA(gn_launch(prep_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, (const GnPrepJob*)jobs, n_jobs, total, (__nv_bfloat16*)dst));
+    else GN_CUDA(gn_launch(prep_kernel<float>, dim3(blocks), dim3(256), 0, stream, (const GnPrepJob*)jobs, n_jobs, total, (float*)dst));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -97,6 +97,10 @@ def hexconv_wgrad(x, dy, ksize, in_scale=None, in_shift=None, want_bias=True, ki
         return dwp, db
     dwp = torch.zeros((n_taps(ksize), cin, cout), device=x.device, dtype=torch.float32)
     if _use_tc(B, cin, cout, H, W, ksize):
+        if TENSOR_CORE_GEN != '1' and _lib.load().gn_hexconv_tc2_supported(cin, cout, H, W, ksize):
+            db = torch.zeros((cout,), device=x.device, dtype=torch.float32) if want_bias else None
+            call('gn_hexconv_wgrad_tc2', ptr(x), ptr(in_scale), ptr(in_shift), ptr(dy), ptr(dwp), ptr(db), B, cin, cout, H, W, stream())
+            return dwp, db
         ws, wptr = _aligned_workspace(_lib.load().gn_hexconv_tc_wgrad_workspace_bytes(B, H, W), x.device)
         call('gn_hexconv_wgrad_tc', ptr(x), ptr(in_scale), ptr(in_shift), ptr(dy), ptr(dwp), B, cin, cout, H, W, wptr, stream())
         db = None

@@ -57,7 +57,7 @@ def test_hexconv_fwd_bwd_matches_oracle(k, cfg):
         assert rel_err(a.grad, r.grad) < TOL
 
 
-@pytest.mark.parametrize('gen', ['2', '1'])
+@pytest.mark.parametrize('gen', ['2', '2u', '1'])
 @pytest.mark.parametrize('cfg', [(7, 32, 2, 78, 64), (32, 32, 3, 78, 64), (32, 7, 2, 78, 64), (3, 5, 2, 7, 9), (4, 4, 1, 4, 4), (14, 32, 1, 9, 70),
                                  (32, 32, 17, 78, 64), (20, 12, 3, 11, 33), (32, 32, 5, 27, 64), (16, 24, 2, 53, 32), (32, 32, 40, 78, 64)])
 def test_hexconv_tensor_core_path_matches_oracle(cfg, gen, monkeypatch):
@@ -67,7 +67,9 @@ def test_hexconv_tensor_core_path_matches_oracle(cfg, gen, monkeypatch):
     (53, 32): three strips, half-width rows; B = 40: several strips per CTA (ring / staging phases wrap many times)."""
     from gridnext_b200 import hexagdly as hx
     monkeypatch.setattr(hx, 'TENSOR_CORE_MODE', '1')
-    monkeypatch.setattr(hx, 'TENSOR_CORE_GEN', gen)
+    # '2u': the second-generation weight gradient (csrc/hexconv_wgrad_tc2.cu) with one MMA per tap instead of the taps stacked along N
+    monkeypatch.setenv('GRIDNEXT_B200_HEXWG2_STACK', '0' if gen == '2u' else '1')
+    monkeypatch.setattr(hx, 'TENSOR_CORE_GEN', gen[0])
     cin, cout, B, H, W = cfg
     ks, b, x, dy = rand_hex(cin, cout, 1, B, H, W, seed=77 + cin + H)
     ks_r = [t.clone().double().requires_grad_(True) for t in ks]
@@ -82,6 +84,7 @@ def test_hexconv_tensor_core_path_matches_oracle(cfg, gen, monkeypatch):
     y_g.backward(dy.to(dev()))
     assert rel_err(y_g, y_r) < TOL
     assert rel_err(x_g.grad, x_r.grad) < TOL
+    assert rel_err(b_g.grad, b_r.grad) < TOL
     for a, r in zip(ks_g, ks_r):
         assert rel_err(a.grad, r.grad) < TOL
 
