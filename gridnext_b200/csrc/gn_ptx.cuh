@@ -93,6 +93,22 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (contiguous bytes; address and size multiples of 16), completion on an mbarrier like a TMA load
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 16-byte asynchronous copy global -> shared by the executing thread (LDGSTS: no register, no scoreboard), and the mbarrier arrival that
+// fires when all of the thread's earlier copies have landed (.noinc: it counts against the barrier's expected arrivals)
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // L2 prefetch of a box (no shared-memory destination): hides HBM latency without spending shared memory on deeper rings
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)m), "r"(c0), "r"(c1) : "memory");

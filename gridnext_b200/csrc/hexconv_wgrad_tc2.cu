@@ -9,11 +9,11 @@
 //   * dWp[t][ci][co] = sum over cells s of dY[s, co] * x'[s + off_t(parity of s), ci] is a GEMM whose reduction index is the CELL.  In the
 //     cell-major operand rows of the forward kernel (one 128-byte row per cell: [32 channels hi | 32 channels lo] bf16) the cell is the
 //     row index, i.e. both operands are "MN-major" (gn_ptx.cuh) with the 64 (hi | lo) channel slots as M / N;
-//   * sixteen converter warps read the fp32 rows with coalesced ld.global (lane = grid column: 128 B per warp and channel; the TMA boxes
-//     of the forward kernel walk such 256-byte rows one at a time and top out at 2 TB/s), apply the previous BatchNorm+ReLU to x
-//     (gridnet_models.py:134-136), split into bf16 hi + lo and write the operand rows into two rings of row PAIRS (x: 5 pairs, dY: 3);
-//     loads run two jobs ahead of the conversion (24 registers per thread, ~48 KB in flight per SM).  An x row slot holds 72 cells: four
-//     zero cells on either side of the 64 columns, so that the column shifts of the neighbourhood are operand START ADDRESSES;
+//   * two producer warps bring the fp32 rows into a staging ring with 16-byte asynchronous copies (a job = one row pair of one tensor = per
+//     channel 2 W contiguous floats = one warp instruction; four jobs = 64 KB in flight per SM); sixteen converter warps apply the previous
+//     BatchNorm+ReLU to x (gridnet_models.py:134-136), split into bf16 hi + lo and write the operand rows into two rings of row PAIRS
+//     (x: 5 pairs, dY: 3).  An x row slot holds 72 cells: four zero cells on either side of the 64 columns, so that the column shifts
+//     of the neighbourhood are operand START ADDRESSES;
 //   * one thread issues, per grid row y (its 64 cells = 4 K steps of 16 cells) and K step, A = dY row (M = 64 channel slots, aliased
 //     to 128 with LBO = 0) against
 //         same row  : B = x row y   from column -1,                     N = 192 = taps (x-1, x, x+1)
@@ -22,10 +22,10 @@
 //     where the taps are stacked along N with LBO = 128 bytes: the next 64-slot group of the MN-major operand is the SAME rows one cell
 //     further on.  12 MMAs per grid row instead of 28 (GRIDNEXT_B200_HEXWG2_STACK=0 issues the 28);
 //   * the 128 x 448 fp32 accumulator (7 taps x 64 slots) stays in tensor memory for the life of the persistent CTA; at the end
-//     hi x hi + hi x lo + lo x hi are folded and added to dWp with atomics.  The bias gradient (channel sums of dY) is accumulated by the
-//     converters on the way (the first generation needed another pass over dY for it).
+//     hi x hi + hi x lo + lo x hi are folded and added to dWp with atomics.  The bias gradient (channel sums of dY) is one more MMA per
+//     K step against an all-ones operand (accumulator column 448; the first generation needed another pass over dY for it).
 //
-//   warp 0: MMA issuer   warps 1-16: converters (row of the pair x column half x channel quarter), then the final fold
+//   warp 0: MMA issuer   warps 1-2: copy producers   warps 3-18: converters (channel quarter x row of the pair x column half), then the final fold
 #include "gn_common.cuh"
 #include "gn_ptx.cuh"
 #include <stdlib.h>
@@ -39,13 +39,17 @@ using namespace gnptx;
 #define W2_DROW (64 * 128)
 #define W2_DSLOT (2 * W2_DROW)
 #define W2_CONV_WARPS 16
-#define W2_THREADS (32 + 32 * W2_CONV_WARPS)
-#define W2_LA 3                        // converter look-ahead: loads of job j + 2 are in flight while job j is converted
-#define W2_SMEM (W2_XR * W2_XSLOT + W2_DR * W2_DSLOT + 1024)
+#define W2_PROD_WARPS 2
+#define W2_THREADS (32 + 32 * W2_PROD_WARPS + 32 * W2_CONV_WARPS)
+#define W2_NSTG 4                      // fp32 staging ring: jobs (row pairs of one tensor) in flight
+#define W2_STAGE 16384                 // 32 channels x 2 rows x 64 columns fp32
+#define W2_ONES 2048                    // the all-ones operand of the bias gradient: 16 cells x 128 B
+#define W2_SMEM (W2_XR * W2_XSLOT + W2_DR * W2_DSLOT + W2_ONES + W2_NSTG * W2_STAGE + 1024)
 
 struct HexWg2Params {
     int B, H, W, Cin, Cout, NPA;       // NPA: row pairs per array
     int stack;
+    int dbg;                           // development (GRIDNEXT_B200_HEXWG2_DBG): 1 no MMAs, 2 no conversion, 4 no copies
     const float* x;
     const float* dy;
     const float* in_scale;
@@ -82,14 +86,15 @@ struct W2Gen {
 
 __global__ void __launch_bounds__(W2_THREADS, 1) hexconv_wgrad_tc2_kernel(const HexWg2Params p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t xfull[W2_XR], xfree[W2_XR], dfull[W2_DR], dfree[W2_DR], bar_done;
+    __shared__ __align__(8) uint64_t xfull[W2_XR], xfree[W2_XR], dfull[W2_DR], dfree[W2_DR], stg_full[W2_NSTG], stg_free[W2_NSTG], bar_done;
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_pro[2][32];
-    __shared__ float s_db[32];
+    __shared__ float2 s_pro[32];                        // {scale, shift} of the BatchNorm+ReLU in front of x
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     uint8_t* s_x = sm;                                   // [W2_XR][2 rows][72 cells][128 B]
     uint8_t* s_d = sm + W2_XR * W2_XSLOT;                // [W2_DR][2 rows][64 cells][128 B]
+    uint8_t* s_one = s_d + W2_DR * W2_DSLOT;             // [16 cells][128 B]: slot 0 = 1.0, the rest 0 -- dY x ones = the bias gradient
+    uint8_t* s_stg = s_one + W2_ONES;                    // [W2_NSTG][32 channels][2 rows][W] fp32
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // the zero cells on either side of every x row (never written again)
@@ -97,20 +102,23 @@ __global__ void __launch_bounds__(W2_THREADS, 1) hexconv_wgrad_tc2_kernel(const 
         const int row = i >> 6, cell = (i >> 3) & 7, ch = i & 7;
         *reinterpret_cast<uint4*>(s_x + (size_t)row * W2_XROW + (size_t)(cell < 4 ? cell : 64 + cell) * 128 + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
+    for (int i = threadIdx.x; i < W2_ONES / 16; i += blockDim.x) {
+        const int k = i >> 3, ch = i & 7;                // cell k, 16-byte chunk ch: element 0 of the row sits in chunk (0 ^ (k & 7))
+        *reinterpret_cast<uint4*>(s_one + i * 16) = make_uint4(ch == (k & 7) ? 0x3F80u : 0u, 0u, 0u, 0u);
+    }
     fence_proxy_async_smem();
-    if (threadIdx.x < 32) s_db[threadIdx.x] = 0.f;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < W2_XR; ++s) { mbar_init(&xfull[s], W2_CONV_WARPS); mbar_init(&xfree[s], 1); }
         for (int s = 0; s < W2_DR; ++s) { mbar_init(&dfull[s], W2_CONV_WARPS); mbar_init(&dfree[s], 1); }
+        for (int s = 0; s < W2_NSTG; ++s) { mbar_init(&stg_full[s], 32 * W2_PROD_WARPS); mbar_init(&stg_free[s], W2_CONV_WARPS); }
         mbar_init(&bar_done, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<512>(&tmem_slot);
     gn_pdl_wait();
-    if (threadIdx.x < 32) {
-        s_pro[0][threadIdx.x] = (p.in_scale != nullptr && threadIdx.x < p.Cin) ? p.in_scale[threadIdx.x] : 1.f;
-        s_pro[1][threadIdx.x] = (p.in_shift != nullptr && threadIdx.x < p.Cin) ? p.in_shift[threadIdx.x] : 0.f;
-    }
+    if (threadIdx.x < 32)
+        s_pro[threadIdx.x] = make_float2((p.in_scale != nullptr && threadIdx.x < p.Cin) ? p.in_scale[threadIdx.x] : 1.f,
+                                         (p.in_shift != nullptr && threadIdx.x < p.Cin) ? p.in_shift[threadIdx.x] : 0.f);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -128,6 +136,8 @@ __global__ void __launch_bounds__(W2_THREADS, 1) hexconv_wgrad_tc2_kernel(const 
             const uint64_t tA = smem_desc_template(0, 1024, LAYOUT_SW128);          // M = 128: the second 64-slot group aliases the first
             const uint64_t tB = smem_desc_template(128, 1024, LAYOUT_SW128);        // next 64-slot group = one cell further on
             const uint32_t x0 = smem_u32(s_x), d0 = smem_u32(s_d);
+            const uint64_t dOne = smem_desc(tA, smem_u32(s_one));
+            const bool want_db = p.dbias != nullptr;
             W2Gen gen;
             gen.init(g0, g1, p.NPA);
             uint32_t xw = 0, dw = 0, started = 0;
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) hexconv_wgrad_tc2_kernel(const 
                 const uint32_t xs[3] = {x0 + ((xi - 3) % W2_XR) * W2_XSLOT, x0 + ((xi - 2) % W2_XR) * W2_XSLOT, x0 + ((xi - 1) % W2_XR) * W2_XSLOT};
                 const uint32_t ds = d0 + (idx % W2_DR) * W2_DSLOT;
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
+                for (int r = 0; r < ((p.dbg & 1) ? 0 : 2); ++r) {
                     // row y = 2 pair + r (parity r): above = (r ? pair p row 0 : pair p-1 row 1), below = (r ? pair p+1 row 0 : pair p row 1)
                     const uint32_t same = xs[1] + r * W2_XROW;
                     const uint32_t up = r ? xs[1] : xs[0] + W2_XROW;
@@ -165,6 +175,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) hexconv_wgrad_tc2_kernel(const 
                                 umma_bf16(tmem_base + 320 + 64 * t, a, smem_desc(tA, dn + c_ud + t * 128 + ks * 2048), id1, started & 1u);
                             }
                         }
+                        if (want_db) umma_bf16(tmem_base + 448, a, dOne, id1, started & 1u);        // column 448: sum over cells of dY (hi rows, lo rows)
                         started = 1u;
                     }
                 }
@@ -178,102 +189,109 @@ __global__ void __launch_bounds__(W2_THREADS, 1) hexconv_wgrad_tc2_kernel(const 
             umma_commit(&bar_done);
         }
         __syncwarp();
+    } else if (warp <= W2_PROD_WARPS) {
+        // ------------------------------------------------------------------------------------------ producers: 16-byte asynchronous copies
+        // A job's bytes are, per channel, the row pair's 2 W contiguous floats (512 B): one warp instruction, lane l copying bytes 16 l ..
+        // 16 l + 15, into the stage as [channel][row][W].  Measured alternatives for these 32 chunks per job, 19,968 bytes apart
+        // (tools/nchw_read_probe.cu, profiles/r02wg_*): 1-D bulk copies cost ~60-85 cycles EACH whatever their size (512 B chunks: 1.65 TB/s
+        // with 64, 128 or 192 KB in flight; 1.5 KB: 4.3; 6.6 KB: 5.7) -- the same rate the forward kernel's TMA boxes reach on these rows;
+        // register loads by the converters ran one memory latency per job whatever the look-ahead in the source (six scoreboards per warp).
+        const int pw = warp - 1;
+        W2Gen gen;
+        gen.init(g0, g1, p.NPA);
+        int type, bb, pair;
+        uint32_t idx, jobno = 0;
+        const long chan = (long)p.H * p.W;
+        while (gen.next(type, bb, pair, idx)) {
+            const uint32_t st = jobno % W2_NSTG;
+            if (jobno >= W2_NSTG) mbar_wait(&stg_free[st], ((jobno / W2_NSTG) - 1) & 1);
+            const int C = type ? p.Cout : p.Cin;
+            const int y0 = 2 * pair;
+            const int rows = (y0 < 0 || y0 >= p.H || (p.dbg & 4)) ? 0 : (y0 + 1 < p.H ? 2 : 1);
+            const int bytes = rows * p.W * 4;
+            if (16 * lane < bytes) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>((type ? p.dy : p.x) + (long)bb * C * chan + (long)y0 * p.W) + 16 * lane;
+                uint8_t* dst = s_stg + (size_t)st * W2_STAGE + 16 * lane;
+                for (int c = pw; c < C; c += W2_PROD_WARPS) cp_async_16(dst + (size_t)c * 2 * p.W * 4, src + (size_t)c * chan * 4);
+            }
+            cp_async_arrive(&stg_full[st]);                              // every lane, also without copies: the barrier expects the producers' 64 arrivals
+            ++jobno;
+        }
     } else {
         // ------------------------------------------------------------------------------------------ converters
-        const int cw = warp - 1;                       // 0..15
+        // All sixteen warps work on every job; thread = (channel quarter, row of the pair, column).  The fp32 values come from the staging
+        // ring (lanes = consecutive columns: conflict-free), so a job's serial path holds no global-memory latency.
+        const int cw = warp - 1 - W2_PROD_WARPS;       // 0..15
         const int q = cw & 3;                          // channels 8q .. 8q+7
         const int r = (cw >> 2) & 1;                   // row of the pair
         const int x = ((cw >> 3) << 5) | lane;         // column 0..63
-        const long chan = (long)p.H * p.W;
         const bool has_pro = p.in_scale != nullptr;
         float sc[8], sh[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { sc[j] = s_pro[0][8 * q + j]; sh[j] = s_pro[1][8 * q + j]; }
-        float db[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) db[j] = 0.f;
+        for (int j = 0; j < 8; ++j) { sc[j] = s_pro[8 * q + j].x; sh[j] = s_pro[8 * q + j].y; }
 
         W2Gen gen;
         gen.init(g0, g1, p.NPA);
-        float v[W2_LA][8];
-        int jt[W2_LA];                                  // -1: none, 0: x (cell in the grid), 1: dY, 2: x (outside the grid: zeros)
-        uint32_t jidx[W2_LA];
-        auto load = [&](int s) {
-            int type, bb, pair;
-            uint32_t idx;
-            if (!gen.next(type, bb, pair, idx)) { jt[s] = -1; return; }
+        int type, bb, pair;
+        uint32_t idx, jobno = 0;
+        while (gen.next(type, bb, pair, idx)) {
+            const uint32_t st = jobno % W2_NSTG;
             const int y = 2 * pair + r;
             const int C = type ? p.Cout : p.Cin;
-            const bool in = y >= 0 && y < p.H && x < p.W;
-            const float* src = (type ? p.dy : p.x) + ((long)bb * C * p.H + (in ? y : 0)) * p.W + (in ? x : 0) + (long)(8 * q) * chan;
+            const bool in = y >= 0 && y < p.H && x < p.W && !(p.dbg & 6);
+            float w[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[s][j] = (in && 8 * q + j < C) ? __ldg(src + j * chan) : 0.f;
-            jt[s] = type ? 1 : (in ? 0 : 2);
-            jidx[s] = idx;
-        };
+            for (int j = 0; j < 8; ++j) w[j] = 0.f;
+            mbar_wait_backoff(&stg_full[st], (jobno / W2_NSTG) & 1);
+            if (in) {
+                const float* src = reinterpret_cast<const float*>(s_stg + (size_t)st * W2_STAGE) + (8 * q) * 2 * p.W + r * p.W + x;      // [channel][row][W]
 #pragma unroll
-        for (int s = 0; s < W2_LA - 1; ++s) load(s);
-        bool more = true;
-        while (more) {
+                for (int j = 0; j < 8; ++j)
+                    if (8 * q + j < C) w[j] = src[j * 2 * p.W];
+                if (has_pro && type == 0) {
 #pragma unroll
-            for (int s = 0; s < W2_LA; ++s) {
-                load((s + W2_LA - 1) % W2_LA);          // job j + 2 into the register set job j - 1 has left
-                if (jt[s] < 0) { more = false; break; }
-                const bool isd = jt[s] == 1;
-                const uint32_t idx = jidx[s];
-                float w[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = v[s][j];
-                if (isd) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) db[j] += w[j];
-                } else if (has_pro && jt[s] == 0) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) w[j] = 8 * q + j < p.Cin ? fmaxf(fmaf(w[j], sc[j], sh[j]), 0.f) : 0.f;
+                    for (int j = 0; j < 8; ++j) w[j] = 8 * q + j < C ? fmaxf(fmaf(w[j], sc[j], sh[j]), 0.f) : 0.f;
                 }
-                uint32_t hi[4], lo[4];
+            }
+            uint32_t hi[4], lo[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(w[2 * j], w[2 * j + 1]);
-                    const float2 hf = __bfloat1622float2(h);
-                    const __nv_bfloat162 l = __floats2bfloat162_rn(w[2 * j] - hf.x, w[2 * j + 1] - hf.y);
-                    hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-                    lo[j] = *reinterpret_cast<const uint32_t*>(&l);
-                }
-                uint8_t* row;
-                uint32_t sw;
-                if (isd) {
-                    const uint32_t slot = idx % W2_DR;
-                    if (idx >= W2_DR) mbar_wait_backoff(&dfree[slot], ((idx / W2_DR) - 1) & 1);
-                    row = s_d + (size_t)slot * W2_DSLOT + (size_t)r * W2_DROW + (size_t)x * 128;
-                    sw = (uint32_t)(x & 7);
-                } else {
-                    const uint32_t slot = idx % W2_XR;
-                    if (idx >= W2_XR) mbar_wait_backoff(&xfree[slot], ((idx / W2_XR) - 1) & 1);
-                    row = s_x + (size_t)slot * W2_XSLOT + (size_t)r * W2_XROW + (size_t)(x + 4) * 128;
-                    sw = (uint32_t)((x + 4) & 7);
-                }
-                // chunk c of the 128-byte operand row is stored at (c ^ row-in-atom) (SWIZZLE_128B; slots and rows are 1024-byte aligned)
+            for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(w[2 * j], w[2 * j + 1]);
+                const float2 hf = __bfloat1622float2(h);
+                const __nv_bfloat162 l = __floats2bfloat162_rn(w[2 * j] - hf.x, w[2 * j + 1] - hf.y);
+                hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+                lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stg_free[st]);                   // the values are in registers (the conversion consumed them)
+            uint8_t* row;
+            uint32_t sw;
+            if (type) {
+                const uint32_t slot = idx % W2_DR;
+                if (idx >= W2_DR) mbar_wait_backoff(&dfree[slot], ((idx / W2_DR) - 1) & 1);
+                row = s_d + (size_t)slot * W2_DSLOT + (size_t)r * W2_DROW + (size_t)x * 128;
+                sw = (uint32_t)(x & 7);
+            } else {
+                const uint32_t slot = idx % W2_XR;
+                if (idx >= W2_XR) mbar_wait_backoff(&xfree[slot], ((idx / W2_XR) - 1) & 1);
+                row = s_x + (size_t)slot * W2_XSLOT + (size_t)r * W2_XROW + (size_t)(x + 4) * 128;
+                sw = (uint32_t)((x + 4) & 7);
+            }
+            // chunk c of the 128-byte operand row is stored at (c ^ row-in-atom) (SWIZZLE_128B; slots and rows are 1024-byte aligned)
+            if (!(p.dbg & 2)) {
                 *reinterpret_cast<uint4*>(row + (((uint32_t)q ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4*>(row + (((uint32_t)(4 + q) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(isd ? &dfull[idx % W2_DR] : &xfull[idx % W2_XR]);
             }
-        }
-        // bias gradient: channel sums of dY
-        if (p.dbias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float a = gn_warp_sum(db[j]);
-                if (lane == 0 && 8 * q + j < p.Cout) atomicAdd(&s_db[8 * q + j], a);
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(type ? &dfull[idx % W2_DR] : &xfull[idx % W2_XR]);
+            ++jobno;
         }
         // ------------------------------------------------------------------------------------------ final fold (8 of the converter warps)
         // accumulator lanes 0..31 = dY_hi[co], 32..63 = dY_lo[co]; columns 64 t + (0..31) = x_hi[ci], + (32..63) = x_lo[ci]
         const int lg = warp & 3;                        // a warp may only touch the TMEM lane quarter warp % 4
         if (lg < 2 && g1 > g0) {
-            const int part = (warp - 1) >> 2;           // 0..3: the warps 1, 5, 9, 13 (lane quarter 1) and 4, 8, 12, 16 (quarter 0) share the 7 taps
+            const int part = (warp >> 2) - 1;           // 0..3: the warps 4, 8, 12, 16 (lane quarter 0) and 5, 9, 13, 17 (quarter 1) share the 7 taps
             mbar_wait_backoff(&bar_done, 0);
             tc_fence_after();
             const int co = lane;
@@ -292,12 +310,17 @@ __global__ void __launch_bounds__(W2_THREADS, 1) hexconv_wgrad_tc2_kernel(const 
                     }
                 }
             }
+            if (part == 3 && p.dbias != nullptr) {      // the warps with one tap only
+                uint32_t rb[4];
+                tmem_ld4(tmem_base + ((uint32_t)(lg * 32) << 16) + 448u, rb);
+                tmem_ld_wait();
+                if (co < p.Cout) atomicAdd(p.dbias + co, __uint_as_float(rb[0]));
+            }
             tc_fence_before();
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (p.dbias != nullptr && threadIdx.x < p.Cout) atomicAdd(p.dbias + threadIdx.x, s_db[threadIdx.x]);
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
@@ -306,8 +329,9 @@ __global__ void __launch_bounds__(W2_THREADS, 1) hexconv_wgrad_tc2_kernel(const 
 GN_API int gn_hexconv_wgrad_tc2(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, float* dbias, int B,
                                 int cin, int cout, int H, int W, cudaStream_t stream) {
     GN_REQUIRE(x && dy && dwp && B > 0, GN_EINVAL, "hexconv_wgrad_tc2: bad arguments");
-    GN_REQUIRE(cin >= 1 && cin <= 32 && cout >= 1 && cout <= 32 && H >= 2 && W >= 1 && W <= 64, GN_EUNSUPPORTED,
-               "hexconv_wgrad_tc2: needs kernel_size 1, <= 32 channels, W <= 64");
+    GN_REQUIRE(cin >= 1 && cin <= 32 && cout >= 1 && cout <= 32 && H >= 2 && W >= 4 && W <= 64 && W % 4 == 0, GN_EUNSUPPORTED,
+               "hexconv_wgrad_tc2: needs kernel_size 1, <= 32 channels, W <= 64 and W % 4 == 0");
+    GN_REQUIRE((((uintptr_t)x | (uintptr_t)dy) & 15) == 0, GN_EALIGN, "hexconv_wgrad_tc2: x and dy must be 16-byte aligned (bulk copies)");
     GN_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), GN_EINVAL, "hexconv_wgrad_tc2: in_scale/in_shift must come together");
     GN_REQUIRE((long)B * ((H + 1) / 2) < (1L << 30), GN_EUNSUPPORTED, "hexconv_wgrad_tc2: batch too large");
     HexWg2Params p;
@@ -318,6 +342,8 @@ GN_API int gn_hexconv_wgrad_tc2(const float* x, const float* in_scale, const flo
     {
         const char* e = getenv("GRIDNEXT_B200_HEXWG2_STACK");
         p.stack = e ? atoi(e) != 0 : 1;
+        e = getenv("GRIDNEXT_B200_HEXWG2_DBG");
+        p.dbg = e ? atoi(e) : 0;
     }
     static bool attr_set = false;
     if (!attr_set) {

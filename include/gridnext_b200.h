@@ -62,7 +62,7 @@ int gn_hexconv_wgrad_tc(const float* x, const float* in_scale, const float* in_s
                         int cout, int H, int W, void* workspace, gn_stream_t stream);
 /* Second generation of the tensor-core weight gradient (csrc/hexconv_wgrad_tc2.cu): x and dY are read once, straight from the fp32 NCHW
  * tensors, converted to bf16 hi | lo operand rows in shared memory; the cell is the reduction index, the neighbourhood's column shifts
- * are operand start addresses, taps stacked along UMMA N; no workspace.  Shapes as gn_hexconv_tc2_supported (any W <= 64).  Also
+ * are operand start addresses, taps stacked along UMMA N; no workspace.  Shapes as gn_hexconv_tc2_supported.  Also
  * produces dbias (nullable) on the way.  Same contract as gn_hexconv_wgrad: dwp / dbias are accumulated into, caller zeroes. */
 int gn_hexconv_wgrad_tc2(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, float* dbias, int B,
                          int cin, int cout, int H, int W, gn_stream_t stream);
