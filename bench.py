@@ -441,9 +441,11 @@ def main():
         wl.step_resident(k_res[0] % wl.n_slots())
         k_res[0] += 1
     run_step, graphed = run_eager, False
-    if not args.no_graph:
+    if not args.no_graph and cfg != 'c3':
         # The step is a fixed launch sequence: capture it once per rotating input and replay, so the timed region measures the
-        # GPU and not the Python/ctypes launch overhead of the host loop.
+        # GPU and not the Python/ctypes launch overhead of the host loop.  (c3 is launched eagerly: its 12-array step keeps as many
+        # chunks of DenseNet activations as device memory holds and recomputes the rest, a decision taken from the allocator's state
+        # that cannot be made under capture -- 902 ms eager against 1,030 ms replayed with every chunk recomputed.)
         try:
             torch.cuda.synchronize()
             torch.cuda.empty_cache()          # the eager warm-up's cached blocks would otherwise sit beside the graph's private pool
@@ -671,7 +673,7 @@ def roofline_from_profile(prof, wl, step_ms, args):
         px = g[4] * g[5] * g[6]
         add('gn_conv3x3_wgrad_bf16', 2.0 * 9 * px * g[7] * g[8], 2.0 * px * (g[7] + g[8]))
     # g-side kernels: algorithmic bytes 4 (Cin + Cout) per cell forward; weight gradient reads x and dy
-    for name in ('gn_hexconv_fwd', 'gn_hexconv_fwd_tc'):
+    for name in ('gn_hexconv_fwd', 'gn_hexconv_fwd_tc', 'gn_hexconv_fwd_tc2'):
         for a, b, g in prof.get(name, []):
             B_, ci_, co_, H_, W_ = g[7], g[8], g[9], g[10], g[11]
             add(name, 2.0 * 7 * ci_ * co_ * B_ * H_ * W_, 4.0 * (ci_ + co_) * B_ * H_ * W_)
@@ -681,6 +683,9 @@ def roofline_from_profile(prof, wl, step_ms, args):
     for a, b, g in prof.get('gn_hexconv_wgrad_tc', []):
         B_, ci_, co_, H_, W_ = g[5], g[6], g[7], g[8], g[9]
         add('gn_hexconv_wgrad_tc', 2.0 * 7 * ci_ * co_ * B_ * H_ * W_, 4.0 * (ci_ + co_) * B_ * H_ * W_)
+    for a, b, g in prof.get('gn_hexconv_wgrad_tc2', []):
+        B_, ci_, co_, H_, W_ = g[6], g[7], g[8], g[9], g[10]
+        add('gn_hexconv_wgrad_tc2', 2.0 * 7 * ci_ * co_ * B_ * H_ * W_, 4.0 * (ci_ + co_) * B_ * H_ * W_)
     for a, b, g in prof.get('gn_patch_gather', []):
         add('gn_patch_gather', 0.0, float(g[5]) * 3 * g[6] * g[6] * (1 + (2 if g[10] else 4)))
     for k in table:
@@ -715,6 +720,9 @@ def roofline_from_profile(prof, wl, step_ms, args):
     if wl.cfg == 'c4':
         cells = SPOTS * wl.arrays
         roof['whole_step_hbm_frac'] = G_BYTES_PER_CELL * cells / (step_ms * 1e-3) / 1e9 / pk['hbm']
+        # the g-only step is a handful of kernels: carry all of them (ms summed over their launches, algorithmic GB/s where defined)
+        roof['kernels'] = {k: dict(calls=t['calls'], ms=round(t['ms'], 4), **({'gbs': round(t['gbs'], 1)} if 'gbs' in t else {}))
+                           for k, t in sorted(table.items(), key=lambda kv: -kv[1]['ms'])}
     if args.profile_out and wl.cfg != 'c4':
         def ints(g):
             return [a if isinstance(a, int) else (None if a is None else 'p') for a in g]

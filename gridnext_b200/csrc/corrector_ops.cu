@@ -92,23 +92,49 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
 }
 
 // sums[c] += sum g ; sums[C+c] += sum g * xhat,  g = dA * [relu: (h*scale+shift) > 0]
+// Block (c, j) walks the planes b = j, j + gridDim.y, ... of channel c with 16-byte loads (no per-element index division; fp32 partial sums of
+// the <= HW / 1024 vectors a thread sees per plane, fp64 across planes): at 256 arrays x 32 channels the two kernels of the BatchNorm
+// backward took 0.44 ms against the 0.13 ms their 0.8 GB need (64-bit divisions and fp64 multiply-adds per element).
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const float* __restrict__ dA, const float* __restrict__ h,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 const float* __restrict__ mean_invstd, double* __restrict__ sums,
-                                                                int B, int C, long HW, int relu) {
+                                                                int B, int C, long HW, int relu, int vec) {
     gn_pdl_sync();
     const int c = blockIdx.x;
     const float sc = scale[c], sh_ = shift[c], mean = mean_invstd[c], invstd = mean_invstd[C + c];
     double s = 0.0, q = 0.0;
-    const long per = (long)B * HW;
-    for (long e = blockIdx.y * (long)blockDim.x + threadIdx.x; e < per; e += (long)gridDim.y * blockDim.x) {
-        long b = e / HW, p = e % HW;
-        long idx = (b * C + c) * HW + p;
-        float hv = __ldg(h + idx);
-        float g = __ldg(dA + idx);
-        if (relu && !(fmaf(hv, sc, sh_) > 0.f)) g = 0.f;
-        s += g;
-        q += (double)g * (double)((hv - mean) * invstd);
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const float* hp = h + ((long)b * C + c) * HW;
+        const float* gp = dA + ((long)b * C + c) * HW;
+        float fs = 0.f, fq = 0.f;
+        if (vec) {
+            const int n4 = (int)(HW >> 2);
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+                const float4 hv = __ldg(reinterpret_cast<const float4*>(hp) + i);
+                float4 g = __ldg(reinterpret_cast<const float4*>(gp) + i);
+                if (relu) {
+                    if (!(fmaf(hv.x, sc, sh_) > 0.f)) g.x = 0.f;
+                    if (!(fmaf(hv.y, sc, sh_) > 0.f)) g.y = 0.f;
+                    if (!(fmaf(hv.z, sc, sh_) > 0.f)) g.z = 0.f;
+                    if (!(fmaf(hv.w, sc, sh_) > 0.f)) g.w = 0.f;
+                }
+                fs += (g.x + g.y) + (g.z + g.w);
+                fq = fmaf(g.x, (hv.x - mean) * invstd, fq);
+                fq = fmaf(g.y, (hv.y - mean) * invstd, fq);
+                fq = fmaf(g.z, (hv.z - mean) * invstd, fq);
+                fq = fmaf(g.w, (hv.w - mean) * invstd, fq);
+            }
+        } else {
+            for (long i = threadIdx.x; i < HW; i += blockDim.x) {
+                const float hv = __ldg(hp + i);
+                float g = __ldg(gp + i);
+                if (relu && !(fmaf(hv, sc, sh_) > 0.f)) g = 0.f;
+                fs += g;
+                fq = fmaf(g, (hv - mean) * invstd, fq);
+            }
+        }
+        s += (double)fs;
+        q += (double)fq;
     }
     __shared__ double shm[2][8];
     s = gn_warp_sum(s);
@@ -130,7 +156,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const float* __re
                                                                const float* __restrict__ mean_invstd, const double* __restrict__ sums,
                                                                double count, int training, float* __restrict__ dH,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                               int B, int C, long HW, int relu) {
+                                                               int B, int C, long HW, int relu, int vec) {
     gn_pdl_sync();
     const int c = blockIdx.x;
     const float sc = scale[c], sh_ = shift[c], mean = mean_invstd[c], invstd = mean_invstd[C + c];
@@ -140,15 +166,37 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const float* __re
         if (dgamma) dgamma[c] = (float)sums[C + c];
         if (dbeta) dbeta[c] = (float)sums[c];
     }
-    const long per = (long)B * HW;
-    for (long e = blockIdx.y * (long)blockDim.x + threadIdx.x; e < per; e += (long)gridDim.y * blockDim.x) {
-        long b = e / HW, p = e % HW;
-        long idx = (b * C + c) * HW + p;
-        float hv = __ldg(h + idx);
-        float g = __ldg(dA + idx);
-        if (relu && !(fmaf(hv, sc, sh_) > 0.f)) g = 0.f;
-        float xhat = (hv - mean) * invstd;
-        dH[idx] = sc * (g - mg - xhat * mgx);
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const long off = ((long)b * C + c) * HW;
+        const float* hp = h + off;
+        const float* gp = dA + off;
+        float* op = dH + off;
+        if (vec) {
+            const int n4 = (int)(HW >> 2);
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+                const float4 hv = __ldg(reinterpret_cast<const float4*>(hp) + i);
+                float4 g = __ldg(reinterpret_cast<const float4*>(gp) + i);
+                if (relu) {
+                    if (!(fmaf(hv.x, sc, sh_) > 0.f)) g.x = 0.f;
+                    if (!(fmaf(hv.y, sc, sh_) > 0.f)) g.y = 0.f;
+                    if (!(fmaf(hv.z, sc, sh_) > 0.f)) g.z = 0.f;
+                    if (!(fmaf(hv.w, sc, sh_) > 0.f)) g.w = 0.f;
+                }
+                float4 o;
+                o.x = sc * (g.x - mg - (hv.x - mean) * invstd * mgx);
+                o.y = sc * (g.y - mg - (hv.y - mean) * invstd * mgx);
+                o.z = sc * (g.z - mg - (hv.z - mean) * invstd * mgx);
+                o.w = sc * (g.w - mg - (hv.w - mean) * invstd * mgx);
+                reinterpret_cast<float4*>(op)[i] = o;
+            }
+        } else {
+            for (long i = threadIdx.x; i < HW; i += blockDim.x) {
+                const float hv = __ldg(hp + i);
+                float g = __ldg(gp + i);
+                if (relu && !(fmaf(hv, sc, sh_) > 0.f)) g = 0.f;
+                op[i] = sc * (g - mg - (hv - mean) * invstd * mgx);
+            }
+        }
     }
 }
 
@@ -281,6 +329,16 @@ GN_API int gn_bn_eval_affine(const float* gamma, const float* beta, const float*
     return GN_OK;
 }
 
+// blocks per channel of the plane-wise BatchNorm-backward kernels: ~8 blocks per SM over all channels, at most one per array
+static inline int plane_chunks_for(int B, int C) {
+    long want = (8L * gn_num_sms() + C - 1) / C;
+    if (want > B) want = B;
+    return (int)(want < 1 ? 1 : want);
+}
+static inline int bn_vec_ok(const void* a, const void* b, const void* c, long HW) {
+    return (HW & 3) == 0 && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0);
+}
+
 static inline int chunks_for(long per, int C) {
     long want = (4L * gn_num_sms() + C - 1) / C;
     long maxc = (per + 255) / 256;
@@ -312,11 +370,12 @@ GN_API int gn_bn_act_bwd(const float* dA, const float* h, const float* scale, co
                          float* dbeta, int B, int C, long HW, int relu, cudaStream_t stream) {
     GN_REQUIRE(dA && h && scale && shift && mean_invstd && sums && dH && B > 0 && C > 0 && HW > 0, GN_EINVAL, "bn_act_bwd: bad arguments");
     GN_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), stream));
-    dim3 grid(C, chunks_for((long)B * HW, C));
-    GN_CUDA(gn_launch(bn_act_bwd_reduce_kernel, dim3(grid), dim3(256), 0, stream, dA, h, scale, shift, mean_invstd, sums, B, C, HW, relu));
+    dim3 grid(C, plane_chunks_for(B, C));
+    const int vec = bn_vec_ok(dA, h, dH, HW);
+    GN_CUDA(gn_launch(bn_act_bwd_reduce_kernel, dim3(grid), dim3(256), 0, stream, dA, h, scale, shift, mean_invstd, sums, B, C, HW, relu, vec));
     GN_LAUNCH_CHECK();
     GN_CUDA(gn_launch(bn_act_bwd_apply_kernel, dim3(grid), dim3(256), 0, stream, dA, h, scale, shift, mean_invstd, sums, count, training, dH, dgamma, dbeta, B, C,
-                                                      HW, relu));
+                                                      HW, relu, vec));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -326,8 +385,8 @@ GN_API int gn_bn_act_bwd_reduce(const float* dA, const float* h, const float* sc
                                 double* sums /* [2C], zeroed here */, int B, int C, long HW, int relu, cudaStream_t stream) {
     GN_REQUIRE(dA && h && scale && shift && mean_invstd && sums && B > 0 && C > 0 && HW > 0, GN_EINVAL, "bn_act_bwd_reduce: bad arguments");
     GN_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), stream));
-    dim3 grid(C, chunks_for((long)B * HW, C));
-    GN_CUDA(gn_launch(bn_act_bwd_reduce_kernel, dim3(grid), dim3(256), 0, stream, dA, h, scale, shift, mean_invstd, sums, B, C, HW, relu));
+    dim3 grid(C, plane_chunks_for(B, C));
+    GN_CUDA(gn_launch(bn_act_bwd_reduce_kernel, dim3(grid), dim3(256), 0, stream, dA, h, scale, shift, mean_invstd, sums, B, C, HW, relu, bn_vec_ok(dA, h, nullptr, HW)));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }
@@ -336,9 +395,9 @@ GN_API int gn_bn_act_bwd_apply(const float* dA, const float* h, const float* sca
                                const double* sums, double count, int training, float* dH, float* dgamma, float* dbeta, int B, int C,
                                long HW, int relu, cudaStream_t stream) {
     GN_REQUIRE(dA && h && scale && shift && mean_invstd && sums && dH && B > 0 && C > 0 && HW > 0, GN_EINVAL, "bn_act_bwd_apply: bad arguments");
-    dim3 grid(C, chunks_for((long)B * HW, C));
+    dim3 grid(C, plane_chunks_for(B, C));
     GN_CUDA(gn_launch(bn_act_bwd_apply_kernel, dim3(grid), dim3(256), 0, stream, dA, h, scale, shift, mean_invstd, sums, count, training, dH, dgamma, dbeta, B, C,
-                                                      HW, relu));
+                                                      HW, relu, bn_vec_ok(dA, h, dH, HW)));
     GN_LAUNCH_CHECK();
     return GN_OK;
 }

@@ -105,6 +105,10 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 __device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+// the same copy with src_bytes (0 or 16) taken from global memory and the rest of the 16 bytes written as zeros
+__device__ __forceinline__ void cp_async_16_zfill(void* dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -58,6 +58,8 @@ struct Hex2Params {
     int strips_per_img, n_strips;
     long long* trace;        // development: per-role clock64 timestamps of CTA 0 ([13 events][64]), see tools/hextc_trace.py
     int dbg;                 // development switches (GRIDNEXT_B200_H2_DBG): 1 no output stores, 2 no MMAs, 4 no conversion, 8 no TMEM reads
+    int tma_in;              // 0 (GRIDNEXT_B200_H2_CPASYNC=1): the input rows by 16-byte asynchronous copies instead of TMA boxes
+    const float* x;
     const float* bias;
     const float* in_scale;
     const float* in_shift;
@@ -111,7 +113,7 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tma_prefetch_desc(&tmX2);
         tma_prefetch_desc(&tmW);
         mbar_init(&bar_w, 1);
-        for (int s = 0; s < H2_STAGES; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_free[s], 4); }
+        for (int s = 0; s < H2_STAGES; ++s) { mbar_init(&stg_full[s], p.tma_in ? 1 : 32); mbar_init(&stg_free[s], 4); }
         for (int s = 0; s < H2_RP; ++s) { mbar_init(&ring_full[s], 4); mbar_init(&ring_free[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tm_full[s], 1); mbar_init(&tm_free[s], 8); }
         fence_barrier_init();
@@ -130,7 +132,46 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const uint32_t tmem_base = tmem_slot;
     const bool has_pro = p.in_scale != nullptr;
 
-    if (warp == 0) {
+    if (warp == 0 && !p.tma_in) {
+        // ------------------------------------------------------------------------------------------ producer: 16-byte asynchronous copies
+        // (experiment, GRIDNEXT_B200_H2_CPASYNC=1) One warp instruction per channel: lane = (row of the pair, 4 columns), 512 contiguous
+        // bytes of a regular pair; rows / columns / channels outside the tensor are written as zeros (src-size 0), which is what the TMA
+        // boxes' out-of-bounds fill does.  This input path took the weight gradient (hexconv_wgrad_tc2.cu) from 1.6 to 2.4 TB/s; HERE it
+        // changes nothing (0.161 vs 0.151 ms at 256 arrays, profiles/r02wg_hextc_time.txt): with eight boxes per pair the forward is bound
+        // by its epilogue (~3,000 cycles per tile), not by its loads.
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bar_w, H2_W_BYTES);
+            for (int i = 0; i < H2_W_ROWS / 64; ++i) tma_load_2d(&tmW, &bar_w, s_w + i * 64 * 128, 0, i * 64);      // 7 boxes of 64 rows
+        }
+        const int rr = lane >> 4, x4 = (lane & 15) * 4;
+        const long chan = (long)p.H * p.W;
+        uint32_t gk = 0;
+        for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
+            const int b = strip / p.strips_per_img, y0 = (strip - b * p.strips_per_img) * H2_RB;
+            for (int k = 0; k < H2_CHUNKS; ++k, ++gk) {
+                const int st = gk % H2_STAGES;
+                if (gk >= H2_STAGES) mbar_wait(&stg_free[st], ((gk / H2_STAGES) - 1) & 1);
+                uint8_t* dst = s_stg + (size_t)st * 2 * H2_ROW_F32;
+                const int r_lo = y0 - 2 + 2 * k;
+                const bool first = k == 0, last = k == H2_CHUNKS - 1;
+                // staged layout [channel][row of the pair][x] for a regular pair; a halo pair's one row as [channel][x] in its half of the stage
+                const bool mine = first ? rr == 1 : (last ? rr == 0 : true);
+                if (mine) {
+                    const int row = r_lo + rr;
+                    const bool ok = row >= 0 && row < p.H && x4 < p.W;
+                    const float* src = ok ? p.x + ((long)b * p.Cin * p.H + row) * p.W + x4 : p.x;
+                    uint8_t* d = dst + ((first || last) ? (first ? H2_ROW_F32 : 0) + x4 * 4 : rr * 256 + x4 * 4);
+                    const int cstride = (first || last) ? 256 : 512;
+#pragma unroll 8
+                    for (int c = 0; c < 32; ++c) {
+                        const bool okc = ok && c < p.Cin;
+                        cp_async_16_zfill(d + c * cstride, okc ? src + c * chan : p.x, okc ? 16u : 0u);
+                    }
+                }
+                cp_async_arrive(&stg_full[st]);
+            }
+        }
+    } else if (warp == 0) {
         // ------------------------------------------------------------------------------------------ TMA producer
         if (elect_one()) {
             mbar_arrive_expect_tx(&bar_w, H2_W_BYTES);
@@ -442,6 +483,8 @@ GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias
     {
         const char* e = getenv("GRIDNEXT_B200_H2_DBG");
         p.dbg = e ? atoi(e) : 0;
+        p.tma_in = !gn_env_flag("GRIDNEXT_B200_H2_CPASYNC");
+        p.x = x;
     }
     p.trace = g_h2_trace;
     __nv_bfloat16* wt = (__nv_bfloat16*)workspace;

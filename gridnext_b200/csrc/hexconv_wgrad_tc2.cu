@@ -14,14 +14,14 @@
 //     BatchNorm+ReLU to x (gridnet_models.py:134-136), split into bf16 hi + lo and write the operand rows into two rings of row PAIRS
 //     (x: 5 pairs, dY: 3).  An x row slot holds 72 cells: four zero cells on either side of the 64 columns, so that the column shifts
 //     of the neighbourhood are operand START ADDRESSES;
-//   * one thread issues, per grid row y (its 64 cells = 4 K steps of 16 cells) and K step, A = dY row (M = 64 channel slots, aliased
-//     to 128 with LBO = 0) against
+//   * one thread issues, per grid row y (its 64 cells = 4 K steps of 16 cells) and K step, A = dY row (M = 64 channel slots; the first
+//     version aliased them to M = 128 with LBO = 0 and kept the tensor pipe 62 % busy with half of it wasted) against
 //         same row  : B = x row y   from column -1,                     N = 192 = taps (x-1, x, x+1)
 //         row above : B = x row y-1 from column -1 (y even) / 0 (odd),  N = 128 = taps (a = 0, 1)
 //         row below : B = x row y+1 likewise,                           N = 128
 //     where the taps are stacked along N with LBO = 128 bytes: the next 64-slot group of the MN-major operand is the SAME rows one cell
 //     further on.  12 MMAs per grid row instead of 28 (GRIDNEXT_B200_HEXWG2_STACK=0 issues the 28);
-//   * the 128 x 448 fp32 accumulator (7 taps x 64 slots) stays in tensor memory for the life of the persistent CTA; at the end
+//   * the 64 x 448 fp32 accumulator (7 taps x 64 slots) stays in tensor memory for the life of the persistent CTA; at the end
 //     hi x hi + hi x lo + lo x hi are folded and added to dWp with atomics.  The bias gradient (channel sums of dY) is one more MMA per
 //     K step against an all-ones operand (accumulator column 448; the first generation needed another pass over dY for it).
 //
@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(W2_THREADS, 1) hexconv_wgrad_tc2_kernel(const 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------------ MMA issuer
         if (elect_one() && g1 > g0) {
-            const uint32_t idS = idesc_bf16(128, 192, 1, 1), idU = idesc_bf16(128, 128, 1, 1), id1 = idesc_bf16(128, 64, 1, 1);
-            const uint64_t tA = smem_desc_template(0, 1024, LAYOUT_SW128);          // M = 128: the second 64-slot group aliases the first
+            const uint32_t idS = idesc_bf16(64, 192, 1, 1), idU = idesc_bf16(64, 128, 1, 1), id1 = idesc_bf16(64, 64, 1, 1);
+            const uint64_t tA = smem_desc_template(0, 1024, LAYOUT_SW128);          // M = 64: one group of 64 channel slots
             const uint64_t tB = smem_desc_template(128, 1024, LAYOUT_SW128);        // next 64-slot group = one cell further on
             const uint32_t x0 = smem_u32(s_x), d0 = smem_u32(s_d);
             const uint64_t dOne = smem_desc(tA, smem_u32(s_one));
@@ -287,34 +287,37 @@ __global__ void __launch_bounds__(W2_THREADS, 1) hexconv_wgrad_tc2_kernel(const 
             if (lane == 0) mbar_arrive(type ? &dfull[idx % W2_DR] : &xfull[idx % W2_XR]);
             ++jobno;
         }
-        // ------------------------------------------------------------------------------------------ final fold (8 of the converter warps)
-        // accumulator lanes 0..31 = dY_hi[co], 32..63 = dY_lo[co]; columns 64 t + (0..31) = x_hi[ci], + (32..63) = x_lo[ci]
-        const int lg = warp & 3;                        // a warp may only touch the TMEM lane quarter warp % 4
-        if (lg < 2 && g1 > g0) {
-            const int part = (warp >> 2) - 1;           // 0..3: the warps 4, 8, 12, 16 (lane quarter 0) and 5, 9, 13, 17 (quarter 1) share the 7 taps
+        // ------------------------------------------------------------------------------------------ final fold (all sixteen converter warps)
+        // M = 64: accumulator row i sits in TMEM lane 32 (i / 16) + i % 16 (tools/umma_m64_probe.py), i.e. lane quarter 0 / 1 hold dY_hi of
+        // channels 0..15 / 16..31 in their first 16 lanes, quarters 2 / 3 dY_lo; columns 64 t + (0..31) = x_hi[ci], + (32..63) = x_lo[ci]
+        if (g1 > g0) {
+            const int qd = warp & 3;                    // a warp may only touch the TMEM lane quarter warp % 4
+            const int part = (warp - 1 - W2_PROD_WARPS) >> 2;       // 0..3: four warps (one per quarter) share a subset of the 7 taps
+            const bool hi_rows = qd < 2;
+            const int co = (qd & 1) * 16 + lane;
+            const bool live = lane < 16 && co < p.Cout;
             mbar_wait_backoff(&bar_done, 0);
             tc_fence_after();
-            const int co = lane;
             for (int t = part; t < 7; t += 4) {
                 uint32_t r0[32], r1[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * 64), r0);               // x x_hi[ci]
-                if (lg == 0) tmem_ld32(tmem_base + (uint32_t)(t * 64 + 32), r1);                            // dY_hi x x_lo[ci]
+                tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(t * 64), r0);                     // x x_hi[ci]
+                if (hi_rows) tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(t * 64 + 32), r1);   // dY_hi x x_lo[ci]
                 tmem_ld_wait();
-                if (co < p.Cout) {
+                if (live) {
                     float* o = p.dwp + (long)t * p.Cin * p.Cout + co;
 #pragma unroll
                     for (int ci = 0; ci < 32; ++ci) {
                         float a = __uint_as_float(r0[ci]);
-                        if (lg == 0) a += __uint_as_float(r1[ci]);
+                        if (hi_rows) a += __uint_as_float(r1[ci]);
                         if (ci < p.Cin) atomicAdd(o + (long)ci * p.Cout, a);
                     }
                 }
             }
             if (part == 3 && p.dbias != nullptr) {      // the warps with one tap only
                 uint32_t rb[4];
-                tmem_ld4(tmem_base + ((uint32_t)(lg * 32) << 16) + 448u, rb);
+                tmem_ld4(tmem_base + ((uint32_t)(qd * 32) << 16) + 448u, rb);
                 tmem_ld_wait();
-                if (co < p.Cout) atomicAdd(p.dbias + co, __uint_as_float(rb[0]));
+                if (live) atomicAdd(p.dbias + co, __uint_as_float(rb[0]));
             }
             tc_fence_before();
         }

@@ -773,8 +773,10 @@ class _DenseNetFn(torch.autograd.Function):
                     try:
                         o, kept[i] = _forward_chunk(net, geo, cst, plan, xi, True)
                     except torch.cuda.OutOfMemoryError:
+                        # the allocator's figures were too optimistic (e.g. cached blocks of a CUDA graph's private pool are counted as
+                        # reserved but cannot serve this stream): give everything kept so far back and recompute all chunks in the backward
                         may_keep = False
-                        kept.pop(i, None)
+                        kept.clear()
                         torch.cuda.empty_cache()
                         o = _forward_chunk(net, geo, cst, plan, xi, False)[0]
                 else:

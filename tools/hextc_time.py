@@ -20,8 +20,9 @@ sh = torch.randn(C, device='cuda') * 0.1
 for B in (16, 64, 256):
     x = torch.randn(B, C, 78, 64, device='cuda')
     st = torch.zeros(2 * C, device='cuda', dtype=torch.float64)
-    for gen in ('1', '2'):
-        hx.TENSOR_CORE_GEN = gen
+    for gen in ('1', '2', '2cp'):
+        hx.TENSOR_CORE_GEN = gen[0]
+        os.environ['GRIDNEXT_B200_H2_CPASYNC'] = '1' if gen == '2cp' else '0'      # gen 2 with 16-byte asynchronous copies instead of TMA boxes on the input
         for name, fn in (('fwd', lambda: hx.hexconv_fwd(x, wp, conv.bias_tensor, C, 1)),
                          ('fwd+bn_prologue+stats', lambda: hx.hexconv_fwd(x, wp, conv.bias_tensor, C, 1, sc, sh, st))):
             fn(); torch.cuda.synchronize()

@@ -39,6 +39,25 @@ def hexconv():
     torch.cuda.synchronize()
 
 
+def hexwg():
+    """The second-generation weight gradient and the BatchNorm backward at the C4 corner (256 arrays, 32 channels)."""
+    from gridnext_b200._lib import call, ptr, stream
+    hx.TENSOR_CORE_MODE = '1'
+    B, C = 256, 32
+    x = torch.randn(B, C, H, W, device=dev)
+    dy = torch.randn(B, C, H, W, device=dev)
+    sc = torch.rand(C, device=dev) + 0.5
+    sh = torch.randn(C, device=dev) * 0.1
+    mi = torch.cat([torch.zeros(C, device=dev), torch.ones(C, device=dev)])
+    sums = torch.zeros(2 * C, device=dev, dtype=torch.float64)
+    dH = torch.empty_like(x)
+    dg, db = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    for _ in range(2):
+        hx.hexconv_wgrad(x, dy, 1, sc, sh)
+        call('gn_bn_act_bwd', ptr(dy), ptr(x), ptr(sc), ptr(sh), ptr(mi), ptr(sums), float(B * H * W), 1, ptr(dH), ptr(dg), ptr(db), B, C, H * W, 1, stream())
+    torch.cuda.synchronize()
+
+
 def corrector():
     from gridnext_b200.gridnet_models import GridNetHexOddr
     from gridnext_b200.losses import masked_cross_entropy
