@@ -7,7 +7,7 @@
 // cell): 580 B of traffic per cell against the 256 algorithmic bytes -- at most 44 % of the HBM roofline, measured 25-29 %.
 // Here the traffic is the algorithmic one (+ one halo row pair per 26 rows):
 //
-//   * a persistent CTA walks strips of 26 consecutive grid rows of one array; the producer warp TMA-loads the fp32 rows (box =
+//   * a persistent CTA walks segments of consecutive grid rows of one array (H2Seg); the producer warp TMA-loads the fp32 rows (box =
 //     64 columns x 1 row x 32 channels, out-of-grid rows / columns / channels zero-filled) into a staging ring;
 //   * four converter warps apply the previous layer's BatchNorm+ReLU (gridnet_models.py:134-136), split every value into
 //     bf16 hi + lo (x = hi + lo to 16 mantissa bits; fp32-grade accuracy with x_hi w_hi + x_lo w_hi + x_hi w_lo, north_star
@@ -41,9 +41,7 @@ using namespace gnptx;
         if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 64) p.trace[(ev) * 64 + (idx)] = clock64(); \
     } while (0)
 
-#define H2_RB 26                     // grid rows per strip (even)
-#define H2_TILES (H2_RB / 2)         // 13 tiles per strip
-#define H2_CHUNKS (H2_TILES + 2)     // 15 row pairs per strip: pair k = rows y0 - 2 + 2k, y0 - 1 + 2k (first / last: one halo row)
+// a segment of nt tiles (H2Seg below) loads nt + 2 row pairs: pair k = rows y0 - 2 + 2k, y0 - 1 + 2k (first / last: one halo row)
 #define H2_STAGES 3                  // fp32 staging ring (one row pair = 16 KB per stage)
 #define H2_RP 6                      // operand ring depth in row pairs: a tile reads 3, so the converters may run 3 pairs ahead of the MMAs
                                      // (with 4 the converter <-> MMA barrier hand-offs were on the critical path: 2.4 us per tile with all work switched off)
@@ -55,7 +53,8 @@ using namespace gnptx;
 
 struct Hex2Params {
     int B, H, W, Cin, Cout;
-    int strips_per_img, n_strips;
+    int TPA;                 // tiles (row pairs) per array
+    long n_tiles;            // B * TPA
     long long* trace;        // development: per-role clock64 timestamps of CTA 0 ([13 events][64]), see tools/hextc_trace.py
     int dbg;                 // development switches (GRIDNEXT_B200_H2_DBG): 1 no output stores, 2 no MMAs, 4 no conversion, 8 no TMEM reads
     int tma_in;              // 0 (GRIDNEXT_B200_H2_CPASYNC=1): the input rows by 16-byte asynchronous copies instead of TMA boxes
@@ -65,6 +64,29 @@ struct Hex2Params {
     const float* in_shift;
     float* y;
     double* stats;
+};
+
+// A CTA owns a contiguous range of the tiles (array-major); it walks it in SEGMENTS of consecutive row pairs of one array -- the
+// range start and every array boundary start a new segment with its own halo pairs.  (First version: fixed strips of 26 rows dealt
+// round-robin, 768 strips on 148 CTAs = 6 strips for some and 5 for others, 15 pairs loaded per 13 tiles.)
+struct H2Seg {
+    long cur, t1;
+    int TPA, b, y0, nt;
+    __device__ void init(const long n_tiles, int TPA_) {
+        cur = n_tiles * blockIdx.x / gridDim.x;
+        t1 = n_tiles * (blockIdx.x + 1) / gridDim.x;
+        TPA = TPA_;
+    }
+    __device__ bool next() {
+        if (cur >= t1) return false;
+        b = (int)(cur / TPA);
+        const int p0 = (int)(cur - (long)b * TPA);
+        const long left = t1 - cur;
+        nt = left < (long)(TPA - p0) ? (int)left : TPA - p0;
+        y0 = 2 * p0;
+        cur += nt;
+        return true;
+    }
 };
 
 // wp fp32 [7][cin][cout] (gn_hexconv_pack, mode 0 forward / mode 1 data gradient) -> bf16 B-operand tiles, 128-byte rows:
@@ -146,14 +168,17 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const int rr = lane >> 4, x4 = (lane & 15) * 4;
         const long chan = (long)p.H * p.W;
         uint32_t gk = 0;
-        for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
-            const int b = strip / p.strips_per_img, y0 = (strip - b * p.strips_per_img) * H2_RB;
-            for (int k = 0; k < H2_CHUNKS; ++k, ++gk) {
+        H2Seg seg;
+        seg.init(p.n_tiles, p.TPA);
+        while (seg.next()) {
+            const int b = seg.b, y0 = seg.y0, nt = seg.nt, nchunks = nt + 2;
+            (void)nt; (void)nchunks;
+            for (int k = 0; k < nchunks; ++k, ++gk) {
                 const int st = gk % H2_STAGES;
                 if (gk >= H2_STAGES) mbar_wait(&stg_free[st], ((gk / H2_STAGES) - 1) & 1);
                 uint8_t* dst = s_stg + (size_t)st * 2 * H2_ROW_F32;
                 const int r_lo = y0 - 2 + 2 * k;
-                const bool first = k == 0, last = k == H2_CHUNKS - 1;
+                const bool first = k == 0, last = k == nchunks - 1;
                 // staged layout [channel][row of the pair][x] for a regular pair; a halo pair's one row as [channel][x] in its half of the stage
                 const bool mine = first ? rr == 1 : (last ? rr == 0 : true);
                 if (mine) {
@@ -177,16 +202,19 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             mbar_arrive_expect_tx(&bar_w, H2_W_BYTES);
             for (int i = 0; i < H2_W_ROWS / 64; ++i) tma_load_2d(&tmW, &bar_w, s_w + i * 64 * 128, 0, i * 64);      // 7 boxes of 64 rows
             uint32_t gk = 0;                                            // running row-pair index of this CTA
-            for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
-                const int b = strip / p.strips_per_img, y0 = (strip - b * p.strips_per_img) * H2_RB;
-                for (int k = 0; k < H2_CHUNKS; ++k, ++gk) {
+            H2Seg seg;
+            seg.init(p.n_tiles, p.TPA);
+            while (seg.next()) {
+                const int b = seg.b, y0 = seg.y0, nt = seg.nt, nchunks = nt + 2;
+                (void)nt; (void)nchunks;
+                for (int k = 0; k < nchunks; ++k, ++gk) {
                     const int st = gk % H2_STAGES;
                     if (gk >= H2_STAGES) mbar_wait(&stg_free[st], ((gk / H2_STAGES) - 1) & 1);
                     uint8_t* dst = s_stg + (size_t)st * 2 * H2_ROW_F32;
                     const int r_lo = y0 - 2 + 2 * k;
-                    const bool first = k == 0, last = k == H2_CHUNKS - 1;
+                    const bool first = k == 0, last = k == nchunks - 1;
                     // staged layout [channel][row of the pair][x]: a regular pair is ONE box (64 x 2 rows x 32 channels: 512 contiguous bytes per
-                    // channel); the halo pairs at the strip ends load their single row into the same layout with the one-row map
+                    // channel); the halo pairs at the segment ends load their single row into the same layout with the one-row map
                     mbar_arrive_expect_tx(&stg_full[st], (first || last) ? H2_ROW_F32 : 2 * H2_ROW_F32);
                     // A TMA operation walks the rows of its box (here 256-byte rows 20 KB apart) nearly one at a time: with one 64-row box
                     // per pair the loads alone took 0.19 ms for 256 arrays (1.7 TB/s; measured with every other role switched off).  Eight
@@ -211,15 +239,18 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const uint64_t dD_hi = smem_desc(tmpl, w0 + 320 * 128), dD_lo = smem_desc(tmpl, w0 + 384 * 128);
             mbar_wait(&bar_w, 0);
             uint32_t gk = 0, waited = 0, tile_seq = 0;
-            for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
-                for (int t = 0; t < H2_TILES; ++t, ++tile_seq) {
+            H2Seg seg;
+            seg.init(p.n_tiles, p.TPA);
+            while (seg.next()) {
+                const int nt = seg.nt, nchunks = nt + 2;
+                for (int t = 0; t < nt; ++t, ++tile_seq) {
                     // row pairs gk + t, + t + 1, + t + 2 must be converted
                     while (waited < gk + t + 3) { mbar_wait(&ring_full[waited % H2_RP], (waited / H2_RP) & 1); ++waited; }
                     const int acc = tile_seq & 1;
                     if (tile_seq >= 2) mbar_wait(&tm_free[acc], ((tile_seq >> 1) - 1) & 1);
                     tc_fence_after();
                     H2_TRACE(4, tile_seq);
-                    // slot of row index i (running over all strips: 2 * (gk + pair) + row): i mod 12; a pair starting at the last slot continues
+                    // slot of row index i (running over all segments: 2 * (gk + pair) + row): i mod 12; a pair starting at the last slot continues
                     // in the mirror slot behind it
                     const uint32_t i_own = 2 * (gk + t + 1);                     // first own row (even slot)
                     const uint32_t a_own = ring0 + ((i_own % (2 * H2_RP)) * H2_SLOT);
@@ -236,20 +267,22 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     for (int k = 0; k < 4; ++k) umma_bf16(d + 96, dA_up + (uint64_t)(2 * k), dU_hi + (uint64_t)(2 * k), idU, k > 0);
 #pragma unroll
                     for (int k = 0; k < 2; ++k) umma_bf16(d + 96, dA_up + (uint64_t)(2 * k), dU_lo + (uint64_t)(2 * k), idU, 1u);
+                    // the rows below go into the SAME two column blocks as the rows above: both taps a = 0 / 1 of either row take the same lane
+                    // shift, so the tensor core adds them (64 accumulator columns and 32 TMEM loads + adds per epilogue thread fewer)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(d + 160, dA_dn + (uint64_t)(2 * k), dD_hi + (uint64_t)(2 * k), idU, k > 0);
+                    for (int k = 0; k < 4; ++k) umma_bf16(d + 96, dA_dn + (uint64_t)(2 * k), dD_hi + (uint64_t)(2 * k), idU, 1u);
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) umma_bf16(d + 160, dA_dn + (uint64_t)(2 * k), dD_lo + (uint64_t)(2 * k), idU, 1u);
+                    for (int k = 0; k < 2; ++k) umma_bf16(d + 96, dA_dn + (uint64_t)(2 * k), dD_lo + (uint64_t)(2 * k), idU, 1u);
                     }
                     umma_commit(&tm_full[acc]);
                     umma_commit(&ring_free[(gk + t) % H2_RP]);                   // row pair gk + t is not read again
-                    if (t == H2_TILES - 1) {
+                    if (t == nt - 1) {
                         umma_commit(&ring_free[(gk + t + 1) % H2_RP]);
                         umma_commit(&ring_free[(gk + t + 2) % H2_RP]);
                     }
                     H2_TRACE(5, tile_seq);
                 }
-                gk += H2_CHUNKS;
+                gk += nchunks;
             }
         }
     } else if (warp < 6) {
@@ -258,20 +291,23 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const int r = cw >> 1;                      // row of the pair
         const int x = ((cw & 1) << 5) | lane;       // column 0..63
         uint32_t gk = 0;
-        for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
-            const int b = strip / p.strips_per_img, y0 = (strip - b * p.strips_per_img) * H2_RB;
+        H2Seg seg;
+        seg.init(p.n_tiles, p.TPA);
+        while (seg.next()) {
+            const int b = seg.b, y0 = seg.y0, nt = seg.nt, nchunks = nt + 2;
+            (void)nt; (void)nchunks;
             (void)b;
-            for (int k = 0; k < H2_CHUNKS; ++k, ++gk) {
+            for (int k = 0; k < nchunks; ++k, ++gk) {
                 const int st = gk % H2_STAGES, rs = gk % H2_RP;
                 mbar_wait_backoff(&stg_full[st], (gk / H2_STAGES) & 1);
                 if (threadIdx.x == 64) H2_TRACE(1, gk);
                 if (gk >= H2_RP) mbar_wait_backoff(&ring_free[rs], ((gk / H2_RP) - 1) & 1);
                 if (threadIdx.x == 64) H2_TRACE(2, gk);
                 const int gy = y0 - 2 + 2 * k + r;
-                const bool loaded = !((k == 0 && r == 0) || (k == H2_CHUNKS - 1 && r == 1));
+                const bool loaded = !((k == 0 && r == 0) || (k == nchunks - 1 && r == 1));
                 if (loaded && !(p.dbg & 4)) {
                     // regular pair: [c][r][x] (128 floats per channel); halo pair: its one row as [c][x] in the half of the stage it was loaded to
-                    const bool halo = k == 0 || k == H2_CHUNKS - 1;
+                    const bool halo = k == 0 || k == nchunks - 1;
                     const int cs = halo ? 64 : 128;
                     const float* src = reinterpret_cast<const float*>(s_stg + (size_t)st * 2 * H2_ROW_F32) + (halo ? r * (H2_ROW_F32 / 4) : r * 64) + x;
                     const bool live = has_pro && gy >= 0 && gy < p.H && x < p.W;     // zero padding stays zero
@@ -329,9 +365,12 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (int e = 0; e < 16; ++e) sg[e] = sq[e] = 0.f;
         const long chan = (long)p.H * p.W;
         uint32_t tile_seq = 0;
-        for (int strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
-            const int b = strip / p.strips_per_img, y0 = (strip - b * p.strips_per_img) * H2_RB;
-            for (int t = 0; t < H2_TILES; ++t, ++tile_seq) {
+        H2Seg seg;
+        seg.init(p.n_tiles, p.TPA);
+        while (seg.next()) {
+            const int b = seg.b, y0 = seg.y0, nt = seg.nt, nchunks = nt + 2;
+            (void)nt; (void)nchunks;
+            for (int t = 0; t < nt; ++t, ++tile_seq) {
                 const int acc = tile_seq & 1;
                 const int yy = y0 + 2 * t + par;
                 const bool valid = yy < p.H && x < p.W;
@@ -354,16 +393,14 @@ hexconv_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 }
 #pragma unroll
                 for (int q8 = 0; q8 < ((p.dbg & 8) ? 0 : 2); ++q8) {                           // 8 channels at a time (register budget: 146 per thread)
-                    uint32_t u0[8], u1[8], d0[8], d1[8];
+                    uint32_t u0[8], u1[8];
                     tmem_ld8(ta + 96 + 8 * q8, u0);
                     tmem_ld8(ta + 128 + 8 * q8, u1);
-                    tmem_ld8(ta + 160 + 8 * q8, d0);
-                    tmem_ld8(ta + 192 + 8 * q8, d1);
                     tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const float a0 = __uint_as_float(u0[e]) + __uint_as_float(d0[e]);      // tap a = 0 of the rows above / below
-                        const float a1 = __uint_as_float(u1[e]) + __uint_as_float(d1[e]);      // tap a = 1
+                        const float a0 = __uint_as_float(u0[e]);      // tap a = 0 of the rows above + below (summed in the accumulator)
+                        const float a1 = __uint_as_float(u1[e]);      // tap a = 1
                         if (par == 0) { L[8 * q8 + e] += a0; C[8 * q8 + e] += a1; }            // even row: columns x-1, x
                         else { C[8 * q8 + e] += a0; R[8 * q8 + e] += a1; }                     // odd row:  columns x, x+1
                     }
@@ -477,8 +514,8 @@ GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias
     Hex2Params p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.H = H; p.W = W; p.Cin = cin; p.Cout = cout;
-    p.strips_per_img = gn_ceil_div(H, H2_RB);
-    p.n_strips = B * p.strips_per_img;
+    p.TPA = (H + 1) / 2;
+    p.n_tiles = (long)B * p.TPA;
     p.bias = bias; p.in_scale = in_scale; p.in_shift = in_shift; p.y = y; p.stats = stats;
     {
         const char* e = getenv("GRIDNEXT_B200_H2_DBG");
@@ -514,7 +551,7 @@ GN_API int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias
         GN_CUDA(cudaFuncSetAttribute(hexconv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const int grid = p.n_strips < gn_num_sms() ? p.n_strips : gn_num_sms();
+    const int grid = p.n_tiles < gn_num_sms() ? (int)p.n_tiles : gn_num_sms();
     GN_CUDA(gn_launch(hexconv_tc2_kernel, dim3(grid), dim3(H2_THREADS), smem, stream, tmX, tmX2, tmW, p));
     GN_LAUNCH_CHECK();
     return GN_OK;
