@@ -7,6 +7,7 @@ fallback: if the library is missing or a call fails, the caller gets an exceptio
 import ctypes
 import os
 import torch
+import torch.distributed as _dist
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libgridnext_b200.so')
@@ -19,6 +20,7 @@ vp, ci, cl, cf, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_floa
 _SIGS = {
     'gn_version': [],
     'gn_device_sm_count': [],
+    'gn_set_pdl': [ci],
     'gn_hexconv_n_taps': [ci],
     'gn_hexconv_pack': [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp],
     'gn_hexconv_unpack_grad': [vp, vp, vp, vp, vp, ci, ci, ci, vp],
@@ -139,13 +141,29 @@ def check(rc, what=''):
 
 # kernels launched per C-ABI call (for the benchmark's gpu_launches count); default 1
 KERNELS_PER_CALL = {'gn_corrector_fused_supported': 0, 'gn_cell_inverse': 2, 'gn_mm_fg_consistency': 2, 'gn_hexconv_fwd_tc': 3, 'gn_hexconv_wgrad_tc': 3, 'gn_hexconv_tc_supported': 0, 'gn_hexconv_tc2_supported': 0, 'gn_hexconv_tc2_set_trace': 0, 'gn_hexconv_fwd_tc2': 2, 'gn_masked_ce': 3, 'gn_bn_act_bwd': 2, 'gn_spot_table': 1, 'gn_linear_small_bwd': 2, 'gn_version': 0, 'gn_prep_job_bytes': 0,
-                    'gn_device_sm_count': 0, 'gn_hexconv_n_taps': 0}
+                    'gn_device_sm_count': 0, 'gn_hexconv_n_taps': 0, 'gn_set_pdl': 0}
 LAUNCHES = [0]
 PROFILE = None      # when a dict: name -> [n_calls, [cuda event pairs]]
 
 
+_PDL_DECIDED = [False]
+
+
+def _decide_pdl(lib):
+    """Programmatic dependent launch stays on for single-process runs and is switched off once a process group with more than one rank
+    exists (the 2-GPU step with NCCL's all-reduce between kernels that trigger their dependents early hung on the B200 pool)."""
+    if not _dist.is_available():
+        _PDL_DECIDED[0] = True
+    elif _dist.is_initialized():
+        if _dist.get_world_size() > 1:
+            lib.gn_set_pdl(0)
+        _PDL_DECIDED[0] = True
+
+
 def call(name, *args):
     lib = load()
+    if not _PDL_DECIDED[0]:
+        _decide_pdl(lib)
     LAUNCHES[0] += KERNELS_PER_CALL.get(name, 1)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

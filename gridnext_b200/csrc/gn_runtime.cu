@@ -29,10 +29,18 @@ int gn_num_sms() {
 
 GN_API int gn_device_sm_count(void) { return gn_num_sms(); }
 
+static int g_pdl = -1;
 int gn_pdl_enabled() {
-    static int on = -1;
-    if (on < 0) on = gn_env_flag("GN_NO_PDL") ? 0 : 1;
-    return on;
+    if (g_pdl < 0) g_pdl = gn_env_flag("GN_NO_PDL") ? 0 : 1;
+    return g_pdl;
+}
+// Switch programmatic dependent launch on / off for every later launch of this process (returns the previous setting).  The host
+// side switches it OFF in data-parallel runs: with kernels that trigger their dependents early, the 2-GPU step (NCCL all-reduce
+// between backward and optimizer) hung on the B200 pool, while every single-process configuration ran clean.
+GN_API int gn_set_pdl(int on) {
+    const int prev = gn_pdl_enabled();
+    g_pdl = (on && !gn_env_flag("GN_NO_PDL")) ? 1 : 0;
+    return prev;
 }
 
 // ------------------------------------------------------------------------------------------------

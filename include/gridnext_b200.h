@@ -25,6 +25,10 @@ typedef void* gn_stream_t; /* cudaStream_t */
 int gn_version(void);
 const char* gn_last_error(void);
 int gn_device_sm_count(void);
+/* Programmatic dependent launch of the hot-path kernels (csrc/gn_common.cuh: each kernel's prologue overlaps the tail of its predecessor)
+ * on (default; GN_NO_PDL=1 in the environment forces off) or off for every later launch of this process; returns the previous setting.
+ * The host side switches it off in data-parallel runs (NCCL kernels between kernels that trigger their dependents early: 2-GPU hang). */
+int gn_set_pdl(int on);
 
 /* ---- hexagonal convolution: replaces hexagdly.Conv2d.forward/backward (stride 1) as built by
  * gridnext/gridnet_models.py:128-148 plus the rot90/flip pair of gridnet_models.py:177-185.
