@@ -34,6 +34,14 @@ def _worker(rank, world, port, out):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         assert parallel.is_distributed() and parallel.rank() == rank and parallel.world_size() == world
+        # programmatic dependent launch must be off in a process group with more than one rank (the 2-GPU step hung with NCCL's
+        # all-reduce between kernels that trigger their dependents early): the first C-ABI call after init_process_group decides it
+        from gridnext_b200 import _lib
+        lib = _lib.load()
+        assert lib.gn_set_pdl(1) in (0, 1)
+        _lib._PDL_DECIDED[0] = False
+        _lib._decide_pdl(lib)
+        assert _lib._PDL_DECIDED[0] and lib.gn_set_pdl(0) == 0
         model = _model()
         bucket = parallel.GradBucket(model.parameters())
         x, y = _data()
