@@ -97,7 +97,8 @@ def hexconv_wgrad(x, dy, ksize, in_scale=None, in_shift=None, want_bias=True, ki
         return dwp, db
     dwp = torch.zeros((n_taps(ksize), cin, cout), device=x.device, dtype=torch.float32)
     if _use_tc(B, cin, cout, H, W, ksize):
-        if TENSOR_CORE_GEN != '1' and _lib.load().gn_hexconv_tc2_supported(cin, cout, H, W, ksize):
+        if (TENSOR_CORE_GEN != '1' and _lib.load().gn_hexconv_tc2_supported(cin, cout, H, W, ksize)
+                and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0):       # 16-byte asynchronous copies; an odd view takes generation 1
             db = torch.zeros((cout,), device=x.device, dtype=torch.float32) if want_bias else None
             call('gn_hexconv_wgrad_tc2', ptr(x), ptr(in_scale), ptr(in_shift), ptr(dy), ptr(dwp), ptr(db), B, cin, cout, H, W, stream())
             return dwp, db
