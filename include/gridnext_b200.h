@@ -25,7 +25,8 @@ typedef void* gn_stream_t; /* cudaStream_t */
 int gn_version(void);
 const char* gn_last_error(void);
 int gn_device_sm_count(void);
-/* Programmatic dependent launch of the hot-path kernels (csrc/gn_common.cuh: each kernel's prologue overlaps the tail of its predecessor)
+/* Runtime switch without a counterpart in the reference (which has no native code): programmatic dependent launch of the hot-path
+ * kernels (csrc/gn_common.cuh: each kernel's prologue overlaps the tail of its predecessor)
  * on (default; GN_NO_PDL=1 in the environment forces off) or off for every later launch of this process; returns the previous setting.
  * The host side switches it off in data-parallel runs (NCCL kernels between kernels that trigger their dependents early: 2-GPU hang). */
 int gn_set_pdl(int on);
@@ -64,7 +65,8 @@ int gn_hexconv_fwd_tc2(const float* x, const float* wp, const float* bias, const
 long gn_hexconv_tc_wgrad_workspace_bytes(int B, int H, int W);
 int gn_hexconv_wgrad_tc(const float* x, const float* in_scale, const float* in_shift, const float* dy, float* dwp, int B, int cin,
                         int cout, int H, int W, void* workspace, gn_stream_t stream);
-/* Second generation of the tensor-core weight gradient (csrc/hexconv_wgrad_tc2.cu): x and dY are read once, straight from the fp32 NCHW
+/* Second generation of the tensor-core weight gradient -- autograd's dW / db of the hexagdly.Conv2d layers built at
+ * /root/reference/gridnext/gridnet_models.py:128-148, reached from training.py:141-171 (csrc/hexconv_wgrad_tc2.cu): x and dY are read once, straight from the fp32 NCHW
  * tensors, converted to bf16 hi | lo operand rows in shared memory; the cell is the reduction index, the neighbourhood's column shifts
  * are operand start addresses, taps stacked along UMMA N; no workspace.  Shapes as gn_hexconv_tc2_supported.  Also
  * produces dbias (nullable) on the way.  Same contract as gn_hexconv_wgrad: dwp / dbias are accumulated into, caller zeroes. */
