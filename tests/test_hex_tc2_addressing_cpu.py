@@ -153,3 +153,49 @@ def test_forward_tile_ranges_cover_every_tile_once(B, H, n_ctas):
     if (B, H) == (256, 78):
         # the C4 corner: at most 3 segments per CTA -> 8 % more row pairs loaded than tiles computed (the 26-row strips: 15 %)
         assert loads / n_tiles < 1.09
+
+
+def emulate_fwd_tc2(x, ks):
+    """The forward kernel's arithmetic per tile of two grid rows (y even, y + 1), restated: taps stacked along N, the column shifts applied
+    as neighbour-LANE sums in the epilogue, and -- the last change -- the rows below accumulated into the SAME two column blocks as the
+    rows above.  x (B, Cin, H, W) float64, ks = hexagdly kernels; returns (B, Cout, H, W)."""
+    B, Cin, H, W = x.shape
+    taps = R.tap_table(1)
+    Wt = [ks[i][:, :, a, side].numpy().T for (i, a, side, *_r) in taps]          # [7] x (Cin, Cout)
+    Cout = Wt[0].shape[1]
+    out = np.zeros((B, Cout, H, W))
+    xp = np.zeros((B, H + 4, W, Cin))                                            # rows -2 .. H+1, cell-major [x][channel]
+    xp[:, 2:H + 2] = x.transpose(0, 2, 3, 1)
+    for b in range(B):
+        for y in range(0, H, 2):
+            own = xp[b, y + 2:y + 4].reshape(2 * W, Cin)                         # the tile's 2 W accumulator rows: (row of the pair, x)
+            up = xp[b, y + 1:y + 3].reshape(2 * W, Cin)                          # rows (y - 1, y): a whole-slot operand shift
+            dn = xp[b, y + 3:y + 5].reshape(2 * W, Cin)                          # rows (y + 1, y + 2)
+            E_l, E_c, E_r = own @ Wt[0], own @ Wt[1], own @ Wt[2]                # same row: N = 96
+            a0 = up @ Wt[3] + dn @ Wt[5]                                         # tap a = 0 of the row above + below: one column block
+            a1 = up @ Wt[4] + dn @ Wt[6]                                         # tap a = 1
+            for par in range(2):
+                if y + par >= H:
+                    continue
+                s = slice(par * W, (par + 1) * W)
+                L, C, Rr = E_l[s].copy(), E_c[s].copy(), E_r[s].copy()
+                if par == 0:                                                     # even row: columns x - 1, x
+                    L += a0[s]; C += a1[s]
+                else:                                                            # odd row: columns x, x + 1
+                    C += a0[s]; Rr += a1[s]
+                o = C.copy()                                                     # out[x] = L[x - 1] + C[x] + R[x + 1], zero padding at the ends
+                o[1:] += L[:-1]
+                o[:-1] += Rr[1:]
+                out[b, :, y + par, :] = o.T
+    return out
+
+
+@pytest.mark.parametrize('shape', [(2, 3, 4, 9, 8), (1, 5, 2, 78, 64), (3, 2, 2, 4, 4)])
+def test_forward_tc2_lane_sums_and_merged_rows_match_oracle(shape):
+    B, cin, cout, H, W = shape
+    g = torch.Generator(); g.manual_seed(H * 7 + W)
+    ks = [torch.randn(s, dtype=torch.float64, generator=g) for s in R.kernel_shapes(cin, cout, 1)]
+    x = torch.randn(B, cin, H, W, dtype=torch.float64, generator=g)
+    ref = R.hexconv_visium(x, ks).numpy()
+    got = emulate_fwd_tc2(x.numpy(), ks)
+    assert np.abs(got - ref).max() < 1e-10 * max(1.0, np.abs(ref).max())
